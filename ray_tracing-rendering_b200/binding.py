@@ -1,0 +1,214 @@
+"""ctypes binding of librtb200.so (include/rtb200.h).
+
+Plumbing only: every call goes straight through the C-ABI; there is no Python or
+CPU implementation of anything behind it.  Loading fails loudly when the library
+has not been built, and creating a context fails loudly without a CUDA device.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librtb200.so")
+
+RTB_OK = 0
+STATUS_NAMES = {0: "RTB_OK", -1: "RTB_ERR_INVALID_ARGUMENT", -2: "RTB_ERR_NO_DEVICE",
+                -3: "RTB_ERR_CUDA", -4: "RTB_ERR_BAD_SCENE", -5: "RTB_ERR_NO_SCENE",
+                -6: "RTB_ERR_CANCELLED", -7: "RTB_ERR_OUT_OF_MEMORY"}
+RENDER_COUNT_VISITS = 1
+
+# Every symbol include/rtb200.h declares (tests check the library exports them all).
+EXPORTS = ["rtb_version", "rtb_context_create", "rtb_context_destroy", "rtb_last_error",
+           "rtb_scene_upload", "rtb_scene_get_stats", "rtb_camera_derived", "rtb_render",
+           "rtb_render_device", "rtb_cancel", "rtb_resolve_rgb8", "rtb_trace_batch",
+           "rtb_bsdf_eval_batch", "rtb_bsdf_sample_batch", "rtb_light_eval_batch",
+           "rtb_texture_eval_batch"]
+
+
+class RenderParams(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("spp", C.c_int32),
+                ("max_depth", C.c_int32), ("rr_start_depth", C.c_int32), ("integrator", C.c_int32),
+                ("sample_offset", C.c_int32), ("sample_stride", C.c_int32), ("seed", C.c_uint64),
+                ("pool_paths", C.c_int32), ("flags", C.c_int32)]
+
+
+class RenderStats(C.Structure):
+    _fields_ = [("paths", C.c_uint64), ("rays_closest", C.c_uint64), ("rays_shadow", C.c_uint64),
+                ("nodes_visited", C.c_uint64), ("prim_tests", C.c_uint64), ("iterations", C.c_uint64),
+                ("kernel_launches", C.c_uint64), ("device_ms", C.c_double), ("extend_ms", C.c_double),
+                ("extend_launches", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class SceneStats(C.Structure):
+    _fields_ = [("n_prims", C.c_int32), ("n_nodes", C.c_int32), ("n_instances", C.c_int32),
+                ("n_materials", C.c_int32), ("n_lights", C.c_int32), ("has_media", C.c_int32),
+                ("device_bytes", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class RtbError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"{STATUS_NAMES.get(status, status)}: {message}")
+        self.status = status
+
+
+_lib = None
+
+
+def load():
+    """dlopen librtb200.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with __graft_entry__.build() "
+                          "(there is no fallback implementation)")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
+    L.rtb_version.restype = C.c_char_p
+    L.rtb_context_create.argtypes = [i32, C.POINTER(vp)]
+    L.rtb_context_destroy.argtypes = [vp]
+    L.rtb_context_destroy.restype = None
+    L.rtb_last_error.argtypes = [vp]
+    L.rtb_last_error.restype = C.c_char_p
+    L.rtb_scene_upload.argtypes = [vp, vp, u64]
+    L.rtb_scene_get_stats.argtypes = [vp, C.POINTER(SceneStats)]
+    L.rtb_camera_derived.argtypes = [vp, vp]
+    L.rtb_render.argtypes = [vp, C.POINTER(RenderParams), vp, C.POINTER(RenderStats)]
+    L.rtb_render_device.argtypes = [vp, C.POINTER(RenderParams), vp, vp, C.POINTER(RenderStats)]
+    L.rtb_cancel.argtypes = [vp]
+    L.rtb_resolve_rgb8.argtypes = [vp, C.c_int32, vp]
+    L.rtb_trace_batch.argtypes = [vp, vp, u64, i32, vp, vp]
+    L.rtb_bsdf_eval_batch.argtypes = [vp, i32, vp, u64, i32, vp]
+    L.rtb_bsdf_sample_batch.argtypes = [vp, i32, vp, u64, i32, u64, vp]
+    L.rtb_light_eval_batch.argtypes = [vp, i32, vp, u64, i32, u64, vp]
+    L.rtb_texture_eval_batch.argtypes = [vp, i32, vp, u64, i32, vp]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One rtb_context (one GPU)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load()
+        h = C.c_void_p()
+        rc = self._lib.rtb_context_create(int(device), C.byref(h))
+        if rc != RTB_OK:
+            raise RtbError(rc, self._lib.rtb_last_error(None).decode())
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rtb_context_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != RTB_OK:
+            raise RtbError(rc, self._lib.rtb_last_error(self._h).decode())
+
+    # ---- scene
+    def upload_scene(self, blob: bytes):
+        buf = C.create_string_buffer(blob, len(blob))
+        self._check(self._lib.rtb_scene_upload(self._h, C.cast(buf, C.c_void_p), len(blob)))
+
+    def scene_stats(self) -> dict:
+        s = SceneStats()
+        self._check(self._lib.rtb_scene_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def camera_derived(self):
+        out = np.zeros(24)
+        self._check(self._lib.rtb_camera_derived(self._h, _ptr(out)))
+        return out
+
+    # ---- render
+    @staticmethod
+    def params(width, height, spp, integrator, max_depth=50, rr_start_depth=3, seed=1,
+               sample_offset=0, sample_stride=1, pool_paths=0, flags=0) -> RenderParams:
+        return RenderParams(width, height, spp, max_depth, rr_start_depth, integrator, sample_offset,
+                            sample_stride, seed, pool_paths, flags)
+
+    def render(self, params: RenderParams, out=None):
+        """Host-buffer render: returns (accum[h, w, 4] float32 linear SUMS, stats dict)."""
+        if out is None:
+            out = np.empty((params.height, params.width, 4), np.float32)
+        st = RenderStats()
+        self._check(self._lib.rtb_render(self._h, C.byref(params), _ptr(out), C.byref(st)))
+        return out, st.as_dict()
+
+    def render_device(self, params: RenderParams, device_ptr: int, stream: int = 0):
+        """Render into a caller-owned device buffer (e.g. a torch tensor's data_ptr())."""
+        st = RenderStats()
+        self._check(self._lib.rtb_render_device(self._h, C.byref(params), C.c_void_p(device_ptr),
+                                                C.c_void_p(stream), C.byref(st)))
+        return st.as_dict()
+
+    def cancel(self):
+        self._check(self._lib.rtb_cancel(self._h))
+
+    def resolve_rgb8(self, width, height, spp):
+        out = np.empty((height, width, 3), np.uint8)
+        self._check(self._lib.rtb_resolve_rgb8(self._h, spp, _ptr(out)))
+        return out
+
+    # ---- parity-layer batches
+    def trace(self, rays, precision=64, want_visits=False):
+        rays = np.ascontiguousarray(rays, dtype=abi.RAY)
+        hits = np.zeros(rays.size, abi.HIT)
+        visits = np.zeros(2, np.uint64)
+        self._check(self._lib.rtb_trace_batch(self._h, _ptr(rays), rays.size, precision, _ptr(hits),
+                                              _ptr(visits) if want_visits else None))
+        return (hits, visits) if want_visits else hits
+
+    def bsdf_eval(self, material, queries, precision=64):
+        q = np.ascontiguousarray(queries, dtype=abi.BSDF_QUERY)
+        out = np.zeros(q.size, abi.BSDF_VALUE)
+        self._check(self._lib.rtb_bsdf_eval_batch(self._h, material, _ptr(q), q.size, precision, _ptr(out)))
+        return out
+
+    def bsdf_sample(self, material, queries, precision=64, seed=1):
+        q = np.ascontiguousarray(queries, dtype=abi.BSDF_QUERY)
+        out = np.zeros(q.size, abi.BSDF_SAMPLE)
+        self._check(self._lib.rtb_bsdf_sample_batch(self._h, material, _ptr(q), q.size, precision, seed,
+                                                    _ptr(out)))
+        return out
+
+    def light_eval(self, light, queries, precision=64, seed=1):
+        q = np.ascontiguousarray(queries, dtype=abi.LIGHT_QUERY)
+        out = np.zeros(q.size, abi.LIGHT_VALUE)
+        self._check(self._lib.rtb_light_eval_batch(self._h, light, _ptr(q), q.size, precision, seed,
+                                                   _ptr(out)))
+        return out
+
+    def texture_eval(self, texture, uvp, precision=64):
+        uvp = np.ascontiguousarray(uvp, dtype=np.float64).reshape(-1, 5)
+        out = np.zeros((uvp.shape[0], 3))
+        self._check(self._lib.rtb_texture_eval_batch(self._h, texture, _ptr(uvp), uvp.shape[0], precision,
+                                                     _ptr(out)))
+        return out

@@ -1,0 +1,411 @@
+// rtb_api.cu — the extern "C" boundary of librtb200.so (include/rtb200.h).
+// Owns the context, copies scenes and query batches to the device, launches the
+// kernels of rtb_batch.cu / rtb_wavefront.cu and translates every failure into a
+// status code + message.  No exception leaves this file.  There is no host
+// compute path: every entry point needs a live CUDA context.
+#include "rtb_internal.hpp"
+
+#include <cstring>
+#include <new>
+
+using namespace rtb;
+
+namespace {
+
+thread_local std::string g_create_error = "";
+
+struct Cancelled {};
+
+int fail(rtb_context *ctx, int code, const std::string &msg) {
+    if (ctx)
+        ctx->last_error = msg;
+    else
+        g_create_error = msg;
+    return code;
+}
+
+template <class F> int guarded(rtb_context *ctx, F &&body) {
+    try {
+        cudaError_t e = cudaSetDevice(ctx->device);
+        if (e != cudaSuccess)
+            return fail(ctx, RTB_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+        body();
+        return RTB_OK;
+    } catch (const CudaError &e) {
+        cudaGetLastError(); // clear the sticky-less error state
+        const std::string m = e.what();
+        return fail(ctx, m.find("out of memory") != std::string::npos ? RTB_ERR_OUT_OF_MEMORY : RTB_ERR_CUDA, m);
+    } catch (const std::bad_alloc &) {
+        return fail(ctx, RTB_ERR_OUT_OF_MEMORY, "host allocation failed");
+    } catch (const std::exception &e) {
+        const std::string m = e.what();
+        if (m == "cancelled")
+            return fail(ctx, RTB_ERR_CANCELLED, "render cancelled");
+        if (m.rfind("scene", 0) == 0 || m.rfind("prim_box", 0) == 0)
+            return fail(ctx, RTB_ERR_BAD_SCENE, m);
+        return fail(ctx, RTB_ERR_INVALID_ARGUMENT, m);
+    }
+}
+
+template <class R> void upload_typed(DeviceTyped<R> &D, const TypedTables<R> &T, cudaStream_t s, size_t &bytes) {
+    D.prims.upload(T.prims, s);
+    D.maux.upload(T.maux, s);
+    D.ops.upload(T.ops, s);
+    D.mats.upload(T.mats, s);
+    D.texs.upload(T.texs, s);
+    D.perlins.upload(T.perlins, s);
+    D.lights.upload(T.lights, s);
+    bytes += D.prims.bytes() + D.maux.bytes() + D.ops.bytes() + D.mats.bytes() + D.texs.bytes() +
+             D.perlins.bytes() + D.lights.bytes();
+}
+
+int check_params(rtb_context *ctx, const rtb_render_params *p) {
+    if (!p)
+        return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "render: params is NULL");
+    if (p->width < 2 || p->height < 2 || p->width > 65536 || p->height > 65536)
+        return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "render: width/height must be in [2, 65536]");
+    if (p->spp < 0 || p->max_depth < 0 || p->rr_start_depth < 0)
+        return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "render: spp, max_depth, rr_start_depth must be >= 0");
+    if (p->integrator < 0 || p->integrator > RTB_INTEGRATOR_MIS)
+        return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "render: integrator must be 0..4");
+    if (p->sample_stride < 0 || p->sample_offset < 0 ||
+        (p->sample_stride > 0 && p->sample_offset >= p->sample_stride))
+        return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "render: need 0 <= sample_offset < sample_stride");
+    if (p->pool_paths < 0)
+        return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "render: pool_paths must be >= 0");
+    if (!ctx->scene)
+        return fail(ctx, RTB_ERR_NO_SCENE, "render: no scene uploaded");
+    return RTB_OK;
+}
+
+// Stages a host batch on the device, runs `launch`, copies the result back.
+template <class In, class Out, class L>
+void run_batch(rtb_context *ctx, const In *in, uint64_t n, Out *out, L &&launch) {
+    DeviceBuffer d_in, d_out;
+    d_in.alloc(n * sizeof(In));
+    d_out.alloc(n * sizeof(Out));
+    RTB_CUDA(cudaMemcpyAsync(d_in.as<In>(), in, n * sizeof(In), cudaMemcpyHostToDevice, ctx->stream));
+    launch(d_in.as<In>(), d_out.as<Out>());
+    RTB_CUDA(cudaMemcpyAsync(out, d_out.as<Out>(), n * sizeof(Out), cudaMemcpyDeviceToHost, ctx->stream));
+    RTB_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+int check_batch(rtb_context *ctx, const void *in, const void *out, uint64_t n, int precision) {
+    if (!ctx)
+        return RTB_ERR_INVALID_ARGUMENT;
+    if (!ctx->scene)
+        return fail(ctx, RTB_ERR_NO_SCENE, "batch: no scene uploaded");
+    if (n && (!in || !out))
+        return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "batch: NULL buffer");
+    if (precision != 32 && precision != 64)
+        return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "batch: precision must be 32 or 64");
+    return RTB_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *rtb_version(void) { return "rtb200 0.1.0 sm_100a"; }
+
+int rtb_context_create(int device_id, rtb_context **out) {
+    if (!out)
+        return fail(nullptr, RTB_ERR_INVALID_ARGUMENT, "rtb_context_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(nullptr, RTB_ERR_NO_DEVICE,
+                    std::string("no CUDA device available (") +
+                        (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                        "); librtb200 has no CPU path");
+    }
+    if (device_id < 0 || device_id >= count)
+        return fail(nullptr, RTB_ERR_INVALID_ARGUMENT, "rtb_context_create: device_id out of range");
+    rtb_context *ctx = new (std::nothrow) rtb_context();
+    if (!ctx)
+        return fail(nullptr, RTB_ERR_OUT_OF_MEMORY, "host allocation failed");
+    ctx->device = device_id;
+    const int rc = guarded(ctx, [&] {
+        cudaDeviceProp prop;
+        RTB_CUDA(cudaGetDeviceProperties(&prop, device_id));
+        if (prop.major < 10)
+            throw CudaError(std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                            std::to_string(prop.minor) + "; librtb200 is built for sm_100a only");
+        ctx->sm_count = prop.multiProcessorCount;
+        RTB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    });
+    if (rc != RTB_OK) {
+        g_create_error = ctx->last_error;
+        delete ctx;
+        return rc;
+    }
+    *out = ctx;
+    return RTB_OK;
+}
+
+void rtb_context_destroy(rtb_context *ctx) {
+    if (!ctx)
+        return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream)
+        cudaStreamSynchronize(ctx->stream);
+    wavefront_release(ctx);
+    ctx->scene.reset();
+    ctx->accum.release();
+    if (ctx->stream)
+        cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *rtb_last_error(const rtb_context *ctx) {
+    return ctx ? ctx->last_error.c_str() : g_create_error.c_str();
+}
+
+int rtb_scene_upload(rtb_context *ctx, const void *blob, uint64_t nbytes) {
+    if (!ctx)
+        return RTB_ERR_INVALID_ARGUMENT;
+    if (!blob)
+        return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_scene_upload: blob is NULL");
+    return guarded(ctx, [&] {
+        std::unique_ptr<DeviceScene> sc(new DeviceScene());
+        try {
+            SceneView view(blob, nbytes);
+            sc->host = build_host_scene(view);
+        } catch (const CudaError &) {
+            throw;
+        } catch (const std::exception &e) {
+            throw std::runtime_error(std::string("scene: ") + e.what());
+        }
+        const HostScene &H = sc->host;
+        cudaStream_t s = ctx->stream;
+        size_t bytes = 0;
+        upload_typed(sc->f32, H.f32, s, bytes);
+        upload_typed(sc->f64, H.f64, s, bytes);
+        sc->nodes.upload(H.nodes, s);
+        sc->chains.upload(H.chains, s);
+        sc->prim_chain.upload(H.prim_chain, s);
+        sc->prim_orig.upload(H.prim_orig, s);
+        sc->orig_to_sorted.upload(H.orig_to_sorted, s);
+        sc->images.upload(H.images, s);
+        sc->image_bytes.upload(H.image_bytes, s);
+        sc->env_texels.upload(H.env_texels, s);
+        sc->env_tables.upload(H.env_tables, s);
+        bytes += sc->nodes.bytes() + sc->chains.bytes() + sc->prim_chain.bytes() + sc->prim_orig.bytes() +
+                 sc->orig_to_sorted.bytes() + sc->images.bytes() + sc->image_bytes.bytes() +
+                 sc->env_texels.bytes() + sc->env_tables.bytes();
+        sc->device_bytes = bytes;
+        RTB_CUDA(cudaStreamSynchronize(s));
+        ctx->scene = std::move(sc);
+    });
+}
+
+int rtb_scene_get_stats(rtb_context *ctx, rtb_scene_stats *out) {
+    if (!ctx || !out)
+        return RTB_ERR_INVALID_ARGUMENT;
+    if (!ctx->scene)
+        return fail(ctx, RTB_ERR_NO_SCENE, "no scene uploaded");
+    const HostScene &H = ctx->scene->host;
+    out->n_prims = int32_t(H.orig_to_sorted.size());
+    out->n_nodes = int32_t(H.nodes.size());
+    out->n_instances = H.n_instances;
+    out->n_materials = int32_t(H.f32.mats.size());
+    out->n_lights = int32_t(H.f32.lights.size());
+    out->has_media = H.has_media ? 1 : 0;
+    out->device_bytes = ctx->scene->device_bytes;
+    return RTB_OK;
+}
+
+int rtb_camera_derived(rtb_context *ctx, double out[24]) {
+    if (!ctx || !out)
+        return RTB_ERR_INVALID_ARGUMENT;
+    if (!ctx->scene)
+        return fail(ctx, RTB_ERR_NO_SCENE, "no scene uploaded");
+    const CameraT<double> &c = ctx->scene->host.f64.camera;
+    const V3<double> *vs[7] = {&c.origin, &c.lower_left_corner, &c.horizontal, &c.vertical, &c.u, &c.v, &c.w};
+    for (int i = 0; i < 7; ++i) {
+        out[3 * i] = vs[i]->x;
+        out[3 * i + 1] = vs[i]->y;
+        out[3 * i + 2] = vs[i]->z;
+    }
+    out[21] = c.lens_radius;
+    out[22] = c.time0;
+    out[23] = c.time1;
+    return RTB_OK;
+}
+
+int rtb_render_device(rtb_context *ctx, const rtb_render_params *params, void *accum_rgba_device,
+                      void *cuda_stream, rtb_render_stats *stats) {
+    if (!ctx)
+        return RTB_ERR_INVALID_ARGUMENT;
+    const int rc = check_params(ctx, params);
+    if (rc != RTB_OK)
+        return rc;
+    if (!accum_rgba_device)
+        return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "render: accumulator buffer is NULL");
+    ctx->cancel.store(0);
+    return guarded(ctx, [&] {
+        cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+        wavefront_render(ctx, *params, static_cast<float4 *>(accum_rgba_device), st, stats);
+    });
+}
+
+int rtb_render(rtb_context *ctx, const rtb_render_params *params, float *accum_rgba_host,
+               rtb_render_stats *stats) {
+    if (!ctx)
+        return RTB_ERR_INVALID_ARGUMENT;
+    const int rc = check_params(ctx, params);
+    if (rc != RTB_OK)
+        return rc;
+    if (!accum_rgba_host)
+        return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "render: accumulator buffer is NULL");
+    ctx->cancel.store(0);
+    return guarded(ctx, [&] {
+        const size_t bytes = size_t(params->width) * params->height * sizeof(float4);
+        if (ctx->accum.bytes() != bytes)
+            ctx->accum.alloc(bytes);
+        ctx->accum_w = params->width;
+        ctx->accum_h = params->height;
+        wavefront_render(ctx, *params, ctx->accum.as<float4>(), ctx->stream, stats);
+        RTB_CUDA(cudaMemcpyAsync(accum_rgba_host, ctx->accum.as<float4>(), bytes, cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+        RTB_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int rtb_cancel(rtb_context *ctx) {
+    if (!ctx)
+        return RTB_ERR_INVALID_ARGUMENT;
+    ctx->cancel.store(1);
+    return RTB_OK;
+}
+
+int rtb_resolve_rgb8(rtb_context *ctx, int32_t spp, uint8_t *rgb8_host) {
+    if (!ctx || !rgb8_host)
+        return RTB_ERR_INVALID_ARGUMENT;
+    if (spp <= 0 || ctx->accum_w == 0)
+        return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "resolve: spp must be > 0 and a render must have run");
+    return guarded(ctx, [&] {
+        const size_t n = size_t(ctx->accum_w) * ctx->accum_h * 3;
+        DeviceBuffer d;
+        d.alloc(n);
+        launch_resolve_rgb8(ctx, ctx->accum.as<float4>(), ctx->accum_w, ctx->accum_h, spp, d.as<uint8_t>(),
+                            ctx->stream);
+        RTB_CUDA(cudaMemcpyAsync(rgb8_host, d.as<uint8_t>(), n, cudaMemcpyDeviceToHost, ctx->stream));
+        RTB_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int rtb_trace_batch(rtb_context *ctx, const rtb_ray *rays, uint64_t n, int precision, rtb_hit *hits,
+                    uint64_t *visits) {
+    const int rc = check_batch(ctx, rays, hits, n, precision);
+    if (rc != RTB_OK)
+        return rc;
+    return guarded(ctx, [&] {
+        DeviceBuffer d_vis;
+        unsigned long long *dv = nullptr;
+        if (visits) {
+            d_vis.alloc(2 * sizeof(unsigned long long));
+            RTB_CUDA(cudaMemsetAsync(d_vis.as<void>(), 0, 2 * sizeof(unsigned long long), ctx->stream));
+            dv = d_vis.as<unsigned long long>();
+        }
+        if (n)
+            run_batch(ctx, rays, n, hits, [&](const rtb_ray *di, rtb_hit *dout) {
+                if (precision == 64)
+                    launch_trace_batch<double>(ctx, di, n, dout, dv);
+                else
+                    launch_trace_batch<float>(ctx, di, n, dout, dv);
+            });
+        if (visits) {
+            unsigned long long h[2] = {0, 0};
+            RTB_CUDA(cudaMemcpy(h, dv, sizeof(h), cudaMemcpyDeviceToHost));
+            visits[0] = h[0];
+            visits[1] = h[1];
+        }
+    });
+}
+
+int rtb_bsdf_eval_batch(rtb_context *ctx, int material, const rtb_bsdf_query *queries, uint64_t n,
+                        int precision, rtb_bsdf_value *out) {
+    const int rc = check_batch(ctx, queries, out, n, precision);
+    if (rc != RTB_OK)
+        return rc;
+    if (material < 0 || size_t(material) >= ctx->scene->host.f32.mats.size())
+        return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "bsdf batch: material index out of range");
+    if (!n)
+        return RTB_OK;
+    return guarded(ctx, [&] {
+        run_batch(ctx, queries, n, out, [&](const rtb_bsdf_query *di, rtb_bsdf_value *dout) {
+            if (precision == 64)
+                launch_bsdf_eval<double>(ctx, material, di, n, dout);
+            else
+                launch_bsdf_eval<float>(ctx, material, di, n, dout);
+        });
+    });
+}
+
+int rtb_bsdf_sample_batch(rtb_context *ctx, int material, const rtb_bsdf_query *queries, uint64_t n,
+                          int precision, uint64_t seed, rtb_bsdf_sample *out) {
+    const int rc = check_batch(ctx, queries, out, n, precision);
+    if (rc != RTB_OK)
+        return rc;
+    if (material < 0 || size_t(material) >= ctx->scene->host.f32.mats.size())
+        return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "bsdf batch: material index out of range");
+    if (!n)
+        return RTB_OK;
+    return guarded(ctx, [&] {
+        run_batch(ctx, queries, n, out, [&](const rtb_bsdf_query *di, rtb_bsdf_sample *dout) {
+            if (precision == 64)
+                launch_bsdf_sample<double>(ctx, material, di, n, seed, dout);
+            else
+                launch_bsdf_sample<float>(ctx, material, di, n, seed, dout);
+        });
+    });
+}
+
+int rtb_light_eval_batch(rtb_context *ctx, int light, const rtb_light_query *queries, uint64_t n, int precision,
+                         uint64_t seed, rtb_light_value *out) {
+    const int rc = check_batch(ctx, queries, out, n, precision);
+    if (rc != RTB_OK)
+        return rc;
+    if (light < 0 || size_t(light) >= ctx->scene->host.f32.lights.size())
+        return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "light batch: light index out of range");
+    if (!n)
+        return RTB_OK;
+    return guarded(ctx, [&] {
+        run_batch(ctx, queries, n, out, [&](const rtb_light_query *di, rtb_light_value *dout) {
+            if (precision == 64)
+                launch_light_eval<double>(ctx, light, di, n, seed, dout);
+            else
+                launch_light_eval<float>(ctx, light, di, n, seed, dout);
+        });
+    });
+}
+
+int rtb_texture_eval_batch(rtb_context *ctx, int texture, const double *uvp, uint64_t n, int precision,
+                           double *rgb) {
+    const int rc = check_batch(ctx, uvp, rgb, n, precision);
+    if (rc != RTB_OK)
+        return rc;
+    if (texture < 0 || size_t(texture) >= ctx->scene->host.f32.texs.size())
+        return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "texture batch: texture index out of range");
+    if (!n)
+        return RTB_OK;
+    return guarded(ctx, [&] {
+        DeviceBuffer d_in, d_out;
+        d_in.alloc(n * 5 * sizeof(double));
+        d_out.alloc(n * 3 * sizeof(double));
+        RTB_CUDA(cudaMemcpyAsync(d_in.as<double>(), uvp, n * 5 * sizeof(double), cudaMemcpyHostToDevice,
+                                 ctx->stream));
+        if (precision == 64)
+            launch_texture_eval<double>(ctx, texture, d_in.as<double>(), n, d_out.as<double>());
+        else
+            launch_texture_eval<float>(ctx, texture, d_in.as<double>(), n, d_out.as<double>());
+        RTB_CUDA(cudaMemcpyAsync(rgb, d_out.as<double>(), n * 3 * sizeof(double), cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+        RTB_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+} // extern "C"

@@ -1,0 +1,532 @@
+// rtb_geom.cuh — device geometry tables, primitive tests, instance chains, the
+// two-level BVH traversal and hit-record reconstruction.  Templated on R
+// (float production / double validation).  In the double instantiation every
+// expression that feeds `t` is written in the reference's operation order.
+//
+// Reference counterparts:
+//   bvh_node::hit            src/geometry/bvh.h:40-50      -> traverse()
+//   aabb::hit                src/geometry/aabb.h:31-48     -> slab()
+//   sphere::hit              src/geometry/sphere.h:33-60   -> hit_sphere()
+//   moving_sphere::hit       src/geometry/moving_sphere.h:36-62
+//   xy/xz/yz_rect::hit       src/geometry/aarect.h:79-135  -> hit_rect()
+//   translate/rotate_y/flip  src/geometry/hittable.h:51-62,127-156,163-170
+//   constant_medium::hit     src/geometry/constant_medium.h:55-104
+//
+// The reference walks a pointer graph; here the world is a flat array of
+// 32-byte primitive records ordered by BVH leaf, a flat array of 32-byte BVH
+// nodes (top level over world-space items, one bottom level per distinct
+// wrapper chain) and small tables of wrapper ops.
+#ifndef RTB_GEOM_CUH
+#define RTB_GEOM_CUH
+
+#include "rtb_math.cuh"
+
+namespace rtb {
+
+enum : uint32_t {
+    PT_SPHERE = 0,
+    PT_MSPHERE = 1,
+    PT_XY = 2,
+    PT_XZ = 3,
+    PT_YZ = 4,
+    PT_MEDIUM = 5,
+    PT_INSTANCE = 6,
+    PT_TYPE_MASK = 7,
+    PT_DUP_LEAF = 8, // reference tests this object twice per ray (bvh.h:68-69)
+    PT_MAT_SHIFT = 8
+};
+
+constexpr uint32_t kNoPrim = 0xffffffffu;
+constexpr int kMaxChainOps = 8;
+constexpr int kStackDepth = 48;
+
+// One primitive.  float: 32 bytes exactly (one sector); double: 56 bytes.
+//   SPHERE   d = cx cy cz r
+//   MSPHERE  d = c0x c0y c0z r ; aux -> MovingAux
+//   RECT     d = a0 a1 b0 b1 k   (XY: a=x b=y | XZ: a=x b=z | YZ: a=y b=z)
+//   MEDIUM   d[0] = neg_inv_density ; aux = first boundary prim, aux2 = count
+//   INSTANCE aux = BLAS root node, aux2 = chain id
+template <class R> struct PrimT {
+    R d[5];
+    uint32_t type_mat;
+    uint32_t aux;
+    uint32_t aux2;
+};
+static_assert(sizeof(PrimT<float>) == 32, "production primitive record must be one 32-byte sector");
+
+template <class R> struct MovingAux {
+    R c1[3];
+    R time0, time1;
+};
+
+template <class R> struct XfOp {
+    int32_t kind; // rtb_xform_kind
+    R a, b, c;
+};
+
+struct ChainRec {
+    int32_t first, count;
+};
+
+// 32-byte BVH node.  Interior: `first` = index of the left child, right child =
+// first + 1 (siblings are adjacent, the pair is 64-byte aligned), count == 0.
+// Leaf: count = kLeafFlag | n, primitives [first, first + n).
+constexpr uint32_t kLeafFlag = 0x80000000u;
+struct alignas(32) Node32 {
+    float lo[3];
+    uint32_t first;
+    float hi[3];
+    uint32_t count;
+};
+static_assert(sizeof(Node32) == 32, "BVH node must be 32 bytes");
+
+template <class R> struct GeomView {
+    const Node32 *nodes;
+    const PrimT<R> *prims;
+    const MovingAux<R> *maux;
+    const XfOp<R> *ops;
+    const ChainRec *chains;
+    const int32_t *prim_chain; // per sorted prim: chain id or -1
+    const int32_t *prim_orig;  // per sorted prim: flat (blob) primitive id, -1 for instances
+    int32_t n_nodes;
+    int32_t n_prims;
+};
+
+template <class R> struct RayT {
+    V3<R> o, d;
+    R time;
+};
+
+// ---- wrapper chains ---------------------------------------------------------------------
+// hittable.h:53 (translate) and hittable.h:129-138 (rotate_y): the RAY is moved
+// into object space; t is unchanged because directions are not normalised.
+template <class R> RTB_HD void apply_op(const XfOp<R> &op, V3<R> &o, V3<R> &d) {
+    if (op.kind == 0) { // translate
+        o = V3<R>(o.x - op.a, o.y - op.b, o.z - op.c);
+    } else if (op.kind == 1) { // rotate_y : a = sin, b = cos
+        const R ox = op.b * o.x - op.a * o.z;
+        const R oz = op.a * o.x + op.b * o.z;
+        const R dx = op.b * d.x - op.a * d.z;
+        const R dz = op.a * d.x + op.b * d.z;
+        o.x = ox;
+        o.z = oz;
+        d.x = dx;
+        d.z = dz;
+    }
+}
+
+template <class R> RTB_HD void apply_chain(const GeomView<R> &g, int chain, V3<R> &o, V3<R> &d) {
+    if (chain < 0)
+        return;
+    const ChainRec c = g.chains[chain];
+    for (int i = 0; i < c.count; ++i)
+        apply_op(g.ops[c.first + i], o, d);
+}
+
+// ---- primitive tests (return t or a negative "no hit" marker) --------------------------------
+
+// sphere.h:33-50.  ROBUST (float production): `on_surface` says the ray starts on
+// this very sphere, whose near root is then analytically 0 (rejected by t_min in
+// the fp64 reference) and whose other root is -2*half_b/a.
+template <class R, bool ROBUST>
+RTB_HD bool hit_sphere(V3<R> c, R radius, V3<R> o, V3<R> d, R t_min, R t_max, bool on_surface,
+                       R &t_out) {
+    const V3<R> oc = o - c;
+    const R a = length_squared(d);
+    const R half_b = dot(oc, d);
+    if (ROBUST) {
+        if (on_surface) {
+            const R t = R(-2) * half_b / a;
+            if (t < t_min || t > t_max)
+                return false;
+            t_out = t;
+            return true;
+        }
+        // Haines et al., "Precision improvements for ray/sphere intersection":
+        // the discriminant from the perpendicular distance, the roots via q.
+        const R inv_a = R(1) / a;
+        const V3<R> l = oc - (half_b * inv_a) * d;
+        const R disc = radius * radius - length_squared(l);
+        if (disc < 0)
+            return false;
+        const R cc = length_squared(oc) - radius * radius;
+        const R s = sqrt_(a * disc);
+        const R q = -half_b + (half_b > 0 ? -s : s); // q = -(half_b + sign(half_b) s)
+        R t0 = q * inv_a, t1 = (q != 0) ? cc / q : t0;
+        if (t0 > t1) {
+            const R tmp = t0;
+            t0 = t1;
+            t1 = tmp;
+        }
+        R root = t0;
+        if (root < t_min || root > t_max) {
+            root = t1;
+            if (root < t_min || root > t_max)
+                return false;
+        }
+        t_out = root;
+        return true;
+    } else {
+        const R cc = length_squared(oc) - radius * radius;
+        const R discriminant = half_b * half_b - a * cc;
+        if (discriminant < 0)
+            return false;
+        const R sqrtd = sqrt_(discriminant);
+        R root = (-half_b - sqrtd) / a;
+        if (root < t_min || root > t_max) {
+            root = (-half_b + sqrtd) / a;
+            if (root < t_min || root > t_max)
+                return false;
+        }
+        t_out = root;
+        return true;
+    }
+}
+
+// moving_sphere.h:32-34
+template <class R> RTB_HD V3<R> moving_center(const PrimT<R> &p, const MovingAux<R> &m, R time) {
+    const V3<R> c0(p.d[0], p.d[1], p.d[2]);
+    const V3<R> c1(m.c1[0], m.c1[1], m.c1[2]);
+    return c0 + ((time - m.time0) / (m.time1 - m.time0)) * (c1 - c0);
+}
+
+// aarect.h:79-135.  AX = index of the constant axis, A/B the two in-plane axes.
+template <class R, bool ROBUST>
+RTB_HD bool hit_rect(const PrimT<R> &p, int AX, int A, int B, V3<R> o, V3<R> d, V3<R> idir, R t_min,
+                     R t_max, R &t_out) {
+    const R t = ROBUST ? (p.d[4] - o[AX]) * idir[AX] : (p.d[4] - o[AX]) / d[AX];
+    if (t < t_min || t > t_max)
+        return false;
+    const R a = o[A] + t * d[A];
+    const R b = o[B] + t * d[B];
+    if (a < p.d[0] || a > p.d[1] || b < p.d[2] || b > p.d[3])
+        return false;
+    t_out = t;
+    return true;
+}
+
+// One non-instance, non-medium primitive in ITS OWN object space.
+template <class R, bool ROBUST>
+RTB_HD bool hit_simple(const GeomView<R> &g, const PrimT<R> &p, uint32_t type, V3<R> o, V3<R> d,
+                       V3<R> idir, R time, R t_min, R t_max, bool is_origin, R &t_out) {
+    switch (type) {
+    case PT_SPHERE:
+        return hit_sphere<R, ROBUST>(V3<R>(p.d[0], p.d[1], p.d[2]), p.d[3], o, d, t_min, t_max,
+                                     is_origin, t_out);
+    case PT_MSPHERE:
+        return hit_sphere<R, ROBUST>(moving_center(p, g.maux[p.aux], time), p.d[3], o, d, t_min,
+                                     t_max, false, t_out);
+    case PT_XY:
+        if (ROBUST && is_origin)
+            return false;
+        return hit_rect<R, ROBUST>(p, 2, 0, 1, o, d, idir, t_min, t_max, t_out);
+    case PT_XZ:
+        if (ROBUST && is_origin)
+            return false;
+        return hit_rect<R, ROBUST>(p, 1, 0, 2, o, d, idir, t_min, t_max, t_out);
+    case PT_YZ:
+        if (ROBUST && is_origin)
+            return false;
+        return hit_rect<R, ROBUST>(p, 0, 1, 2, o, d, idir, t_min, t_max, t_out);
+    default:
+        return false;
+    }
+}
+
+template <class R> RTB_HD V3<R> safe_inv(V3<R> d) { return V3<R>(R(1) / d.x, R(1) / d.y, R(1) / d.z); }
+
+// Closest hit of the WORLD-space ray against boundary primitives [first, first+count)
+// — constant_medium's `boundary->hit()` (constant_medium.h:64-68).  Each boundary
+// primitive carries its full wrapper chain.
+template <class R, bool ROBUST>
+RTB_HD bool hit_boundary(const GeomView<R> &g, uint32_t first, uint32_t count, V3<R> o, V3<R> d,
+                         R time, R t_min, R t_max, R &t_out) {
+    bool any = false;
+    int cur_chain = -2;
+    V3<R> lo = o, ld = d, lid = safe_inv(d);
+    for (uint32_t i = first; i < first + count; ++i) {
+        const PrimT<R> p = g.prims[i];
+        const int ch = g.prim_chain[i];
+        if (ch != cur_chain) {
+            lo = o;
+            ld = d;
+            apply_chain(g, ch, lo, ld);
+            lid = safe_inv(ld);
+            cur_chain = ch;
+        }
+        R t;
+        if (hit_simple<R, ROBUST>(g, p, p.type_mat & PT_TYPE_MASK, lo, ld, lid, time, t_min, t_max,
+                                  false, t)) {
+            any = true;
+            t_max = t;
+            t_out = t;
+        }
+    }
+    return any;
+}
+
+// constant_medium.h:55-104.  `xi` must be uniform in (0,1).
+template <class R, bool ROBUST>
+RTB_HD bool hit_medium(const GeomView<R> &g, const PrimT<R> &p, V3<R> o, V3<R> d, R time, R t_min,
+                       R t_max, R xi, R &t_out) {
+    const R inf = Consts<R>::inf();
+    R t1, t2;
+    if (!hit_boundary<R, ROBUST>(g, p.aux, p.aux2, o, d, time, -inf, inf, t1))
+        return false;
+    // ROBUST: 1e-4 is below one fp32 ulp once |t1| > ~800 (a ray deep inside a large
+    // boundary), which would return the entry point again; step by a few ulps instead
+    const R step = ROBUST ? fmax_(R(0.0001), fabs_(t1) * R(1e-6)) : R(0.0001);
+    if (!hit_boundary<R, ROBUST>(g, p.aux, p.aux2, o, d, time, t1 + step, inf, t2))
+        return false;
+    if (t1 < t_min)
+        t1 = t_min;
+    if (t2 > t_max)
+        t2 = t_max;
+    if (t1 >= t2)
+        return false;
+    if (t1 < 0)
+        t1 = 0;
+    const R ray_length = length(d);
+    const R distance_inside_boundary = (t2 - t1) * ray_length;
+    const R hit_distance = p.d[0] * log_(xi);
+    if (hit_distance > distance_inside_boundary)
+        return false;
+    t_out = t1 + hit_distance / ray_length;
+    return true;
+}
+
+// ---- BVH traversal -----------------------------------------------------------------------
+
+// Slab test of one node against [t_min, t_max]; returns entry distance via t_near.
+// Conservative (<=) where the reference rejects on equality (aabb.h:43): node
+// boxes here are padded outward, so nothing the reference accepts is culled.
+template <class R>
+RTB_HD bool slab(const Node32 &n, V3<R> o, V3<R> idir, R t_min, R t_max, R &t_near) {
+    const R x0 = (R(n.lo[0]) - o.x) * idir.x, x1 = (R(n.hi[0]) - o.x) * idir.x;
+    const R y0 = (R(n.lo[1]) - o.y) * idir.y, y1 = (R(n.hi[1]) - o.y) * idir.y;
+    const R z0 = (R(n.lo[2]) - o.z) * idir.z, z1 = (R(n.hi[2]) - o.z) * idir.z;
+    const R tn = fmax_(fmax_(fmin_(x0, x1), fmin_(y0, y1)), fmax_(fmin_(z0, z1), t_min));
+    const R tf = fmin_(fmin_(fmax_(x0, x1), fmax_(y0, y1)), fmin_(fmax_(z0, z1), t_max));
+    t_near = tn;
+    return tn <= tf;
+}
+
+// Node / primitive fetch policy: global memory through the read-only path, or a
+// shared-memory copy of the first n entries (the whole scene when it is small,
+// the top BVH levels otherwise — nodes are laid out breadth-first).
+template <class R> struct GlobalFetch {
+    const GeomView<R> &g;
+    RTB_HD explicit GlobalFetch(const GeomView<R> &gg) : g(gg) {}
+    RTB_HD Node32 node(uint32_t i) const {
+#ifdef __CUDA_ARCH__
+        const float4 *q = reinterpret_cast<const float4 *>(g.nodes + i);
+        const float4 a = __ldg(q), b = __ldg(q + 1);
+        Node32 n;
+        n.lo[0] = a.x; n.lo[1] = a.y; n.lo[2] = a.z; n.first = __float_as_uint(a.w);
+        n.hi[0] = b.x; n.hi[1] = b.y; n.hi[2] = b.z; n.count = __float_as_uint(b.w);
+        return n;
+#else
+        return g.nodes[i];
+#endif
+    }
+    RTB_HD PrimT<R> prim(uint32_t i) const { return g.prims[i]; }
+};
+
+// Closest hit (ANY = false) or first hit (ANY = true) of the world-space ray.
+// Returns the SORTED primitive index or kNoPrim, and t.
+//   origin_prim : sorted index of the primitive the ray leaves (ROBUST only).
+//   rng         : callable returning R uniform in (0,1) — drawn once per medium test,
+//                 as constant_medium::hit does (constant_medium.h:85).
+template <class R, bool ANY, bool ROBUST, class Fetch, class Rng>
+RTB_HD uint32_t traverse(const GeomView<R> &g, const Fetch &F, V3<R> o, V3<R> d, R time, R t_min,
+                         R t_max, uint32_t origin_prim, Rng &rng, R &t_hit, uint64_t *n_nodes,
+                         uint64_t *n_tests) {
+    constexpr uint32_t kSentinel = 0xfffffffeu;
+    uint32_t stack[kStackDepth];
+    int sp = 0;
+    uint32_t best = kNoPrim;
+    V3<R> co = o, cd = d, cid = safe_inv(d); // current-level ray
+    uint32_t cur = 0;
+    while (true) {
+        const Node32 n = F.node(cur);
+        if (n_nodes)
+            ++*n_nodes;
+        bool popping = true;
+        if (!(n.count & kLeafFlag)) {
+            const Node32 c0 = F.node(n.first), c1 = F.node(n.first + 1);
+            R e0, e1;
+            const bool h0 = slab(c0, co, cid, t_min, t_max, e0);
+            const bool h1 = slab(c1, co, cid, t_min, t_max, e1);
+            if (h0 && h1) {
+                const bool swap = e1 < e0;
+                if (sp < kStackDepth)
+                    stack[sp++] = swap ? n.first : n.first + 1;
+                cur = swap ? n.first + 1 : n.first;
+                popping = false;
+            } else if (h0 || h1) {
+                cur = h0 ? n.first : n.first + 1;
+                popping = false;
+            }
+        } else {
+            const uint32_t leaf_end = n.first + (n.count & ~kLeafFlag);
+            for (uint32_t i = n.first; i < leaf_end; ++i) {
+                const PrimT<R> p = F.prim(i);
+                const uint32_t type = p.type_mat & PT_TYPE_MASK;
+                if (type == PT_INSTANCE) {
+                    // builder guarantee: an instance is alone in its leaf and only
+                    // appears in the top level
+                    if (sp < kStackDepth)
+                        stack[sp++] = kSentinel;
+                    apply_chain(g, int(p.aux2), co, cd);
+                    cid = safe_inv(cd);
+                    cur = p.aux;
+                    popping = false;
+                    break;
+                }
+                if (n_tests)
+                    ++*n_tests;
+                R t;
+                bool h;
+                if (type == PT_MEDIUM) {
+                    h = hit_medium<R, ROBUST>(g, p, co, cd, time, t_min, t_max, rng(), t);
+                    if (p.type_mat & PT_DUP_LEAF) {
+                        // second visit of a one-object bvh_node (bvh.h:46-47):
+                        // t_max has already shrunk to the first answer
+                        R t2;
+                        if (hit_medium<R, ROBUST>(g, p, co, cd, time, t_min, h ? t : t_max, rng(), t2)) {
+                            h = true;
+                            t = t2;
+                        }
+                    }
+                } else {
+                    h = hit_simple<R, ROBUST>(g, p, type, co, cd, cid, time, t_min, t_max,
+                                              ROBUST && i == origin_prim, t);
+                }
+                if (h) {
+                    best = i;
+                    t_max = t;
+                    if (ANY) {
+                        t_hit = t;
+                        return best;
+                    }
+                }
+            }
+        }
+        while (popping) {
+            if (sp == 0) {
+                t_hit = t_max;
+                return best;
+            }
+            cur = stack[--sp];
+            if (cur == kSentinel) { // leaving the instance: back to the world ray
+                co = o;
+                cd = d;
+                cid = safe_inv(d);
+            } else
+                popping = false;
+        }
+    }
+}
+
+// ---- hit record ---------------------------------------------------------------------------
+
+template <class R> struct RecT {
+    V3<R> p, normal;
+    R t, u, v;
+    bool front_face;
+};
+
+// hittable.h:19-22
+template <class R> RTB_HD void set_face_normal(RecT<R> &rec, V3<R> dir, V3<R> outward) {
+    rec.front_face = dot(dir, outward) < 0;
+    rec.normal = rec.front_face ? outward : -outward;
+}
+
+// sphere.h:25-31
+template <class R> RTB_HD void sphere_uv(V3<R> p, R &u, R &v) {
+    const R pi = Consts<R>::pi();
+    const R theta = acos_(-p.y);
+    const R phi = atan2_(-p.z, p.x) + pi;
+    u = phi / (R(2) * pi);
+    v = theta / pi;
+}
+
+// Rebuilds what the reference's nested hit() calls leave in hit_record for the
+// closest primitive `pi` at parameter t: the leaf fills the record in object
+// space (sphere.h:52-57, aarect.h:88-96), then every wrapper on the way out
+// post-processes it (hittable.h:58-59, 142-153, 168).  WANT_UV = false skips the
+// acos/atan2 of sphere uv (only textures that read u,v need it).
+template <class R, bool ROBUST, bool WANT_UV>
+RTB_HD RecT<R> make_record(const GeomView<R> &g, uint32_t pi, V3<R> o, V3<R> d, R time, R t) {
+    RecT<R> rec;
+    rec.t = t;
+    rec.u = 0;
+    rec.v = 0;
+    const PrimT<R> p = g.prims[pi];
+    const uint32_t type = p.type_mat & PT_TYPE_MASK;
+    const int chain = g.prim_chain[pi];
+    // forward pass: directions after each wrapper (set_face_normal needs them)
+    V3<R> dirs[kMaxChainOps + 1];
+    int nops = 0, first = 0;
+    V3<R> lo = o, ld = d;
+    dirs[0] = d;
+    if (chain >= 0) {
+        const ChainRec c = g.chains[chain];
+        first = c.first;
+        nops = c.count < kMaxChainOps ? c.count : kMaxChainOps;
+        for (int i = 0; i < nops; ++i) {
+            apply_op(g.ops[first + i], lo, ld);
+            dirs[i + 1] = ld;
+        }
+    }
+    rec.p = lo + t * ld;
+    if (type == PT_SPHERE || type == PT_MSPHERE) {
+        const V3<R> c = type == PT_SPHERE ? V3<R>(p.d[0], p.d[1], p.d[2])
+                                          : moving_center(p, g.maux[p.aux], time);
+        V3<R> outward = (rec.p - c) / p.d[3]; // r < 0 => points inward (hollow glass)
+        if (ROBUST) { // pull the point back onto the sphere
+            outward = unit_vector(outward);
+            rec.p = c + p.d[3] * outward;
+        }
+        set_face_normal(rec, ld, outward);
+        if (WANT_UV && type == PT_SPHERE)
+            sphere_uv(outward, rec.u, rec.v);
+    } else if (type == PT_MEDIUM) {
+        rec.normal = V3<R>(1, 0, 0); // constant_medium.h:99-100, "arbitrary"
+        rec.front_face = true;
+    } else {
+        const int AX = type == PT_XY ? 2 : (type == PT_XZ ? 1 : 0);
+        const int A = type == PT_YZ ? 1 : 0;
+        const int B = type == PT_XY ? 1 : 2;
+        rec.u = (rec.p[A] - p.d[0]) / (p.d[1] - p.d[0]);
+        rec.v = (rec.p[B] - p.d[2]) / (p.d[3] - p.d[2]);
+        if (ROBUST)
+            rec.p.set(AX, p.d[4]);
+        V3<R> outward(0, 0, 0);
+        outward.set(AX, R(1));
+        set_face_normal(rec, ld, outward);
+    }
+    // reverse pass
+    for (int i = nops - 1; i >= 0; --i) {
+        const XfOp<R> op = g.ops[first + i];
+        if (op.kind == 0) { // hittable.h:58-59
+            rec.p = V3<R>(rec.p.x + op.a, rec.p.y + op.b, rec.p.z + op.c);
+            set_face_normal(rec, dirs[i + 1], rec.normal);
+        } else if (op.kind == 1) { // hittable.h:142-153 : a = sin, b = cos
+            const R px = op.b * rec.p.x + op.a * rec.p.z;
+            const R pz = -op.a * rec.p.x + op.b * rec.p.z;
+            const R nx = op.b * rec.normal.x + op.a * rec.normal.z;
+            const R nz = -op.a * rec.normal.x + op.b * rec.normal.z;
+            rec.p.x = px;
+            rec.p.z = pz;
+            set_face_normal(rec, dirs[i + 1], V3<R>(nx, rec.normal.y, nz));
+        } else { // hittable.h:168
+            rec.front_face = !rec.front_face;
+        }
+    }
+    return rec;
+}
+
+} // namespace rtb
+
+#endif // RTB_GEOM_CUH

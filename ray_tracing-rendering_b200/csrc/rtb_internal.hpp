@@ -1,0 +1,154 @@
+// rtb_internal.hpp — context, device-resident scene and the launch interfaces
+// between the translation units of librtb200.so.
+#ifndef RTB_INTERNAL_HPP
+#define RTB_INTERNAL_HPP
+
+#include "rtb200.h"
+#include "rtb_scene_host.hpp"
+
+#include <atomic>
+#include <cuda_runtime.h>
+#include <memory>
+#include <stdexcept>
+#include <string>
+
+namespace rtb {
+
+struct CudaError : std::runtime_error {
+    explicit CudaError(const std::string &m) : std::runtime_error(m) {}
+};
+
+#define RTB_CUDA(call)                                                                             \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            throw ::rtb::CudaError(std::string(#call) + ": " + cudaGetErrorString(e_));           \
+    } while (0)
+
+// Owning device allocation.
+class DeviceBuffer {
+  public:
+    DeviceBuffer() = default;
+    DeviceBuffer(const DeviceBuffer &) = delete;
+    DeviceBuffer &operator=(const DeviceBuffer &) = delete;
+    ~DeviceBuffer() { release(); }
+    void release() {
+        if (p_)
+            cudaFree(p_);
+        p_ = nullptr;
+        bytes_ = 0;
+    }
+    void alloc(size_t bytes) {
+        release();
+        if (bytes == 0)
+            bytes = 16; // keep pointers non-null so views are always dereferenceable
+        cudaError_t e = cudaMalloc(&p_, bytes);
+        if (e != cudaSuccess) {
+            p_ = nullptr;
+            throw CudaError(std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+        }
+        bytes_ = bytes;
+    }
+    template <class T> void upload(const std::vector<T> &v, cudaStream_t s) {
+        alloc(v.size() * sizeof(T));
+        if (!v.empty())
+            RTB_CUDA(cudaMemcpyAsync(p_, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    template <class T> T *as() const { return static_cast<T *>(p_); }
+    size_t bytes() const { return bytes_; }
+
+  private:
+    void *p_ = nullptr;
+    size_t bytes_ = 0;
+};
+
+template <class R> struct DeviceTyped {
+    DeviceBuffer prims, maux, ops, mats, texs, perlins, lights;
+};
+
+struct DeviceScene {
+    HostScene host; // kept for ids, counts and the host-side maps
+    DeviceTyped<float> f32;
+    DeviceTyped<double> f64;
+    DeviceBuffer nodes, chains, prim_chain, prim_orig, orig_to_sorted, images, image_bytes, env_texels,
+        env_tables;
+    size_t device_bytes = 0;
+
+    template <class R> const DeviceTyped<R> &typed() const;
+    template <class R> GeomView<R> geom() const {
+        const DeviceTyped<R> &T = typed<R>();
+        GeomView<R> g;
+        g.nodes = nodes.as<Node32>();
+        g.prims = T.prims.template as<PrimT<R>>();
+        g.maux = T.maux.template as<MovingAux<R>>();
+        g.ops = T.ops.template as<XfOp<R>>();
+        g.chains = chains.as<ChainRec>();
+        g.prim_chain = prim_chain.as<int32_t>();
+        g.prim_orig = prim_orig.as<int32_t>();
+        g.n_nodes = int32_t(host.nodes.size());
+        g.n_prims = int32_t(host.prim_orig.size());
+        return g;
+    }
+    template <class R> ShadeView<R> shade() const {
+        const DeviceTyped<R> &T = typed<R>();
+        ShadeView<R> s;
+        s.mats = T.mats.template as<MatT<R>>();
+        s.texs = T.texs.template as<TexT<R>>();
+        s.images = images.as<ImageRec>();
+        s.image_bytes = image_bytes.as<uint8_t>();
+        s.perlins = T.perlins.template as<PerlinT<R>>();
+        s.lights = T.lights.template as<LightT<R>>();
+        s.env_texels = env_texels.as<float>();
+        s.env_tables = env_tables.as<double>();
+        s.n_lights = int32_t(host.f32.lights.size());
+        s.n_infinite_lights = host.n_infinite_lights;
+        return s;
+    }
+};
+template <> inline const DeviceTyped<float> &DeviceScene::typed<float>() const { return f32; }
+template <> inline const DeviceTyped<double> &DeviceScene::typed<double>() const { return f64; }
+
+struct WavefrontPool; // rtb_wavefront.cu
+
+} // namespace rtb
+
+struct rtb_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string last_error;
+    std::unique_ptr<rtb::DeviceScene> scene;
+    rtb::WavefrontPool *pool = nullptr; // owned; freed by wavefront_release
+    rtb::DeviceBuffer accum;            // float4 accumulators of the last rtb_render
+    int accum_w = 0, accum_h = 0;
+    std::atomic<int> cancel{0};
+    int sm_count = 0;
+};
+
+namespace rtb {
+
+// rtb_batch_f32.cu / rtb_batch_f64.cu (same source, RTB_REAL = float / double)
+template <class R>
+void launch_trace_batch(rtb_context *ctx, const rtb_ray *d_rays, uint64_t n, rtb_hit *d_hits,
+                        unsigned long long *d_visits);
+template <class R>
+void launch_bsdf_eval(rtb_context *ctx, int material, const rtb_bsdf_query *d_q, uint64_t n,
+                      rtb_bsdf_value *d_out);
+template <class R>
+void launch_bsdf_sample(rtb_context *ctx, int material, const rtb_bsdf_query *d_q, uint64_t n, uint64_t seed,
+                        rtb_bsdf_sample *d_out);
+template <class R>
+void launch_light_eval(rtb_context *ctx, int light, const rtb_light_query *d_q, uint64_t n, uint64_t seed,
+                       rtb_light_value *d_out);
+template <class R>
+void launch_texture_eval(rtb_context *ctx, int texture, const double *d_uvp, uint64_t n, double *d_rgb);
+
+// rtb_wavefront.cu
+void wavefront_render(rtb_context *ctx, const rtb_render_params &p, float4 *d_accum, cudaStream_t stream,
+                      rtb_render_stats *stats);
+void wavefront_release(rtb_context *ctx);
+void launch_resolve_rgb8(rtb_context *ctx, const float4 *d_accum, int w, int h, int spp, uint8_t *d_rgb8,
+                         cudaStream_t stream);
+
+} // namespace rtb
+
+#endif // RTB_INTERNAL_HPP

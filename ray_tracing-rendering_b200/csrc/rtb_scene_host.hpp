@@ -1,0 +1,536 @@
+// rtb_scene_host.hpp — scene blob (include/rtb200_scene.h) -> host copies of the
+// device tables: leaf-ordered primitive records in fp32 and fp64, the two-level
+// BVH, wrapper chains, materials, textures, lights (+ env-map CDF tables) and the
+// camera.  Pure host C++ (no CUDA calls) so it can be unit-tested without a GPU.
+#ifndef RTB_SCENE_HOST_HPP
+#define RTB_SCENE_HOST_HPP
+
+#include "rtb200_blob.hpp"
+#include "rtb_bvh.hpp"
+#include "rtb_shading.cuh"
+
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <vector>
+
+namespace rtb {
+
+template <class R> struct TypedTables {
+    std::vector<PrimT<R>> prims;
+    std::vector<MovingAux<R>> maux;
+    std::vector<XfOp<R>> ops;
+    std::vector<MatT<R>> mats;
+    std::vector<TexT<R>> texs;
+    std::vector<PerlinT<R>> perlins;
+    std::vector<LightT<R>> lights;
+    CameraT<R> camera;
+};
+
+struct HostScene {
+    TypedTables<float> f32;
+    TypedTables<double> f64;
+    std::vector<Node32> nodes;
+    std::vector<ChainRec> chains;
+    std::vector<int32_t> prim_chain;     // per sorted prim
+    std::vector<int32_t> prim_orig;      // per sorted prim -> blob prim id (-1: instance)
+    std::vector<int32_t> orig_to_sorted; // blob prim id -> sorted index
+    std::vector<ImageRec> images;
+    std::vector<uint8_t> image_bytes;
+    std::vector<float> env_texels;
+    std::vector<double> env_tables;
+    rtb_globals globals{};
+    int n_infinite_lights = 0;
+    uint32_t mat_type_mask = 0; // bit t set: some primitive uses a material of type t
+    bool has_media = false;
+    int n_instances = 0;
+};
+
+namespace detail {
+
+inline void xf_point_to_world(const rtb_xform_op *ops, int first, int count, double p[3]) {
+    // inverse of the ray transform: what the wrappers do to rec.p on the way out
+    // (hittable.h:58, :145-146), innermost wrapper first
+    for (int i = count - 1; i >= 0; --i) {
+        const rtb_xform_op &op = ops[first + i];
+        if (op.kind == RTB_XF_TRANSLATE) {
+            p[0] += op.a;
+            p[1] += op.b;
+            p[2] += op.c;
+        } else if (op.kind == RTB_XF_ROTATE_Y) {
+            const double x = op.b * p[0] + op.a * p[2];
+            const double z = -op.a * p[0] + op.b * p[2];
+            p[0] = x;
+            p[2] = z;
+        }
+    }
+}
+
+inline Box box_to_world(const Box &b, const rtb_xform_op *ops, int first, int count) {
+    Box w;
+    for (int c = 0; c < 8; ++c) {
+        double p[3] = {(c & 1) ? b.hi[0] : b.lo[0], (c & 2) ? b.hi[1] : b.lo[1],
+                       (c & 4) ? b.hi[2] : b.lo[2]};
+        xf_point_to_world(ops, first, count, p);
+        w.grow(p);
+    }
+    return w;
+}
+
+// object-space bounds of a simple primitive (sphere.h:62-66, moving_sphere.h:64-71,
+// aarect.h:24-28 with its 1e-4 padding)
+inline Box prim_box(const rtb_prim &p, const rtb_camera &cam) {
+    Box b;
+    switch (p.type) {
+    case RTB_PRIM_SPHERE: {
+        const double r = std::fabs(p.d[3]);
+        for (int k = 0; k < 3; ++k) {
+            b.lo[k] = p.d[k] - r;
+            b.hi[k] = p.d[k] + r;
+        }
+        break;
+    }
+    case RTB_PRIM_MOVING_SPHERE: {
+        const double r = std::fabs(p.d[8]);
+        // ray times lie in the shutter interval; shadow rays use time 0
+        // (direct_light_integrator.h:115)
+        const double times[3] = {cam.time0, cam.time1, 0.0};
+        for (double tm : times) {
+            const double s = (tm - p.d[6]) / (p.d[7] - p.d[6]);
+            for (int k = 0; k < 3; ++k) {
+                const double c = p.d[k] + s * (p.d[3 + k] - p.d[k]);
+                b.lo[k] = std::min(b.lo[k], c - r);
+                b.hi[k] = std::max(b.hi[k], c + r);
+            }
+        }
+        break;
+    }
+    case RTB_PRIM_XY_RECT:
+    case RTB_PRIM_XZ_RECT:
+    case RTB_PRIM_YZ_RECT: {
+        const int AX = p.type == RTB_PRIM_XY_RECT ? 2 : (p.type == RTB_PRIM_XZ_RECT ? 1 : 0);
+        const int A = p.type == RTB_PRIM_YZ_RECT ? 1 : 0;
+        const int B = p.type == RTB_PRIM_XY_RECT ? 1 : 2;
+        b.lo[A] = std::min(p.d[0], p.d[1]);
+        b.hi[A] = std::max(p.d[0], p.d[1]);
+        b.lo[B] = std::min(p.d[2], p.d[3]);
+        b.hi[B] = std::max(p.d[2], p.d[3]);
+        b.lo[AX] = p.d[4] - 0.0001;
+        b.hi[AX] = p.d[4] + 0.0001;
+        break;
+    }
+    default:
+        throw std::runtime_error("prim_box: not a simple primitive");
+    }
+    return b;
+}
+
+template <class R> PrimT<R> make_prim(const rtb_prim &p, uint32_t aux, uint32_t aux2) {
+    PrimT<R> q;
+    std::memset(&q, 0, sizeof(q));
+    uint32_t type = 0;
+    switch (p.type) {
+    case RTB_PRIM_SPHERE:
+        type = PT_SPHERE;
+        for (int k = 0; k < 4; ++k)
+            q.d[k] = R(p.d[k]);
+        break;
+    case RTB_PRIM_MOVING_SPHERE:
+        type = PT_MSPHERE;
+        for (int k = 0; k < 3; ++k)
+            q.d[k] = R(p.d[k]);
+        q.d[3] = R(p.d[8]);
+        break;
+    case RTB_PRIM_XY_RECT:
+    case RTB_PRIM_XZ_RECT:
+    case RTB_PRIM_YZ_RECT:
+        type = p.type == RTB_PRIM_XY_RECT ? PT_XY : (p.type == RTB_PRIM_XZ_RECT ? PT_XZ : PT_YZ);
+        for (int k = 0; k < 5; ++k)
+            q.d[k] = R(p.d[k]);
+        break;
+    case RTB_PRIM_MEDIUM:
+        type = PT_MEDIUM;
+        q.d[0] = R(p.d[0]);
+        break;
+    }
+    q.type_mat = type | ((p.flags & RTB_PRIM_DUP_LEAF) ? uint32_t(PT_DUP_LEAF) : 0u) |
+                 (uint32_t(p.material) << PT_MAT_SHIFT);
+    q.aux = aux;
+    q.aux2 = aux2;
+    return q;
+}
+
+template <class R, class V> void set3(R dst[3], const V &src) {
+    for (int k = 0; k < 3; ++k)
+        dst[k] = R(src[k]);
+}
+
+// camera::camera, camera.h:9-30, operation by operation in fp64
+inline CameraT<double> derive_camera(const rtb_camera &c) {
+    typedef V3<double> V;
+    const double pi = Consts<double>::pi();
+    const double theta = c.vfov * pi / 180.0; // rtweekend.h:20-22
+    const double h = std::tan(theta / 2);
+    const double viewport_height = 2.0 * h;
+    const double viewport_width = c.aspect_ratio * viewport_height;
+    const V lookfrom(c.lookfrom[0], c.lookfrom[1], c.lookfrom[2]);
+    const V lookat(c.lookat[0], c.lookat[1], c.lookat[2]);
+    const V vup(c.vup[0], c.vup[1], c.vup[2]);
+    CameraT<double> o;
+    o.w = unit_vector(lookfrom - lookat);
+    o.u = unit_vector(cross(vup, o.w));
+    o.v = cross(o.w, o.u);
+    o.origin = lookfrom;
+    o.horizontal = (c.focus_dist * viewport_width) * o.u;
+    o.vertical = (c.focus_dist * viewport_height) * o.v;
+    o.lower_left_corner = o.origin - o.horizontal / 2.0 - o.vertical / 2.0 - c.focus_dist * o.w;
+    o.lens_radius = c.aperture / 2;
+    o.time0 = c.time0;
+    o.time1 = c.time1;
+    return o;
+}
+
+template <class R> CameraT<R> cast_camera(const CameraT<double> &c) {
+    CameraT<R> o;
+    auto cv = [](const V3<double> &v) { return V3<R>(R(v.x), R(v.y), R(v.z)); };
+    o.origin = cv(c.origin);
+    o.lower_left_corner = cv(c.lower_left_corner);
+    o.horizontal = cv(c.horizontal);
+    o.vertical = cv(c.vertical);
+    o.u = cv(c.u);
+    o.v = cv(c.v);
+    o.w = cv(c.w);
+    o.lens_radius = R(c.lens_radius);
+    o.time0 = R(c.time0);
+    o.time1 = R(c.time1);
+    return o;
+}
+
+// Distribution2D over luminance*sin(theta), environmental_light.h:146-180 and :15-27
+inline void build_env_tables(const float *tex, int W, int H, std::vector<double> &out) {
+    const double pi = Consts<double>::pi();
+    const size_t base = out.size();
+    out.resize(base + EnvTables::doubles(W, H));
+    double *cond_func = out.data() + base;
+    double *cond_cdf = cond_func + size_t(W) * H;
+    double *cond_int = cond_cdf + size_t(W + 1) * H;
+    double *marg_cdf = cond_int + H;
+    double *marg_int = marg_cdf + (H + 1);
+    for (int v = 0; v < H; ++v) {
+        const double sin_theta = std::sin(pi * (v + 0.5) / H);
+        for (int u = 0; u < W; ++u) {
+            const size_t idx = size_t(v) * W + u;
+            const double r = tex[3 * idx], g = tex[3 * idx + 1], b = tex[3 * idx + 2];
+            const double lum = 0.2126 * r + 0.7152 * g + 0.0722 * b;
+            cond_func[idx] = lum * sin_theta;
+        }
+        double *cdf = cond_cdf + size_t(v) * (W + 1);
+        cdf[0] = 0;
+        for (int i = 1; i <= W; ++i)
+            cdf[i] = cdf[i - 1] + cond_func[size_t(v) * W + i - 1];
+        cond_int[v] = cdf[W];
+        if (cond_int[v] > 0)
+            for (int i = 0; i <= W; ++i)
+                cdf[i] /= cond_int[v];
+    }
+    marg_cdf[0] = 0;
+    for (int i = 1; i <= H; ++i)
+        marg_cdf[i] = marg_cdf[i - 1] + cond_int[i - 1];
+    *marg_int = marg_cdf[H];
+    if (*marg_int > 0)
+        for (int i = 0; i <= H; ++i)
+            marg_cdf[i] /= *marg_int;
+}
+
+} // namespace detail
+
+inline bool texture_reads_uv(const rtb::SceneView &S, int tex, int depth = 0) {
+    if (tex < 0 || depth > 8)
+        return false;
+    const rtb_texture &t = S.textures()[tex];
+    if (t.type == RTB_TEX_IMAGE)
+        return true;
+    if (t.type == RTB_TEX_CHECKER)
+        return texture_reads_uv(S, t.even, depth + 1) || texture_reads_uv(S, t.odd, depth + 1);
+    return false;
+}
+
+// max_leaf: primitives per BVH leaf.
+inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4) {
+    using namespace detail;
+    S.validate();
+    HostScene H;
+    H.globals = S.globals();
+    const rtb_prim *P = S.prims();
+    const int np = int(S.n_prims());
+    const rtb_chain *C = S.chains();
+    const rtb_xform_op *X = S.xform_ops();
+    const rtb_camera &cam = S.camera();
+
+    for (uint64_t i = 0; i < S.n_chains(); ++i) {
+        if (C[i].count > kMaxChainOps)
+            throw std::runtime_error("scene: wrapper chain longer than kMaxChainOps");
+        H.chains.push_back(ChainRec{C[i].first, C[i].count});
+    }
+    for (uint64_t i = 0; i < S.n_xform_ops(); ++i) {
+        XfOp<double> d{X[i].kind, X[i].a, X[i].b, X[i].c};
+        XfOp<float> f{X[i].kind, float(X[i].a), float(X[i].b), float(X[i].c)};
+        H.f64.ops.push_back(d);
+        H.f32.ops.push_back(f);
+    }
+    auto chain_moves = [&](int chain) { // does the chain transform the ray at all?
+        if (chain < 0)
+            return false;
+        for (int i = 0; i < C[chain].count; ++i)
+            if (X[C[chain].first + i].kind != RTB_XF_FLIP_FACE)
+                return true;
+        return false;
+    };
+    auto world_box_of = [&](int i) -> Box { // world-space bounds of blob prim i
+        const rtb_prim &p = P[i];
+        if (p.type == RTB_PRIM_MEDIUM) {
+            Box b;
+            for (int k = p.aux0; k < p.aux0 + p.aux1; ++k) {
+                Box ob = prim_box(P[k], cam);
+                if (P[k].chain >= 0)
+                    ob = box_to_world(ob, X, C[P[k].chain].first, C[P[k].chain].count);
+                b.grow(ob);
+            }
+            return b; // the medium's own (outer) chain is applied by the caller
+        }
+        return prim_box(p, cam);
+    };
+
+    // ---- group world primitives: top-level items and one BLAS per moving chain
+    std::vector<BuildItem> top;
+    std::map<int, std::vector<BuildItem>> groups; // chain id -> object-space items
+    for (int i = 0; i < np; ++i) {
+        if (P[i].flags & RTB_PRIM_BOUNDARY_ONLY)
+            continue;
+        H.mat_type_mask |= 1u << S.materials()[P[i].material].type;
+        if (P[i].type == RTB_PRIM_MEDIUM)
+            H.has_media = true;
+        if (P[i].type == RTB_PRIM_MEDIUM && chain_moves(P[i].chain))
+            throw std::runtime_error("scene: a constant_medium under translate/rotate_y is not supported");
+        BuildItem it;
+        it.box = world_box_of(i);
+        it.id = uint32_t(i);
+        it.solitary = false;
+        if (chain_moves(P[i].chain))
+            groups[P[i].chain].push_back(it);
+        else
+            top.push_back(it);
+    }
+    // instances join the top level with their world-space bounds
+    struct Inst {
+        int chain;
+        Box obj_box;
+    };
+    std::vector<Inst> insts;
+    for (auto &kv : groups) {
+        Inst in;
+        in.chain = kv.first;
+        for (const BuildItem &it : kv.second)
+            in.obj_box.grow(it.box);
+        BuildItem ti;
+        ti.box = box_to_world(in.obj_box, X, C[in.chain].first, C[in.chain].count);
+        ti.id = uint32_t(np + insts.size()); // ids >= np denote instances
+        ti.solitary = true;
+        top.push_back(ti);
+        insts.push_back(in);
+    }
+    H.n_instances = int(insts.size());
+
+    // ---- build trees; primitive array = [top items][BLAS 0 prims]...[boundary prims]
+    struct Slot { // what sits at each sorted position
+        int orig; // blob prim id, or -1 for an instance
+        int inst; // instance index, or -1
+    };
+    std::vector<Slot> slots;
+    BuildResult tlas = build_bvh(top, max_leaf, 0, 0);
+    for (uint32_t id : tlas.order)
+        slots.push_back(id < uint32_t(np) ? Slot{int(id), -1} : Slot{-1, int(id) - np});
+    H.nodes = tlas.nodes;
+    std::vector<uint32_t> blas_root(insts.size());
+    {
+        size_t gi = 0;
+        for (auto &kv : groups) {
+            const uint32_t node_off = uint32_t(H.nodes.size());
+            BuildResult b = build_bvh(kv.second, max_leaf, uint32_t(slots.size()), node_off);
+            blas_root[gi++] = node_off;
+            for (uint32_t id : b.order)
+                slots.push_back(Slot{int(id), -1});
+            H.nodes.insert(H.nodes.end(), b.nodes.begin(), b.nodes.end());
+        }
+    }
+    H.orig_to_sorted.assign(np, -1);
+    for (size_t s = 0; s < slots.size(); ++s)
+        if (slots[s].orig >= 0)
+            H.orig_to_sorted[slots[s].orig] = int(s);
+    // boundary-only prims keep their blob order (media reference them as ranges)
+    for (int i = 0; i < np; ++i)
+        if (P[i].flags & RTB_PRIM_BOUNDARY_ONLY) {
+            H.orig_to_sorted[i] = int(slots.size());
+            slots.push_back(Slot{i, -1});
+        }
+
+    // ---- emit typed primitive records
+    auto emit = [&](auto &T) {
+        typedef typename std::remove_reference<decltype(T.prims[0].d[0])>::type R;
+        T.prims.clear();
+        T.maux.clear();
+        for (const Slot &s : slots) {
+            if (s.inst >= 0) {
+                PrimT<R> q;
+                std::memset(&q, 0, sizeof(q));
+                q.type_mat = PT_INSTANCE;
+                q.aux = blas_root[s.inst];
+                q.aux2 = uint32_t(insts[s.inst].chain);
+                T.prims.push_back(q);
+                continue;
+            }
+            const rtb_prim &p = P[s.orig];
+            uint32_t aux = 0, aux2 = 0;
+            if (p.type == RTB_PRIM_MOVING_SPHERE) {
+                MovingAux<R> m;
+                for (int k = 0; k < 3; ++k)
+                    m.c1[k] = R(p.d[3 + k]);
+                m.time0 = R(p.d[6]);
+                m.time1 = R(p.d[7]);
+                aux = uint32_t(T.maux.size());
+                T.maux.push_back(m);
+            } else if (p.type == RTB_PRIM_MEDIUM) {
+                aux = uint32_t(H.orig_to_sorted[p.aux0]);
+                aux2 = uint32_t(p.aux1);
+                for (int k = 0; k < p.aux1; ++k)
+                    if (H.orig_to_sorted[p.aux0 + k] != int(aux) + k)
+                        throw std::runtime_error("scene: medium boundary not contiguous");
+            }
+            T.prims.push_back(make_prim<R>(p, aux, aux2));
+        }
+    };
+    emit(H.f32);
+    emit(H.f64);
+    for (const Slot &s : slots) {
+        H.prim_orig.push_back(s.orig);
+        H.prim_chain.push_back(s.inst >= 0 ? insts[s.inst].chain : P[s.orig].chain);
+    }
+
+    // ---- materials / textures
+    for (uint64_t i = 0; i < S.n_materials(); ++i) {
+        const rtb_material &m = S.materials()[i];
+        int flags = 0;
+        for (int k = 0; k < 4; ++k)
+            if (texture_reads_uv(S, m.tex[k]))
+                flags |= 1;
+        MatT<double> d;
+        MatT<float> f;
+        d.type = f.type = m.type;
+        for (int k = 0; k < 4; ++k)
+            d.tex[k] = f.tex[k] = m.tex[k];
+        d.flags = f.flags = flags;
+        set3(d.color, m.color);
+        set3(f.color, m.color);
+        d.fuzz = m.fuzz;
+        f.fuzz = float(m.fuzz);
+        d.ir = m.ir;
+        f.ir = float(m.ir);
+        H.f64.mats.push_back(d);
+        H.f32.mats.push_back(f);
+    }
+    for (uint64_t i = 0; i < S.n_textures(); ++i) {
+        const rtb_texture &t = S.textures()[i];
+        TexT<double> d;
+        TexT<float> f;
+        d.type = f.type = t.type;
+        d.even = f.even = t.even;
+        d.odd = f.odd = t.odd;
+        d.image = f.image = t.image;
+        d.perlin = f.perlin = t.perlin;
+        set3(d.color, t.color);
+        set3(f.color, t.color);
+        d.scale = t.scale;
+        f.scale = float(t.scale);
+        H.f64.texs.push_back(d);
+        H.f32.texs.push_back(f);
+    }
+    for (uint64_t i = 0; i < S.n_images(); ++i)
+        H.images.push_back(ImageRec{S.images()[i].width, S.images()[i].height, S.images()[i].offset});
+    if (S.n_image_bytes())
+        H.image_bytes.assign(S.image_bytes(), S.image_bytes() + S.n_image_bytes());
+    for (uint64_t i = 0; i < S.n_perlins(); ++i) {
+        const rtb_perlin &p = S.perlins()[i];
+        PerlinT<double> d;
+        PerlinT<float> f;
+        for (int k = 0; k < 256; ++k) {
+            for (int c = 0; c < 3; ++c) {
+                d.ranvec[k][c] = p.ranvec[k][c];
+                f.ranvec[k][c] = float(p.ranvec[k][c]);
+            }
+            d.perm_x[k] = f.perm_x[k] = p.perm_x[k];
+            d.perm_y[k] = f.perm_y[k] = p.perm_y[k];
+            d.perm_z[k] = f.perm_z[k] = p.perm_z[k];
+        }
+        H.f64.perlins.push_back(d);
+        H.f32.perlins.push_back(f);
+    }
+
+    // ---- lights
+    if (S.n_env_texels())
+        H.env_texels.assign(S.env_texels(), S.env_texels() + S.n_env_texels());
+    for (uint64_t i = 0; i < S.n_lights(); ++i) {
+        const rtb_light &l = S.lights()[i];
+        LightT<double> d;
+        std::memset(&d, 0, sizeof(d));
+        d.type = l.type;
+        d.env_w = l.env_width;
+        d.env_h = l.env_height;
+        d.env_probe = l.env_is_probe;
+        d.env_texel_offset = l.env_offset;
+        set3(d.Q, l.Q);
+        set3(d.u, l.u);
+        set3(d.v, l.v);
+        set3(d.intensity, l.intensity);
+        d.cos_cutoff = l.cos_cutoff;
+        if (l.type == RTB_LIGHT_QUAD) { // quad_light.h:9-16
+            const V3<double> n = cross(V3<double>(l.u[0], l.u[1], l.u[2]), V3<double>(l.v[0], l.v[1], l.v[2]));
+            d.area = length(n);
+            const V3<double> nn = unit_vector(n);
+            d.normal[0] = nn.x;
+            d.normal[1] = nn.y;
+            d.normal[2] = nn.z;
+        }
+        if (l.type == RTB_LIGHT_ENV) {
+            H.n_infinite_lights++;
+            if (l.env_width > 0 && l.env_height > 0) {
+                d.env_table_offset = H.env_tables.size();
+                build_env_tables(H.env_texels.data() + l.env_offset, l.env_width, l.env_height, H.env_tables);
+            }
+        }
+        LightT<float> f;
+        std::memset(&f, 0, sizeof(f));
+        f.type = d.type;
+        f.env_w = d.env_w;
+        f.env_h = d.env_h;
+        f.env_probe = d.env_probe;
+        f.env_texel_offset = d.env_texel_offset;
+        f.env_table_offset = d.env_table_offset;
+        set3(f.Q, d.Q);
+        set3(f.u, d.u);
+        set3(f.v, d.v);
+        set3(f.intensity, d.intensity);
+        set3(f.normal, d.normal);
+        f.area = float(d.area);
+        f.cos_cutoff = float(d.cos_cutoff);
+        H.f64.lights.push_back(d);
+        H.f32.lights.push_back(f);
+    }
+
+    H.f64.camera = derive_camera(cam);
+    H.f32.camera = cast_camera<float>(H.f64.camera);
+    return H;
+}
+
+} // namespace rtb
+
+#endif // RTB_SCENE_HOST_HPP

@@ -1,0 +1,818 @@
+// rtb_wavefront.cu — the production renderer: a wavefront path tracer with path
+// regeneration, replacing Renderer::render + Integrator::Li of the reference
+// (src/renderer/renderer.h:30-102 and the five *_integrator.h files).
+//
+// Data layout (all in HBM, sized for `P` resident paths):
+//   path state, SoA of 16-byte vectors (one coalesced 128-bit access each):
+//     ray_o[P]  float4  origin.xyz, time
+//     ray_d[P]  float4  direction.xyz (NOT normalised, as in the reference), origin primitive
+//     thr[P]    float4  throughput.rgb, pixel index
+//     aux[P]    uint4   rng state (2 x u32), depth | specular_bounce << 16, prev_bsdf_pdf
+//     hit[P]    float4  t, primitive index, -, -            (extend -> shade)
+//   queues of 32-bit path indices, filled with warp-aggregated atomics:
+//     q_ext[2][P]   paths that need a closest-hit ray (double buffered)
+//     q_mat[6][P]   paths whose hit landed on material type m   (material-sorted shading)
+//     q_miss[P]     paths whose ray left the scene
+//   shadow-ray queue, SoA of 3 float4 per entry (written by shade, read by connect).
+//   accum[H*W] float4: linear radiance SUMS, updated with vector atomics (RED.ADD.v4.f32).
+//
+// One wavefront iteration = extend -> shade_<material> (x present types) -> miss -> connect.
+// Every kernel is a persistent-thread kernel: the grid is a fixed multiple of the SM
+// count and warps pull 32-entry chunks off a queue through one atomic per warp.
+// When a path ends (miss, absorbed, Russian roulette, max depth) the same thread
+// immediately starts the next camera sample in the same slot, so the extend queue
+// stays full until the job runs out of samples; only then does it drain.
+// Queue counters live in three rotating sets so that no kernel ever has to wait for a
+// reset: iteration i uses set i%3 and clears set (i+2)%3.
+#include "rtb_internal.hpp"
+
+#include <algorithm>
+#include <vector>
+
+namespace rtb {
+
+namespace {
+
+constexpr int kMatTypes = RTB_MAT_TYPE_COUNT; // 6
+constexpr uint32_t kFullMask = 0xffffffffu;
+
+struct alignas(16) Counters {
+    uint32_t n_ext;  // entries in this iteration's extend queue
+    uint32_t n_mat[kMatTypes];
+    uint32_t n_miss;
+    uint32_t n_shadow;
+    uint32_t head_ext; // work-distribution cursors
+    uint32_t head_mat[kMatTypes];
+    uint32_t head_miss;
+    uint32_t head_shadow;
+    uint32_t pad[5];
+};
+static_assert(sizeof(Counters) % 16 == 0, "Counters must be clearable with uint4 stores");
+
+struct Globals {
+    unsigned long long next_sample; // next local sample index to hand out
+    unsigned long long rays_closest;
+    unsigned long long rays_shadow;
+    unsigned long long nodes_visited;
+    unsigned long long prim_tests;
+    unsigned long long paths;
+};
+
+struct WfParams {
+    GeomView<float> geom;
+    ShadeView<float> shade;
+    CameraT<float> cam;
+    float4 *ray_o, *ray_d, *thr, *hit;
+    uint4 *aux;
+    uint32_t *q_ext[2];
+    uint32_t *q_mat;  // kMatTypes * P
+    uint32_t *q_miss; // P
+    float4 *sh_a, *sh_b, *sh_c; // shadow queue
+    Counters *ctr;              // 3 sets
+    Globals *glob;
+    float4 *accum;
+    uint32_t P;
+    int32_t width, height, spp, max_depth, rr_start, integrator;
+    int32_t sample_offset, sample_stride;
+    uint32_t npix;
+    unsigned long long total_samples; // samples this call renders = npix * local spp
+    uint64_t seed;
+    float bg[3];
+    uint32_t mat_mask;
+    int32_t has_media;
+};
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// One atomic per warp: reserves a slot in a queue for every lane with want == true.
+// Must be called by all 32 lanes.
+__device__ __forceinline__ uint32_t warp_reserve(uint32_t *counter, bool want) {
+    const uint32_t m = __ballot_sync(kFullMask, want);
+    if (m == 0)
+        return 0;
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (int(lane_id()) == leader)
+        base = atomicAdd(counter, uint32_t(__popc(m)));
+    base = __shfl_sync(kFullMask, base, leader);
+    return base + __popc(m & ((1u << lane_id()) - 1u));
+}
+__device__ __forceinline__ unsigned long long warp_reserve64(unsigned long long *counter, bool want) {
+    const uint32_t m = __ballot_sync(kFullMask, want);
+    if (m == 0)
+        return 0;
+    const int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if (int(lane_id()) == leader)
+        base = atomicAdd(counter, (unsigned long long)__popc(m));
+    base = __shfl_sync(kFullMask, base, leader);
+    return base + __popc(m & ((1u << lane_id()) - 1u));
+}
+// Persistent-thread work fetch: the warp takes the next 32 queue entries.
+__device__ __forceinline__ uint32_t warp_fetch(uint32_t *head) {
+    uint32_t base = 0;
+    if (lane_id() == 0)
+        base = atomicAdd(head, 32u);
+    return __shfl_sync(kFullMask, base, 0);
+}
+
+// RED.ADD.v4.f32 — one vector reduction per contribution instead of three scalar ones.
+__device__ __forceinline__ void accum_add(float4 *accum, uint32_t pix, V3<float> c) {
+    if (c.x == 0.f && c.y == 0.f && c.z == 0.f)
+        return;
+    atomicAdd(accum + pix, make_float4(c.x, c.y, c.z, 0.f));
+}
+
+struct PathState {
+    V3<float> o, d, T;
+    float time, prev_pdf;
+    uint32_t origin_prim, pix, depth;
+    bool spec;
+    Pcg rng;
+};
+
+__device__ __forceinline__ void store_ray(const WfParams &p, uint32_t slot, const PathState &s) {
+    p.ray_o[slot] = make_float4(s.o.x, s.o.y, s.o.z, s.time);
+    p.ray_d[slot] = make_float4(s.d.x, s.d.y, s.d.z, __uint_as_float(s.origin_prim));
+}
+__device__ __forceinline__ void store_rest(const WfParams &p, uint32_t slot, const PathState &s) {
+    p.thr[slot] = make_float4(s.T.x, s.T.y, s.T.z, __uint_as_float(s.pix));
+    p.aux[slot] = make_uint4(uint32_t(s.rng.s), uint32_t(s.rng.s >> 32), s.depth | (s.spec ? 0x10000u : 0u),
+                             __float_as_uint(s.prev_pdf));
+}
+__device__ __forceinline__ PathState load_state(const WfParams &p, uint32_t slot) {
+    PathState s;
+    const float4 a = p.ray_o[slot], b = p.ray_d[slot], c = p.thr[slot];
+    const uint4 x = p.aux[slot];
+    s.o = V3<float>(a.x, a.y, a.z);
+    s.time = a.w;
+    s.d = V3<float>(b.x, b.y, b.z);
+    s.origin_prim = __float_as_uint(b.w);
+    s.T = V3<float>(c.x, c.y, c.z);
+    s.pix = __float_as_uint(c.w);
+    s.rng.s = uint64_t(x.x) | (uint64_t(x.y) << 32);
+    s.depth = x.z & 0xffffu;
+    s.spec = (x.z & 0x10000u) != 0;
+    s.prev_pdf = __uint_as_float(x.w);
+    return s;
+}
+
+// renderer.h:72-75: one camera sample.  Local sample index g -> (pixel, sample-in-pixel)
+// in sample-major order, so concurrently resident paths belong to different pixels.
+__device__ __forceinline__ void new_path(const WfParams &p, unsigned long long g, PathState &s) {
+    const uint32_t k = uint32_t(g / p.npix);
+    const uint32_t pix = uint32_t(g - (unsigned long long)k * p.npix);
+    const uint32_t smp = uint32_t(p.sample_offset) + k * uint32_t(p.sample_stride);
+    s.rng = pcg_seed((unsigned long long)pix * uint32_t(p.spp) + smp, p.seed);
+    RngT<float> r;
+    r.g = s.rng;
+    const uint32_t i = pix % uint32_t(p.width), j = pix / uint32_t(p.width);
+    const float u = (float(i) + r.next()) / float(p.width - 1);
+    const float v = (float(j) + r.next()) / float(p.height - 1);
+    camera_ray(p.cam, u, v, r, s.o, s.d, s.time);
+    s.rng = r.g;
+    s.T = V3<float>(1, 1, 1);
+    s.pix = pix;
+    s.depth = 0;
+    s.spec = false;
+    s.prev_pdf = 0.f;
+    s.origin_prim = kNoPrim;
+}
+
+// Ends the iteration for one lane: a finished path is replaced by the next camera
+// sample (if any remain); a live path is written back; either way the slot is queued
+// for the next extend.  Called by all 32 lanes (done == false for idle lanes is fine
+// as long as `valid` is false).
+__device__ __forceinline__ void finish_lane(const WfParams &p, Counters &next, uint32_t *q_next, bool valid,
+                                            bool alive, uint32_t slot, PathState &s) {
+    const bool want_new = valid && !alive;
+    const unsigned long long g = warp_reserve64(&p.glob->next_sample, want_new);
+    bool queued = valid && alive;
+    if (want_new && g < p.total_samples) {
+        new_path(p, g, s);
+        queued = true;
+    }
+    if (queued) {
+        store_ray(p, slot, s);
+        store_rest(p, slot, s);
+    }
+    const uint32_t pos = warp_reserve(&next.n_ext, queued);
+    if (queued)
+        q_next[pos] = slot;
+}
+
+// ---- kernels ------------------------------------------------------------------------------
+
+__global__ void k_clear(Counters *ctr, Globals *glob) {
+    if (blockIdx.x == 0 && threadIdx.x < 3 * sizeof(Counters) / 4)
+        reinterpret_cast<uint32_t *>(ctr)[threadIdx.x] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        glob->next_sample = 0;
+        glob->rays_closest = glob->rays_shadow = glob->nodes_visited = glob->prim_tests = glob->paths = 0;
+    }
+}
+
+// Initial fill: slot i starts local sample i.
+__global__ void __launch_bounds__(256) k_generate(WfParams p) {
+    const unsigned long long n = p.total_samples < p.P ? p.total_samples : (unsigned long long)p.P;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        PathState s;
+        new_path(p, i, s);
+        store_ray(p, i, s);
+        store_rest(p, i, s);
+        p.q_ext[0][i] = i;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        p.ctr[0].n_ext = uint32_t(n);
+        p.glob->next_sample = n;
+    }
+}
+
+struct PathDraw { // RNG adaptor handed to traverse() for constant_medium tests
+    Pcg *g;
+    __device__ float operator()() { return g->next_open(); }
+};
+
+// extend: closest hit for every queued path; classifies the result into the
+// material queues.  Replaces scene.hit(current_ray, 0.001, infinity, rec)
+// (e.g. rr_path_integrator.h:29) and everything under bvh_node::hit.
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_extend(WfParams p, int it) {
+    Counters &C = p.ctr[it % 3];
+    if (blockIdx.x == 0 && threadIdx.x < sizeof(Counters) / 4)
+        reinterpret_cast<uint32_t *>(&p.ctr[(it + 2) % 3])[threadIdx.x] = 0;
+    const uint32_t n = C.n_ext;
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(&p.glob->rays_closest, (unsigned long long)n);
+    const uint32_t *q = p.q_ext[it & 1];
+    const GlobalFetch<float> F(p.geom);
+    uint64_t nodes = 0, tests = 0;
+    while (true) {
+        const uint32_t base = warp_fetch(&C.head_ext);
+        if (base >= n)
+            break;
+        const uint32_t idx = base + lane_id();
+        const bool valid = idx < n;
+        uint32_t slot = 0, key = kMatTypes + 1; // key: material type, kMatTypes = miss
+        if (valid) {
+            slot = q[idx];
+            const float4 a = p.ray_o[slot], b = p.ray_d[slot];
+            const V3<float> o(a.x, a.y, a.z), d(b.x, b.y, b.z);
+            float t;
+            uint32_t pi;
+            if (p.has_media) {
+                const uint4 x = p.aux[slot];
+                Pcg g;
+                g.s = uint64_t(x.x) | (uint64_t(x.y) << 32);
+                PathDraw draw{&g};
+                pi = traverse<float, false, true>(p.geom, F, o, d, a.w, 0.001f, Consts<float>::inf(),
+                                                  __float_as_uint(b.w), draw, t, COUNT ? &nodes : nullptr,
+                                                  COUNT ? &tests : nullptr);
+                p.aux[slot] = make_uint4(uint32_t(g.s), uint32_t(g.s >> 32), x.z, x.w);
+            } else {
+                Pcg g;
+                g.s = 0;
+                PathDraw draw{&g};
+                pi = traverse<float, false, true>(p.geom, F, o, d, a.w, 0.001f, Consts<float>::inf(),
+                                                  __float_as_uint(b.w), draw, t, COUNT ? &nodes : nullptr,
+                                                  COUNT ? &tests : nullptr);
+            }
+            p.hit[slot] = make_float4(t, __uint_as_float(pi), 0.f, 0.f);
+            key = kMatTypes;
+            if (pi != kNoPrim)
+                key = uint32_t(p.shade.mats[p.geom.prims[pi].type_mat >> PT_MAT_SHIFT].type);
+        }
+#pragma unroll
+        for (uint32_t k = 0; k <= kMatTypes; ++k) {
+            if (k < kMatTypes && !((p.mat_mask >> k) & 1u))
+                continue;
+            uint32_t *cnt = k < kMatTypes ? &C.n_mat[k] : &C.n_miss;
+            uint32_t *dst = k < kMatTypes ? p.q_mat + size_t(k) * p.P : p.q_miss;
+            const uint32_t pos = warp_reserve(cnt, key == k);
+            if (key == k)
+                dst[pos] = slot;
+        }
+    }
+    if (COUNT) {
+        atomicAdd(&p.glob->nodes_visited, (unsigned long long)nodes);
+        atomicAdd(&p.glob->prim_tests, (unsigned long long)tests);
+    }
+}
+
+// mis_path_integrator.h:154-162
+__device__ __forceinline__ V3<float> clamp_radiance(V3<float> L, float max_value) {
+    if (L.x > max_value || L.y > max_value || L.z > max_value) {
+        const float max_c = max3(L);
+        if (max_c > max_value)
+            return L * (max_value / max_c);
+    }
+    return L;
+}
+// mis_path_integrator.h:165-170
+__device__ __forceinline__ float power_heuristic(float a, float b) {
+    const float a2 = a * a, b2 = b * b, denom = a2 + b2;
+    return denom > 0.f ? a2 / denom : 0.f;
+}
+// mis_path_integrator.h:173-188 (also :53-60): sum over ALL lights of pdf(o,d)/N
+__device__ float all_lights_pdf(const WfParams &p, V3<float> o, V3<float> d) {
+    float total = 0.f;
+    const float sel = 1.0f / float(p.shade.n_lights);
+    for (int i = 0; i < p.shade.n_lights; ++i)
+        total += light_pdf(p.shade, p.shade.lights[i], o, d) * sel;
+    return total;
+}
+
+// shade_<material>: everything Integrator::Li does at a surface hit, for the paths
+// whose hit landed on material type M.  OLD = integrators 0/1 (legacy scatter() +
+// two-sided emitted(u,v,p)), otherwise integrators 2/3/4 (sample/eval/pdf +
+// one-sided emitted(rec,wo), NEE, MIS).
+template <int M, bool OLD>
+__global__ void __launch_bounds__(128) k_shade(WfParams p, int it) {
+    Counters &C = p.ctr[it % 3];
+    Counters &N = p.ctr[(it + 1) % 3];
+    const uint32_t n = C.n_mat[M];
+    const uint32_t *q = p.q_mat + size_t(M) * p.P;
+    uint32_t *q_next = p.q_ext[(it + 1) & 1];
+    while (true) {
+        const uint32_t base = warp_fetch(&C.head_mat[M]);
+        if (base >= n)
+            break;
+        const uint32_t idx = base + lane_id();
+        const bool valid = idx < n;
+        uint32_t slot = 0;
+        bool alive = false;
+        PathState s;
+        // shadow-ray request produced by this lane (integrators 3/4)
+        bool want_shadow = false;
+        V3<float> sh_o(0, 0, 0), sh_d(0, 0, 0), sh_c(0, 0, 0);
+        float sh_tmax = 0.f;
+        uint32_t sh_origin = kNoPrim;
+        if (valid) {
+            slot = q[idx];
+            s = load_state(p, slot);
+            const float4 h = p.hit[slot];
+            const float t = h.x;
+            const uint32_t pi = __float_as_uint(h.y);
+            MatT<float> m = p.shade.mats[p.geom.prims[pi].type_mat >> PT_MAT_SHIFT];
+            m.type = M; // compile-time constant: prunes the per-type switches
+            const RecT<float> rec = (m.flags & 1)
+                                        ? make_record<float, true, true>(p.geom, pi, s.o, s.d, s.time, t)
+                                        : make_record<float, true, false>(p.geom, pi, s.o, s.d, s.time, t);
+            RngT<float> rng;
+            rng.g = s.rng;
+            alive = true;
+            if (OLD) {
+                // path_integrator.h:32-44, rr_path_integrator.h:35-57
+                if (M == RTB_MAT_DIFFUSE_LIGHT)
+                    accum_add(p.accum, s.pix, s.T * mat_emitted_old(p.shade, m, rec));
+                V3<float> atten, dout;
+                if (!mat_scatter(p.shade, m, rec, s.d, rng, atten, dout)) {
+                    alive = false;
+                } else {
+                    s.T = s.T * atten;
+                    if (p.integrator == RTB_INTEGRATOR_RR && int(s.depth) >= p.rr_start) {
+                        const float ps = clamp_(max3(s.T), 0.005f, 0.95f);
+                        if (rng.next() > ps)
+                            alive = false;
+                        else
+                            s.T = s.T / ps;
+                    }
+                    s.o = rec.p;
+                    s.d = dout;
+                    s.origin_prim = pi;
+                }
+            } else {
+                const V3<float> wo = -unit_vector(s.d);
+                if (M == RTB_MAT_DIFFUSE_LIGHT) {
+                    const V3<float> e = mat_emitted_new(p.shade, m, rec);
+                    if (p.integrator == RTB_INTEGRATOR_PBR) {
+                        accum_add(p.accum, s.pix, s.T * e); // pbr_path_integrator.h:38-39
+                    } else if (p.integrator == RTB_INTEGRATOR_DIRECT) {
+                        if (s.depth == 0 || s.spec) // direct_light_integrator.h:52-55
+                            accum_add(p.accum, s.pix, s.T * e);
+                    } else if (length_squared(e) > 0.f) { // mis_path_integrator.h:72-94
+                        V3<float> Le;
+                        if (s.depth == 0 || s.spec)
+                            Le = s.T * e;
+                        else if (p.shade.n_lights > 0)
+                            Le = (s.T * e) * power_heuristic(s.prev_pdf, all_lights_pdf(p, s.o, s.d));
+                        else
+                            Le = s.T * e;
+                        accum_add(p.accum, s.pix, s.depth == 0 ? Le : clamp_radiance(Le, 100.f));
+                    }
+                }
+                s.spec = false; // material::is_specular() is never overridden (material.h:37)
+                // next-event estimation: direct_light_integrator.h:98-142, mis_path_integrator.h:192-234.
+                // eval() is identically 0 for metal / dielectric / diffuse_light / isotropic, so
+                // only lambertian and PBR can contribute; the others skip the (wasted) shadow ray.
+                if ((M == RTB_MAT_LAMBERTIAN || M == RTB_MAT_PBR) && p.integrator >= RTB_INTEGRATOR_DIRECT &&
+                    p.shade.n_lights > 0) {
+                    const int nl = p.shade.n_lights;
+                    int li = int(float(nl) * rng.next()); // random_int(0, n-1), rtweekend.h:48-50
+                    li = li < nl ? li : nl - 1;
+                    const float sel = 1.0f / float(nl);
+                    const float u0 = rng.next(), u1 = rng.next();
+                    const LightT<float> &L = p.shade.lights[li];
+                    const LightSampleT<float> ls = light_sample(p.shade, L, rec.p, u0, u1, rng);
+                    if (ls.pdf > 0.f && length_squared(ls.Li) > 0.f) {
+                        const V3<float> f = mat_eval(p.shade, m, rec, wo, ls.wi);
+                        const float cos_theta = fabsf(dot(ls.wi, rec.normal));
+                        V3<float> Ld;
+                        if (p.integrator == RTB_INTEGRATOR_DIRECT) {
+                            Ld = ls.is_delta ? (f * ls.Li) * (cos_theta / sel)
+                                             : (f * ls.Li) * (cos_theta / (ls.pdf * sel));
+                            // direct_light_integrator.h:133-139: sequential per-channel rescale
+                            if (Ld.x > 100.f)
+                                Ld = Ld * (100.f / Ld.x);
+                            if (Ld.y > 100.f)
+                                Ld = Ld * (100.f / Ld.y);
+                            if (Ld.z > 100.f)
+                                Ld = Ld * (100.f / Ld.z);
+                            Ld = s.T * Ld;
+                        } else {
+                            if (ls.is_delta) {
+                                Ld = (f * ls.Li) * (cos_theta / sel);
+                            } else {
+                                const float bsdf_pdf = mat_pdf(p.shade, m, rec, wo, ls.wi);
+                                const float light_p = ls.pdf * sel;
+                                Ld = (f * ls.Li) * (cos_theta * power_heuristic(light_p, bsdf_pdf) / light_p);
+                            }
+                            Ld = clamp_radiance(s.T * Ld, 100.f);
+                        }
+                        if (Ld.x != 0.f || Ld.y != 0.f || Ld.z != 0.f) {
+                            want_shadow = true;
+                            sh_o = rec.p;
+                            sh_c = Ld;
+                            sh_origin = pi;
+                            if (isfinite(ls.dist)) {
+                                // segment form: d = light_point - p, t in [0.001/dist, 1 - 0.001/dist];
+                                // the same interval as (wi, [0.001, dist - 0.001]) of the reference but
+                                // well-conditioned in fp32 (the far end is exactly t = 1)
+                                const float inv = 1.0f / ls.dist;
+                                sh_d = ls.to_light;
+                                sh_tmax = 1.0f - 0.001f * inv;
+                            } else {
+                                sh_d = ls.wi;
+                                sh_tmax = Consts<float>::inf();
+                            }
+                        }
+                    }
+                }
+                BsdfSampleT<float> bs;
+                if (!mat_sample(p.shade, m, rec, wo, rng, bs)) {
+                    // mis_path_integrator.h:106-117: only integrator 4 falls back to scatter()
+                    V3<float> atten, dout;
+                    if (p.integrator == RTB_INTEGRATOR_MIS && mat_scatter(p.shade, m, rec, s.d, rng, atten, dout)) {
+                        s.T = s.T * atten;
+                        s.d = dout;
+                        s.spec = false;
+                        s.prev_pdf = 0.f;
+                    } else {
+                        alive = false;
+                    }
+                } else if (bs.pdf < 1e-8f && !bs.is_specular) {
+                    alive = false;
+                } else {
+                    s.spec = bs.is_specular;
+                    s.prev_pdf = bs.is_specular ? 0.f : bs.pdf;
+                    const float cos_theta = fabsf(dot(bs.wi, rec.normal));
+                    s.T = bs.is_specular ? s.T * bs.f : s.T * (bs.f * (cos_theta / bs.pdf));
+                    s.d = bs.wi;
+                }
+                if (alive) {
+                    s.o = rec.p;
+                    s.origin_prim = pi;
+                    if (int(s.depth) >= p.rr_start) { // e.g. mis_path_integrator.h:137-146
+                        const float ps = clamp_(max3(s.T), 0.05f, 0.95f);
+                        if (rng.next() > ps)
+                            alive = false;
+                        else
+                            s.T = s.T / ps;
+                    }
+                }
+            }
+            s.rng = rng.g;
+            s.depth += 1;
+            if (int(s.depth) >= p.max_depth)
+                alive = false;
+        }
+        if (!OLD) {
+            const uint32_t pos = warp_reserve(&C.n_shadow, want_shadow);
+            if (want_shadow) {
+                p.sh_a[pos] = make_float4(sh_o.x, sh_o.y, sh_o.z, sh_tmax);
+                p.sh_b[pos] = make_float4(sh_d.x, sh_d.y, sh_d.z, __uint_as_float(s.pix));
+                p.sh_c[pos] = make_float4(sh_c.x, sh_c.y, sh_c.z, __uint_as_float(sh_origin));
+            }
+        }
+        finish_lane(p, N, q_next, valid, alive, slot, s);
+    }
+}
+
+// miss: the ray left the scene.  Background for integrators 0-2 (e.g.
+// rr_path_integrator.h:30-33); environment lights for 3/4
+// (direct_light_integrator.h:35-48, mis_path_integrator.h:37-67).
+__global__ void __launch_bounds__(128) k_miss(WfParams p, int it) {
+    Counters &C = p.ctr[it % 3];
+    Counters &N = p.ctr[(it + 1) % 3];
+    const uint32_t n = C.n_miss;
+    uint32_t *q_next = p.q_ext[(it + 1) & 1];
+    while (true) {
+        const uint32_t base = warp_fetch(&C.head_miss);
+        if (base >= n)
+            break;
+        const uint32_t idx = base + lane_id();
+        const bool valid = idx < n;
+        uint32_t slot = 0;
+        PathState s;
+        if (valid) {
+            slot = p.q_miss[idx];
+            s = load_state(p, slot);
+            const V3<float> bg(p.bg[0], p.bg[1], p.bg[2]);
+            V3<float> L = s.T * bg;
+            if (p.integrator >= RTB_INTEGRATOR_DIRECT && p.shade.n_infinite_lights > 0) {
+                V3<float> env(0, 0, 0);
+                for (int i = 0; i < p.shade.n_lights; ++i)
+                    if (p.shade.lights[i].type == RTB_LIGHT_ENV)
+                        env = env + light_Le(p.shade, p.shade.lights[i], s.d);
+                if (p.integrator == RTB_INTEGRATOR_DIRECT || s.depth == 0 || s.spec)
+                    L = s.T * env;
+                else
+                    L = (s.T * env) * power_heuristic(s.prev_pdf, all_lights_pdf(p, s.o, s.d));
+            }
+            accum_add(p.accum, s.pix, L);
+        }
+        finish_lane(p, N, q_next, valid, false, slot, s);
+    }
+}
+
+struct HashDraw { // RNG for shadow rays through media, keyed by the queue entry
+    Pcg g;
+    __device__ float operator()() { return g.next_open(); }
+};
+
+// connect: any-hit test of the shadow rays queued by shade; unoccluded ones add their
+// (already weighted) contribution.  Replaces scene.hit(shadow_ray, 0.001, dist - 0.001)
+// (direct_light_integrator.h:115-130, mis_path_integrator.h:209-230).
+__global__ void __launch_bounds__(128) k_connect(WfParams p, int it) {
+    Counters &C = p.ctr[it % 3];
+    const uint32_t n = C.n_shadow;
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(&p.glob->rays_shadow, (unsigned long long)n);
+    const GlobalFetch<float> F(p.geom);
+    while (true) {
+        const uint32_t base = warp_fetch(&C.head_shadow);
+        if (base >= n)
+            break;
+        const uint32_t idx = base + lane_id();
+        if (idx < n) {
+            const float4 a = p.sh_a[idx], b = p.sh_b[idx], c = p.sh_c[idx];
+            const V3<float> o(a.x, a.y, a.z), d(b.x, b.y, b.z);
+            // t_min: 0.001 in units of the unit direction; the stored direction may be the
+            // unnormalised segment
+            const float len = isfinite(a.w) ? length(d) : 1.0f;
+            HashDraw draw;
+            draw.g = pcg_seed((uint64_t(__float_as_uint(a.x)) << 32) ^ __float_as_uint(b.y), p.seed ^ idx);
+            float t;
+            // shadow rays carry time 0 regardless of the path's time (direct_light_integrator.h:115)
+            const uint32_t pi = traverse<float, true, true>(p.geom, F, o, d, 0.0f, 0.001f / len, a.w,
+                                                            __float_as_uint(c.w), draw, t, nullptr, nullptr);
+            if (pi == kNoPrim)
+                accum_add(p.accum, __float_as_uint(b.w), V3<float>(c.x, c.y, c.z));
+        }
+    }
+}
+
+// renderer.h:126-140 + render_buffer.h:35-55: sqrt(sum/spp), clamp, (uchar)(x*255), y flip.
+__global__ void k_resolve_rgb8(const float4 *__restrict__ accum, int w, int h, float inv_spp,
+                               uint8_t *__restrict__ rgb8) {
+    const int n = w * h;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int row = i / w, col = i - row * w; // row in the PNG (top first)
+        const float4 a = accum[size_t(h - 1 - row) * w + col];
+        const float r = clamp_(sqrtf(inv_spp * a.x), 0.0f, 1.0f);
+        const float g = clamp_(sqrtf(inv_spp * a.y), 0.0f, 1.0f);
+        const float b = clamp_(sqrtf(inv_spp * a.z), 0.0f, 1.0f);
+        rgb8[3 * size_t(i)] = uint8_t(r * 255.f);
+        rgb8[3 * size_t(i) + 1] = uint8_t(g * 255.f);
+        rgb8[3 * size_t(i) + 2] = uint8_t(b * 255.f);
+    }
+}
+
+template <bool OLD> void launch_shade(int mtype, const WfParams &P, int it, int grid, cudaStream_t st) {
+    switch (mtype) {
+    case 0: k_shade<0, OLD><<<grid, 128, 0, st>>>(P, it); break;
+    case 1: k_shade<1, OLD><<<grid, 128, 0, st>>>(P, it); break;
+    case 2: k_shade<2, OLD><<<grid, 128, 0, st>>>(P, it); break;
+    case 3: k_shade<3, OLD><<<grid, 128, 0, st>>>(P, it); break;
+    case 4: k_shade<4, OLD><<<grid, 128, 0, st>>>(P, it); break;
+    default: k_shade<5, OLD><<<grid, 128, 0, st>>>(P, it); break;
+    }
+}
+
+} // namespace
+
+// Device memory of the path pool; kept across renders on a context.
+struct WavefrontPool {
+    uint32_t P = 0;
+    DeviceBuffer ray_o, ray_d, thr, hit, aux, q_ext0, q_ext1, q_mat, q_miss, sh_a, sh_b, sh_c, ctr, glob;
+    uint32_t *h_live = nullptr; // pinned: extend-queue length probes
+    Globals *h_glob = nullptr;  // pinned
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    void ensure(uint32_t want) {
+        if (!h_live) {
+            RTB_CUDA(cudaMallocHost(&h_live, 64 * sizeof(uint32_t)));
+            RTB_CUDA(cudaMallocHost(&h_glob, sizeof(Globals)));
+            for (auto &e : ev)
+                RTB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            RTB_CUDA(cudaEventCreate(&ev_begin));
+            RTB_CUDA(cudaEventCreate(&ev_end));
+            ctr.alloc(3 * sizeof(Counters));
+            glob.alloc(sizeof(Globals));
+        }
+        if (want == P)
+            return;
+        P = 0;
+        const size_t n = want;
+        ray_o.alloc(n * 16);
+        ray_d.alloc(n * 16);
+        thr.alloc(n * 16);
+        hit.alloc(n * 16);
+        aux.alloc(n * 16);
+        q_ext0.alloc(n * 4);
+        q_ext1.alloc(n * 4);
+        q_mat.alloc(n * 4 * kMatTypes);
+        q_miss.alloc(n * 4);
+        sh_a.alloc(n * 16);
+        sh_b.alloc(n * 16);
+        sh_c.alloc(n * 16);
+        P = want;
+    }
+    ~WavefrontPool() {
+        if (h_live)
+            cudaFreeHost(h_live);
+        if (h_glob)
+            cudaFreeHost(h_glob);
+        for (auto &e : ev)
+            if (e)
+                cudaEventDestroy(e);
+        if (ev_begin)
+            cudaEventDestroy(ev_begin);
+        if (ev_end)
+            cudaEventDestroy(ev_end);
+    }
+};
+
+void wavefront_release(rtb_context *ctx) {
+    delete ctx->pool;
+    ctx->pool = nullptr;
+}
+
+void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_accum, cudaStream_t st,
+                      rtb_render_stats *stats) {
+    const DeviceScene &sc = *ctx->scene;
+    if (!ctx->pool)
+        ctx->pool = new WavefrontPool();
+    WavefrontPool &pool = *ctx->pool;
+
+    const uint32_t npix = uint32_t(rp.width) * uint32_t(rp.height);
+    const int stride = rp.sample_stride > 0 ? rp.sample_stride : 1;
+    const int offset = rp.sample_offset;
+    const int local_spp = offset < rp.spp ? (rp.spp - offset + stride - 1) / stride : 0;
+    const unsigned long long total = (unsigned long long)npix * (unsigned long long)local_spp;
+    uint32_t P = rp.pool_paths > 0 ? uint32_t(rp.pool_paths) : (1u << 21);
+    P = (P + 31u) & ~31u;
+    if ((unsigned long long)P > total)
+        P = uint32_t((total + 31ull) & ~31ull);
+    if (P < 32)
+        P = 32;
+    pool.ensure(P);
+
+    WfParams W;
+    W.geom = sc.geom<float>();
+    W.shade = sc.shade<float>();
+    W.cam = sc.host.f32.camera;
+    W.ray_o = pool.ray_o.as<float4>();
+    W.ray_d = pool.ray_d.as<float4>();
+    W.thr = pool.thr.as<float4>();
+    W.hit = pool.hit.as<float4>();
+    W.aux = pool.aux.as<uint4>();
+    W.q_ext[0] = pool.q_ext0.as<uint32_t>();
+    W.q_ext[1] = pool.q_ext1.as<uint32_t>();
+    W.q_mat = pool.q_mat.as<uint32_t>();
+    W.q_miss = pool.q_miss.as<uint32_t>();
+    W.sh_a = pool.sh_a.as<float4>();
+    W.sh_b = pool.sh_b.as<float4>();
+    W.sh_c = pool.sh_c.as<float4>();
+    W.ctr = pool.ctr.as<Counters>();
+    W.glob = pool.glob.as<Globals>();
+    W.accum = d_accum;
+    W.P = P;
+    W.width = rp.width;
+    W.height = rp.height;
+    W.spp = rp.spp;
+    W.max_depth = rp.max_depth;
+    W.rr_start = rp.rr_start_depth;
+    W.integrator = rp.integrator;
+    W.sample_offset = offset;
+    W.sample_stride = stride;
+    W.npix = npix;
+    W.total_samples = total;
+    W.seed = rp.seed;
+    for (int k = 0; k < 3; ++k)
+        W.bg[k] = float(sc.host.globals.background[k]);
+    W.mat_mask = sc.host.mat_type_mask;
+    W.has_media = sc.host.has_media ? 1 : 0;
+
+    const bool old_api = rp.integrator <= RTB_INTEGRATOR_RR;
+    const bool nee = rp.integrator >= RTB_INTEGRATOR_DIRECT && !sc.host.f32.lights.empty();
+    const bool count = (rp.flags & RTB_RENDER_COUNT_VISITS) != 0;
+    const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
+    const int grid = sms * 8; // 8 resident CTAs of 128 threads per SM
+
+    uint64_t launches = 0;
+    RTB_CUDA(cudaEventRecord(pool.ev_begin, st));
+    RTB_CUDA(cudaMemsetAsync(d_accum, 0, size_t(npix) * sizeof(float4), st));
+    k_clear<<<1, 128, 0, st>>>(W.ctr, W.glob);
+    k_generate<<<sms * 4, 256, 0, st>>>(W);
+    launches += 2;
+    RTB_CUDA(cudaGetLastError());
+
+    constexpr int kBatch = 4; // iterations between two host-side liveness probes
+    int it = 0;
+    int probe = 0;
+    bool done = total == 0;
+    bool cancelled = false;
+    int pending[2] = {-1, -1}; // probe slots in flight
+    while (!done) {
+        for (int b = 0; b < kBatch; ++b, ++it) {
+            if (count)
+                k_extend<true><<<grid, 128, 0, st>>>(W, it);
+            else
+                k_extend<false><<<grid, 128, 0, st>>>(W, it);
+            ++launches;
+            for (int m = 0; m < kMatTypes; ++m)
+                if ((W.mat_mask >> m) & 1u) {
+                    if (old_api)
+                        launch_shade<true>(m, W, it, grid, st);
+                    else
+                        launch_shade<false>(m, W, it, grid, st);
+                    ++launches;
+                }
+            k_miss<<<grid, 128, 0, st>>>(W, it);
+            ++launches;
+            if (nee) {
+                k_connect<<<grid, 128, 0, st>>>(W, it);
+                ++launches;
+            }
+        }
+        RTB_CUDA(cudaGetLastError());
+        // length of the NEXT extend queue, read back without stalling the pipeline: the
+        // host only waits for the probe of the PREVIOUS batch
+        const int slot = probe & 1;
+        RTB_CUDA(cudaMemcpyAsync(&pool.h_live[slot], &W.ctr[it % 3].n_ext, sizeof(uint32_t),
+                                 cudaMemcpyDeviceToHost, st));
+        RTB_CUDA(cudaEventRecord(pool.ev[slot], st));
+        pending[slot] = it;
+        const int prev = (probe + 1) & 1;
+        if (pending[prev] >= 0) {
+            RTB_CUDA(cudaEventSynchronize(pool.ev[prev]));
+            if (pool.h_live[prev] == 0)
+                done = true;
+        }
+        ++probe;
+        if (ctx->cancel.load(std::memory_order_relaxed)) {
+            cancelled = true;
+            break;
+        }
+        if (it > 4 * (rp.max_depth + 2) + int(8 * (total / P + 1)))
+            throw std::runtime_error("wavefront: iteration bound exceeded (internal error)");
+    }
+    RTB_CUDA(cudaMemcpyAsync(pool.h_glob, W.glob, sizeof(Globals), cudaMemcpyDeviceToHost, st));
+    RTB_CUDA(cudaEventRecord(pool.ev_end, st));
+    RTB_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    RTB_CUDA(cudaEventElapsedTime(&ms, pool.ev_begin, pool.ev_end));
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        stats->paths = pool.h_glob->next_sample < total ? pool.h_glob->next_sample : total;
+        stats->rays_closest = pool.h_glob->rays_closest;
+        stats->rays_shadow = pool.h_glob->rays_shadow;
+        stats->nodes_visited = pool.h_glob->nodes_visited;
+        stats->prim_tests = pool.h_glob->prim_tests;
+        stats->iterations = uint64_t(it);
+        stats->kernel_launches = launches;
+        stats->device_ms = ms;
+    }
+    if (cancelled)
+        throw std::runtime_error("cancelled");
+}
+
+void launch_resolve_rgb8(rtb_context *ctx, const float4 *d_accum, int w, int h, int spp, uint8_t *d_rgb8,
+                         cudaStream_t st) {
+    const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
+    k_resolve_rgb8<<<sms * 4, 256, 0, st>>>(d_accum, w, h, 1.0f / float(spp), d_rgb8);
+    RTB_CUDA(cudaGetLastError());
+}
+
+} // namespace rtb

@@ -1,0 +1,245 @@
+// tests/hostcheck/hostcheck.cpp — DEVELOPMENT AID, NOT A PRODUCT PATH.
+//
+// The device headers under ray_tracing-rendering_b200/csrc are written as
+// `__host__ __device__` templates.  This file instantiates them with g++ so that
+// the flattener, the BVH builder, the traversal, the record reconstruction and the
+// material / light math can be exercised against the oracle in the GPU-less build
+// container (`pytest -m "not gpu"`), before GPU minutes are spent.  It is compiled
+// into tests/hostcheck/libhostcheck.so, which only tests load; the product library
+// (librtb200.so) contains no host execution path and fails loudly without a GPU.
+#include "rtb200_types.h"
+#include "rtb_scene_host.hpp"
+
+#include <cstdio>
+#include <cstring>
+
+using namespace rtb;
+
+namespace {
+template <class R> TypedTables<R> &typed(HostScene &H);
+template <> TypedTables<float> &typed<float>(HostScene &H) { return H.f32; }
+template <> TypedTables<double> &typed<double>(HostScene &H) { return H.f64; }
+
+template <class R> GeomView<R> geom_view(HostScene &H) {
+    TypedTables<R> &T = typed<R>(H);
+    GeomView<R> g;
+    g.nodes = H.nodes.data();
+    g.prims = T.prims.data();
+    g.maux = T.maux.data();
+    g.ops = T.ops.data();
+    g.chains = H.chains.data();
+    g.prim_chain = H.prim_chain.data();
+    g.prim_orig = H.prim_orig.data();
+    g.n_nodes = int(H.nodes.size());
+    g.n_prims = int(T.prims.size());
+    return g;
+}
+template <class R> ShadeView<R> shade_view(HostScene &H) {
+    TypedTables<R> &T = typed<R>(H);
+    ShadeView<R> s;
+    s.mats = T.mats.data();
+    s.texs = T.texs.data();
+    s.images = H.images.data();
+    s.image_bytes = H.image_bytes.data();
+    s.perlins = T.perlins.data();
+    s.lights = T.lights.data();
+    s.env_texels = H.env_texels.data();
+    s.env_tables = H.env_tables.data();
+    s.n_lights = int(T.lights.size());
+    s.n_infinite_lights = H.n_infinite_lights;
+    return s;
+}
+
+template <class R, bool ROBUST>
+void trace_batch(HostScene &H, const rtb_ray *rays, uint64_t n, rtb_hit *hits, uint64_t stats[2]) {
+    const GeomView<R> g = geom_view<R>(H);
+    const GlobalFetch<R> F(g);
+    RngT<R> rng;
+    rng.g = pcg_seed(1, 2);
+    auto draw = [&]() { return rng.next_open(); };
+    for (uint64_t i = 0; i < n; ++i) {
+        const rtb_ray &q = rays[i];
+        const V3<R> o{R(q.o[0]), R(q.o[1]), R(q.o[2])}, d{R(q.d[0]), R(q.d[1]), R(q.d[2])};
+        uint32_t origin = kNoPrim;
+        if (ROBUST && q.origin_prim >= 0 && q.origin_prim < int(H.orig_to_sorted.size()))
+            origin = uint32_t(H.orig_to_sorted[q.origin_prim]);
+        R t;
+        const uint32_t pi = traverse<R, false, ROBUST>(g, F, o, d, R(q.time), R(q.t_min), R(q.t_max),
+                                                       origin, draw, t, &stats[0], &stats[1]);
+        rtb_hit &h = hits[i];
+        std::memset(&h, 0, sizeof(h));
+        h.prim = -1;
+        h.material = -1;
+        if (pi == kNoPrim)
+            continue;
+        const RecT<R> rec = make_record<R, ROBUST, true>(g, pi, o, d, R(q.time), t);
+        h.t = rec.t;
+        h.p[0] = rec.p.x; h.p[1] = rec.p.y; h.p[2] = rec.p.z;
+        h.normal[0] = rec.normal.x; h.normal[1] = rec.normal.y; h.normal[2] = rec.normal.z;
+        h.u = rec.u;
+        h.v = rec.v;
+        h.prim = g.prim_orig[pi];
+        h.front_face = rec.front_face;
+        h.material = int(g.prims[pi].type_mat >> PT_MAT_SHIFT);
+    }
+}
+
+template <class R> RecT<R> rec_of(const rtb_bsdf_query &q) {
+    RecT<R> r;
+    r.p = V3<R>(R(q.p[0]), R(q.p[1]), R(q.p[2]));
+    r.normal = V3<R>(R(q.normal[0]), R(q.normal[1]), R(q.normal[2]));
+    r.u = R(q.u);
+    r.v = R(q.v);
+    r.t = 1;
+    r.front_face = q.front_face != 0;
+    return r;
+}
+
+template <class R>
+void bsdf_eval(HostScene &H, int mat, const rtb_bsdf_query *q, uint64_t n, rtb_bsdf_value *out) {
+    const ShadeView<R> S = shade_view<R>(H);
+    const MatT<R> m = S.mats[mat];
+    for (uint64_t i = 0; i < n; ++i) {
+        const RecT<R> rec = rec_of<R>(q[i]);
+        const V3<R> wo(R(q[i].wo[0]), R(q[i].wo[1]), R(q[i].wo[2]));
+        const V3<R> wi(R(q[i].wi[0]), R(q[i].wi[1]), R(q[i].wi[2]));
+        const V3<R> f = mat_eval(S, m, rec, wo, wi);
+        const V3<R> e0 = mat_emitted_old(S, m, rec), e1 = mat_emitted_new(S, m, rec);
+        out[i].f[0] = f.x; out[i].f[1] = f.y; out[i].f[2] = f.z;
+        out[i].pdf = mat_pdf(S, m, rec, wo, wi);
+        out[i].emitted_old[0] = e0.x; out[i].emitted_old[1] = e0.y; out[i].emitted_old[2] = e0.z;
+        out[i].emitted_new[0] = e1.x; out[i].emitted_new[1] = e1.y; out[i].emitted_new[2] = e1.z;
+    }
+}
+
+template <class R>
+void bsdf_sample(HostScene &H, int mat, const rtb_bsdf_query *q, uint64_t n, uint64_t seed,
+                 rtb_bsdf_sample *out) {
+    const ShadeView<R> S = shade_view<R>(H);
+    const MatT<R> m = S.mats[mat];
+    for (uint64_t i = 0; i < n; ++i) {
+        RngT<R> g;
+        g.g = pcg_seed(i, seed);
+        std::memset(&out[i], 0, sizeof(out[i]));
+        const RecT<R> rec = rec_of<R>(q[i]);
+        const V3<R> wo(R(q[i].wo[0]), R(q[i].wo[1]), R(q[i].wo[2]));
+        BsdfSampleT<R> bs;
+        bs.pdf = 0;
+        bs.is_specular = false;
+        const bool ok = mat_sample(S, m, rec, wo, g, bs);
+        out[i].ok = ok;
+        if (ok) {
+            out[i].wi[0] = bs.wi.x; out[i].wi[1] = bs.wi.y; out[i].wi[2] = bs.wi.z;
+            out[i].f[0] = bs.f.x; out[i].f[1] = bs.f.y; out[i].f[2] = bs.f.z;
+            out[i].pdf = bs.pdf;
+            out[i].is_specular = bs.is_specular;
+        }
+        V3<R> atten, dout;
+        const bool sok = mat_scatter(S, m, rec, -wo, g, atten, dout);
+        out[i].scatter_ok = sok;
+        if (sok) {
+            out[i].scatter_dir[0] = dout.x; out[i].scatter_dir[1] = dout.y; out[i].scatter_dir[2] = dout.z;
+            out[i].scatter_atten[0] = atten.x; out[i].scatter_atten[1] = atten.y; out[i].scatter_atten[2] = atten.z;
+        }
+    }
+}
+
+template <class R>
+void light_eval(HostScene &H, int light, const rtb_light_query *q, uint64_t n, uint64_t seed,
+                rtb_light_value *out) {
+    const ShadeView<R> S = shade_view<R>(H);
+    const LightT<R> l = S.lights[light];
+    for (uint64_t i = 0; i < n; ++i) {
+        RngT<R> g;
+        g.g = pcg_seed(i, seed);
+        std::memset(&out[i], 0, sizeof(out[i]));
+        const V3<R> p(R(q[i].p[0]), R(q[i].p[1]), R(q[i].p[2]));
+        const V3<R> d(R(q[i].d[0]), R(q[i].d[1]), R(q[i].d[2]));
+        const LightSampleT<R> ls = light_sample(S, l, p, R(q[i].u[0]), R(q[i].u[1]), g);
+        out[i].Li[0] = ls.Li.x; out[i].Li[1] = ls.Li.y; out[i].Li[2] = ls.Li.z;
+        out[i].wi[0] = ls.wi.x; out[i].wi[1] = ls.wi.y; out[i].wi[2] = ls.wi.z;
+        out[i].pdf = ls.pdf;
+        out[i].dist = ls.dist;
+        out[i].is_delta = ls.is_delta;
+        out[i].pdf_dir = light_pdf(S, l, p, d);
+        const V3<R> le = light_Le(S, l, d);
+        out[i].Le[0] = le.x; out[i].Le[1] = le.y; out[i].Le[2] = le.z;
+    }
+}
+} // namespace
+
+extern "C" {
+
+void *hc_scene_create(const void *blob, uint64_t nbytes, int max_leaf) {
+    try {
+        SceneView S(blob, nbytes);
+        return new HostScene(build_host_scene(S, max_leaf));
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "hc_scene_create: %s\n", e.what());
+        return nullptr;
+    }
+}
+void hc_scene_destroy(void *h) { delete static_cast<HostScene *>(h); }
+
+// sizes = {nodes, sorted prims, instances}
+void hc_scene_info(void *h, int64_t sizes[3]) {
+    auto *H = static_cast<HostScene *>(h);
+    sizes[0] = int64_t(H->nodes.size());
+    sizes[1] = int64_t(H->prim_orig.size());
+    sizes[2] = H->n_instances;
+}
+
+// precision 64: the validation arithmetic (reference operation order, no self-hit
+// logic); 32: the production arithmetic.  stats = {nodes visited, primitive tests}.
+void hc_trace_batch(void *h, const rtb_ray *rays, uint64_t n, int precision, rtb_hit *hits,
+                    uint64_t stats[2]) {
+    auto *H = static_cast<HostScene *>(h);
+    uint64_t local[2] = {0, 0};
+    if (precision == 64)
+        trace_batch<double, false>(*H, rays, n, hits, local);
+    else
+        trace_batch<float, true>(*H, rays, n, hits, local);
+    if (stats) {
+        stats[0] = local[0];
+        stats[1] = local[1];
+    }
+}
+
+void hc_bsdf_eval(void *h, int mat, const rtb_bsdf_query *q, uint64_t n, int precision,
+                  rtb_bsdf_value *out) {
+    auto *H = static_cast<HostScene *>(h);
+    if (precision == 64)
+        bsdf_eval<double>(*H, mat, q, n, out);
+    else
+        bsdf_eval<float>(*H, mat, q, n, out);
+}
+void hc_bsdf_sample(void *h, int mat, const rtb_bsdf_query *q, uint64_t n, int precision, uint64_t seed,
+                    rtb_bsdf_sample *out) {
+    auto *H = static_cast<HostScene *>(h);
+    if (precision == 64)
+        bsdf_sample<double>(*H, mat, q, n, seed, out);
+    else
+        bsdf_sample<float>(*H, mat, q, n, seed, out);
+}
+void hc_light_eval(void *h, int light, const rtb_light_query *q, uint64_t n, int precision, uint64_t seed,
+                   rtb_light_value *out) {
+    auto *H = static_cast<HostScene *>(h);
+    if (precision == 64)
+        light_eval<double>(*H, light, q, n, seed, out);
+    else
+        light_eval<float>(*H, light, q, n, seed, out);
+}
+void hc_camera_derived(void *h, double out[24]) {
+    auto *H = static_cast<HostScene *>(h);
+    const CameraT<double> &c = H->f64.camera;
+    const V3<double> *vs[7] = {&c.origin, &c.lower_left_corner, &c.horizontal, &c.vertical, &c.u, &c.v, &c.w};
+    for (int i = 0; i < 7; ++i) {
+        out[3 * i] = vs[i]->x;
+        out[3 * i + 1] = vs[i]->y;
+        out[3 * i + 2] = vs[i]->z;
+    }
+    out[21] = c.lens_radius;
+    out[22] = c.time0;
+    out[23] = c.time1;
+}
+}
