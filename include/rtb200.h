@@ -82,7 +82,8 @@ typedef struct rtb_render_params {
 } rtb_render_params;
 
 enum rtb_render_flags {
-    RTB_RENDER_COUNT_VISITS = 1 /* also count BVH nodes visited / primitive tests (slower) */
+    RTB_RENDER_COUNT_VISITS = 1, /* also count BVH nodes visited / primitive tests (slower) */
+    RTB_RENDER_TIME_EXTEND = 2   /* bracket every extend launch with CUDA events (extend_ms) */
 };
 
 typedef struct rtb_render_stats {

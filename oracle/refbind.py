@@ -142,8 +142,20 @@ def render_timed(scene_id, integrator, width=0, spp=0, max_depth=50, want_image=
     if want_image:
         img = np.zeros(4096 * 4096 * 3)
         cap = img.size
-    s = lib().ref_render_timed(scene_id, integrator, width, spp, max_depth, C.byref(w), C.byref(h),
-                               _ptr(img) if img is not None else None, cap)
+    # Renderer::render prints "Rendering finished in ..." on the C++ stdout (renderer.h:100);
+    # keep it off this process's stdout (bench.py prints exactly one JSON line there)
+    import sys
+    sys.stdout.flush()
+    saved = os.dup(1)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 1)
+    try:
+        s = lib().ref_render_timed(scene_id, integrator, width, spp, max_depth, C.byref(w), C.byref(h),
+                                   _ptr(img) if img is not None else None, cap)
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
+        os.close(devnull)
     if img is not None:
         img = img[:w.value * h.value * 3].reshape(h.value, w.value, 3).copy()
     return s, w.value, h.value, img

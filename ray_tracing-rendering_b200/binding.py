@@ -19,6 +19,7 @@ STATUS_NAMES = {0: "RTB_OK", -1: "RTB_ERR_INVALID_ARGUMENT", -2: "RTB_ERR_NO_DEV
                 -3: "RTB_ERR_CUDA", -4: "RTB_ERR_BAD_SCENE", -5: "RTB_ERR_NO_SCENE",
                 -6: "RTB_ERR_CANCELLED", -7: "RTB_ERR_OUT_OF_MEMORY"}
 RENDER_COUNT_VISITS = 1
+RENDER_TIME_EXTEND = 2
 
 # Every symbol include/rtb200.h declares (tests check the library exports them all).
 EXPORTS = ["rtb_version", "rtb_context_create", "rtb_context_destroy", "rtb_last_error",

@@ -619,6 +619,15 @@ struct WavefrontPool {
     Globals *h_glob = nullptr;  // pinned
     cudaEvent_t ev[2] = {nullptr, nullptr};
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    std::vector<cudaEvent_t> ev_ext; // pairs bracketing extend launches (RTB_RENDER_TIME_EXTEND)
+    cudaEvent_t ext_event(size_t i) {
+        while (ev_ext.size() <= i) {
+            cudaEvent_t e;
+            RTB_CUDA(cudaEventCreate(&e));
+            ev_ext.push_back(e);
+        }
+        return ev_ext[i];
+    }
     void ensure(uint32_t want) {
         if (!h_live) {
             RTB_CUDA(cudaMallocHost(&h_live, 64 * sizeof(uint32_t)));
@@ -660,6 +669,8 @@ struct WavefrontPool {
             cudaEventDestroy(ev_begin);
         if (ev_end)
             cudaEventDestroy(ev_end);
+        for (auto &e : ev_ext)
+            cudaEventDestroy(e);
     }
 };
 
@@ -679,7 +690,10 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
     const int stride = rp.sample_stride > 0 ? rp.sample_stride : 1;
     const int offset = rp.sample_offset;
     const int local_spp = offset < rp.spp ? (rp.spp - offset + stride - 1) / stride : 0;
-    const unsigned long long total = (unsigned long long)npix * (unsigned long long)local_spp;
+    const unsigned long long n_samples = (unsigned long long)npix * (unsigned long long)local_spp;
+    // max_depth 0: every Li() returns black without tracing anything (the depth loop of
+    // e.g. rr_path_integrator.h:27 never runs)
+    const unsigned long long total = rp.max_depth > 0 ? n_samples : 0ull;
     uint32_t P = rp.pool_paths > 0 ? uint32_t(rp.pool_paths) : (1u << 21);
     P = (P + 31u) & ~31u;
     if ((unsigned long long)P > total)
@@ -727,6 +741,8 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
     const bool old_api = rp.integrator <= RTB_INTEGRATOR_RR;
     const bool nee = rp.integrator >= RTB_INTEGRATOR_DIRECT && !sc.host.f32.lights.empty();
     const bool count = (rp.flags & RTB_RENDER_COUNT_VISITS) != 0;
+    const bool time_extend = (rp.flags & RTB_RENDER_TIME_EXTEND) != 0;
+    size_t n_ext_events = 0;
     const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
     const int grid = sms * 8; // 8 resident CTAs of 128 threads per SM
 
@@ -746,10 +762,14 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
     int pending[2] = {-1, -1}; // probe slots in flight
     while (!done) {
         for (int b = 0; b < kBatch; ++b, ++it) {
+            if (time_extend)
+                RTB_CUDA(cudaEventRecord(pool.ext_event(n_ext_events++), st));
             if (count)
                 k_extend<true><<<grid, 128, 0, st>>>(W, it);
             else
                 k_extend<false><<<grid, 128, 0, st>>>(W, it);
+            if (time_extend)
+                RTB_CUDA(cudaEventRecord(pool.ext_event(n_ext_events++), st));
             ++launches;
             for (int m = 0; m < kMatTypes; ++m)
                 if ((W.mat_mask >> m) & 1u) {
@@ -785,7 +805,9 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
             cancelled = true;
             break;
         }
-        if (it > 4 * (rp.max_depth + 2) + int(8 * (total / P + 1)))
+        // every slot is busy on every iteration until the samples run out, so the last sample
+        // starts no later than iteration total*max_depth/P; the tail adds at most max_depth
+        if ((unsigned long long)it > total * (unsigned long long)rp.max_depth / P + rp.max_depth + 4 * kBatch)
             throw std::runtime_error("wavefront: iteration bound exceeded (internal error)");
     }
     RTB_CUDA(cudaMemcpyAsync(pool.h_glob, W.glob, sizeof(Globals), cudaMemcpyDeviceToHost, st));
@@ -795,7 +817,8 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
     RTB_CUDA(cudaEventElapsedTime(&ms, pool.ev_begin, pool.ev_end));
     if (stats) {
         std::memset(stats, 0, sizeof(*stats));
-        stats->paths = pool.h_glob->next_sample < total ? pool.h_glob->next_sample : total;
+        stats->paths = rp.max_depth > 0 ? (pool.h_glob->next_sample < total ? pool.h_glob->next_sample : total)
+                                        : n_samples;
         stats->rays_closest = pool.h_glob->rays_closest;
         stats->rays_shadow = pool.h_glob->rays_shadow;
         stats->nodes_visited = pool.h_glob->nodes_visited;
@@ -803,6 +826,12 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
         stats->iterations = uint64_t(it);
         stats->kernel_launches = launches;
         stats->device_ms = ms;
+        for (size_t i = 0; i + 1 < n_ext_events; i += 2) {
+            float e = 0.f;
+            RTB_CUDA(cudaEventElapsedTime(&e, pool.ev_ext[i], pool.ev_ext[i + 1]));
+            stats->extend_ms += e;
+        }
+        stats->extend_launches = n_ext_events / 2;
     }
     if (cancelled)
         throw std::runtime_error("cancelled");
