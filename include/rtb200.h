@@ -83,7 +83,8 @@ typedef struct rtb_render_params {
 
 enum rtb_render_flags {
     RTB_RENDER_COUNT_VISITS = 1, /* also count BVH nodes visited / primitive tests (slower) */
-    RTB_RENDER_TIME_EXTEND = 2   /* bracket every extend launch with CUDA events (extend_ms) */
+    RTB_RENDER_TIME_EXTEND = 2,  /* bracket every launch of the dominant kernel with CUDA events (extend_ms) */
+    RTB_RENDER_FORCE_WAVEFRONT = 4 /* use the wavefront schedule even where the fused one applies */
 };
 
 typedef struct rtb_render_stats {
@@ -97,6 +98,8 @@ typedef struct rtb_render_stats {
     double device_ms;        /* CUDA-event time of the whole render on its stream */
     double extend_ms;        /* CUDA-event time spent in the extend kernel (0 unless timed) */
     uint64_t extend_launches;
+    int32_t schedule;        /* 0 = wavefront (queues in HBM), 1 = fused (small scene, state in registers) */
+    int32_t reserved;
 } rtb_render_stats;
 
 typedef struct rtb_scene_stats {
@@ -119,6 +122,13 @@ RTB_API void rtb_context_destroy(rtb_context *ctx);
 /* Message of the last failure on ctx; with ctx == NULL, of the last failed
  * rtb_context_create on this thread.  Never NULL. */
 RTB_API const char *rtb_last_error(const rtb_context *ctx);
+
+/* Tuning switches (all default to 1):
+ *   RTB_OPT_FLAT_TRAVERSAL  scenes of <= 64 primitive records are traversed in lockstep from
+ *                           shared memory instead of through the BVH;
+ *   RTB_OPT_FUSED_SCHEDULE  such scenes are rendered by the fused persistent kernel. */
+enum rtb_option { RTB_OPT_FLAT_TRAVERSAL = 1, RTB_OPT_FUSED_SCHEDULE = 2 };
+RTB_API int rtb_set_option(rtb_context *ctx, int option, int64_t value);
 
 /* ---- scene ---------------------------------------------------------------------------- */
 

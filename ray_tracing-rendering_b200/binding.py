@@ -20,10 +20,12 @@ STATUS_NAMES = {0: "RTB_OK", -1: "RTB_ERR_INVALID_ARGUMENT", -2: "RTB_ERR_NO_DEV
                 -6: "RTB_ERR_CANCELLED", -7: "RTB_ERR_OUT_OF_MEMORY"}
 RENDER_COUNT_VISITS = 1
 RENDER_TIME_EXTEND = 2
+RENDER_FORCE_WAVEFRONT = 4
+OPT_FLAT_TRAVERSAL, OPT_FUSED_SCHEDULE = 1, 2
 
 # Every symbol include/rtb200.h declares (tests check the library exports them all).
 EXPORTS = ["rtb_version", "rtb_context_create", "rtb_context_destroy", "rtb_last_error",
-           "rtb_scene_upload", "rtb_scene_get_stats", "rtb_camera_derived", "rtb_render",
+           "rtb_set_option", "rtb_scene_upload", "rtb_scene_get_stats", "rtb_camera_derived", "rtb_render",
            "rtb_render_device", "rtb_cancel", "rtb_resolve_rgb8", "rtb_trace_batch",
            "rtb_bsdf_eval_batch", "rtb_bsdf_sample_batch", "rtb_light_eval_batch",
            "rtb_texture_eval_batch"]
@@ -40,7 +42,7 @@ class RenderStats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("rays_closest", C.c_uint64), ("rays_shadow", C.c_uint64),
                 ("nodes_visited", C.c_uint64), ("prim_tests", C.c_uint64), ("iterations", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("device_ms", C.c_double), ("extend_ms", C.c_double),
-                ("extend_launches", C.c_uint64)]
+                ("extend_launches", C.c_uint64), ("schedule", C.c_int32), ("reserved", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -80,6 +82,7 @@ def load():
     L.rtb_context_destroy.restype = None
     L.rtb_last_error.argtypes = [vp]
     L.rtb_last_error.restype = C.c_char_p
+    L.rtb_set_option.argtypes = [vp, i32, C.c_int64]
     L.rtb_scene_upload.argtypes = [vp, vp, u64]
     L.rtb_scene_get_stats.argtypes = [vp, C.POINTER(SceneStats)]
     L.rtb_camera_derived.argtypes = [vp, vp]
@@ -132,6 +135,9 @@ class Context:
     def _check(self, rc):
         if rc != RTB_OK:
             raise RtbError(rc, self._lib.rtb_last_error(self._h).decode())
+
+    def set_option(self, option: int, value: int):
+        self._check(self._lib.rtb_set_option(self._h, option, value))
 
     # ---- scene
     def upload_scene(self, blob: bytes):

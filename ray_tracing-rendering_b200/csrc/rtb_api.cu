@@ -163,6 +163,18 @@ const char *rtb_last_error(const rtb_context *ctx) {
     return ctx ? ctx->last_error.c_str() : g_create_error.c_str();
 }
 
+int rtb_set_option(rtb_context *ctx, int option, int64_t value) {
+    if (!ctx)
+        return RTB_ERR_INVALID_ARGUMENT;
+    if (option == RTB_OPT_FLAT_TRAVERSAL)
+        ctx->opt_flat = value != 0;
+    else if (option == RTB_OPT_FUSED_SCHEDULE)
+        ctx->opt_fused = value != 0;
+    else
+        return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_set_option: unknown option");
+    return RTB_OK;
+}
+
 int rtb_scene_upload(rtb_context *ctx, const void *blob, uint64_t nbytes) {
     if (!ctx)
         return RTB_ERR_INVALID_ARGUMENT;

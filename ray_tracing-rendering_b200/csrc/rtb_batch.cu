@@ -47,9 +47,13 @@ k_trace_batch(GeomView<Real> g, const int32_t *__restrict__ orig_to_sorted, int 
         rng.g = pcg_seed(i, 0x51ed270b);
         DrawOpen draw{&rng};
         Real t;
+        // the fp32 instantiation traces the way the renderer does: lockstep for small scenes
         const uint32_t pi =
-            traverse<Real, false, kRobust>(g, F, o, d, Real(q.time), Real(q.t_min), Real(q.t_max), origin,
-                                           draw, t, visits ? &nodes : nullptr, visits ? &tests : nullptr);
+            (kRobust && g.flat)
+                ? traverse_flat<Real, false, kRobust>(g, o, d, Real(q.time), Real(q.t_min), Real(q.t_max), origin,
+                                                      draw, t, visits ? &nodes : nullptr, visits ? &tests : nullptr)
+                : traverse<Real, false, kRobust>(g, F, o, d, Real(q.time), Real(q.t_min), Real(q.t_max), origin,
+                                                 draw, t, visits ? &nodes : nullptr, visits ? &tests : nullptr);
         rtb_hit h;
         h.t = 0;
         h.p[0] = h.p[1] = h.p[2] = 0;
@@ -208,8 +212,11 @@ void launch_trace_batch<Real>(rtb_context *ctx, const rtb_ray *d_rays, uint64_t 
     if (!n)
         return;
     const DeviceScene &sc = *ctx->scene;
+    GeomView<Real> gv = sc.geom<Real>();
+    if (ctx->opt_flat == 0)
+        gv.flat = 0;
     k_trace_batch<<<grid_for(ctx, n, 128), 128, 0, ctx->stream>>>(
-        sc.geom<Real>(), sc.orig_to_sorted.as<int32_t>(), int(sc.host.orig_to_sorted.size()), d_rays, n,
+        gv, sc.orig_to_sorted.as<int32_t>(), int(sc.host.orig_to_sorted.size()), d_rays, n,
         d_hits, d_visits);
     RTB_CUDA(cudaGetLastError());
 }

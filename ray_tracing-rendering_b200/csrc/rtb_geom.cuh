@@ -90,7 +90,17 @@ template <class R> struct GeomView {
     const int32_t *prim_orig;  // per sorted prim: flat (blob) primitive id, -1 for instances
     int32_t n_nodes;
     int32_t n_prims;
+    int32_t n_ops;
+    int32_t n_chains;
+    int32_t n_top; // prims[0 .. n_top) are the top-level items (primitives and instance records)
+    int32_t flat;  // != 0: the scene is small enough for the lockstep traversal (traverse_flat)
 };
+
+// Scenes with at most this many primitive records are traversed in lockstep from shared
+// memory instead of through the BVH.
+constexpr int kFlatMaxPrims = 64;
+constexpr int kFlatMaxOps = 32;
+constexpr int kFlatMaxChains = 16;
 
 template <class R> struct RayT {
     V3<R> o, d;
@@ -426,6 +436,79 @@ RTB_HD uint32_t traverse(const GeomView<R> &g, const Fetch &F, V3<R> o, V3<R> d,
                 popping = false;
         }
     }
+}
+
+// Lockstep traversal for small scenes (the Cornell-box class: a few dozen primitives).
+// A BVH does not pay there: the 32 rays of a warp take different branches of a tiny tree
+// and the warp serialises them (measured on scene07: 9 of 32 lanes active per instruction).
+// Instead every lane walks the SAME item list in the SAME order — top-level items, and
+// inside an instance its primitive range after one ray transform — so control flow and
+// primitive fetches are warp-uniform (shared-memory broadcasts) and the only divergence
+// left is inside the individual tests.  Formally this is the same two-level structure
+// with each level collapsed into one wide leaf; closest-hit results are identical.
+// `g` must describe the flat layout ([top items][instance ranges][boundary prims]); in the
+// kernels its table pointers point at the shared-memory copy.
+template <class R, bool ANY, bool ROBUST, class Rng>
+RTB_HD uint32_t traverse_flat(const GeomView<R> &g, V3<R> o, V3<R> d, R time, R t_min, R t_max,
+                              uint32_t origin_prim, Rng &rng, R &t_hit, uint64_t *n_nodes,
+                              uint64_t *n_tests) {
+    uint32_t best = kNoPrim;
+    const V3<R> idir = safe_inv(d);
+    const uint32_t n_top = uint32_t(g.n_top);
+    for (uint32_t i = 0; i < n_top; ++i) {
+        const PrimT<R> p = g.prims[i];
+        const uint32_t type = p.type_mat & PT_TYPE_MASK;
+        if (type == PT_INSTANCE) {
+            if (n_nodes)
+                ++*n_nodes; // one "node" = one instance entry (ray transform)
+            V3<R> lo = o, ld = d;
+            apply_chain(g, int(p.aux2), lo, ld);
+            const V3<R> lid = safe_inv(ld);
+            const uint32_t first = uint32_t(p.d[0]), last = first + uint32_t(p.d[1]);
+            for (uint32_t j = first; j < last; ++j) {
+                const PrimT<R> q = g.prims[j];
+                if (n_tests)
+                    ++*n_tests;
+                R t;
+                if (hit_simple<R, ROBUST>(g, q, q.type_mat & PT_TYPE_MASK, lo, ld, lid, time, t_min, t_max,
+                                          ROBUST && j == origin_prim, t)) {
+                    best = j;
+                    t_max = t;
+                    if (ANY) {
+                        t_hit = t;
+                        return best;
+                    }
+                }
+            }
+            continue;
+        }
+        if (n_tests)
+            ++*n_tests;
+        R t;
+        bool h;
+        if (type == PT_MEDIUM) {
+            h = hit_medium<R, ROBUST>(g, p, o, d, time, t_min, t_max, rng(), t);
+            if (p.type_mat & PT_DUP_LEAF) {
+                R t2;
+                if (hit_medium<R, ROBUST>(g, p, o, d, time, t_min, h ? t : t_max, rng(), t2)) {
+                    h = true;
+                    t = t2;
+                }
+            }
+        } else {
+            h = hit_simple<R, ROBUST>(g, p, type, o, d, idir, time, t_min, t_max, ROBUST && i == origin_prim, t);
+        }
+        if (h) {
+            best = i;
+            t_max = t;
+            if (ANY) {
+                t_hit = t;
+                return best;
+            }
+        }
+    }
+    t_hit = t_max;
+    return best;
 }
 
 // ---- hit record ---------------------------------------------------------------------------

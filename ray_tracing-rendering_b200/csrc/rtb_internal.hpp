@@ -87,6 +87,10 @@ struct DeviceScene {
         g.prim_orig = prim_orig.as<int32_t>();
         g.n_nodes = int32_t(host.nodes.size());
         g.n_prims = int32_t(host.prim_orig.size());
+        g.n_ops = int32_t(host.f32.ops.size());
+        g.n_chains = int32_t(host.chains.size());
+        g.n_top = host.n_top_items;
+        g.flat = host.flat_ok ? 1 : 0;
         return g;
     }
     template <class R> ShadeView<R> shade() const {
@@ -122,6 +126,8 @@ struct rtb_context {
     int accum_w = 0, accum_h = 0;
     std::atomic<int> cancel{0};
     int sm_count = 0;
+    int opt_flat = 1;  // RTB_OPT_FLAT_TRAVERSAL
+    int opt_fused = 1; // RTB_OPT_FUSED_SCHEDULE
 };
 
 namespace rtb {

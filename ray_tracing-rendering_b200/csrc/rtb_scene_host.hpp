@@ -44,6 +44,8 @@ struct HostScene {
     uint32_t mat_type_mask = 0; // bit t set: some primitive uses a material of type t
     bool has_media = false;
     int n_instances = 0;
+    int n_top_items = 0; // primitives + instance records of the top level = prims[0 .. n_top_items)
+    bool flat_ok = false; // small enough for the lockstep / shared-memory traversal
 };
 
 namespace detail {
@@ -351,12 +353,15 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4) {
     for (uint32_t id : tlas.order)
         slots.push_back(id < uint32_t(np) ? Slot{int(id), -1} : Slot{-1, int(id) - np});
     H.nodes = tlas.nodes;
-    std::vector<uint32_t> blas_root(insts.size());
+    H.n_top_items = int(slots.size());
+    std::vector<uint32_t> blas_root(insts.size()), blas_first(insts.size()), blas_count(insts.size());
     {
         size_t gi = 0;
         for (auto &kv : groups) {
             const uint32_t node_off = uint32_t(H.nodes.size());
             BuildResult b = build_bvh(kv.second, max_leaf, uint32_t(slots.size()), node_off);
+            blas_first[gi] = uint32_t(slots.size());
+            blas_count[gi] = uint32_t(b.order.size());
             blas_root[gi++] = node_off;
             for (uint32_t id : b.order)
                 slots.push_back(Slot{int(id), -1});
@@ -386,6 +391,10 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4) {
                 q.type_mat = PT_INSTANCE;
                 q.aux = blas_root[s.inst];
                 q.aux2 = uint32_t(insts[s.inst].chain);
+                // the instance's primitives as a contiguous range (used by the lockstep
+                // traversal of small scenes): d[0] = first, d[1] = count
+                q.d[0] = R(blas_first[s.inst]);
+                q.d[1] = R(blas_count[s.inst]);
                 T.prims.push_back(q);
                 continue;
             }
@@ -526,6 +535,8 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4) {
         H.f32.lights.push_back(f);
     }
 
+    H.flat_ok = int(H.prim_orig.size()) <= kFlatMaxPrims && int(S.n_xform_ops()) <= kFlatMaxOps &&
+                int(S.n_chains()) <= kFlatMaxChains;
     H.f64.camera = derive_camera(cam);
     H.f32.camera = cast_camera<float>(H.f64.camera);
     return H;

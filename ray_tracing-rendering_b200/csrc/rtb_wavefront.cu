@@ -1,29 +1,38 @@
-// rtb_wavefront.cu — the production renderer: a wavefront path tracer with path
-// regeneration, replacing Renderer::render + Integrator::Li of the reference
-// (src/renderer/renderer.h:30-102 and the five *_integrator.h files).
+// rtb_wavefront.cu — the production renderer, replacing Renderer::render + Integrator::Li
+// of the reference (src/renderer/renderer.h:30-102 and the five *_integrator.h files).
 //
-// Data layout (all in HBM, sized for `P` resident paths):
-//   path state, SoA of 16-byte vectors (one coalesced 128-bit access each):
+// Two schedules over the SAME stage functions (trace, shade_surface<M>, miss_surface,
+// shadow test):
+//
+// (A) WAVEFRONT — the general schedule (any scene size).
+//   path state in HBM, SoA of 16-byte vectors (one 128-bit access each), P resident paths:
 //     ray_o[P]  float4  origin.xyz, time
 //     ray_d[P]  float4  direction.xyz (NOT normalised, as in the reference), origin primitive
 //     thr[P]    float4  throughput.rgb, pixel index
 //     aux[P]    uint4   rng state (2 x u32), depth | specular_bounce << 16, prev_bsdf_pdf
-//     hit[P]    float4  t, primitive index, -, -            (extend -> shade)
+//     hit[P]    float4  t, primitive index                       (extend -> shade)
 //   queues of 32-bit path indices, filled with warp-aggregated atomics:
-//     q_ext[2][P]   paths that need a closest-hit ray (double buffered)
-//     q_mat[6][P]   paths whose hit landed on material type m   (material-sorted shading)
-//     q_miss[P]     paths whose ray left the scene
-//   shadow-ray queue, SoA of 3 float4 per entry (written by shade, read by connect).
-//   accum[H*W] float4: linear radiance SUMS, updated with vector atomics (RED.ADD.v4.f32).
+//     q_ext[2][P]  paths that need a closest-hit ray (double buffered)
+//     q_mat[6][P]  paths whose hit landed on material type m  (material-sorted shading)
+//     q_miss[P]    paths whose ray left the scene
+//   shadow-ray queue, 3 float4 per entry (written by shade, read by connect).
+//   One iteration = k_extend -> k_shade<M> (x present material types) -> k_miss -> k_connect.
+//   Persistent-thread kernels: the grid is a fixed multiple of the SM count and warps pull
+//   32-entry chunks off a queue through one atomic per warp.  A path that ends is replaced
+//   in place by the next camera sample, so the extend queue stays full until the job runs
+//   out of samples.  Queue counters rotate over three sets (iteration i uses set i%3 and
+//   clears set (i+2)%3): no reset kernel, no host round trip per iteration.
 //
-// One wavefront iteration = extend -> shade_<material> (x present types) -> miss -> connect.
-// Every kernel is a persistent-thread kernel: the grid is a fixed multiple of the SM
-// count and warps pull 32-entry chunks off a queue through one atomic per warp.
-// When a path ends (miss, absorbed, Russian roulette, max depth) the same thread
-// immediately starts the next camera sample in the same slot, so the extend queue
-// stays full until the job runs out of samples; only then does it drain.
-// Queue counters live in three rotating sets so that no kernel ever has to wait for a
-// reset: iteration i uses set i%3 and clears set (i+2)%3.
+// (B) FUSED — scenes whose geometry fits in shared memory (<= 64 primitive records: the
+//   Cornell-box class of BASELINE configs C1/C3/C4).  There the wavefront's costs are all
+//   overhead: the scene is ~1 KB, so a bounce is a few hundred instructions, far less than
+//   moving 144 B of path state through HBM and three queues.  One persistent kernel
+//   (k_fused) keeps the path state in REGISTERS, traces in lockstep against the
+//   shared-memory scene (traverse_flat), shades through the same shade_surface<M>, tests
+//   the shadow ray inline and regenerates finished lanes from warp-private sample chunks.
+//   The only global traffic is one vector reduction (RED.ADD.v4.f32) per contribution.
+//
+// accum[H*W] float4: linear radiance SUMS.
 #include "rtb_internal.hpp"
 
 #include <algorithm>
@@ -37,7 +46,7 @@ constexpr int kMatTypes = RTB_MAT_TYPE_COUNT; // 6
 constexpr uint32_t kFullMask = 0xffffffffu;
 
 struct alignas(16) Counters {
-    uint32_t n_ext;  // entries in this iteration's extend queue
+    uint32_t n_ext; // entries in this iteration's extend queue
     uint32_t n_mat[kMatTypes];
     uint32_t n_miss;
     uint32_t n_shadow;
@@ -65,8 +74,8 @@ struct WfParams {
     float4 *ray_o, *ray_d, *thr, *hit;
     uint4 *aux;
     uint32_t *q_ext[2];
-    uint32_t *q_mat;  // kMatTypes * P
-    uint32_t *q_miss; // P
+    uint32_t *q_mat;            // kMatTypes * P
+    uint32_t *q_miss;           // P
     float4 *sh_a, *sh_b, *sh_c; // shadow queue
     Counters *ctr;              // 3 sets
     Globals *glob;
@@ -76,6 +85,7 @@ struct WfParams {
     int32_t sample_offset, sample_stride;
     uint32_t npix;
     unsigned long long total_samples; // samples this call renders = npix * local spp
+    unsigned long long window_end;    // fused schedule: samples [next_sample, window_end) this launch
     uint64_t seed;
     float bg[3];
     uint32_t mat_mask;
@@ -115,6 +125,11 @@ __device__ __forceinline__ uint32_t warp_fetch(uint32_t *head) {
         base = atomicAdd(head, 32u);
     return __shfl_sync(kFullMask, base, 0);
 }
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(kFullMask, v, o);
+    return v;
+}
 
 // RED.ADD.v4.f32 — one vector reduction per contribution instead of three scalar ones.
 __device__ __forceinline__ void accum_add(float4 *accum, uint32_t pix, V3<float> c) {
@@ -123,12 +138,67 @@ __device__ __forceinline__ void accum_add(float4 *accum, uint32_t pix, V3<float>
     atomicAdd(accum + pix, make_float4(c.x, c.y, c.z, 0.f));
 }
 
+// ---- shared-memory copy of a small scene ---------------------------------------------------
+struct FlatSmem {
+    PrimT<float> prims[kFlatMaxPrims];
+    XfOp<float> ops[kFlatMaxOps];
+    ChainRec chains[kFlatMaxChains];
+    int32_t prim_chain[kFlatMaxPrims];
+};
+
+// Cooperative copy by the whole block; returns a view whose tables live in shared memory.
+// When the scene is not flat the global view is returned unchanged.
+__device__ __forceinline__ GeomView<float> stage_scene(const GeomView<float> &g, FlatSmem &sm) {
+    if (!g.flat)
+        return g;
+    const int n4 = g.n_prims * int(sizeof(PrimT<float>) / 16);
+    const float4 *src = reinterpret_cast<const float4 *>(g.prims);
+    float4 *dst = reinterpret_cast<float4 *>(sm.prims);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x)
+        dst[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < g.n_prims; i += blockDim.x)
+        sm.prim_chain[i] = g.prim_chain[i];
+    for (int i = threadIdx.x; i < kFlatMaxOps; i += blockDim.x)
+        if (i < g.n_ops)
+            sm.ops[i] = g.ops[i];
+    for (int i = threadIdx.x; i < kFlatMaxChains; i += blockDim.x)
+        if (i < g.n_chains)
+            sm.chains[i] = g.chains[i];
+    __syncthreads();
+    GeomView<float> s = g;
+    s.prims = sm.prims;
+    s.ops = sm.ops;
+    s.chains = sm.chains;
+    s.prim_chain = sm.prim_chain;
+    return s;
+}
+
+template <bool ANY, bool COUNT, class Rng>
+__device__ __forceinline__ uint32_t trace(const GeomView<float> &g, V3<float> o, V3<float> d, float time,
+                                          float t_min, float t_max, uint32_t origin, Rng &rng, float &t,
+                                          uint64_t &nodes, uint64_t &tests) {
+    if (g.flat)
+        return traverse_flat<float, ANY, true>(g, o, d, time, t_min, t_max, origin, rng, t,
+                                               COUNT ? &nodes : nullptr, COUNT ? &tests : nullptr);
+    const GlobalFetch<float> F(g);
+    return traverse<float, ANY, true>(g, F, o, d, time, t_min, t_max, origin, rng, t, COUNT ? &nodes : nullptr,
+                                      COUNT ? &tests : nullptr);
+}
+
+// ---- path state ----------------------------------------------------------------------------
 struct PathState {
     V3<float> o, d, T;
     float time, prev_pdf;
     uint32_t origin_prim, pix, depth;
     bool spec;
     Pcg rng;
+};
+
+struct ShadowReq { // a next-event-estimation sample waiting for its visibility test
+    bool want;
+    V3<float> o, d, c; // origin, direction (segment or unit), weighted contribution
+    float tmax;
+    uint32_t origin;
 };
 
 __device__ __forceinline__ void store_ray(const WfParams &p, uint32_t slot, const PathState &s) {
@@ -179,10 +249,222 @@ __device__ __forceinline__ void new_path(const WfParams &p, unsigned long long g
     s.origin_prim = kNoPrim;
 }
 
-// Ends the iteration for one lane: a finished path is replaced by the next camera
-// sample (if any remain); a live path is written back; either way the slot is queued
-// for the next extend.  Called by all 32 lanes (done == false for idle lanes is fine
-// as long as `valid` is false).
+// ---- integrator stage functions (shared by both schedules) ----------------------------------
+
+// mis_path_integrator.h:154-162
+__device__ __forceinline__ V3<float> clamp_radiance(V3<float> L, float max_value) {
+    if (L.x > max_value || L.y > max_value || L.z > max_value) {
+        const float max_c = max3(L);
+        if (max_c > max_value)
+            return L * (max_value / max_c);
+    }
+    return L;
+}
+// mis_path_integrator.h:165-170
+__device__ __forceinline__ float power_heuristic(float a, float b) {
+    const float a2 = a * a, b2 = b * b, denom = a2 + b2;
+    return denom > 0.f ? a2 / denom : 0.f;
+}
+// mis_path_integrator.h:173-188 (also :53-60): sum over ALL lights of pdf(o,d)/N
+__device__ float all_lights_pdf(const WfParams &p, V3<float> o, V3<float> d) {
+    float total = 0.f;
+    const float sel = 1.0f / float(p.shade.n_lights);
+    for (int i = 0; i < p.shade.n_lights; ++i)
+        total += light_pdf(p.shade, p.shade.lights[i], o, d) * sel;
+    return total;
+}
+
+// Everything Integrator::Li does at a surface hit on a material of type M.  OLD =
+// integrators 0/1 (legacy scatter() + two-sided emitted(u,v,p)), otherwise integrators
+// 2/3/4 (sample/eval/pdf + one-sided emitted(rec,wo), NEE, MIS).  Updates the path in
+// place (next ray, throughput, depth, rng), adds emission to the image, and returns the
+// NEE sample (if any) for the caller to test for visibility.
+template <int M, bool OLD>
+__device__ __forceinline__ void shade_surface(const WfParams &p, const GeomView<float> &g, PathState &s, float t,
+                                              uint32_t pi, bool &alive, ShadowReq &sh) {
+    sh.want = false;
+    MatT<float> m = p.shade.mats[g.prims[pi].type_mat >> PT_MAT_SHIFT];
+    m.type = M; // compile-time constant: prunes the per-type switches
+    const RecT<float> rec = (m.flags & 1) ? make_record<float, true, true>(g, pi, s.o, s.d, s.time, t)
+                                          : make_record<float, true, false>(g, pi, s.o, s.d, s.time, t);
+    RngT<float> rng;
+    rng.g = s.rng;
+    alive = true;
+    if (OLD) {
+        // path_integrator.h:32-44, rr_path_integrator.h:35-57
+        if (M == RTB_MAT_DIFFUSE_LIGHT)
+            accum_add(p.accum, s.pix, s.T * mat_emitted_old(p.shade, m, rec));
+        V3<float> atten, dout;
+        if (!mat_scatter(p.shade, m, rec, s.d, rng, atten, dout)) {
+            alive = false;
+        } else {
+            s.T = s.T * atten;
+            if (p.integrator == RTB_INTEGRATOR_RR && int(s.depth) >= p.rr_start) {
+                const float ps = clamp_(max3(s.T), 0.005f, 0.95f);
+                if (rng.next() > ps)
+                    alive = false;
+                else
+                    s.T = s.T / ps;
+            }
+            s.o = rec.p;
+            s.d = dout;
+            s.origin_prim = pi;
+        }
+    } else {
+        const V3<float> wo = -unit_vector(s.d);
+        if (M == RTB_MAT_DIFFUSE_LIGHT) {
+            const V3<float> e = mat_emitted_new(p.shade, m, rec);
+            if (p.integrator == RTB_INTEGRATOR_PBR) {
+                accum_add(p.accum, s.pix, s.T * e); // pbr_path_integrator.h:38-39
+            } else if (p.integrator == RTB_INTEGRATOR_DIRECT) {
+                if (s.depth == 0 || s.spec) // direct_light_integrator.h:52-55
+                    accum_add(p.accum, s.pix, s.T * e);
+            } else if (length_squared(e) > 0.f) { // mis_path_integrator.h:72-94
+                V3<float> Le;
+                if (s.depth == 0 || s.spec)
+                    Le = s.T * e;
+                else if (p.shade.n_lights > 0)
+                    Le = (s.T * e) * power_heuristic(s.prev_pdf, all_lights_pdf(p, s.o, s.d));
+                else
+                    Le = s.T * e;
+                accum_add(p.accum, s.pix, s.depth == 0 ? Le : clamp_radiance(Le, 100.f));
+            }
+        }
+        s.spec = false; // material::is_specular() is never overridden (material.h:37)
+        // next-event estimation: direct_light_integrator.h:98-142, mis_path_integrator.h:192-234.
+        // eval() is identically 0 for metal / dielectric / diffuse_light / isotropic, so only
+        // lambertian and PBR can contribute; the others skip the (wasted) shadow ray.
+        if ((M == RTB_MAT_LAMBERTIAN || M == RTB_MAT_PBR) && p.integrator >= RTB_INTEGRATOR_DIRECT &&
+            p.shade.n_lights > 0) {
+            const int nl = p.shade.n_lights;
+            int li = int(float(nl) * rng.next()); // random_int(0, n-1), rtweekend.h:48-50
+            li = li < nl ? li : nl - 1;
+            const float sel = 1.0f / float(nl);
+            const float u0 = rng.next(), u1 = rng.next();
+            const LightT<float> &L = p.shade.lights[li];
+            const LightSampleT<float> ls = light_sample(p.shade, L, rec.p, u0, u1, rng);
+            if (ls.pdf > 0.f && length_squared(ls.Li) > 0.f) {
+                const V3<float> f = mat_eval(p.shade, m, rec, wo, ls.wi);
+                const float cos_theta = fabsf(dot(ls.wi, rec.normal));
+                V3<float> Ld;
+                if (p.integrator == RTB_INTEGRATOR_DIRECT) {
+                    Ld = ls.is_delta ? (f * ls.Li) * (cos_theta / sel) : (f * ls.Li) * (cos_theta / (ls.pdf * sel));
+                    // direct_light_integrator.h:133-139: sequential per-channel rescale
+                    if (Ld.x > 100.f)
+                        Ld = Ld * (100.f / Ld.x);
+                    if (Ld.y > 100.f)
+                        Ld = Ld * (100.f / Ld.y);
+                    if (Ld.z > 100.f)
+                        Ld = Ld * (100.f / Ld.z);
+                    Ld = s.T * Ld;
+                } else {
+                    if (ls.is_delta) {
+                        Ld = (f * ls.Li) * (cos_theta / sel);
+                    } else {
+                        const float bsdf_pdf = mat_pdf(p.shade, m, rec, wo, ls.wi);
+                        const float light_p = ls.pdf * sel;
+                        Ld = (f * ls.Li) * (cos_theta * power_heuristic(light_p, bsdf_pdf) / light_p);
+                    }
+                    Ld = clamp_radiance(s.T * Ld, 100.f);
+                }
+                if (Ld.x != 0.f || Ld.y != 0.f || Ld.z != 0.f) {
+                    sh.want = true;
+                    sh.o = rec.p;
+                    sh.c = Ld;
+                    sh.origin = pi;
+                    if (isfinite(ls.dist)) {
+                        // segment form: d = light_point - p, t in [0.001/dist, 1 - 0.001/dist]; the
+                        // same interval as (wi, [0.001, dist - 0.001]) of the reference, but
+                        // well-conditioned in fp32 (the far end is exactly t = 1)
+                        sh.d = ls.to_light;
+                        sh.tmax = 1.0f - 0.001f / ls.dist;
+                    } else {
+                        sh.d = ls.wi;
+                        sh.tmax = Consts<float>::inf();
+                    }
+                }
+            }
+        }
+        BsdfSampleT<float> bs;
+        if (!mat_sample(p.shade, m, rec, wo, rng, bs)) {
+            // mis_path_integrator.h:106-117: only integrator 4 falls back to scatter()
+            V3<float> atten, dout;
+            if (p.integrator == RTB_INTEGRATOR_MIS && mat_scatter(p.shade, m, rec, s.d, rng, atten, dout)) {
+                s.T = s.T * atten;
+                s.d = dout;
+                s.spec = false;
+                s.prev_pdf = 0.f;
+            } else {
+                alive = false;
+            }
+        } else if (bs.pdf < 1e-8f && !bs.is_specular) {
+            alive = false;
+        } else {
+            s.spec = bs.is_specular;
+            s.prev_pdf = bs.is_specular ? 0.f : bs.pdf;
+            const float cos_theta = fabsf(dot(bs.wi, rec.normal));
+            s.T = bs.is_specular ? s.T * bs.f : s.T * (bs.f * (cos_theta / bs.pdf));
+            s.d = bs.wi;
+        }
+        if (alive) {
+            s.o = rec.p;
+            s.origin_prim = pi;
+            if (int(s.depth) >= p.rr_start) { // e.g. mis_path_integrator.h:137-146
+                const float ps = clamp_(max3(s.T), 0.05f, 0.95f);
+                if (rng.next() > ps)
+                    alive = false;
+                else
+                    s.T = s.T / ps;
+            }
+        }
+    }
+    s.rng = rng.g;
+    s.depth += 1;
+    if (int(s.depth) >= p.max_depth)
+        alive = false;
+}
+
+// The ray left the scene: background for integrators 0-2 (e.g. rr_path_integrator.h:30-33),
+// environment lights for 3/4 (direct_light_integrator.h:35-48, mis_path_integrator.h:37-67).
+__device__ __forceinline__ void miss_surface(const WfParams &p, const PathState &s) {
+    const V3<float> bg(p.bg[0], p.bg[1], p.bg[2]);
+    V3<float> L = s.T * bg;
+    if (p.integrator >= RTB_INTEGRATOR_DIRECT && p.shade.n_infinite_lights > 0) {
+        V3<float> env(0, 0, 0);
+        for (int i = 0; i < p.shade.n_lights; ++i)
+            if (p.shade.lights[i].type == RTB_LIGHT_ENV)
+                env = env + light_Le(p.shade, p.shade.lights[i], s.d);
+        if (p.integrator == RTB_INTEGRATOR_DIRECT || s.depth == 0 || s.spec)
+            L = s.T * env;
+        else
+            L = (s.T * env) * power_heuristic(s.prev_pdf, all_lights_pdf(p, s.o, s.d));
+    }
+    accum_add(p.accum, s.pix, L);
+}
+
+struct PathDraw { // RNG adaptor handed to the traversal for constant_medium tests
+    Pcg *g;
+    __device__ float operator()() { return g->next_open(); }
+};
+
+// Visibility of one NEE sample: scene.hit(shadow_ray, 0.001, dist - 0.001)
+// (direct_light_integrator.h:115-130, mis_path_integrator.h:209-230).  Shadow rays carry
+// time 0 regardless of the path's time (direct_light_integrator.h:115).
+template <bool COUNT>
+__device__ __forceinline__ bool shadow_visible(const GeomView<float> &g, V3<float> o, V3<float> d, float tmax,
+                                               uint32_t origin, Pcg &rng, uint64_t &nodes, uint64_t &tests) {
+    // t_min is 0.001 along the UNIT direction; the stored direction may be the unnormalised segment
+    const float len = isfinite(tmax) ? length(d) : 1.0f;
+    PathDraw draw{&rng};
+    float t;
+    return trace<true, COUNT>(g, o, d, 0.0f, 0.001f / len, tmax, origin, draw, t, nodes, tests) == kNoPrim;
+}
+
+// ---- (A) wavefront kernels -------------------------------------------------------------------
+
+// Ends the iteration for one lane: a finished path is replaced by the next camera sample (if
+// any remain); a live path is written back; either way the slot is queued for the next
+// extend.  Called by all 32 lanes.
 __device__ __forceinline__ void finish_lane(const WfParams &p, Counters &next, uint32_t *q_next, bool valid,
                                             bool alive, uint32_t slot, PathState &s) {
     const bool want_new = valid && !alive;
@@ -200,8 +482,6 @@ __device__ __forceinline__ void finish_lane(const WfParams &p, Counters &next, u
     if (queued)
         q_next[pos] = slot;
 }
-
-// ---- kernels ------------------------------------------------------------------------------
 
 __global__ void k_clear(Counters *ctr, Globals *glob) {
     if (blockIdx.x == 0 && threadIdx.x < 3 * sizeof(Counters) / 4)
@@ -228,16 +508,13 @@ __global__ void __launch_bounds__(256) k_generate(WfParams p) {
     }
 }
 
-struct PathDraw { // RNG adaptor handed to traverse() for constant_medium tests
-    Pcg *g;
-    __device__ float operator()() { return g->next_open(); }
-};
-
-// extend: closest hit for every queued path; classifies the result into the
-// material queues.  Replaces scene.hit(current_ray, 0.001, infinity, rec)
-// (e.g. rr_path_integrator.h:29) and everything under bvh_node::hit.
+// extend: closest hit for every queued path; classifies the result into the material queues.
+// Replaces scene.hit(current_ray, 0.001, infinity, rec) (e.g. rr_path_integrator.h:29) and
+// everything under bvh_node::hit.
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_extend(WfParams p, int it) {
+    __shared__ FlatSmem sm;
+    const GeomView<float> g = stage_scene(p.geom, sm);
     Counters &C = p.ctr[it % 3];
     if (blockIdx.x == 0 && threadIdx.x < sizeof(Counters) / 4)
         reinterpret_cast<uint32_t *>(&p.ctr[(it + 2) % 3])[threadIdx.x] = 0;
@@ -245,7 +522,6 @@ __global__ void __launch_bounds__(128) k_extend(WfParams p, int it) {
     if (blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(&p.glob->rays_closest, (unsigned long long)n);
     const uint32_t *q = p.q_ext[it & 1];
-    const GlobalFetch<float> F(p.geom);
     uint64_t nodes = 0, tests = 0;
     while (true) {
         const uint32_t base = warp_fetch(&C.head_ext);
@@ -260,27 +536,22 @@ __global__ void __launch_bounds__(128) k_extend(WfParams p, int it) {
             const V3<float> o(a.x, a.y, a.z), d(b.x, b.y, b.z);
             float t;
             uint32_t pi;
-            if (p.has_media) {
-                const uint4 x = p.aux[slot];
-                Pcg g;
-                g.s = uint64_t(x.x) | (uint64_t(x.y) << 32);
-                PathDraw draw{&g};
-                pi = traverse<float, false, true>(p.geom, F, o, d, a.w, 0.001f, Consts<float>::inf(),
-                                                  __float_as_uint(b.w), draw, t, COUNT ? &nodes : nullptr,
-                                                  COUNT ? &tests : nullptr);
-                p.aux[slot] = make_uint4(uint32_t(g.s), uint32_t(g.s >> 32), x.z, x.w);
-            } else {
-                Pcg g;
-                g.s = 0;
-                PathDraw draw{&g};
-                pi = traverse<float, false, true>(p.geom, F, o, d, a.w, 0.001f, Consts<float>::inf(),
-                                                  __float_as_uint(b.w), draw, t, COUNT ? &nodes : nullptr,
-                                                  COUNT ? &tests : nullptr);
+            Pcg rg;
+            rg.s = 0;
+            uint4 x = make_uint4(0, 0, 0, 0);
+            if (p.has_media) { // constant_medium::hit draws from the path's stream
+                x = p.aux[slot];
+                rg.s = uint64_t(x.x) | (uint64_t(x.y) << 32);
             }
+            PathDraw draw{&rg};
+            pi = trace<false, COUNT>(g, o, d, a.w, 0.001f, Consts<float>::inf(), __float_as_uint(b.w), draw, t, nodes,
+                                     tests);
+            if (p.has_media)
+                p.aux[slot] = make_uint4(uint32_t(rg.s), uint32_t(rg.s >> 32), x.z, x.w);
             p.hit[slot] = make_float4(t, __uint_as_float(pi), 0.f, 0.f);
             key = kMatTypes;
             if (pi != kNoPrim)
-                key = uint32_t(p.shade.mats[p.geom.prims[pi].type_mat >> PT_MAT_SHIFT].type);
+                key = uint32_t(p.shade.mats[g.prims[pi].type_mat >> PT_MAT_SHIFT].type);
         }
 #pragma unroll
         for (uint32_t k = 0; k <= kMatTypes; ++k) {
@@ -299,35 +570,11 @@ __global__ void __launch_bounds__(128) k_extend(WfParams p, int it) {
     }
 }
 
-// mis_path_integrator.h:154-162
-__device__ __forceinline__ V3<float> clamp_radiance(V3<float> L, float max_value) {
-    if (L.x > max_value || L.y > max_value || L.z > max_value) {
-        const float max_c = max3(L);
-        if (max_c > max_value)
-            return L * (max_value / max_c);
-    }
-    return L;
-}
-// mis_path_integrator.h:165-170
-__device__ __forceinline__ float power_heuristic(float a, float b) {
-    const float a2 = a * a, b2 = b * b, denom = a2 + b2;
-    return denom > 0.f ? a2 / denom : 0.f;
-}
-// mis_path_integrator.h:173-188 (also :53-60): sum over ALL lights of pdf(o,d)/N
-__device__ float all_lights_pdf(const WfParams &p, V3<float> o, V3<float> d) {
-    float total = 0.f;
-    const float sel = 1.0f / float(p.shade.n_lights);
-    for (int i = 0; i < p.shade.n_lights; ++i)
-        total += light_pdf(p.shade, p.shade.lights[i], o, d) * sel;
-    return total;
-}
-
-// shade_<material>: everything Integrator::Li does at a surface hit, for the paths
-// whose hit landed on material type M.  OLD = integrators 0/1 (legacy scatter() +
-// two-sided emitted(u,v,p)), otherwise integrators 2/3/4 (sample/eval/pdf +
-// one-sided emitted(rec,wo), NEE, MIS).
+// shade_<material>: shade_surface<M> for the paths whose hit landed on material type M.
 template <int M, bool OLD>
 __global__ void __launch_bounds__(128) k_shade(WfParams p, int it) {
+    __shared__ FlatSmem sm;
+    const GeomView<float> g = stage_scene(p.geom, sm);
     Counters &C = p.ctr[it % 3];
     Counters &N = p.ctr[(it + 1) % 3];
     const uint32_t n = C.n_mat[M];
@@ -342,175 +589,28 @@ __global__ void __launch_bounds__(128) k_shade(WfParams p, int it) {
         uint32_t slot = 0;
         bool alive = false;
         PathState s;
-        // shadow-ray request produced by this lane (integrators 3/4)
-        bool want_shadow = false;
-        V3<float> sh_o(0, 0, 0), sh_d(0, 0, 0), sh_c(0, 0, 0);
-        float sh_tmax = 0.f;
-        uint32_t sh_origin = kNoPrim;
+        ShadowReq sh;
+        sh.want = false;
+        uint32_t sh_pix = 0;
         if (valid) {
             slot = q[idx];
             s = load_state(p, slot);
             const float4 h = p.hit[slot];
-            const float t = h.x;
-            const uint32_t pi = __float_as_uint(h.y);
-            MatT<float> m = p.shade.mats[p.geom.prims[pi].type_mat >> PT_MAT_SHIFT];
-            m.type = M; // compile-time constant: prunes the per-type switches
-            const RecT<float> rec = (m.flags & 1)
-                                        ? make_record<float, true, true>(p.geom, pi, s.o, s.d, s.time, t)
-                                        : make_record<float, true, false>(p.geom, pi, s.o, s.d, s.time, t);
-            RngT<float> rng;
-            rng.g = s.rng;
-            alive = true;
-            if (OLD) {
-                // path_integrator.h:32-44, rr_path_integrator.h:35-57
-                if (M == RTB_MAT_DIFFUSE_LIGHT)
-                    accum_add(p.accum, s.pix, s.T * mat_emitted_old(p.shade, m, rec));
-                V3<float> atten, dout;
-                if (!mat_scatter(p.shade, m, rec, s.d, rng, atten, dout)) {
-                    alive = false;
-                } else {
-                    s.T = s.T * atten;
-                    if (p.integrator == RTB_INTEGRATOR_RR && int(s.depth) >= p.rr_start) {
-                        const float ps = clamp_(max3(s.T), 0.005f, 0.95f);
-                        if (rng.next() > ps)
-                            alive = false;
-                        else
-                            s.T = s.T / ps;
-                    }
-                    s.o = rec.p;
-                    s.d = dout;
-                    s.origin_prim = pi;
-                }
-            } else {
-                const V3<float> wo = -unit_vector(s.d);
-                if (M == RTB_MAT_DIFFUSE_LIGHT) {
-                    const V3<float> e = mat_emitted_new(p.shade, m, rec);
-                    if (p.integrator == RTB_INTEGRATOR_PBR) {
-                        accum_add(p.accum, s.pix, s.T * e); // pbr_path_integrator.h:38-39
-                    } else if (p.integrator == RTB_INTEGRATOR_DIRECT) {
-                        if (s.depth == 0 || s.spec) // direct_light_integrator.h:52-55
-                            accum_add(p.accum, s.pix, s.T * e);
-                    } else if (length_squared(e) > 0.f) { // mis_path_integrator.h:72-94
-                        V3<float> Le;
-                        if (s.depth == 0 || s.spec)
-                            Le = s.T * e;
-                        else if (p.shade.n_lights > 0)
-                            Le = (s.T * e) * power_heuristic(s.prev_pdf, all_lights_pdf(p, s.o, s.d));
-                        else
-                            Le = s.T * e;
-                        accum_add(p.accum, s.pix, s.depth == 0 ? Le : clamp_radiance(Le, 100.f));
-                    }
-                }
-                s.spec = false; // material::is_specular() is never overridden (material.h:37)
-                // next-event estimation: direct_light_integrator.h:98-142, mis_path_integrator.h:192-234.
-                // eval() is identically 0 for metal / dielectric / diffuse_light / isotropic, so
-                // only lambertian and PBR can contribute; the others skip the (wasted) shadow ray.
-                if ((M == RTB_MAT_LAMBERTIAN || M == RTB_MAT_PBR) && p.integrator >= RTB_INTEGRATOR_DIRECT &&
-                    p.shade.n_lights > 0) {
-                    const int nl = p.shade.n_lights;
-                    int li = int(float(nl) * rng.next()); // random_int(0, n-1), rtweekend.h:48-50
-                    li = li < nl ? li : nl - 1;
-                    const float sel = 1.0f / float(nl);
-                    const float u0 = rng.next(), u1 = rng.next();
-                    const LightT<float> &L = p.shade.lights[li];
-                    const LightSampleT<float> ls = light_sample(p.shade, L, rec.p, u0, u1, rng);
-                    if (ls.pdf > 0.f && length_squared(ls.Li) > 0.f) {
-                        const V3<float> f = mat_eval(p.shade, m, rec, wo, ls.wi);
-                        const float cos_theta = fabsf(dot(ls.wi, rec.normal));
-                        V3<float> Ld;
-                        if (p.integrator == RTB_INTEGRATOR_DIRECT) {
-                            Ld = ls.is_delta ? (f * ls.Li) * (cos_theta / sel)
-                                             : (f * ls.Li) * (cos_theta / (ls.pdf * sel));
-                            // direct_light_integrator.h:133-139: sequential per-channel rescale
-                            if (Ld.x > 100.f)
-                                Ld = Ld * (100.f / Ld.x);
-                            if (Ld.y > 100.f)
-                                Ld = Ld * (100.f / Ld.y);
-                            if (Ld.z > 100.f)
-                                Ld = Ld * (100.f / Ld.z);
-                            Ld = s.T * Ld;
-                        } else {
-                            if (ls.is_delta) {
-                                Ld = (f * ls.Li) * (cos_theta / sel);
-                            } else {
-                                const float bsdf_pdf = mat_pdf(p.shade, m, rec, wo, ls.wi);
-                                const float light_p = ls.pdf * sel;
-                                Ld = (f * ls.Li) * (cos_theta * power_heuristic(light_p, bsdf_pdf) / light_p);
-                            }
-                            Ld = clamp_radiance(s.T * Ld, 100.f);
-                        }
-                        if (Ld.x != 0.f || Ld.y != 0.f || Ld.z != 0.f) {
-                            want_shadow = true;
-                            sh_o = rec.p;
-                            sh_c = Ld;
-                            sh_origin = pi;
-                            if (isfinite(ls.dist)) {
-                                // segment form: d = light_point - p, t in [0.001/dist, 1 - 0.001/dist];
-                                // the same interval as (wi, [0.001, dist - 0.001]) of the reference but
-                                // well-conditioned in fp32 (the far end is exactly t = 1)
-                                const float inv = 1.0f / ls.dist;
-                                sh_d = ls.to_light;
-                                sh_tmax = 1.0f - 0.001f * inv;
-                            } else {
-                                sh_d = ls.wi;
-                                sh_tmax = Consts<float>::inf();
-                            }
-                        }
-                    }
-                }
-                BsdfSampleT<float> bs;
-                if (!mat_sample(p.shade, m, rec, wo, rng, bs)) {
-                    // mis_path_integrator.h:106-117: only integrator 4 falls back to scatter()
-                    V3<float> atten, dout;
-                    if (p.integrator == RTB_INTEGRATOR_MIS && mat_scatter(p.shade, m, rec, s.d, rng, atten, dout)) {
-                        s.T = s.T * atten;
-                        s.d = dout;
-                        s.spec = false;
-                        s.prev_pdf = 0.f;
-                    } else {
-                        alive = false;
-                    }
-                } else if (bs.pdf < 1e-8f && !bs.is_specular) {
-                    alive = false;
-                } else {
-                    s.spec = bs.is_specular;
-                    s.prev_pdf = bs.is_specular ? 0.f : bs.pdf;
-                    const float cos_theta = fabsf(dot(bs.wi, rec.normal));
-                    s.T = bs.is_specular ? s.T * bs.f : s.T * (bs.f * (cos_theta / bs.pdf));
-                    s.d = bs.wi;
-                }
-                if (alive) {
-                    s.o = rec.p;
-                    s.origin_prim = pi;
-                    if (int(s.depth) >= p.rr_start) { // e.g. mis_path_integrator.h:137-146
-                        const float ps = clamp_(max3(s.T), 0.05f, 0.95f);
-                        if (rng.next() > ps)
-                            alive = false;
-                        else
-                            s.T = s.T / ps;
-                    }
-                }
-            }
-            s.rng = rng.g;
-            s.depth += 1;
-            if (int(s.depth) >= p.max_depth)
-                alive = false;
+            sh_pix = s.pix;
+            shade_surface<M, OLD>(p, g, s, h.x, __float_as_uint(h.y), alive, sh);
         }
         if (!OLD) {
-            const uint32_t pos = warp_reserve(&C.n_shadow, want_shadow);
-            if (want_shadow) {
-                p.sh_a[pos] = make_float4(sh_o.x, sh_o.y, sh_o.z, sh_tmax);
-                p.sh_b[pos] = make_float4(sh_d.x, sh_d.y, sh_d.z, __uint_as_float(s.pix));
-                p.sh_c[pos] = make_float4(sh_c.x, sh_c.y, sh_c.z, __uint_as_float(sh_origin));
+            const uint32_t pos = warp_reserve(&C.n_shadow, sh.want);
+            if (sh.want) {
+                p.sh_a[pos] = make_float4(sh.o.x, sh.o.y, sh.o.z, sh.tmax);
+                p.sh_b[pos] = make_float4(sh.d.x, sh.d.y, sh.d.z, __uint_as_float(sh_pix));
+                p.sh_c[pos] = make_float4(sh.c.x, sh.c.y, sh.c.z, __uint_as_float(sh.origin));
             }
         }
         finish_lane(p, N, q_next, valid, alive, slot, s);
     }
 }
 
-// miss: the ray left the scene.  Background for integrators 0-2 (e.g.
-// rr_path_integrator.h:30-33); environment lights for 3/4
-// (direct_light_integrator.h:35-48, mis_path_integrator.h:37-67).
 __global__ void __launch_bounds__(128) k_miss(WfParams p, int it) {
     Counters &C = p.ctr[it % 3];
     Counters &N = p.ctr[(it + 1) % 3];
@@ -527,38 +627,23 @@ __global__ void __launch_bounds__(128) k_miss(WfParams p, int it) {
         if (valid) {
             slot = p.q_miss[idx];
             s = load_state(p, slot);
-            const V3<float> bg(p.bg[0], p.bg[1], p.bg[2]);
-            V3<float> L = s.T * bg;
-            if (p.integrator >= RTB_INTEGRATOR_DIRECT && p.shade.n_infinite_lights > 0) {
-                V3<float> env(0, 0, 0);
-                for (int i = 0; i < p.shade.n_lights; ++i)
-                    if (p.shade.lights[i].type == RTB_LIGHT_ENV)
-                        env = env + light_Le(p.shade, p.shade.lights[i], s.d);
-                if (p.integrator == RTB_INTEGRATOR_DIRECT || s.depth == 0 || s.spec)
-                    L = s.T * env;
-                else
-                    L = (s.T * env) * power_heuristic(s.prev_pdf, all_lights_pdf(p, s.o, s.d));
-            }
-            accum_add(p.accum, s.pix, L);
+            miss_surface(p, s);
         }
         finish_lane(p, N, q_next, valid, false, slot, s);
     }
 }
 
-struct HashDraw { // RNG for shadow rays through media, keyed by the queue entry
-    Pcg g;
-    __device__ float operator()() { return g.next_open(); }
-};
-
 // connect: any-hit test of the shadow rays queued by shade; unoccluded ones add their
-// (already weighted) contribution.  Replaces scene.hit(shadow_ray, 0.001, dist - 0.001)
-// (direct_light_integrator.h:115-130, mis_path_integrator.h:209-230).
+// (already weighted) contribution.
+template <bool COUNT>
 __global__ void __launch_bounds__(128) k_connect(WfParams p, int it) {
+    __shared__ FlatSmem sm;
+    const GeomView<float> g = stage_scene(p.geom, sm);
     Counters &C = p.ctr[it % 3];
     const uint32_t n = C.n_shadow;
     if (blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(&p.glob->rays_shadow, (unsigned long long)n);
-    const GlobalFetch<float> F(p.geom);
+    uint64_t nodes = 0, tests = 0;
     while (true) {
         const uint32_t base = warp_fetch(&C.head_shadow);
         if (base >= n)
@@ -566,21 +651,108 @@ __global__ void __launch_bounds__(128) k_connect(WfParams p, int it) {
         const uint32_t idx = base + lane_id();
         if (idx < n) {
             const float4 a = p.sh_a[idx], b = p.sh_b[idx], c = p.sh_c[idx];
-            const V3<float> o(a.x, a.y, a.z), d(b.x, b.y, b.z);
-            // t_min: 0.001 in units of the unit direction; the stored direction may be the
-            // unnormalised segment
-            const float len = isfinite(a.w) ? length(d) : 1.0f;
-            HashDraw draw;
-            draw.g = pcg_seed((uint64_t(__float_as_uint(a.x)) << 32) ^ __float_as_uint(b.y), p.seed ^ idx);
-            float t;
-            // shadow rays carry time 0 regardless of the path's time (direct_light_integrator.h:115)
-            const uint32_t pi = traverse<float, true, true>(p.geom, F, o, d, 0.0f, 0.001f / len, a.w,
-                                                            __float_as_uint(c.w), draw, t, nullptr, nullptr);
-            if (pi == kNoPrim)
+            // media on a shadow ray draw from a stream keyed by the queue entry
+            Pcg rg = pcg_seed((uint64_t(__float_as_uint(a.x)) << 32) ^ __float_as_uint(b.y), p.seed ^ idx);
+            if (shadow_visible<COUNT>(g, V3<float>(a.x, a.y, a.z), V3<float>(b.x, b.y, b.z), a.w, __float_as_uint(c.w),
+                                      rg, nodes, tests))
                 accum_add(p.accum, __float_as_uint(b.w), V3<float>(c.x, c.y, c.z));
         }
     }
+    if (COUNT) {
+        atomicAdd(&p.glob->nodes_visited, (unsigned long long)nodes);
+        atomicAdd(&p.glob->prim_tests, (unsigned long long)tests);
+    }
 }
+
+// ---- (B) fused kernel for shared-memory-resident scenes ----------------------------------------
+
+constexpr uint32_t kSampleChunk = 256; // samples a warp reserves per atomic
+
+template <bool OLD, bool COUNT>
+__global__ void __launch_bounds__(128) k_fused(WfParams p) {
+    __shared__ FlatSmem sm;
+    const GeomView<float> g = stage_scene(p.geom, sm);
+    PathState s;
+    bool alive = false, exhausted = false;
+    unsigned long long chunk_next = 0, chunk_end = 0; // warp-uniform: this warp's private sample range
+    uint64_t n_closest = 0, n_shadow = 0, n_paths = 0, nodes = 0, tests = 0;
+    while (true) {
+        // regeneration: every idle lane takes the next sample of the warp's chunk
+        const bool need = !alive && !exhausted;
+        const uint32_t m = __ballot_sync(kFullMask, need);
+        if (m) {
+            const uint32_t n = __popc(m), rank = __popc(m & ((1u << lane_id()) - 1u));
+            const unsigned long long avail = chunk_end - chunk_next;
+            unsigned long long id;
+            if (avail >= n) {
+                id = chunk_next + rank;
+                chunk_next += n;
+            } else {
+                unsigned long long base = 0;
+                if (lane_id() == 0)
+                    base = atomicAdd(&p.glob->next_sample, (unsigned long long)kSampleChunk);
+                base = __shfl_sync(kFullMask, base, 0);
+                id = rank < avail ? chunk_next + rank : base + (rank - avail);
+                chunk_next = base + (n - avail);
+                chunk_end = base + kSampleChunk;
+            }
+            if (need) {
+                if (id < p.window_end) {
+                    new_path(p, id, s);
+                    alive = true;
+                    ++n_paths;
+                } else {
+                    exhausted = true;
+                }
+            }
+        }
+        if (!__any_sync(kFullMask, alive))
+            break;
+        if (alive) {
+            PathDraw draw{&s.rng};
+            float t;
+            const uint32_t pi = trace<false, COUNT>(g, s.o, s.d, s.time, 0.001f, Consts<float>::inf(), s.origin_prim,
+                                                    draw, t, nodes, tests);
+            ++n_closest;
+            if (pi == kNoPrim) {
+                miss_surface(p, s);
+                alive = false;
+            } else {
+                ShadowReq sh;
+                const uint32_t pix = s.pix;
+                switch (p.shade.mats[g.prims[pi].type_mat >> PT_MAT_SHIFT].type) {
+                case 0: shade_surface<0, OLD>(p, g, s, t, pi, alive, sh); break;
+                case 1: shade_surface<1, OLD>(p, g, s, t, pi, alive, sh); break;
+                case 2: shade_surface<2, OLD>(p, g, s, t, pi, alive, sh); break;
+                case 3: shade_surface<3, OLD>(p, g, s, t, pi, alive, sh); break;
+                case 4: shade_surface<4, OLD>(p, g, s, t, pi, alive, sh); break;
+                default: shade_surface<5, OLD>(p, g, s, t, pi, alive, sh); break;
+                }
+                if (!OLD && sh.want) {
+                    ++n_shadow;
+                    Pcg rg = s.rng; // a copy: the shadow test must not advance the path's stream
+                    if (shadow_visible<COUNT>(g, sh.o, sh.d, sh.tmax, sh.origin, rg, nodes, tests))
+                        accum_add(p.accum, pix, sh.c);
+                }
+            }
+        }
+    }
+    const unsigned long long a = warp_sum(n_closest), b = warp_sum(n_shadow), c = warp_sum(n_paths);
+    if (lane_id() == 0) {
+        atomicAdd(&p.glob->rays_closest, a);
+        atomicAdd(&p.glob->rays_shadow, b);
+        atomicAdd(&p.glob->paths, c);
+    }
+    if (COUNT) {
+        const unsigned long long e = warp_sum(nodes), f = warp_sum(tests);
+        if (lane_id() == 0) {
+            atomicAdd(&p.glob->nodes_visited, e);
+            atomicAdd(&p.glob->prim_tests, f);
+        }
+    }
+}
+
+__global__ void k_set_next_sample(Globals *glob, unsigned long long v) { glob->next_sample = v; }
 
 // renderer.h:126-140 + render_buffer.h:35-55: sqrt(sum/spp), clamp, (uchar)(x*255), y flip.
 __global__ void k_resolve_rgb8(const float4 *__restrict__ accum, int w, int h, float inv_spp,
@@ -609,6 +781,12 @@ template <bool OLD> void launch_shade(int mtype, const WfParams &P, int it, int 
     }
 }
 
+template <class K> int blocks_per_sm(K kernel, int threads) {
+    int n = 0;
+    RTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, 0));
+    return n > 0 ? n : 1;
+}
+
 } // namespace
 
 // Device memory of the path pool; kept across renders on a context.
@@ -619,7 +797,7 @@ struct WavefrontPool {
     Globals *h_glob = nullptr;  // pinned
     cudaEvent_t ev[2] = {nullptr, nullptr};
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-    std::vector<cudaEvent_t> ev_ext; // pairs bracketing extend launches (RTB_RENDER_TIME_EXTEND)
+    std::vector<cudaEvent_t> ev_ext; // pairs bracketing the dominant kernel's launches (RTB_RENDER_TIME_EXTEND)
     cudaEvent_t ext_event(size_t i) {
         while (ev_ext.size() <= i) {
             cudaEvent_t e;
@@ -628,17 +806,20 @@ struct WavefrontPool {
         }
         return ev_ext[i];
     }
+    void ensure_common() {
+        if (h_live)
+            return;
+        RTB_CUDA(cudaMallocHost(&h_live, 64 * sizeof(uint32_t)));
+        RTB_CUDA(cudaMallocHost(&h_glob, sizeof(Globals)));
+        for (auto &e : ev)
+            RTB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        RTB_CUDA(cudaEventCreate(&ev_begin));
+        RTB_CUDA(cudaEventCreate(&ev_end));
+        ctr.alloc(3 * sizeof(Counters));
+        glob.alloc(sizeof(Globals));
+    }
     void ensure(uint32_t want) {
-        if (!h_live) {
-            RTB_CUDA(cudaMallocHost(&h_live, 64 * sizeof(uint32_t)));
-            RTB_CUDA(cudaMallocHost(&h_glob, sizeof(Globals)));
-            for (auto &e : ev)
-                RTB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            RTB_CUDA(cudaEventCreate(&ev_begin));
-            RTB_CUDA(cudaEventCreate(&ev_end));
-            ctr.alloc(3 * sizeof(Counters));
-            glob.alloc(sizeof(Globals));
-        }
+        ensure_common();
         if (want == P)
             return;
         P = 0;
@@ -694,30 +875,40 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
     // max_depth 0: every Li() returns black without tracing anything (the depth loop of
     // e.g. rr_path_integrator.h:27 never runs)
     const unsigned long long total = rp.max_depth > 0 ? n_samples : 0ull;
-    uint32_t P = rp.pool_paths > 0 ? uint32_t(rp.pool_paths) : (1u << 21);
-    P = (P + 31u) & ~31u;
-    if ((unsigned long long)P > total)
-        P = uint32_t((total + 31ull) & ~31ull);
-    if (P < 32)
-        P = 32;
-    pool.ensure(P);
+
+    GeomView<float> geom = sc.geom<float>();
+    if (ctx->opt_flat == 0)
+        geom.flat = 0;
+    const bool fused = geom.flat && ctx->opt_fused != 0 && !(rp.flags & RTB_RENDER_FORCE_WAVEFRONT);
 
     WfParams W;
-    W.geom = sc.geom<float>();
+    std::memset(&W, 0, sizeof(W));
+    W.geom = geom;
     W.shade = sc.shade<float>();
     W.cam = sc.host.f32.camera;
-    W.ray_o = pool.ray_o.as<float4>();
-    W.ray_d = pool.ray_d.as<float4>();
-    W.thr = pool.thr.as<float4>();
-    W.hit = pool.hit.as<float4>();
-    W.aux = pool.aux.as<uint4>();
-    W.q_ext[0] = pool.q_ext0.as<uint32_t>();
-    W.q_ext[1] = pool.q_ext1.as<uint32_t>();
-    W.q_mat = pool.q_mat.as<uint32_t>();
-    W.q_miss = pool.q_miss.as<uint32_t>();
-    W.sh_a = pool.sh_a.as<float4>();
-    W.sh_b = pool.sh_b.as<float4>();
-    W.sh_c = pool.sh_c.as<float4>();
+    pool.ensure_common();
+    uint32_t P = 0;
+    if (!fused) {
+        P = rp.pool_paths > 0 ? uint32_t(rp.pool_paths) : (1u << 20);
+        P = (P + 31u) & ~31u;
+        if ((unsigned long long)P > total)
+            P = uint32_t((total + 31ull) & ~31ull);
+        if (P < 32)
+            P = 32;
+        pool.ensure(P);
+        W.ray_o = pool.ray_o.as<float4>();
+        W.ray_d = pool.ray_d.as<float4>();
+        W.thr = pool.thr.as<float4>();
+        W.hit = pool.hit.as<float4>();
+        W.aux = pool.aux.as<uint4>();
+        W.q_ext[0] = pool.q_ext0.as<uint32_t>();
+        W.q_ext[1] = pool.q_ext1.as<uint32_t>();
+        W.q_mat = pool.q_mat.as<uint32_t>();
+        W.q_miss = pool.q_miss.as<uint32_t>();
+        W.sh_a = pool.sh_a.as<float4>();
+        W.sh_b = pool.sh_b.as<float4>();
+        W.sh_c = pool.sh_c.as<float4>();
+    }
     W.ctr = pool.ctr.as<Counters>();
     W.glob = pool.glob.as<Globals>();
     W.accum = d_accum;
@@ -732,6 +923,7 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
     W.sample_stride = stride;
     W.npix = npix;
     W.total_samples = total;
+    W.window_end = total;
     W.seed = rp.seed;
     for (int k = 0; k < 3; ++k)
         W.bg[k] = float(sc.host.globals.background[k]);
@@ -741,74 +933,121 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
     const bool old_api = rp.integrator <= RTB_INTEGRATOR_RR;
     const bool nee = rp.integrator >= RTB_INTEGRATOR_DIRECT && !sc.host.f32.lights.empty();
     const bool count = (rp.flags & RTB_RENDER_COUNT_VISITS) != 0;
-    const bool time_extend = (rp.flags & RTB_RENDER_TIME_EXTEND) != 0;
+    const bool time_dom = (rp.flags & RTB_RENDER_TIME_EXTEND) != 0;
     size_t n_ext_events = 0;
     const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
-    const int grid = sms * 8; // 8 resident CTAs of 128 threads per SM
 
     uint64_t launches = 0;
+    int it = 0;
+    bool cancelled = false;
     RTB_CUDA(cudaEventRecord(pool.ev_begin, st));
     RTB_CUDA(cudaMemsetAsync(d_accum, 0, size_t(npix) * sizeof(float4), st));
     k_clear<<<1, 128, 0, st>>>(W.ctr, W.glob);
-    k_generate<<<sms * 4, 256, 0, st>>>(W);
-    launches += 2;
-    RTB_CUDA(cudaGetLastError());
+    ++launches;
 
-    constexpr int kBatch = 4; // iterations between two host-side liveness probes
-    int it = 0;
-    int probe = 0;
-    bool done = total == 0;
-    bool cancelled = false;
-    int pending[2] = {-1, -1}; // probe slots in flight
-    while (!done) {
-        for (int b = 0; b < kBatch; ++b, ++it) {
-            if (time_extend)
+    if (fused) {
+        // One persistent kernel per window of samples (windows keep rtb_cancel responsive).
+        int bps;
+        if (old_api)
+            bps = count ? blocks_per_sm(k_fused<true, true>, 128) : blocks_per_sm(k_fused<true, false>, 128);
+        else
+            bps = count ? blocks_per_sm(k_fused<false, true>, 128) : blocks_per_sm(k_fused<false, false>, 128);
+        const int grid = sms * bps;
+        const unsigned long long window = 1ull << 26;
+        for (unsigned long long begin = 0; begin < total; begin += window) {
+            W.window_end = std::min(total, begin + window);
+            k_set_next_sample<<<1, 1, 0, st>>>(W.glob, begin);
+            if (time_dom)
                 RTB_CUDA(cudaEventRecord(pool.ext_event(n_ext_events++), st));
-            if (count)
-                k_extend<true><<<grid, 128, 0, st>>>(W, it);
-            else
-                k_extend<false><<<grid, 128, 0, st>>>(W, it);
-            if (time_extend)
+            if (old_api) {
+                if (count)
+                    k_fused<true, true><<<grid, 128, 0, st>>>(W);
+                else
+                    k_fused<true, false><<<grid, 128, 0, st>>>(W);
+            } else {
+                if (count)
+                    k_fused<false, true><<<grid, 128, 0, st>>>(W);
+                else
+                    k_fused<false, false><<<grid, 128, 0, st>>>(W);
+            }
+            if (time_dom)
                 RTB_CUDA(cudaEventRecord(pool.ext_event(n_ext_events++), st));
-            ++launches;
-            for (int m = 0; m < kMatTypes; ++m)
-                if ((W.mat_mask >> m) & 1u) {
-                    if (old_api)
-                        launch_shade<true>(m, W, it, grid, st);
-                    else
-                        launch_shade<false>(m, W, it, grid, st);
-                    ++launches;
-                }
-            k_miss<<<grid, 128, 0, st>>>(W, it);
-            ++launches;
-            if (nee) {
-                k_connect<<<grid, 128, 0, st>>>(W, it);
-                ++launches;
+            launches += 2;
+            ++it;
+            RTB_CUDA(cudaGetLastError());
+            if (begin + window < total) { // keep at most two windows in flight
+                const int slot = it & 1;
+                RTB_CUDA(cudaEventRecord(pool.ev[slot], st));
+                if (it >= 2)
+                    RTB_CUDA(cudaEventSynchronize(pool.ev[slot ^ 1]));
+            }
+            if (ctx->cancel.load(std::memory_order_relaxed)) {
+                cancelled = true;
+                break;
             }
         }
+    } else {
+        const int grid = sms * 8; // 8 resident CTAs of 128 threads per SM
+        k_generate<<<sms * 4, 256, 0, st>>>(W);
+        ++launches;
         RTB_CUDA(cudaGetLastError());
-        // length of the NEXT extend queue, read back without stalling the pipeline: the
-        // host only waits for the probe of the PREVIOUS batch
-        const int slot = probe & 1;
-        RTB_CUDA(cudaMemcpyAsync(&pool.h_live[slot], &W.ctr[it % 3].n_ext, sizeof(uint32_t),
-                                 cudaMemcpyDeviceToHost, st));
-        RTB_CUDA(cudaEventRecord(pool.ev[slot], st));
-        pending[slot] = it;
-        const int prev = (probe + 1) & 1;
-        if (pending[prev] >= 0) {
-            RTB_CUDA(cudaEventSynchronize(pool.ev[prev]));
-            if (pool.h_live[prev] == 0)
-                done = true;
+        constexpr int kBatch = 4; // iterations between two host-side liveness probes
+        int probe = 0;
+        bool done = total == 0;
+        int pending[2] = {-1, -1}; // probe slots in flight
+        while (!done) {
+            for (int b = 0; b < kBatch; ++b, ++it) {
+                if (time_dom)
+                    RTB_CUDA(cudaEventRecord(pool.ext_event(n_ext_events++), st));
+                if (count)
+                    k_extend<true><<<grid, 128, 0, st>>>(W, it);
+                else
+                    k_extend<false><<<grid, 128, 0, st>>>(W, it);
+                if (time_dom)
+                    RTB_CUDA(cudaEventRecord(pool.ext_event(n_ext_events++), st));
+                ++launches;
+                for (int m = 0; m < kMatTypes; ++m)
+                    if ((W.mat_mask >> m) & 1u) {
+                        if (old_api)
+                            launch_shade<true>(m, W, it, grid, st);
+                        else
+                            launch_shade<false>(m, W, it, grid, st);
+                        ++launches;
+                    }
+                k_miss<<<grid, 128, 0, st>>>(W, it);
+                ++launches;
+                if (nee) {
+                    if (count)
+                        k_connect<true><<<grid, 128, 0, st>>>(W, it);
+                    else
+                        k_connect<false><<<grid, 128, 0, st>>>(W, it);
+                    ++launches;
+                }
+            }
+            RTB_CUDA(cudaGetLastError());
+            // length of the NEXT extend queue, read back without stalling the pipeline: the
+            // host only waits for the probe of the PREVIOUS batch
+            const int slot = probe & 1;
+            RTB_CUDA(cudaMemcpyAsync(&pool.h_live[slot], &W.ctr[it % 3].n_ext, sizeof(uint32_t),
+                                     cudaMemcpyDeviceToHost, st));
+            RTB_CUDA(cudaEventRecord(pool.ev[slot], st));
+            pending[slot] = it;
+            const int prev = (probe + 1) & 1;
+            if (pending[prev] >= 0) {
+                RTB_CUDA(cudaEventSynchronize(pool.ev[prev]));
+                if (pool.h_live[prev] == 0)
+                    done = true;
+            }
+            ++probe;
+            if (ctx->cancel.load(std::memory_order_relaxed)) {
+                cancelled = true;
+                break;
+            }
+            // every slot is busy on every iteration until the samples run out, so the last
+            // sample starts no later than iteration total*max_depth/P; the tail adds max_depth
+            if ((unsigned long long)it > total * (unsigned long long)rp.max_depth / P + rp.max_depth + 4 * kBatch)
+                throw std::runtime_error("wavefront: iteration bound exceeded (internal error)");
         }
-        ++probe;
-        if (ctx->cancel.load(std::memory_order_relaxed)) {
-            cancelled = true;
-            break;
-        }
-        // every slot is busy on every iteration until the samples run out, so the last sample
-        // starts no later than iteration total*max_depth/P; the tail adds at most max_depth
-        if ((unsigned long long)it > total * (unsigned long long)rp.max_depth / P + rp.max_depth + 4 * kBatch)
-            throw std::runtime_error("wavefront: iteration bound exceeded (internal error)");
     }
     RTB_CUDA(cudaMemcpyAsync(pool.h_glob, W.glob, sizeof(Globals), cudaMemcpyDeviceToHost, st));
     RTB_CUDA(cudaEventRecord(pool.ev_end, st));
@@ -817,8 +1056,12 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
     RTB_CUDA(cudaEventElapsedTime(&ms, pool.ev_begin, pool.ev_end));
     if (stats) {
         std::memset(stats, 0, sizeof(*stats));
-        stats->paths = rp.max_depth > 0 ? (pool.h_glob->next_sample < total ? pool.h_glob->next_sample : total)
-                                        : n_samples;
+        if (rp.max_depth <= 0)
+            stats->paths = n_samples;
+        else if (fused)
+            stats->paths = pool.h_glob->paths;
+        else
+            stats->paths = pool.h_glob->next_sample < total ? pool.h_glob->next_sample : total;
         stats->rays_closest = pool.h_glob->rays_closest;
         stats->rays_shadow = pool.h_glob->rays_shadow;
         stats->nodes_visited = pool.h_glob->nodes_visited;
@@ -832,6 +1075,7 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
             stats->extend_ms += e;
         }
         stats->extend_launches = n_ext_events / 2;
+        stats->schedule = fused ? 1 : 0;
     }
     if (cancelled)
         throw std::runtime_error("cancelled");

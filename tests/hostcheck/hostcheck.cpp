@@ -32,6 +32,10 @@ template <class R> GeomView<R> geom_view(HostScene &H) {
     g.prim_orig = H.prim_orig.data();
     g.n_nodes = int(H.nodes.size());
     g.n_prims = int(T.prims.size());
+    g.n_ops = int(T.ops.size());
+    g.n_chains = int(H.chains.size());
+    g.n_top = H.n_top_items;
+    g.flat = H.flat_ok ? 1 : 0;
     return g;
 }
 template <class R> ShadeView<R> shade_view(HostScene &H) {
@@ -51,7 +55,7 @@ template <class R> ShadeView<R> shade_view(HostScene &H) {
 }
 
 template <class R, bool ROBUST>
-void trace_batch(HostScene &H, const rtb_ray *rays, uint64_t n, rtb_hit *hits, uint64_t stats[2]) {
+void trace_batch(HostScene &H, const rtb_ray *rays, uint64_t n, rtb_hit *hits, uint64_t stats[2], bool use_flat) {
     const GeomView<R> g = geom_view<R>(H);
     const GlobalFetch<R> F(g);
     RngT<R> rng;
@@ -64,8 +68,12 @@ void trace_batch(HostScene &H, const rtb_ray *rays, uint64_t n, rtb_hit *hits, u
         if (ROBUST && q.origin_prim >= 0 && q.origin_prim < int(H.orig_to_sorted.size()))
             origin = uint32_t(H.orig_to_sorted[q.origin_prim]);
         R t;
-        const uint32_t pi = traverse<R, false, ROBUST>(g, F, o, d, R(q.time), R(q.t_min), R(q.t_max),
-                                                       origin, draw, t, &stats[0], &stats[1]);
+        const uint32_t pi =
+            use_flat && g.flat
+                ? traverse_flat<R, false, ROBUST>(g, o, d, R(q.time), R(q.t_min), R(q.t_max), origin, draw, t,
+                                                  &stats[0], &stats[1])
+                : traverse<R, false, ROBUST>(g, F, o, d, R(q.time), R(q.t_min), R(q.t_max), origin, draw, t,
+                                             &stats[0], &stats[1]);
         rtb_hit &h = hits[i];
         std::memset(&h, 0, sizeof(h));
         h.prim = -1;
@@ -195,10 +203,12 @@ void hc_trace_batch(void *h, const rtb_ray *rays, uint64_t n, int precision, rtb
                     uint64_t stats[2]) {
     auto *H = static_cast<HostScene *>(h);
     uint64_t local[2] = {0, 0};
-    if (precision == 64)
-        trace_batch<double, false>(*H, rays, n, hits, local);
+    // 64: fp64 through the BVH; 65: fp64 lockstep; 32: fp32 as the renderer traces this scene
+    // (lockstep when it is small); 33: fp32 forced through the BVH
+    if (precision == 64 || precision == 65)
+        trace_batch<double, false>(*H, rays, n, hits, local, precision == 65);
     else
-        trace_batch<float, true>(*H, rays, n, hits, local);
+        trace_batch<float, true>(*H, rays, n, hits, local, precision == 32);
     if (stats) {
         stats[0] = local[0];
         stats[1] = local[1];

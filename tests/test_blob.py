@@ -63,7 +63,7 @@ def test_env_fixture_has_texels(abi, golden):
     T = abi.parse_blob(golden(19).blob)
     l = T["lights"][0]
     assert l["type"] == 4 and (l["env_width"], l["env_height"], l["env_is_probe"]) == (64, 32, 0)
-    assert len(T["env_texels"]) == 64 * 32 * 3 and T["env_texels"].max() > 1000
+    assert len(T["env_texels"]) == 64 * 32 * 3 and T["env_texels"].max() > 50
     T = abi.parse_blob(golden(26).blob)
     assert T["lights"][0]["env_is_probe"] == 1
     T = abi.parse_blob(golden(24).blob)
