@@ -548,19 +548,15 @@ RTB_HD RecT<R> make_record(const GeomView<R> &g, uint32_t pi, V3<R> o, V3<R> d, 
     const PrimT<R> p = g.prims[pi];
     const uint32_t type = p.type_mat & PT_TYPE_MASK;
     const int chain = g.prim_chain[pi];
-    // forward pass: directions after each wrapper (set_face_normal needs them)
-    V3<R> dirs[kMaxChainOps + 1];
+    // forward pass: the ray in the leaf's object space
     int nops = 0, first = 0;
     V3<R> lo = o, ld = d;
-    dirs[0] = d;
     if (chain >= 0) {
         const ChainRec c = g.chains[chain];
         first = c.first;
         nops = c.count < kMaxChainOps ? c.count : kMaxChainOps;
-        for (int i = 0; i < nops; ++i) {
+        for (int i = 0; i < nops; ++i)
             apply_op(g.ops[first + i], lo, ld);
-            dirs[i + 1] = ld;
-        }
     }
     rec.p = lo + t * ld;
     if (type == PT_SPHERE || type == PT_MSPHERE) {
@@ -589,12 +585,26 @@ RTB_HD RecT<R> make_record(const GeomView<R> &g, uint32_t pi, V3<R> o, V3<R> d, 
         outward.set(AX, R(1));
         set_face_normal(rec, ld, outward);
     }
-    // reverse pass
+    // reverse pass.  Each wrapper re-runs set_face_normal against ITS OWN ray (the ray after
+    // its transform, hittable.h:59,153).  Only directions matter, and only rotate_y changes
+    // them, so the direction after wrapper i is recovered by undoing the rotations of the
+    // wrappers below it (chains are 1-3 ops long; nothing is kept in local memory).
+    V3<R> dir_i = ld; // direction after the innermost wrapper
     for (int i = nops - 1; i >= 0; --i) {
         const XfOp<R> op = g.ops[first + i];
+        if (i < nops - 1) {
+            const XfOp<R> below = g.ops[first + i + 1];
+            if (below.kind == 1) { // exact inverse of apply_op's rotation is not needed bit for
+                // bit: recompute from the world direction to stay bit-exact in fp64
+                V3<R> tmp_o(0, 0, 0);
+                dir_i = d;
+                for (int k = 0; k <= i; ++k)
+                    apply_op(g.ops[first + k], tmp_o, dir_i);
+            }
+        }
         if (op.kind == 0) { // hittable.h:58-59
             rec.p = V3<R>(rec.p.x + op.a, rec.p.y + op.b, rec.p.z + op.c);
-            set_face_normal(rec, dirs[i + 1], rec.normal);
+            set_face_normal(rec, dir_i, rec.normal);
         } else if (op.kind == 1) { // hittable.h:142-153 : a = sin, b = cos
             const R px = op.b * rec.p.x + op.a * rec.p.z;
             const R pz = -op.a * rec.p.x + op.b * rec.p.z;
@@ -602,7 +612,7 @@ RTB_HD RecT<R> make_record(const GeomView<R> &g, uint32_t pi, V3<R> o, V3<R> d, 
             const R nz = -op.a * rec.normal.x + op.b * rec.normal.z;
             rec.p.x = px;
             rec.p.z = pz;
-            set_face_normal(rec, dirs[i + 1], V3<R>(nx, rec.normal.y, nz));
+            set_face_normal(rec, dir_i, V3<R>(nx, rec.normal.y, nz));
         } else { // hittable.h:168
             rec.front_face = !rec.front_face;
         }

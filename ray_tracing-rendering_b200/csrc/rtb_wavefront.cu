@@ -173,11 +173,13 @@ __device__ __forceinline__ GeomView<float> stage_scene(const GeomView<float> &g,
     return s;
 }
 
-template <bool ANY, bool COUNT, class Rng>
+// FLAT_ONLY: the caller only ever runs on flat scenes (fused kernel) — the BVH code and its
+// stack are not even compiled in.
+template <bool ANY, bool COUNT, bool FLAT_ONLY = false, class Rng>
 __device__ __forceinline__ uint32_t trace(const GeomView<float> &g, V3<float> o, V3<float> d, float time,
                                           float t_min, float t_max, uint32_t origin, Rng &rng, float &t,
                                           uint64_t &nodes, uint64_t &tests) {
-    if (g.flat)
+    if (FLAT_ONLY || g.flat)
         return traverse_flat<float, ANY, true>(g, o, d, time, t_min, t_max, origin, rng, t,
                                                COUNT ? &nodes : nullptr, COUNT ? &tests : nullptr);
     const GlobalFetch<float> F(g);
@@ -230,8 +232,14 @@ __device__ __forceinline__ PathState load_state(const WfParams &p, uint32_t slot
 // renderer.h:72-75: one camera sample.  Local sample index g -> (pixel, sample-in-pixel)
 // in sample-major order, so concurrently resident paths belong to different pixels.
 __device__ __forceinline__ void new_path(const WfParams &p, unsigned long long g, PathState &s) {
-    const uint32_t k = uint32_t(g / p.npix);
-    const uint32_t pix = uint32_t(g - (unsigned long long)k * p.npix);
+    uint32_t k, pix;
+    if (p.total_samples <= 0xffffffffull) { // 32-bit divide: ~5x cheaper than the 64-bit one
+        k = uint32_t(g) / p.npix;
+        pix = uint32_t(g) - k * p.npix;
+    } else {
+        k = uint32_t(g / p.npix);
+        pix = uint32_t(g - (unsigned long long)k * p.npix);
+    }
     const uint32_t smp = uint32_t(p.sample_offset) + k * uint32_t(p.sample_stride);
     s.rng = pcg_seed((unsigned long long)pix * uint32_t(p.spp) + smp, p.seed);
     RngT<float> r;
@@ -450,14 +458,14 @@ struct PathDraw { // RNG adaptor handed to the traversal for constant_medium tes
 // Visibility of one NEE sample: scene.hit(shadow_ray, 0.001, dist - 0.001)
 // (direct_light_integrator.h:115-130, mis_path_integrator.h:209-230).  Shadow rays carry
 // time 0 regardless of the path's time (direct_light_integrator.h:115).
-template <bool COUNT>
+template <bool COUNT, bool FLAT_ONLY = false>
 __device__ __forceinline__ bool shadow_visible(const GeomView<float> &g, V3<float> o, V3<float> d, float tmax,
                                                uint32_t origin, Pcg &rng, uint64_t &nodes, uint64_t &tests) {
     // t_min is 0.001 along the UNIT direction; the stored direction may be the unnormalised segment
     const float len = isfinite(tmax) ? length(d) : 1.0f;
     PathDraw draw{&rng};
     float t;
-    return trace<true, COUNT>(g, o, d, 0.0f, 0.001f / len, tmax, origin, draw, t, nodes, tests) == kNoPrim;
+    return trace<true, COUNT, FLAT_ONLY>(g, o, d, 0.0f, 0.001f / len, tmax, origin, draw, t, nodes, tests) == kNoPrim;
 }
 
 // ---- (A) wavefront kernels -------------------------------------------------------------------
@@ -668,8 +676,11 @@ __global__ void __launch_bounds__(128) k_connect(WfParams p, int it) {
 
 constexpr uint32_t kSampleChunk = 256; // samples a warp reserves per atomic
 
-template <bool OLD, bool COUNT>
-__global__ void __launch_bounds__(128) k_fused(WfParams p) {
+// SIMPLE: the scene only uses lambertian and diffuse_light materials (the Cornell boxes): the
+// other four shade_surface instantiations are left out, which halves the kernel's code size
+// (the profile of the general kernel showed instruction-cache misses).
+template <bool OLD, bool COUNT, bool SIMPLE>
+__global__ void __launch_bounds__(128, 4) k_fused(WfParams p) {
     __shared__ FlatSmem sm;
     const GeomView<float> g = stage_scene(p.geom, sm);
     PathState s;
@@ -711,8 +722,8 @@ __global__ void __launch_bounds__(128) k_fused(WfParams p) {
         if (alive) {
             PathDraw draw{&s.rng};
             float t;
-            const uint32_t pi = trace<false, COUNT>(g, s.o, s.d, s.time, 0.001f, Consts<float>::inf(), s.origin_prim,
-                                                    draw, t, nodes, tests);
+            const uint32_t pi = trace<false, COUNT, true>(g, s.o, s.d, s.time, 0.001f, Consts<float>::inf(),
+                                                          s.origin_prim, draw, t, nodes, tests);
             ++n_closest;
             if (pi == kNoPrim) {
                 miss_surface(p, s);
@@ -720,18 +731,26 @@ __global__ void __launch_bounds__(128) k_fused(WfParams p) {
             } else {
                 ShadowReq sh;
                 const uint32_t pix = s.pix;
-                switch (p.shade.mats[g.prims[pi].type_mat >> PT_MAT_SHIFT].type) {
-                case 0: shade_surface<0, OLD>(p, g, s, t, pi, alive, sh); break;
-                case 1: shade_surface<1, OLD>(p, g, s, t, pi, alive, sh); break;
-                case 2: shade_surface<2, OLD>(p, g, s, t, pi, alive, sh); break;
-                case 3: shade_surface<3, OLD>(p, g, s, t, pi, alive, sh); break;
-                case 4: shade_surface<4, OLD>(p, g, s, t, pi, alive, sh); break;
-                default: shade_surface<5, OLD>(p, g, s, t, pi, alive, sh); break;
+                const int mtype = p.shade.mats[g.prims[pi].type_mat >> PT_MAT_SHIFT].type;
+                if (SIMPLE) {
+                    if (mtype == 0)
+                        shade_surface<0, OLD>(p, g, s, t, pi, alive, sh);
+                    else
+                        shade_surface<3, OLD>(p, g, s, t, pi, alive, sh);
+                } else {
+                    switch (mtype) {
+                    case 0: shade_surface<0, OLD>(p, g, s, t, pi, alive, sh); break;
+                    case 1: shade_surface<1, OLD>(p, g, s, t, pi, alive, sh); break;
+                    case 2: shade_surface<2, OLD>(p, g, s, t, pi, alive, sh); break;
+                    case 3: shade_surface<3, OLD>(p, g, s, t, pi, alive, sh); break;
+                    case 4: shade_surface<4, OLD>(p, g, s, t, pi, alive, sh); break;
+                    default: shade_surface<5, OLD>(p, g, s, t, pi, alive, sh); break;
+                    }
                 }
                 if (!OLD && sh.want) {
                     ++n_shadow;
                     Pcg rg = s.rng; // a copy: the shadow test must not advance the path's stream
-                    if (shadow_visible<COUNT>(g, sh.o, sh.d, sh.tmax, sh.origin, rg, nodes, tests))
+                    if (shadow_visible<COUNT, true>(g, sh.o, sh.d, sh.tmax, sh.origin, rg, nodes, tests))
                         accum_add(p.accum, pix, sh.c);
                 }
             }
@@ -947,11 +966,18 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
 
     if (fused) {
         // One persistent kernel per window of samples (windows keep rtb_cancel responsive).
-        int bps;
-        if (old_api)
-            bps = count ? blocks_per_sm(k_fused<true, true>, 128) : blocks_per_sm(k_fused<true, false>, 128);
-        else
-            bps = count ? blocks_per_sm(k_fused<false, true>, 128) : blocks_per_sm(k_fused<false, false>, 128);
+        // pick the instantiation once: (legacy vs BSDF API) x (counting) x (simple material set)
+        const bool simple = (W.mat_mask & ~((1u << RTB_MAT_LAMBERTIAN) | (1u << RTB_MAT_DIFFUSE_LIGHT))) == 0;
+        void (*kern)(WfParams) = nullptr;
+        {
+            void (*table[2][2][2])(WfParams) = {
+                {{k_fused<false, false, false>, k_fused<false, false, true>},
+                 {k_fused<false, true, false>, k_fused<false, true, true>}},
+                {{k_fused<true, false, false>, k_fused<true, false, true>},
+                 {k_fused<true, true, false>, k_fused<true, true, true>}}};
+            kern = table[old_api ? 1 : 0][count ? 1 : 0][simple ? 1 : 0];
+        }
+        const int bps = blocks_per_sm(kern, 128);
         const int grid = sms * bps;
         const unsigned long long window = 1ull << 26;
         for (unsigned long long begin = 0; begin < total; begin += window) {
@@ -959,17 +985,7 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
             k_set_next_sample<<<1, 1, 0, st>>>(W.glob, begin);
             if (time_dom)
                 RTB_CUDA(cudaEventRecord(pool.ext_event(n_ext_events++), st));
-            if (old_api) {
-                if (count)
-                    k_fused<true, true><<<grid, 128, 0, st>>>(W);
-                else
-                    k_fused<true, false><<<grid, 128, 0, st>>>(W);
-            } else {
-                if (count)
-                    k_fused<false, true><<<grid, 128, 0, st>>>(W);
-                else
-                    k_fused<false, false><<<grid, 128, 0, st>>>(W);
-            }
+            kern<<<grid, 128, 0, st>>>(W);
             if (time_dom)
                 RTB_CUDA(cudaEventRecord(pool.ext_event(n_ext_events++), st));
             launches += 2;

@@ -60,12 +60,25 @@ def test_million_ray_batches_vs_live_reference(up, golden, abi, sid, integrator)
     assert len(rays) == n_target
     got64 = ctx.trace(rays, 64)
     mask = parity.deterministic_mask(T, hits, got64)
+    # Exact ties: scene 9's box grid has coincident faces (the z1 face of one box on the z0
+    # face of its neighbour).  Two primitives then answer with the SAME t, point, normal and
+    # material, and which id wins depends on traversal order — in the reference on its
+    # random BVH topology.  Such ties are not differences; everything else must be bit-equal.
     bad = np.zeros(len(rays), bool)
-    for f in ("prim", "t", "p", "normal", "front_face", "material"):
+    for f in ("t", "p", "normal", "front_face", "material"):
         d = hits[f] != got64[f]
         bad |= d.any(axis=1) if d.ndim > 1 else d
+    ties = (hits["prim"] != got64["prim"]) & ~bad & mask
     bad &= mask
-    assert not bad.any(), [(rays[i], hits[i], got64[i]) for i in np.where(bad)[0][:3]]
+    if bad.any():  # keep the evidence: the scene instance is random (scenes 1, 9)
+        import os
+        os.makedirs("gpurun_out", exist_ok=True)
+        np.savez_compressed(f"gpurun_out/mismatch_{sid}_{integrator}.npz", blob=np.frombuffer(blob, np.uint8),
+                            rays=rays[bad], ref=hits[bad], got=got64[bad])
+    assert not bad.any(), f"{bad.sum()} of {len(rays)} differ; first: ref {hits[bad][0]} got {got64[bad][0]}"
+    assert ties.sum() <= 1e-5 * len(rays), f"{ties.sum()} exact ties"
+    if sid != 9:
+        assert ties.sum() == 0
     got32 = ctx.trace(parity.to_segment_form(rays), 32)
     mask = parity.deterministic_mask(T, hits, got32)
     agree = (got32["prim"] == hits["prim"])[mask].mean()
@@ -180,3 +193,24 @@ def test_textures(up, golden, sid):
         got = ctx.texture_eval(t, g[f"tex_q_{t}"], 64)
         # checker / noise go through sin(): compare at 1e-5 relative + tiny absolute
         assert parity.values_close(got, g[f"tex_v_{t}"], parity.VALUE_RTOL, 1e-9).all(), (sid, t)
+
+
+@pytest.mark.parametrize("sid", [7, 21, 23, 8, 17])
+def test_fp32_bvh_and_lockstep_traversals_agree(gpu_ctx, up, golden, abi, binding, sid):
+    """Small scenes are traced in lockstep from shared memory (traverse_flat); with the option
+    off the same queries go through the BVH.  Both must give the reference's primitives."""
+    g = golden(sid)
+    T = abi.parse_blob(g.blob)
+    ctx = up(sid)
+    rays = parity.to_segment_form(g["rays"])
+    flat = ctx.trace(rays, 32)
+    ctx.set_option(binding.OPT_FLAT_TRAVERSAL, 0)
+    try:
+        bvh = ctx.trace(rays, 32)
+    finally:
+        ctx.set_option(binding.OPT_FLAT_TRAVERSAL, 1)
+    for got in (flat, bvh):
+        mask = parity.deterministic_mask(T, g["hits"], got)
+        assert ((got["prim"] != g["hits"]["prim"]) & mask).sum() <= 1
+    both = parity.deterministic_mask(T, flat, bvh)
+    assert (flat["prim"] == bvh["prim"])[both].all()
