@@ -197,6 +197,7 @@ int rtb_scene_upload(rtb_context *ctx, const void *blob, uint64_t nbytes) {
         upload_typed(sc->f64, H.f64, s, bytes);
         sc->nodes.upload(H.nodes, s);
         sc->chains.upload(H.chains, s);
+        sc->affine.upload(H.affine, s);
         sc->prim_chain.upload(H.prim_chain, s);
         sc->prim_orig.upload(H.prim_orig, s);
         sc->orig_to_sorted.upload(H.orig_to_sorted, s);

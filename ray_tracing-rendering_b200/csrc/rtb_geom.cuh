@@ -68,6 +68,13 @@ struct ChainRec {
     int32_t first, count;
 };
 
+// A whole wrapper chain folded into one map (fp32 production path only).  translate and
+// rotate_y compose to "rotate about y, then shift":  o' = Ry(c,s) o + b,  d' = Ry(c,s) d.
+// Built on the host in fp64 from the same ops the validation path applies one by one.
+struct ChainAffine {
+    float c, s, bx, by, bz;
+};
+
 // 32-byte BVH node.  Interior: `first` = index of the left child, right child =
 // first + 1 (siblings are adjacent, the pair is 64-byte aligned), count == 0.
 // Leaf: count = kLeafFlag | n, primitives [first, first + n).
@@ -86,6 +93,7 @@ template <class R> struct GeomView {
     const MovingAux<R> *maux;
     const XfOp<R> *ops;
     const ChainRec *chains;
+    const ChainAffine *affine; // per chain (fp32 view only; null in the fp64 view)
     const int32_t *prim_chain; // per sorted prim: chain id or -1
     const int32_t *prim_orig;  // per sorted prim: flat (blob) primitive id, -1 for instances
     int32_t n_nodes;
@@ -131,6 +139,23 @@ template <class R> RTB_HD void apply_chain(const GeomView<R> &g, int chain, V3<R
     const ChainRec c = g.chains[chain];
     for (int i = 0; i < c.count; ++i)
         apply_op(g.ops[c.first + i], o, d);
+}
+
+// Moves the ray into the object space of an instance.  Validation (fp64): op by op, exactly
+// as the reference.  Production (fp32): one fused rotate+shift, no loop, no branches.
+template <class R, bool ROBUST>
+RTB_HD void enter_instance(const GeomView<R> &g, int chain, V3<R> &o, V3<R> &d) {
+    if (ROBUST && sizeof(R) == 4) {
+        const ChainAffine a = g.affine[chain];
+        const R ox = R(a.c) * o.x - R(a.s) * o.z + R(a.bx);
+        const R oz = R(a.s) * o.x + R(a.c) * o.z + R(a.bz);
+        const R dx = R(a.c) * d.x - R(a.s) * d.z;
+        const R dz = R(a.s) * d.x + R(a.c) * d.z;
+        o = V3<R>(ox, o.y + R(a.by), oz);
+        d = V3<R>(dx, d.y, dz);
+    } else {
+        apply_chain(g, chain, o, d);
+    }
 }
 
 // ---- primitive tests (return t or a negative "no hit" marker) --------------------------------
@@ -204,7 +229,18 @@ template <class R> RTB_HD V3<R> moving_center(const PrimT<R> &p, const MovingAux
 template <class R, bool ROBUST>
 RTB_HD bool hit_rect(const PrimT<R> &p, int AX, int A, int B, V3<R> o, V3<R> d, V3<R> idir, R t_min,
                      R t_max, R &t_out) {
-    const R t = ROBUST ? (p.d[4] - o[AX]) * idir[AX] : (p.d[4] - o[AX]) / d[AX];
+    if (ROBUST) {
+        // production: one predicate, no early exits (in the lockstep traversal every lane of
+        // the warp tests the same rect anyway, so branches only add reconvergence overhead)
+        const R t = (p.d[4] - o[AX]) * idir[AX];
+        const R a = o[A] + t * d[A];
+        const R b = o[B] + t * d[B];
+        const bool ok = (t >= t_min) & (t <= t_max) & (a >= p.d[0]) & (a <= p.d[1]) & (b >= p.d[2]) & (b <= p.d[3]);
+        if (ok)
+            t_out = t;
+        return ok;
+    }
+    const R t = (p.d[4] - o[AX]) / d[AX];
     if (t < t_min || t > t_max)
         return false;
     const R a = o[A] + t * d[A];
@@ -387,7 +423,7 @@ RTB_HD uint32_t traverse(const GeomView<R> &g, const Fetch &F, V3<R> o, V3<R> d,
                     // appears in the top level
                     if (sp < kStackDepth)
                         stack[sp++] = kSentinel;
-                    apply_chain(g, int(p.aux2), co, cd);
+                    enter_instance<R, ROBUST>(g, int(p.aux2), co, cd);
                     cid = safe_inv(cd);
                     cur = p.aux;
                     popping = false;
@@ -462,7 +498,7 @@ RTB_HD uint32_t traverse_flat(const GeomView<R> &g, V3<R> o, V3<R> d, R time, R 
             if (n_nodes)
                 ++*n_nodes; // one "node" = one instance entry (ray transform)
             V3<R> lo = o, ld = d;
-            apply_chain(g, int(p.aux2), lo, ld);
+            enter_instance<R, ROBUST>(g, int(p.aux2), lo, ld);
             const V3<R> lid = safe_inv(ld);
             const uint32_t first = uint32_t(p.d[0]), last = first + uint32_t(p.d[1]);
             for (uint32_t j = first; j < last; ++j) {

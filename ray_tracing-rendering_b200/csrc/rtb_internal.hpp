@@ -70,7 +70,7 @@ struct DeviceScene {
     HostScene host; // kept for ids, counts and the host-side maps
     DeviceTyped<float> f32;
     DeviceTyped<double> f64;
-    DeviceBuffer nodes, chains, prim_chain, prim_orig, orig_to_sorted, images, image_bytes, env_texels,
+    DeviceBuffer nodes, chains, affine, prim_chain, prim_orig, orig_to_sorted, images, image_bytes, env_texels,
         env_tables;
     size_t device_bytes = 0;
 
@@ -83,6 +83,7 @@ struct DeviceScene {
         g.maux = T.maux.template as<MovingAux<R>>();
         g.ops = T.ops.template as<XfOp<R>>();
         g.chains = chains.as<ChainRec>();
+        g.affine = sizeof(R) == 4 ? affine.as<ChainAffine>() : nullptr;
         g.prim_chain = prim_chain.as<int32_t>();
         g.prim_orig = prim_orig.as<int32_t>();
         g.n_nodes = int32_t(host.nodes.size());

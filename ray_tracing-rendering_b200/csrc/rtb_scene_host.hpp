@@ -32,6 +32,7 @@ struct HostScene {
     TypedTables<double> f64;
     std::vector<Node32> nodes;
     std::vector<ChainRec> chains;
+    std::vector<ChainAffine> affine;     // per chain, fp32 production path
     std::vector<int32_t> prim_chain;     // per sorted prim
     std::vector<int32_t> prim_orig;      // per sorted prim -> blob prim id (-1: instance)
     std::vector<int32_t> orig_to_sorted; // blob prim id -> sorted index
@@ -273,6 +274,25 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4) {
         if (C[i].count > kMaxChainOps)
             throw std::runtime_error("scene: wrapper chain longer than kMaxChainOps");
         H.chains.push_back(ChainRec{C[i].first, C[i].count});
+        // fold the chain: start from the identity (c=1, s=0, b=0) and push each op through
+        double c = 1, s = 0, b[3] = {0, 0, 0};
+        for (int k = 0; k < C[i].count; ++k) {
+            const rtb_xform_op &op = X[C[i].first + k];
+            if (op.kind == RTB_XF_TRANSLATE) { // o' = o - offset
+                b[0] -= op.a;
+                b[1] -= op.b;
+                b[2] -= op.c;
+            } else if (op.kind == RTB_XF_ROTATE_Y) { // o' = Ry(cos, sin) o  (hittable.h:132-138)
+                const double cs = op.b, sn = op.a;
+                const double nc = cs * c - sn * s, ns = sn * c + cs * s;
+                const double bx = cs * b[0] - sn * b[2], bz = sn * b[0] + cs * b[2];
+                c = nc;
+                s = ns;
+                b[0] = bx;
+                b[2] = bz;
+            }
+        }
+        H.affine.push_back(ChainAffine{float(c), float(s), float(b[0]), float(b[1]), float(b[2])});
     }
     for (uint64_t i = 0; i < S.n_xform_ops(); ++i) {
         XfOp<double> d{X[i].kind, X[i].a, X[i].b, X[i].c};

@@ -143,6 +143,7 @@ struct FlatSmem {
     PrimT<float> prims[kFlatMaxPrims];
     XfOp<float> ops[kFlatMaxOps];
     ChainRec chains[kFlatMaxChains];
+    ChainAffine affine[kFlatMaxChains];
     int32_t prim_chain[kFlatMaxPrims];
 };
 
@@ -162,14 +163,54 @@ __device__ __forceinline__ GeomView<float> stage_scene(const GeomView<float> &g,
         if (i < g.n_ops)
             sm.ops[i] = g.ops[i];
     for (int i = threadIdx.x; i < kFlatMaxChains; i += blockDim.x)
-        if (i < g.n_chains)
+        if (i < g.n_chains) {
             sm.chains[i] = g.chains[i];
+            sm.affine[i] = g.affine[i];
+        }
     __syncthreads();
     GeomView<float> s = g;
     s.prims = sm.prims;
     s.ops = sm.ops;
     s.chains = sm.chains;
+    s.affine = sm.affine;
     s.prim_chain = sm.prim_chain;
+    return s;
+}
+
+// The same for kernels that only run on flat scenes: without the global/shared merge above
+// the compiler can prove the tables are in shared memory and emits LDS instead of generic LD.
+__device__ __forceinline__ GeomView<float> stage_scene_flat(const GeomView<float> &g, FlatSmem &sm) {
+    const int n4 = g.n_prims * int(sizeof(PrimT<float>) / 16);
+    const float4 *src = reinterpret_cast<const float4 *>(g.prims);
+    float4 *dst = reinterpret_cast<float4 *>(sm.prims);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x)
+        dst[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < g.n_prims; i += blockDim.x)
+        sm.prim_chain[i] = g.prim_chain[i];
+    for (int i = threadIdx.x; i < kFlatMaxOps; i += blockDim.x)
+        if (i < g.n_ops)
+            sm.ops[i] = g.ops[i];
+    for (int i = threadIdx.x; i < kFlatMaxChains; i += blockDim.x)
+        if (i < g.n_chains) {
+            sm.chains[i] = g.chains[i];
+            sm.affine[i] = g.affine[i];
+        }
+    __syncthreads();
+    GeomView<float> s;
+    s.nodes = g.nodes;
+    s.prims = sm.prims;
+    s.maux = g.maux;
+    s.ops = sm.ops;
+    s.chains = sm.chains;
+    s.affine = sm.affine;
+    s.prim_chain = sm.prim_chain;
+    s.prim_orig = g.prim_orig;
+    s.n_nodes = g.n_nodes;
+    s.n_prims = g.n_prims;
+    s.n_ops = g.n_ops;
+    s.n_chains = g.n_chains;
+    s.n_top = g.n_top;
+    s.flat = 1;
     return s;
 }
 
@@ -682,7 +723,7 @@ constexpr uint32_t kSampleChunk = 256; // samples a warp reserves per atomic
 template <bool OLD, bool COUNT, bool SIMPLE>
 __global__ void __launch_bounds__(128, 4) k_fused(WfParams p) {
     __shared__ FlatSmem sm;
-    const GeomView<float> g = stage_scene(p.geom, sm);
+    const GeomView<float> g = stage_scene_flat(p.geom, sm);
     PathState s;
     bool alive = false, exhausted = false;
     unsigned long long chunk_next = 0, chunk_end = 0; // warp-uniform: this warp's private sample range

@@ -28,6 +28,7 @@ template <class R> GeomView<R> geom_view(HostScene &H) {
     g.maux = T.maux.data();
     g.ops = T.ops.data();
     g.chains = H.chains.data();
+    g.affine = sizeof(R) == 4 ? H.affine.data() : nullptr;
     g.prim_chain = H.prim_chain.data();
     g.prim_orig = H.prim_orig.data();
     g.n_nodes = int(H.nodes.size());
