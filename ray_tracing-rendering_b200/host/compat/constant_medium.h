@@ -1,0 +1,2 @@
+// constant_medium.h — same name as the reference header; everything lives in rtb_host.hpp
+#include "../rtb_host.hpp"

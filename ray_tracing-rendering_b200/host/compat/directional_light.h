@@ -1,0 +1,2 @@
+// directional_light.h — same name as the reference header; everything lives in rtb_host.hpp
+#include "../rtb_host.hpp"

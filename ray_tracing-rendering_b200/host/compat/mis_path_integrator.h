@@ -1,0 +1,2 @@
+// mis_path_integrator.h — same name as the reference header; everything lives in rtb_host.hpp
+#include "../rtb_host.hpp"

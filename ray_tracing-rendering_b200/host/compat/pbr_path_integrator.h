@@ -1,0 +1,2 @@
+// pbr_path_integrator.h — same name as the reference header; everything lives in rtb_host.hpp
+#include "../rtb_host.hpp"

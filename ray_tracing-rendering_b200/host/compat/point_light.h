@@ -1,0 +1,2 @@
+// point_light.h — same name as the reference header; everything lives in rtb_host.hpp
+#include "../rtb_host.hpp"

@@ -1,0 +1,2 @@
+// rtw_stb_image.h — same name as the reference header; everything lives in rtb_host.hpp
+#include "../rtb_host.hpp"

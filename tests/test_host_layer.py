@@ -1,0 +1,107 @@
+"""The C++ host layer (ray_tracing-rendering_b200/host): the reference's class API as a scene
+description.  CPU tests: its built-in BASELINE scenes — and, in the build container, the
+REFERENCE'S OWN scenes.cpp compiled unchanged against host/compat — flatten to exactly the
+tables obtained by walking the reference's graphs.  GPU test: the reference-shaped calls
+(hit, eval, sample, Light::sample, Renderer::render, save_to_png) answered by the library."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import PKG, ROOT
+from test_scenes import canonical
+
+HOST_SO = os.path.join(ROOT, PKG, "librtb200_host.so")
+HOST_REF_SO = os.path.join(ROOT, PKG, "librtb200_host_ref.so")
+
+
+def _blob(lib, fn, *args):
+    f = getattr(lib, fn)
+    f.restype = C.POINTER(C.c_uint8)
+    n = C.c_uint64()
+    p = f(*args, C.byref(n))
+    if not p:
+        lib.rtbh_last_error.restype = C.c_char_p
+        raise RuntimeError(lib.rtbh_last_error().decode())
+    data = C.string_at(p, n.value)
+    lib.rtbh_free(p)
+    return data
+
+
+@pytest.fixture(scope="module")
+def host():
+    assert os.path.exists(HOST_SO), "run __graft_entry__.build()"
+    return C.CDLL(HOST_SO)
+
+
+@pytest.mark.parametrize("sid", [7, 21, 23])
+def test_builtin_scenes_match_the_reference(host, abi, golden, sid):
+    mine = canonical(abi.parse_blob(_blob(host, "rtbh_builtin_scene_blob", sid)))
+    ref = canonical(abi.parse_blob(golden(sid).blob))
+    assert mine == ref
+
+
+def test_unknown_builtin_scene_reports_an_error(host):
+    with pytest.raises(RuntimeError):
+        _blob(host, "rtbh_builtin_scene_blob", 3)
+
+
+@pytest.mark.parametrize("sid", [7, 21, 23, 15, 17, 18, 24, 8])
+def test_reference_scenes_cpp_compiles_unchanged_and_flattens_identically(abi, golden, sid):
+    """select_scene() of the reference's scenes.cpp, compiled against host/compat without
+    touching it, produces the same flat scene as the reference's own classes do."""
+    if not os.path.exists(HOST_REF_SO):
+        pytest.skip("librtb200_host_ref.so is only built where /root/reference exists")
+    lib = C.CDLL(HOST_REF_SO)
+    mine = canonical(abi.parse_blob(_blob(lib, "rtbh_reference_scene_blob", sid, 1)))
+    ref = canonical(abi.parse_blob(golden(sid).blob))
+    assert mine[1:] == ref[1:]          # lights, SceneConfig, camera
+    assert mine[0] == ref[0]            # every primitive with its material, textures and wrapper chain
+
+
+@pytest.mark.parametrize("sid", [1, 9])
+def test_reference_random_scenes_have_the_same_census(abi, golden, sid):
+    if not os.path.exists(HOST_REF_SO):
+        pytest.skip("librtb200_host_ref.so is only built where /root/reference exists")
+    lib = C.CDLL(HOST_REF_SO)
+    T = abi.parse_blob(_blob(lib, "rtbh_reference_scene_blob", sid, 7))
+    R = abi.parse_blob(golden(sid).blob)
+    if sid == 9:  # deterministic counts; scene 1 rejects a random subset of its spheres
+        assert np.array_equal(np.bincount(T["prims"]["type"], minlength=6), np.bincount(R["prims"]["type"], minlength=6))
+        assert len(T["materials"]) == len(R["materials"]) and len(T["perlins"]) == len(R["perlins"]) == 1
+    else:
+        assert abs(len(T["prims"]) - len(R["prims"])) < 40
+    # seeded builds are reproducible (the reference's are not, rtweekend.h:26-27)
+    assert _blob(lib, "rtbh_reference_scene_blob", sid, 7) == _blob(lib, "rtbh_reference_scene_blob", sid, 7)
+
+
+@pytest.mark.gpu
+def test_reference_shaped_api_on_the_gpu(tmp_path):
+    exe = str(tmp_path / "host_api_test")
+    pkg = os.path.join(ROOT, PKG)
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(pkg, "host"),
+                           os.path.join(ROOT, "tests", "host_api_test.cpp"), "-o", exe, "-L" + pkg, "-lrtb200",
+                           "-Wl,-rpath," + pkg])
+    out = subprocess.check_output([exe], text=True)
+    kv = {ln.split()[0]: ln.split()[1:] for ln in out.splitlines() if ln and not ln.startswith("Rendering")}
+    assert "exception" not in kv, kv
+    hit = [float(x) for x in kv["hit"]]
+    assert hit[0] == 1 and hit[1] == 1355.0 and hit[2] == 555.0 and hit[3] == -1.0 and hit[5] == 1   # back wall
+    light = [float(x) for x in kv["light"]]
+    assert light[0] == 1 and light[1] == 553.0 and light[2] == 15.0
+    assert kv["miss"] == ["0"]
+    lam = [float(x) for x in kv["lambert"]]
+    assert abs(lam[0] - 0.73 / np.pi) < 1e-15 and abs(lam[1] - (0.8 / np.sqrt(0.81)) / np.pi) < 1e-12
+    smp = [float(x) for x in kv["sample"]]
+    assert smp[0] == 1 and abs(smp[1] - 1) < 1e-12 and abs(smp[2]) < 1e-12 and smp[3] == 0
+    assert kv["lamp_sample"] == ["0"]
+    quad = [float(x) for x in kv["quad"]]
+    assert quad[0] == 554.0 and abs(quad[1] - 554.0 ** 2 / (130 * 105)) < 1e-9 and quad[2] == 15 and quad[3] == 0
+    assert abs(float(kv["checker"][0]) - 0.2) < 1e-12      # sin(.5)^3 > 0 -> even colour
+    rend = [float(x) for x in kv["render"][:3]]
+    assert 0.12 < rend[0] < 0.2 and rend[0] > rend[1] > rend[2] and kv["render"][3] == "0"
+    assert kv["png"] == ["1"]
+    sig = open("/tmp/rtb_host_api_test.png", "rb").read(8)
+    assert sig == bytes([137, 80, 78, 71, 13, 10, 26, 10])
