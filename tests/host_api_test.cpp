@@ -8,9 +8,9 @@
 int main() {
     try {
         rtb::SceneSetup c = rtb::builtin_scene(7);
-        // a camera ray through the image centre hits the back wall (z = 555) of the Cornell box
+        // a ray through the upper right of the opening (clear of both boxes) hits the back wall (z = 555) of the Cornell box
         hit_record rec;
-        ray r(point3(278, 278, -800), vec3(0, 0, 1), 0.5);
+        ray r(point3(500, 500, -800), vec3(0, 0, 1), 0.5);
         const bool ok = c.world->hit(r, 0.001, infinity, rec);
         std::printf("hit %d %.17g %.17g %.17g %.17g %d\n", ok, rec.t, rec.p.z(), rec.normal.z(), rec.u, int(rec.front_face));
         // straight up from the floor centre: the light at y = 554

@@ -88,7 +88,7 @@ def test_reference_shaped_api_on_the_gpu(tmp_path):
     kv = {ln.split()[0]: ln.split()[1:] for ln in out.splitlines() if ln and not ln.startswith("Rendering")}
     assert "exception" not in kv, kv
     hit = [float(x) for x in kv["hit"]]
-    assert hit[0] == 1 and hit[1] == 1355.0 and hit[2] == 555.0 and hit[3] == -1.0 and hit[5] == 1   # back wall
+    assert hit[0] == 1 and hit[1] == 1355.0 and hit[2] == 555.0 and hit[3] == -1.0 and hit[5] == 0   # back wall, seen from behind its +z normal
     light = [float(x) for x in kv["light"]]
     assert light[0] == 1 and light[1] == 553.0 and light[2] == 15.0
     assert kv["miss"] == ["0"]
