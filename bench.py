@@ -71,34 +71,53 @@ class ClockSampler(threading.Thread):
 
 
 def cpu_reference(steps, warmup, budget_s):
-    """The unmodified reference (oracle/_ref) on all host threads: (Mpaths/s, cores, sample text, secs)."""
+    """The reference's CPU implementation of the path on all host threads:
+    (Mpaths/s, cores, kind, sample text, secs per step).  kind "reference" = the unmodified
+    reference compiled from /root/reference (oracle/_ref, Renderer::render untouched); where that
+    library did not travel, kind "port" = the CPU restatement oracle/port on the same scene."""
     from oracle import refbind
-    if not refbind.available():
-        raise RuntimeError("oracle/_ref/libref_oracle.so is missing (built by __graft_entry__.build() where "
-                           "/root/reference exists)")
-    t_probe, _, _, _ = refbind.render_timed(SCENE, INTEGRATOR, W, 8, DEPTH)
-    per_step = budget_s / max(steps + warmup, 1)
-    spp = int(max(1, min(SPP, per_step / max(t_probe / 8, 1e-3))))
-    for _ in range(warmup):
-        refbind.render_timed(SCENE, INTEGRATOR, W, spp, DEPTH)
-    secs = 0.0
-    for _ in range(steps):
-        t, _, _, _ = refbind.render_timed(SCENE, INTEGRATOR, W, spp, DEPTH)
-        secs += t
+    if refbind.available():
+        t_probe, _, _, _ = refbind.render_timed(SCENE, INTEGRATOR, W, 8, DEPTH)
+        per_step = budget_s / max(steps + warmup, 1)
+        spp = int(max(1, min(SPP, per_step / max(t_probe / 8, 1e-3))))
+        for _ in range(warmup):
+            refbind.render_timed(SCENE, INTEGRATOR, W, spp, DEPTH)
+        secs = 0.0
+        for _ in range(steps):
+            t, _, _, _ = refbind.render_timed(SCENE, INTEGRATOR, W, spp, DEPTH)
+            secs += t
+        cores, kind = refbind.hardware_threads(), "reference"
+        what = "Renderer::render of the unmodified reference"
+    else:
+        from oracle import portbind
+        if not portbind.available():
+            raise RuntimeError("neither oracle/_ref/libref_oracle.so nor oracle/liboracle_port.so is built")
+        scenes = importlib.import_module(PKG + ".scenes")
+        sc = portbind.PortScene(scenes.select_scene(SCENE))
+        _, _, _, t_probe = sc.render_linear(INTEGRATOR, W, H, 2, DEPTH, want_images=False)
+        per_step = budget_s / max(steps + warmup, 1)
+        spp = int(max(1, min(SPP, per_step / max(t_probe / 2, 1e-3))))
+        for _ in range(warmup):
+            sc.render_linear(INTEGRATOR, W, H, spp, DEPTH, want_images=False)
+        secs = 0.0
+        for i in range(steps):
+            secs += sc.render_linear(INTEGRATOR, W, H, spp, DEPTH, seed=i + 1, want_images=False)[3]
+        cores, kind = portbind.hardware_threads(), "port"
+        what = "CPU restatement oracle/port (brute-force closest hit, no BVH)"
     paths = W * H * spp * steps
-    return paths / secs / 1e6, refbind.hardware_threads(), f"{W}x{H} at {spp} of {SPP} spp per step, {steps} steps " \
-        f"(cost is linear in spp); Renderer::render of the unmodified reference, all hardware threads", secs / steps
+    sample = f"{W}x{H} at {spp} of {SPP} spp per step, {steps} steps (cost is linear in spp); {what}, all hardware threads"
+    return paths / secs / 1e6, cores, kind, sample, secs / steps
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    value, cores, sample, ms = cpu_reference(args.steps, args.warmup, 120.0)
+    value, cores, kind, sample, ms = cpu_reference(args.steps, args.warmup, 120.0)
     out = {"metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
            "config": {"workload": WORKLOAD, "integrator": INTEGRATOR, "width": W, "height": H, "spp": SPP},
-           "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": cores, "kind": "reference", "sample": sample},
+           "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
@@ -204,20 +223,24 @@ def run_native(args, rank, local_rank, world):
             traffic = json.load(f).get("dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"kernel": "k_extend", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    dominant = "k_fused (trace + shade + regenerate, scene in shared memory)" if st_t.get("schedule") == 1 else "k_extend"
+    roofline = {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "bytes_per_ray": b_ray, "nodes_per_ray": n_node, "prims_per_ray": n_prim,
                 "rays_per_launch": rays_per_launch, "us_per_launch": us_per_launch,
                 "extend_share_of_step": st_t["extend_ms"] / st_t["device_ms"],
                 "grays_per_s_in_kernel": st_t["rays_closest"] / (st_t["extend_ms"] * 1e-3) / 1e9,
-                "note": "scene07 is 18 primitives / 22 nodes (cache resident): the kernel is "
-                        "latency/divergence bound, the HBM fraction is reported as the contract asks"}
+                "note": "scene07 is 18 primitives (1 KB): the dominant kernel reads it from shared memory and "
+                        "keeps path state in registers, so it is issue-bound, not HBM-bound; the algorithmic "
+                        "bytes of SURVEY 8(d) (32 B per instance entry + 32 B per primitive test + 48 B per ray) "
+                        "over the kernel time are reported against the HBM peak as the contract asks, and can "
+                        "exceed it because those bytes never leave the SM"}
 
     cpu = None
     if rank == 0 and world == 1:
         try:
-            v, cores, sample, _ = cpu_reference(1, 0, 20.0)
-            cpu = {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": "reference", "sample": sample}
+            v, cores, kind, sample, _ = cpu_reference(1, 0, 20.0)
+            cpu = {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": kind, "sample": sample}
         except Exception as e:  # the baseline is reported, never required for the product arm
             cpu = {"value": None, "unit": "Mpaths/s", "cores": os.cpu_count(), "kind": "reference",
                    "sample": f"unavailable: {e}"}
@@ -231,8 +254,10 @@ def run_native(args, rank, local_rank, world):
                "config": {"workload": WORKLOAD, "integrator": INTEGRATOR, "width": W, "height": H,
                           "spp_per_gpu": SPP, "paths_per_step_per_gpu": W * H * SPP, "parallelism": f"spp-split x{world}",
                           "collective": "one NCCL SUM-reduce of the float4 accumulators per step" if world > 1 else "none",
-                          "l2": "path pool (1 Mi paths x 160 B + queues = 0.2 GB) exceeds the 126 MB L2 and is "
-                                "rewritten every wavefront iteration; no extra flush"},
+                          "schedule": "fused" if st_t.get("schedule") == 1 else "wavefront",
+                          "l2": "no L2 flush needed: the fused schedule keeps the 1 KB scene in shared memory and "
+                                "path state in registers; every step writes all 5.8 MB of accumulators with "
+                                "atomics after a memset (wavefront schedule: the 0.2 GB path pool exceeds L2)"},
                "e2e": {"value": tot_e2e[0] / (ms_e2e * 1e-3) / 1e6, "unit": "Mpaths/s",
                        "h2d_bytes_per_step": len(blob), "d2h_bytes_per_step": W * H * 16,
                        "ms_per_step": ms_e2e / args.steps},
