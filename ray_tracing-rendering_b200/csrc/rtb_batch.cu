@@ -33,7 +33,6 @@ __global__ void __launch_bounds__(128)
 k_trace_batch(GeomView<Real> g, const int32_t *__restrict__ orig_to_sorted, int n_orig,
               const rtb_ray *__restrict__ rays, uint64_t n, rtb_hit *__restrict__ hits,
               unsigned long long *visits) {
-    const GlobalFetch<Real> F(g);
     uint64_t nodes = 0, tests = 0;
     for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n;
          i += uint64_t(gridDim.x) * blockDim.x) {
@@ -52,7 +51,7 @@ k_trace_batch(GeomView<Real> g, const int32_t *__restrict__ orig_to_sorted, int 
             (kRobust && g.flat)
                 ? traverse_flat<Real, false, kRobust>(g, o, d, Real(q.time), Real(q.t_min), Real(q.t_max), origin,
                                                       draw, t, visits ? &nodes : nullptr, visits ? &tests : nullptr)
-                : traverse<Real, false, kRobust>(g, F, o, d, Real(q.time), Real(q.t_min), Real(q.t_max), origin,
+                : traverse<Real, false, kRobust>(g, o, d, Real(q.time), Real(q.t_min), Real(q.t_max), origin,
                                                  draw, t, visits ? &nodes : nullptr, visits ? &tests : nullptr);
         rtb_hit h;
         h.t = 0;

@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <stdexcept>
 #include <vector>
 
 namespace rtb {
@@ -91,6 +92,7 @@ inline BuildResult build_bvh(const std::vector<BuildItem> &items, int max_leaf, 
                              uint32_t node_offset) {
     constexpr int kBins = 16;
     constexpr int kMaxDepth = 40;
+    max_leaf = std::min(std::max(max_leaf, 1), kMaxLeafPrims);
     BuildResult out;
     const uint32_t n = uint32_t(items.size());
     std::vector<uint32_t> idx(n);
@@ -106,16 +108,19 @@ inline BuildResult build_bvh(const std::vector<BuildItem> &items, int max_leaf, 
     auto make_leaf = [&](const Task &t, const Box &b) {
         Node32 &nd = out.nodes[t.node];
         store_bounds(nd, b);
-        nd.first = first_offset + t.begin;
-        nd.count = kLeafFlag | (t.end - t.begin);
+        const uint32_t first = first_offset + t.begin, count = t.end - t.begin;
+        if (count < 1 || count > uint32_t(kMaxLeafPrims) || first > kLeafFirstMask - 2)
+            throw std::runtime_error("bvh: leaf does not fit the node reference encoding");
+        nd.ref = kLeafFlag | ((count - 1) << 27) | first;
+        nd.count = count;
     };
     if (n == 0) { // empty tree: the root is a leaf over nothing
         Box b;
         for (int k = 0; k < 3; ++k)
             b.lo[k] = b.hi[k] = 0;
         store_bounds(out.nodes[0], b);
-        out.nodes[0].first = first_offset;
-        out.nodes[0].count = kLeafFlag;
+        out.nodes[0].ref = kEmptyRef;
+        out.nodes[0].count = 0;
         return out;
     }
     while (!level.empty()) {
@@ -206,7 +211,7 @@ inline BuildResult build_bvh(const std::vector<BuildItem> &items, int max_leaf, 
             out.nodes.resize(child + 2);
             Node32 &nd = out.nodes[t.node];
             store_bounds(nd, b);
-            nd.first = node_offset + child;
+            nd.ref = node_offset + child;
             nd.count = 0;
             next.push_back({child, t.begin, mid, t.depth + 1});
             next.push_back({child + 1, mid, t.end, t.depth + 1});

@@ -75,13 +75,20 @@ struct ChainAffine {
     float c, s, bx, by, bz;
 };
 
-// 32-byte BVH node.  Interior: `first` = index of the left child, right child =
-// first + 1 (siblings are adjacent, the pair is 64-byte aligned), count == 0.
-// Leaf: count = kLeafFlag | n, primitives [first, first + n).
+// 32-byte BVH node: its own bounds plus a self-describing reference `ref`:
+//   interior  ref = index of its first child; the two children are adjacent (a 64-byte
+//                   aligned pair), so one step of the traversal is one 64-byte fetch;
+//   leaf      ref = kLeafFlag | (count-1) << 27 | first   -> primitives [first, first+count).
+// The traversal keeps only refs on its stack and never re-reads a node to learn what it is.
+// `count` repeats the leaf size (0 for interior nodes) for tools that inspect the tree.
 constexpr uint32_t kLeafFlag = 0x80000000u;
+constexpr uint32_t kLeafFirstMask = 0x07ffffffu;
+constexpr int kMaxLeafPrims = 16;
+constexpr uint32_t kEmptyRef = 0xffffffffu;    // a tree without primitives
+constexpr uint32_t kSentinelRef = 0xfffffffeu; // stack marker: "leave the instance"
 struct alignas(32) Node32 {
     float lo[3];
-    uint32_t first;
+    uint32_t ref;
     float hi[3];
     uint32_t count;
 };
@@ -100,6 +107,7 @@ template <class R> struct GeomView {
     int32_t n_prims;
     int32_t n_ops;
     int32_t n_chains;
+    uint32_t root_ref; // ref of the top-level root (its box is never tested)
     int32_t n_top; // prims[0 .. n_top) are the top-level items (primitives and instance records)
     int32_t flat;  // != 0: the scene is small enough for the lockstep traversal (traverse_flat)
 };
@@ -357,76 +365,76 @@ RTB_HD bool slab(const Node32 &n, V3<R> o, V3<R> idir, R t_min, R t_max, R &t_ne
     return tn <= tf;
 }
 
-// Node / primitive fetch policy: global memory through the read-only path, or a
-// shared-memory copy of the first n entries (the whole scene when it is small,
-// the top BVH levels otherwise — nodes are laid out breadth-first).
-template <class R> struct GlobalFetch {
-    const GeomView<R> &g;
-    RTB_HD explicit GlobalFetch(const GeomView<R> &gg) : g(gg) {}
-    RTB_HD Node32 node(uint32_t i) const {
+RTB_HD Node32 load_node(const Node32 *nodes, uint32_t i) {
 #ifdef __CUDA_ARCH__
-        const float4 *q = reinterpret_cast<const float4 *>(g.nodes + i);
-        const float4 a = __ldg(q), b = __ldg(q + 1);
-        Node32 n;
-        n.lo[0] = a.x; n.lo[1] = a.y; n.lo[2] = a.z; n.first = __float_as_uint(a.w);
-        n.hi[0] = b.x; n.hi[1] = b.y; n.hi[2] = b.z; n.count = __float_as_uint(b.w);
-        return n;
+    const float4 *q = reinterpret_cast<const float4 *>(nodes + i);
+    const float4 a = __ldg(q), b = __ldg(q + 1);
+    Node32 n;
+    n.lo[0] = a.x; n.lo[1] = a.y; n.lo[2] = a.z; n.ref = __float_as_uint(a.w);
+    n.hi[0] = b.x; n.hi[1] = b.y; n.hi[2] = b.z; n.count = __float_as_uint(b.w);
+    return n;
 #else
-        return g.nodes[i];
+    return nodes[i];
 #endif
-    }
-    RTB_HD PrimT<R> prim(uint32_t i) const { return g.prims[i]; }
-};
+}
 
-// Closest hit (ANY = false) or first hit (ANY = true) of the world-space ray.
-// Returns the SORTED primitive index or kNoPrim, and t.
+// Closest hit (ANY = false) or first hit (ANY = true) of the world-space ray through the
+// two-level BVH.  Returns the SORTED primitive index or kNoPrim, and t.
 //   origin_prim : sorted index of the primitive the ray leaves (ROBUST only).
-//   rng         : callable returning R uniform in (0,1) — drawn once per medium test,
-//                 as constant_medium::hit does (constant_medium.h:85).
-template <class R, bool ANY, bool ROBUST, class Fetch, class Rng>
-RTB_HD uint32_t traverse(const GeomView<R> &g, const Fetch &F, V3<R> o, V3<R> d, R time, R t_min,
-                         R t_max, uint32_t origin_prim, Rng &rng, R &t_hit, uint64_t *n_nodes,
-                         uint64_t *n_tests) {
-    constexpr uint32_t kSentinel = 0xfffffffeu;
+//   rng         : callable returning R uniform in (0,1) — drawn once per medium test, as
+//                 constant_medium::hit does (constant_medium.h:85).
+// "while-while" form: the inner loop only descends (one 64-byte child-pair fetch and two slab
+// tests per step, nearer child first), leaves are processed between descents, so the lanes of
+// a warp spend most of their time in the same loop.
+template <class R, bool ANY, bool ROBUST, class Rng>
+RTB_HD uint32_t traverse(const GeomView<R> &g, V3<R> o, V3<R> d, R time, R t_min, R t_max, uint32_t origin_prim,
+                         Rng &rng, R &t_hit, uint64_t *n_nodes, uint64_t *n_tests) {
     uint32_t stack[kStackDepth];
     int sp = 0;
     uint32_t best = kNoPrim;
     V3<R> co = o, cd = d, cid = safe_inv(d); // current-level ray
-    uint32_t cur = 0;
+    uint32_t cur = g.root_ref;
     while (true) {
-        const Node32 n = F.node(cur);
-        if (n_nodes)
-            ++*n_nodes;
-        bool popping = true;
-        if (!(n.count & kLeafFlag)) {
-            const Node32 c0 = F.node(n.first), c1 = F.node(n.first + 1);
+        while (!(cur & kLeafFlag)) { // descend
+            const Node32 c0 = load_node(g.nodes, cur), c1 = load_node(g.nodes, cur + 1);
+            if (n_nodes)
+                *n_nodes += 2;
             R e0, e1;
             const bool h0 = slab(c0, co, cid, t_min, t_max, e0);
             const bool h1 = slab(c1, co, cid, t_min, t_max, e1);
-            if (h0 && h1) {
+            if (h0 & h1) {
                 const bool swap = e1 < e0;
                 if (sp < kStackDepth)
-                    stack[sp++] = swap ? n.first : n.first + 1;
-                cur = swap ? n.first + 1 : n.first;
-                popping = false;
-            } else if (h0 || h1) {
-                cur = h0 ? n.first : n.first + 1;
-                popping = false;
+                    stack[sp++] = swap ? c0.ref : c1.ref;
+                cur = swap ? c1.ref : c0.ref;
+            } else if (h0 | h1) {
+                cur = h0 ? c0.ref : c1.ref;
+            } else {
+                if (sp == 0) {
+                    t_hit = t_max;
+                    return best;
+                }
+                cur = stack[--sp];
             }
-        } else {
-            const uint32_t leaf_end = n.first + (n.count & ~kLeafFlag);
-            for (uint32_t i = n.first; i < leaf_end; ++i) {
-                const PrimT<R> p = F.prim(i);
+        }
+        bool entered = false;
+        if (cur == kSentinelRef) { // leaving the instance: back to the world ray
+            co = o;
+            cd = d;
+            cid = safe_inv(d);
+        } else if (cur != kEmptyRef) {
+            const uint32_t first = cur & kLeafFirstMask, last = first + ((cur >> 27) & 15u) + 1u;
+            for (uint32_t i = first; i < last; ++i) {
+                const PrimT<R> p = g.prims[i];
                 const uint32_t type = p.type_mat & PT_TYPE_MASK;
                 if (type == PT_INSTANCE) {
-                    // builder guarantee: an instance is alone in its leaf and only
-                    // appears in the top level
+                    // builder guarantee: an instance is alone in its leaf, top level only
                     if (sp < kStackDepth)
-                        stack[sp++] = kSentinel;
+                        stack[sp++] = kSentinelRef;
                     enter_instance<R, ROBUST>(g, int(p.aux2), co, cd);
                     cid = safe_inv(cd);
-                    cur = p.aux;
-                    popping = false;
+                    cur = p.aux; // the bottom-level tree's root ref
+                    entered = true;
                     break;
                 }
                 if (n_tests)
@@ -436,8 +444,8 @@ RTB_HD uint32_t traverse(const GeomView<R> &g, const Fetch &F, V3<R> o, V3<R> d,
                 if (type == PT_MEDIUM) {
                     h = hit_medium<R, ROBUST>(g, p, co, cd, time, t_min, t_max, rng(), t);
                     if (p.type_mat & PT_DUP_LEAF) {
-                        // second visit of a one-object bvh_node (bvh.h:46-47):
-                        // t_max has already shrunk to the first answer
+                        // second visit of a one-object bvh_node (bvh.h:46-47): t_max has
+                        // already shrunk to the first answer
                         R t2;
                         if (hit_medium<R, ROBUST>(g, p, co, cd, time, t_min, h ? t : t_max, rng(), t2)) {
                             h = true;
@@ -445,8 +453,7 @@ RTB_HD uint32_t traverse(const GeomView<R> &g, const Fetch &F, V3<R> o, V3<R> d,
                         }
                     }
                 } else {
-                    h = hit_simple<R, ROBUST>(g, p, type, co, cd, cid, time, t_min, t_max,
-                                              ROBUST && i == origin_prim, t);
+                    h = hit_simple<R, ROBUST>(g, p, type, co, cd, cid, time, t_min, t_max, ROBUST && i == origin_prim, t);
                 }
                 if (h) {
                     best = i;
@@ -458,19 +465,13 @@ RTB_HD uint32_t traverse(const GeomView<R> &g, const Fetch &F, V3<R> o, V3<R> d,
                 }
             }
         }
-        while (popping) {
-            if (sp == 0) {
-                t_hit = t_max;
-                return best;
-            }
-            cur = stack[--sp];
-            if (cur == kSentinel) { // leaving the instance: back to the world ray
-                co = o;
-                cd = d;
-                cid = safe_inv(d);
-            } else
-                popping = false;
+        if (entered)
+            continue;
+        if (sp == 0) {
+            t_hit = t_max;
+            return best;
         }
+        cur = stack[--sp];
     }
 }
 

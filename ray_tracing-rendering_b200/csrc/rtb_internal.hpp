@@ -90,6 +90,7 @@ struct DeviceScene {
         g.n_prims = int32_t(host.prim_orig.size());
         g.n_ops = int32_t(host.f32.ops.size());
         g.n_chains = int32_t(host.chains.size());
+        g.root_ref = host.root_ref;
         g.n_top = host.n_top_items;
         g.flat = host.flat_ok ? 1 : 0;
         return g;

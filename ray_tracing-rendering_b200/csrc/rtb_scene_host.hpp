@@ -46,6 +46,7 @@ struct HostScene {
     bool has_media = false;
     int n_instances = 0;
     int n_top_items = 0; // primitives + instance records of the top level = prims[0 .. n_top_items)
+    uint32_t root_ref = kEmptyRef; // ref of the top-level root
     bool flat_ok = false; // small enough for the lockstep / shared-memory traversal
 };
 
@@ -373,6 +374,7 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4) {
     for (uint32_t id : tlas.order)
         slots.push_back(id < uint32_t(np) ? Slot{int(id), -1} : Slot{-1, int(id) - np});
     H.nodes = tlas.nodes;
+    H.root_ref = tlas.nodes[0].ref;
     H.n_top_items = int(slots.size());
     std::vector<uint32_t> blas_root(insts.size()), blas_first(insts.size()), blas_count(insts.size());
     {
@@ -382,7 +384,7 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4) {
             BuildResult b = build_bvh(kv.second, max_leaf, uint32_t(slots.size()), node_off);
             blas_first[gi] = uint32_t(slots.size());
             blas_count[gi] = uint32_t(b.order.size());
-            blas_root[gi++] = node_off;
+            blas_root[gi++] = b.nodes[0].ref; // the instance record carries the root REF
             for (uint32_t id : b.order)
                 slots.push_back(Slot{int(id), -1});
             H.nodes.insert(H.nodes.end(), b.nodes.begin(), b.nodes.end());

@@ -209,6 +209,7 @@ __device__ __forceinline__ GeomView<float> stage_scene_flat(const GeomView<float
     s.n_prims = g.n_prims;
     s.n_ops = g.n_ops;
     s.n_chains = g.n_chains;
+    s.root_ref = g.root_ref;
     s.n_top = g.n_top;
     s.flat = 1;
     return s;
@@ -223,8 +224,7 @@ __device__ __forceinline__ uint32_t trace(const GeomView<float> &g, V3<float> o,
     if (FLAT_ONLY || g.flat)
         return traverse_flat<float, ANY, true>(g, o, d, time, t_min, t_max, origin, rng, t,
                                                COUNT ? &nodes : nullptr, COUNT ? &tests : nullptr);
-    const GlobalFetch<float> F(g);
-    return traverse<float, ANY, true>(g, F, o, d, time, t_min, t_max, origin, rng, t, COUNT ? &nodes : nullptr,
+    return traverse<float, ANY, true>(g, o, d, time, t_min, t_max, origin, rng, t, COUNT ? &nodes : nullptr,
                                       COUNT ? &tests : nullptr);
 }
 

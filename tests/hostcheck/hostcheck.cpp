@@ -35,6 +35,7 @@ template <class R> GeomView<R> geom_view(HostScene &H) {
     g.n_prims = int(T.prims.size());
     g.n_ops = int(T.ops.size());
     g.n_chains = int(H.chains.size());
+    g.root_ref = H.root_ref;
     g.n_top = H.n_top_items;
     g.flat = H.flat_ok ? 1 : 0;
     return g;
@@ -58,7 +59,6 @@ template <class R> ShadeView<R> shade_view(HostScene &H) {
 template <class R, bool ROBUST>
 void trace_batch(HostScene &H, const rtb_ray *rays, uint64_t n, rtb_hit *hits, uint64_t stats[2], bool use_flat) {
     const GeomView<R> g = geom_view<R>(H);
-    const GlobalFetch<R> F(g);
     RngT<R> rng;
     rng.g = pcg_seed(1, 2);
     auto draw = [&]() { return rng.next_open(); };
@@ -73,7 +73,7 @@ void trace_batch(HostScene &H, const rtb_ray *rays, uint64_t n, rtb_hit *hits, u
             use_flat && g.flat
                 ? traverse_flat<R, false, ROBUST>(g, o, d, R(q.time), R(q.t_min), R(q.t_max), origin, draw, t,
                                                   &stats[0], &stats[1])
-                : traverse<R, false, ROBUST>(g, F, o, d, R(q.time), R(q.t_min), R(q.t_max), origin, draw, t,
+                : traverse<R, false, ROBUST>(g, o, d, R(q.time), R(q.t_min), R(q.t_max), origin, draw, t,
                                              &stats[0], &stats[1]);
         rtb_hit &h = hits[i];
         std::memset(&h, 0, sizeof(h));
