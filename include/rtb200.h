@@ -100,6 +100,9 @@ typedef struct rtb_render_stats {
     uint64_t extend_launches;
     int32_t schedule;        /* 0 = wavefront (queues in HBM), 1 = fused (small scene, state in registers) */
     int32_t reserved;
+    /* with RTB_RENDER_TIME_EXTEND on the wavefront schedule: CUDA-event time per stage, summed
+     * over the iterations: [0] extend, [1] shade (all material kernels), [2] miss, [3] connect */
+    double stage_ms[4];
 } rtb_render_stats;
 
 typedef struct rtb_scene_stats {

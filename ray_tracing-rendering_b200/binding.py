@@ -42,10 +42,12 @@ class RenderStats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("rays_closest", C.c_uint64), ("rays_shadow", C.c_uint64),
                 ("nodes_visited", C.c_uint64), ("prim_tests", C.c_uint64), ("iterations", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("device_ms", C.c_double), ("extend_ms", C.c_double),
-                ("extend_launches", C.c_uint64), ("schedule", C.c_int32), ("reserved", C.c_int32)]
+                ("extend_launches", C.c_uint64), ("schedule", C.c_int32), ("reserved", C.c_int32), ("stage_ms", C.c_double * 4)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["stage_ms"] = list(self.stage_ms)
+        return d
 
 
 class SceneStats(C.Structure):

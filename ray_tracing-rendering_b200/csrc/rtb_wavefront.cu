@@ -245,18 +245,18 @@ struct ShadowReq { // a next-event-estimation sample waiting for its visibility 
 };
 
 __device__ __forceinline__ void store_ray(const WfParams &p, uint32_t slot, const PathState &s) {
-    p.ray_o[slot] = make_float4(s.o.x, s.o.y, s.o.z, s.time);
-    p.ray_d[slot] = make_float4(s.d.x, s.d.y, s.d.z, __uint_as_float(s.origin_prim));
+    __stcs(p.ray_o + slot, make_float4(s.o.x, s.o.y, s.o.z, s.time));
+    __stcs(p.ray_d + slot, make_float4(s.d.x, s.d.y, s.d.z, __uint_as_float(s.origin_prim)));
 }
 __device__ __forceinline__ void store_rest(const WfParams &p, uint32_t slot, const PathState &s) {
-    p.thr[slot] = make_float4(s.T.x, s.T.y, s.T.z, __uint_as_float(s.pix));
-    p.aux[slot] = make_uint4(uint32_t(s.rng.s), uint32_t(s.rng.s >> 32), s.depth | (s.spec ? 0x10000u : 0u),
-                             __float_as_uint(s.prev_pdf));
+    __stcs(p.thr + slot, make_float4(s.T.x, s.T.y, s.T.z, __uint_as_float(s.pix)));
+    __stcs(p.aux + slot, make_uint4(uint32_t(s.rng.s), uint32_t(s.rng.s >> 32), s.depth | (s.spec ? 0x10000u : 0u),
+                                    __float_as_uint(s.prev_pdf)));
 }
 __device__ __forceinline__ PathState load_state(const WfParams &p, uint32_t slot) {
     PathState s;
-    const float4 a = p.ray_o[slot], b = p.ray_d[slot], c = p.thr[slot];
-    const uint4 x = p.aux[slot];
+    const float4 a = __ldcs(p.ray_o + slot), b = __ldcs(p.ray_d + slot), c = __ldcs(p.thr + slot);
+    const uint4 x = __ldcs(p.aux + slot);
     s.o = V3<float>(a.x, a.y, a.z);
     s.time = a.w;
     s.d = V3<float>(b.x, b.y, b.z);
@@ -510,6 +510,9 @@ __device__ __forceinline__ bool shadow_visible(const GeomView<float> &g, V3<floa
 }
 
 // ---- (A) wavefront kernels -------------------------------------------------------------------
+// Path state and queue entries are touched exactly once per kernel: they are read with
+// ld.global.cs and written with st.global.cs (evict-first), so that the streaming 0.2-0.5 GB
+// of path state does not push the BVH nodes and primitive records out of the 126 MB L2.
 
 // Ends the iteration for one lane: a finished path is replaced by the next camera sample (if
 // any remain); a live path is written back; either way the slot is queued for the next
@@ -529,7 +532,7 @@ __device__ __forceinline__ void finish_lane(const WfParams &p, Counters &next, u
     }
     const uint32_t pos = warp_reserve(&next.n_ext, queued);
     if (queued)
-        q_next[pos] = slot;
+        __stcs(q_next + pos, slot);
 }
 
 __global__ void k_clear(Counters *ctr, Globals *glob) {
@@ -580,8 +583,8 @@ __global__ void __launch_bounds__(128) k_extend(WfParams p, int it) {
         const bool valid = idx < n;
         uint32_t slot = 0, key = kMatTypes + 1; // key: material type, kMatTypes = miss
         if (valid) {
-            slot = q[idx];
-            const float4 a = p.ray_o[slot], b = p.ray_d[slot];
+            slot = __ldcs(q + idx);
+            const float4 a = __ldcs(p.ray_o + slot), b = __ldcs(p.ray_d + slot);
             const V3<float> o(a.x, a.y, a.z), d(b.x, b.y, b.z);
             float t;
             uint32_t pi;
@@ -589,15 +592,15 @@ __global__ void __launch_bounds__(128) k_extend(WfParams p, int it) {
             rg.s = 0;
             uint4 x = make_uint4(0, 0, 0, 0);
             if (p.has_media) { // constant_medium::hit draws from the path's stream
-                x = p.aux[slot];
+                x = __ldcs(p.aux + slot);
                 rg.s = uint64_t(x.x) | (uint64_t(x.y) << 32);
             }
             PathDraw draw{&rg};
             pi = trace<false, COUNT>(g, o, d, a.w, 0.001f, Consts<float>::inf(), __float_as_uint(b.w), draw, t, nodes,
                                      tests);
             if (p.has_media)
-                p.aux[slot] = make_uint4(uint32_t(rg.s), uint32_t(rg.s >> 32), x.z, x.w);
-            p.hit[slot] = make_float4(t, __uint_as_float(pi), 0.f, 0.f);
+                __stcs(p.aux + slot, make_uint4(uint32_t(rg.s), uint32_t(rg.s >> 32), x.z, x.w));
+            __stcs(p.hit + slot, make_float4(t, __uint_as_float(pi), 0.f, 0.f));
             key = kMatTypes;
             if (pi != kNoPrim)
                 key = uint32_t(p.shade.mats[g.prims[pi].type_mat >> PT_MAT_SHIFT].type);
@@ -610,7 +613,7 @@ __global__ void __launch_bounds__(128) k_extend(WfParams p, int it) {
             uint32_t *dst = k < kMatTypes ? p.q_mat + size_t(k) * p.P : p.q_miss;
             const uint32_t pos = warp_reserve(cnt, key == k);
             if (key == k)
-                dst[pos] = slot;
+                __stcs(dst + pos, slot);
         }
     }
     if (COUNT) {
@@ -642,18 +645,18 @@ __global__ void __launch_bounds__(128) k_shade(WfParams p, int it) {
         sh.want = false;
         uint32_t sh_pix = 0;
         if (valid) {
-            slot = q[idx];
+            slot = __ldcs(q + idx);
             s = load_state(p, slot);
-            const float4 h = p.hit[slot];
+            const float4 h = __ldcs(p.hit + slot);
             sh_pix = s.pix;
             shade_surface<M, OLD>(p, g, s, h.x, __float_as_uint(h.y), alive, sh);
         }
         if (!OLD) {
             const uint32_t pos = warp_reserve(&C.n_shadow, sh.want);
             if (sh.want) {
-                p.sh_a[pos] = make_float4(sh.o.x, sh.o.y, sh.o.z, sh.tmax);
-                p.sh_b[pos] = make_float4(sh.d.x, sh.d.y, sh.d.z, __uint_as_float(sh_pix));
-                p.sh_c[pos] = make_float4(sh.c.x, sh.c.y, sh.c.z, __uint_as_float(sh.origin));
+                __stcs(p.sh_a + pos, make_float4(sh.o.x, sh.o.y, sh.o.z, sh.tmax));
+                __stcs(p.sh_b + pos, make_float4(sh.d.x, sh.d.y, sh.d.z, __uint_as_float(sh_pix)));
+                __stcs(p.sh_c + pos, make_float4(sh.c.x, sh.c.y, sh.c.z, __uint_as_float(sh.origin)));
             }
         }
         finish_lane(p, N, q_next, valid, alive, slot, s);
@@ -674,7 +677,7 @@ __global__ void __launch_bounds__(128) k_miss(WfParams p, int it) {
         uint32_t slot = 0;
         PathState s;
         if (valid) {
-            slot = p.q_miss[idx];
+            slot = __ldcs(p.q_miss + idx);
             s = load_state(p, slot);
             miss_surface(p, s);
         }
@@ -699,7 +702,7 @@ __global__ void __launch_bounds__(128) k_connect(WfParams p, int it) {
             break;
         const uint32_t idx = base + lane_id();
         if (idx < n) {
-            const float4 a = p.sh_a[idx], b = p.sh_b[idx], c = p.sh_c[idx];
+            const float4 a = __ldcs(p.sh_a + idx), b = __ldcs(p.sh_b + idx), c = __ldcs(p.sh_c + idx);
             // media on a shadow ray draw from a stream keyed by the queue entry
             Pcg rg = pcg_seed((uint64_t(__float_as_uint(a.x)) << 32) ^ __float_as_uint(b.y), p.seed ^ idx);
             if (shadow_visible<COUNT>(g, V3<float>(a.x, a.y, a.z), V3<float>(b.x, b.y, b.z), a.w, __float_as_uint(c.w),
@@ -949,7 +952,7 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
     pool.ensure_common();
     uint32_t P = 0;
     if (!fused) {
-        P = rp.pool_paths > 0 ? uint32_t(rp.pool_paths) : (1u << 20);
+        P = rp.pool_paths > 0 ? uint32_t(rp.pool_paths) : (1u << 21);
         P = (P + 31u) & ~31u;
         if ((unsigned long long)P > total)
             P = uint32_t((total + 31ull) & ~31ull);
@@ -1054,14 +1057,17 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
         int pending[2] = {-1, -1}; // probe slots in flight
         while (!done) {
             for (int b = 0; b < kBatch; ++b, ++it) {
-                if (time_dom)
-                    RTB_CUDA(cudaEventRecord(pool.ext_event(n_ext_events++), st));
+                // with time_dom: 5 events per iteration bracket extend | shade | miss | connect
+                auto mark = [&]() {
+                    if (time_dom)
+                        RTB_CUDA(cudaEventRecord(pool.ext_event(n_ext_events++), st));
+                };
+                mark();
                 if (count)
                     k_extend<true><<<grid, 128, 0, st>>>(W, it);
                 else
                     k_extend<false><<<grid, 128, 0, st>>>(W, it);
-                if (time_dom)
-                    RTB_CUDA(cudaEventRecord(pool.ext_event(n_ext_events++), st));
+                mark();
                 ++launches;
                 for (int m = 0; m < kMatTypes; ++m)
                     if ((W.mat_mask >> m) & 1u) {
@@ -1071,8 +1077,10 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
                             launch_shade<false>(m, W, it, grid, st);
                         ++launches;
                     }
+                mark();
                 k_miss<<<grid, 128, 0, st>>>(W, it);
                 ++launches;
+                mark();
                 if (nee) {
                     if (count)
                         k_connect<true><<<grid, 128, 0, st>>>(W, it);
@@ -1080,6 +1088,7 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
                         k_connect<false><<<grid, 128, 0, st>>>(W, it);
                     ++launches;
                 }
+                mark();
             }
             RTB_CUDA(cudaGetLastError());
             // length of the NEXT extend queue, read back without stalling the pipeline: the
@@ -1126,12 +1135,23 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
         stats->iterations = uint64_t(it);
         stats->kernel_launches = launches;
         stats->device_ms = ms;
-        for (size_t i = 0; i + 1 < n_ext_events; i += 2) {
-            float e = 0.f;
-            RTB_CUDA(cudaEventElapsedTime(&e, pool.ev_ext[i], pool.ev_ext[i + 1]));
-            stats->extend_ms += e;
+        if (fused) {
+            for (size_t i = 0; i + 1 < n_ext_events; i += 2) {
+                float e = 0.f;
+                RTB_CUDA(cudaEventElapsedTime(&e, pool.ev_ext[i], pool.ev_ext[i + 1]));
+                stats->extend_ms += e;
+            }
+            stats->extend_launches = n_ext_events / 2;
+        } else {
+            for (size_t i = 0; i + 4 < n_ext_events; i += 5)
+                for (int k = 0; k < 4; ++k) {
+                    float e = 0.f;
+                    RTB_CUDA(cudaEventElapsedTime(&e, pool.ev_ext[i + k], pool.ev_ext[i + k + 1]));
+                    stats->stage_ms[k] += e;
+                }
+            stats->extend_ms = stats->stage_ms[0];
+            stats->extend_launches = n_ext_events / 5;
         }
-        stats->extend_launches = n_ext_events / 2;
         stats->schedule = fused ? 1 : 0;
     }
     if (cancelled)
