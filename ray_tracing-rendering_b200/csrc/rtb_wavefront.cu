@@ -5,23 +5,34 @@
 // shadow test):
 //
 // (A) WAVEFRONT — the general schedule (any scene size).
-//   path state in HBM, SoA of 16-byte vectors (one 128-bit access each), P resident paths:
-//     ray_o[P]  float4  origin.xyz, time
-//     ray_d[P]  float4  direction.xyz (NOT normalised, as in the reference), origin primitive
-//     thr[P]    float4  throughput.rgb, pixel index
-//     aux[P]    uint4   rng state (2 x u32), depth | specular_bounce << 16, prev_bsdf_pdf
-//     hit[P]    float4  t, primitive index                       (extend -> shade)
-//   queues of 32-bit path indices, filled with warp-aggregated atomics:
-//     q_ext[2][P]  paths that need a closest-hit ray (double buffered)
-//     q_mat[6][P]  paths whose hit landed on material type m  (material-sorted shading)
-//     q_miss[P]    paths whose ray left the scene
-//   shadow-ray queue, 3 float4 per entry (written by shade, read by connect).
+//   The path state TRAVELS with the queue entry: every queue is a structure of arrays of
+//   16-byte vectors, read and written by consecutive lanes (one fully coalesced 512-byte
+//   access per warp and array).  [Round-1 measurement behind this: queues of 32-bit indices
+//   into a slot pool made every stage gather 4-5 random 16-byte vectors per path from a
+//   0.3 GB pool, which B200 serves at 25-30 G sectors/s (tools/microbench: gather16 481 GB/s
+//   against 6700 GB/s streaming), i.e. <= 6 G paths/s per stage.]
+//     a  float4  origin.xyz, time
+//     b  float4  direction.xyz (NOT normalised, as in the reference), origin primitive
+//     c  float4  throughput.rgb, pixel index (0xffffffff = empty entry)
+//     d  uint4   rng state (2 x u32), depth | specular_bounce << 16, prev_bsdf_pdf
+//     e  float2  t, primitive index                        (hit queues only)
+//   Queues: q_ext[2] (double buffered: paths that need a closest-hit ray), q_hit[7] (hits
+//   sorted by material type, [6] = rays that left the scene), the shadow-ray queue.
 //   One iteration = k_extend -> k_shade<M> (x present material types) -> k_miss -> k_connect.
-//   Persistent-thread kernels: the grid is a fixed multiple of the SM count and warps pull
-//   32-entry chunks off a queue through one atomic per warp.  A path that ends is replaced
-//   in place by the next camera sample, so the extend queue stays full until the job runs
-//   out of samples.  Queue counters rotate over three sets (iteration i uses set i%3 and
-//   clears set (i+2)%3): no reset kernel, no host round trip per iteration.
+//     k_extend  persistent warps pull 32-entry chunks (next chunk's atomic issued before the
+//               current trace); an EMPTY entry is refilled with the next camera sample from
+//               the warp's private sample range (one global atomic per 128 samples); the hit
+//               is pushed to its material queue with ONE multi-lane atomic per chunk: the
+//               leaders of the __match_any groups add to the 7 counters of one 128-byte line
+//               in a single instruction, which L2 serves as one transaction.
+//     k_shade / k_miss  no atomics on the path: chunk c of material queue M maps to the fixed
+//               position base_M + c*32 + lane of the next extend queue (base_M = entries of
+//               the queues before M), where the lane writes its continued path or an empty
+//               entry.  Only next-event-estimation requests are pushed (one atomic per chunk).
+//   [Measured: same-line atomics serialise at 1.49 G/s on B200, so the former 6 atomics per
+//   32 rays (queue head + 5 material counters in one line) alone cost 260 us per 2 Mi-ray
+//   extend launch.]  Counters rotate over three sets (iteration i uses set i%3 and clears
+//   set (i+2)%3): no reset kernel, no host round trip per iteration.
 //
 // (B) FUSED — scenes whose geometry fits in shared memory (<= 64 primitive records: the
 //   Cornell-box class of BASELINE configs C1/C3/C4).  There the wavefront's costs are all
@@ -45,18 +56,22 @@ namespace {
 constexpr int kMatTypes = RTB_MAT_TYPE_COUNT; // 6
 constexpr uint32_t kFullMask = 0xffffffffu;
 
-struct alignas(16) Counters {
-    uint32_t n_ext; // entries in this iteration's extend queue
-    uint32_t n_mat[kMatTypes];
-    uint32_t n_miss;
-    uint32_t n_shadow;
-    uint32_t head_ext; // work-distribution cursors
-    uint32_t head_mat[kMatTypes];
-    uint32_t head_miss;
-    uint32_t head_shadow;
-    uint32_t pad[5];
+constexpr int kKeys = kMatTypes + 1;          // hit queues: one per material type + [kMatTypes] = miss
+constexpr uint32_t kInvalidPix = 0xffffffffu; // c.w of an empty queue entry
+constexpr uint32_t kWfChunk = 128;            // samples a warp of k_extend reserves per global atomic
+
+// Every contended counter sits on its own 128-byte line (atomics to one line serialise in L2).
+struct alignas(128) CounterLine {
+    uint32_t v[32];
 };
-static_assert(sizeof(Counters) % 16 == 0, "Counters must be clearable with uint4 stores");
+struct Counters {
+    CounterLine key;         // v[k]: entries of hit queue k (7 counters, ONE line: pushed with one multi-lane atomic)
+    CounterLine head_ext;    // work-distribution cursor of k_extend
+    CounterLine n_shadow;    // entries of the shadow queue
+    CounterLine head_shadow; // work-distribution cursor of k_connect
+    CounterLine n_ext;       // entries of this iteration's extend queue (plain store by k_miss of the previous one)
+};
+static_assert(sizeof(Counters) == 5 * 128, "Counters layout");
 
 struct Globals {
     unsigned long long next_sample; // next local sample index to hand out
@@ -71,12 +86,15 @@ struct WfParams {
     GeomView<float> geom;
     ShadeView<float> shade;
     CameraT<float> cam;
-    float4 *ray_o, *ray_d, *thr, *hit;
-    uint4 *aux;
-    uint32_t *q_ext[2];
-    uint32_t *q_mat;            // kMatTypes * P
-    uint32_t *q_miss;           // P
-    float4 *sh_a, *sh_b, *sh_c; // shadow queue
+    // wavefront queues (SoA, see the file header)
+    float4 *ext_a[2], *ext_b[2], *ext_c[2];
+    uint4 *ext_d[2];
+    float4 *hit_a, *hit_b, *hit_c; // kKeys queues of `cap` entries each, queue k at offset k * cap
+    uint4 *hit_d;
+    float2 *hit_e;
+    float4 *sh_a, *sh_b, *sh_c;    // shadow queue
+    unsigned long long *cursor;    // per warp of k_extend: private sample range [next, end)
+    uint32_t cap;                  // entries per queue (P + slack for the final drain of the private ranges)
     Counters *ctr;              // 3 sets
     Globals *glob;
     float4 *accum;
@@ -244,19 +262,19 @@ struct ShadowReq { // a next-event-estimation sample waiting for its visibility 
     uint32_t origin;
 };
 
-__device__ __forceinline__ void store_ray(const WfParams &p, uint32_t slot, const PathState &s) {
-    __stcs(p.ray_o + slot, make_float4(s.o.x, s.o.y, s.o.z, s.time));
-    __stcs(p.ray_d + slot, make_float4(s.d.x, s.d.y, s.d.z, __uint_as_float(s.origin_prim)));
+__device__ __forceinline__ float4 pack_a(const PathState &s) { return make_float4(s.o.x, s.o.y, s.o.z, s.time); }
+__device__ __forceinline__ float4 pack_b(const PathState &s) {
+    return make_float4(s.d.x, s.d.y, s.d.z, __uint_as_float(s.origin_prim));
 }
-__device__ __forceinline__ void store_rest(const WfParams &p, uint32_t slot, const PathState &s) {
-    __stcs(p.thr + slot, make_float4(s.T.x, s.T.y, s.T.z, __uint_as_float(s.pix)));
-    __stcs(p.aux + slot, make_uint4(uint32_t(s.rng.s), uint32_t(s.rng.s >> 32), s.depth | (s.spec ? 0x10000u : 0u),
-                                    __float_as_uint(s.prev_pdf)));
+__device__ __forceinline__ float4 pack_c(const PathState &s) {
+    return make_float4(s.T.x, s.T.y, s.T.z, __uint_as_float(s.pix));
 }
-__device__ __forceinline__ PathState load_state(const WfParams &p, uint32_t slot) {
+__device__ __forceinline__ uint4 pack_d(const PathState &s) {
+    return make_uint4(uint32_t(s.rng.s), uint32_t(s.rng.s >> 32), s.depth | (s.spec ? 0x10000u : 0u),
+                      __float_as_uint(s.prev_pdf));
+}
+__device__ __forceinline__ PathState unpack(float4 a, float4 b, float4 c, uint4 x) {
     PathState s;
-    const float4 a = __ldcs(p.ray_o + slot), b = __ldcs(p.ray_d + slot), c = __ldcs(p.thr + slot);
-    const uint4 x = __ldcs(p.aux + slot);
     s.o = V3<float>(a.x, a.y, a.z);
     s.time = a.w;
     s.d = V3<float>(b.x, b.y, b.z);
@@ -270,10 +288,10 @@ __device__ __forceinline__ PathState load_state(const WfParams &p, uint32_t slot
     return s;
 }
 
-// renderer.h:72-75: one camera sample.  Local sample index g -> (pixel, sample-in-pixel)
-// in sample-major order, so concurrently resident paths belong to different pixels.
-__device__ __forceinline__ void new_path(const WfParams &p, unsigned long long g, PathState &s) {
-    uint32_t k, pix;
+// Local sample index g -> (pixel, sample-in-pixel) in sample-major order, so concurrently
+// resident paths belong to different pixels and consecutive indices are neighbouring pixels.
+__device__ __forceinline__ void decode_sample(const WfParams &p, unsigned long long g, uint32_t &pix, uint32_t &smp) {
+    uint32_t k;
     if (p.total_samples <= 0xffffffffull) { // 32-bit divide: ~5x cheaper than the 64-bit one
         k = uint32_t(g) / p.npix;
         pix = uint32_t(g) - k * p.npix;
@@ -281,8 +299,15 @@ __device__ __forceinline__ void new_path(const WfParams &p, unsigned long long g
         k = uint32_t(g / p.npix);
         pix = uint32_t(g - (unsigned long long)k * p.npix);
     }
-    const uint32_t smp = uint32_t(p.sample_offset) + k * uint32_t(p.sample_stride);
-    s.rng = pcg_seed((unsigned long long)pix * uint32_t(p.spp) + smp, p.seed);
+    smp = uint32_t(p.sample_offset) + k * uint32_t(p.sample_stride);
+}
+__device__ __forceinline__ Pcg sample_stream(const WfParams &p, uint32_t pix, uint32_t smp) {
+    return pcg_seed((unsigned long long)pix * uint32_t(p.spp) + smp, p.seed);
+}
+
+// renderer.h:72-75: one camera sample.
+__device__ __forceinline__ void new_path(const WfParams &p, uint32_t pix, uint32_t smp, PathState &s) {
+    s.rng = sample_stream(p, pix, smp);
     RngT<float> r;
     r.g = s.rng;
     const uint32_t i = pix % uint32_t(p.width), j = pix / uint32_t(p.width);
@@ -296,6 +321,21 @@ __device__ __forceinline__ void new_path(const WfParams &p, unsigned long long g
     s.spec = false;
     s.prev_pdf = 0.f;
     s.origin_prim = kNoPrim;
+}
+__device__ __forceinline__ void new_path(const WfParams &p, unsigned long long g, PathState &s) {
+    uint32_t pix, smp;
+    decode_sample(p, g, pix, smp);
+    new_path(p, pix, smp, s);
+}
+// The generator state new_path() leaves behind, recomputed from the sample's identity: the
+// camera consumes a fixed number of draws (2 jitter + 2 lens if the aperture is open + 1 time),
+// so k_extend does not have to keep the state in registers across the traversal.
+__device__ __forceinline__ Pcg rng_after_camera(const WfParams &p, uint32_t pix, uint32_t smp) {
+    Pcg r = sample_stream(p, pix, smp);
+    const int draws = p.cam.lens_radius != 0.f ? 5 : 3;
+    for (int i = 0; i < draws; ++i)
+        r.s = r.s * 6364136223846793005ULL + 1442695040888963407ULL;
+    return r;
 }
 
 // ---- integrator stage functions (shared by both schedules) ----------------------------------
@@ -510,178 +550,272 @@ __device__ __forceinline__ bool shadow_visible(const GeomView<float> &g, V3<floa
 }
 
 // ---- (A) wavefront kernels -------------------------------------------------------------------
-// Path state and queue entries are touched exactly once per kernel: they are read with
-// ld.global.cs and written with st.global.cs (evict-first), so that the streaming 0.2-0.5 GB
-// of path state does not push the BVH nodes and primitive records out of the 126 MB L2.
-
-// Ends the iteration for one lane: a finished path is replaced by the next camera sample (if
-// any remain); a live path is written back; either way the slot is queued for the next
-// extend.  Called by all 32 lanes.
-__device__ __forceinline__ void finish_lane(const WfParams &p, Counters &next, uint32_t *q_next, bool valid,
-                                            bool alive, uint32_t slot, PathState &s) {
-    const bool want_new = valid && !alive;
-    const unsigned long long g = warp_reserve64(&p.glob->next_sample, want_new);
-    bool queued = valid && alive;
-    if (want_new && g < p.total_samples) {
-        new_path(p, g, s);
-        queued = true;
-    }
-    if (queued) {
-        store_ray(p, slot, s);
-        store_rest(p, slot, s);
-    }
-    const uint32_t pos = warp_reserve(&next.n_ext, queued);
-    if (queued)
-        __stcs(q_next + pos, slot);
-}
+// Queue entries are touched exactly once per kernel: they are read with ld.global.cs and
+// written with st.global.cs (evict-first), so that the streaming path state does not push
+// the BVH nodes and primitive records out of the 126 MB L2.
 
 __global__ void k_clear(Counters *ctr, Globals *glob) {
-    if (blockIdx.x == 0 && threadIdx.x < 3 * sizeof(Counters) / 4)
-        reinterpret_cast<uint32_t *>(ctr)[threadIdx.x] = 0;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (uint32_t i = threadIdx.x; i < 3 * sizeof(Counters) / 4; i += blockDim.x)
+        reinterpret_cast<uint32_t *>(ctr)[i] = 0;
+    if (threadIdx.x == 0) {
         glob->next_sample = 0;
         glob->rays_closest = glob->rays_shadow = glob->nodes_visited = glob->prim_tests = glob->paths = 0;
     }
 }
 
-// Initial fill: slot i starts local sample i.
-__global__ void __launch_bounds__(256) k_generate(WfParams p) {
-    const unsigned long long n = p.total_samples < p.P ? p.total_samples : (unsigned long long)p.P;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        PathState s;
-        new_path(p, i, s);
-        store_ray(p, i, s);
-        store_rest(p, i, s);
-        p.q_ext[0][i] = i;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        p.ctr[0].n_ext = uint32_t(n);
-        p.glob->next_sample = n;
-    }
+// Initial state: n0 empty entries in extend queue 0 (k_extend fills them with camera samples),
+// every warp's private sample range empty.
+__global__ void __launch_bounds__(256) k_init(WfParams p, uint32_t n0, uint32_t n_cursor) {
+    const uint32_t stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (uint32_t i = t0; i < n0; i += stride)
+        p.ext_c[0][i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(kInvalidPix));
+    for (uint32_t i = t0; i < 2 * n_cursor; i += stride)
+        p.cursor[i] = 0ull;
+    if (t0 == 0)
+        p.ctr[0].n_ext.v[0] = n0;
 }
 
-// extend: closest hit for every queued path; classifies the result into the material queues.
-// Replaces scene.hit(current_ray, 0.001, infinity, rec) (e.g. rr_path_integrator.h:29) and
-// everything under bvh_node::hit.
-template <bool COUNT>
-__global__ void __launch_bounds__(128) k_extend(WfParams p, int it) {
+// extend: closest hit for every queued path; an empty entry is first refilled with the next
+// camera sample; the result moves, with the path state, into the queue of the material it hit
+// (or the miss queue).  Replaces scene.hit(current_ray, 0.001, infinity, rec) (e.g.
+// rr_path_integrator.h:29), everything under bvh_node::hit and the pixel loop of
+// renderer.h:66-80.
+template <bool COUNT, bool MEDIA>
+__global__ void __launch_bounds__(128, 6) k_extend(WfParams p, int it) {
     __shared__ FlatSmem sm;
     const GeomView<float> g = stage_scene(p.geom, sm);
     Counters &C = p.ctr[it % 3];
-    if (blockIdx.x == 0 && threadIdx.x < sizeof(Counters) / 4)
-        reinterpret_cast<uint32_t *>(&p.ctr[(it + 2) % 3])[threadIdx.x] = 0;
-    const uint32_t n = C.n_ext;
-    if (blockIdx.x == 0 && threadIdx.x == 0)
-        atomicAdd(&p.glob->rays_closest, (unsigned long long)n);
-    const uint32_t *q = p.q_ext[it & 1];
+    if (blockIdx.x == 0)
+        for (uint32_t i = threadIdx.x; i < sizeof(Counters) / 4; i += blockDim.x)
+            reinterpret_cast<uint32_t *>(&p.ctr[(it + 2) % 3])[i] = 0;
+    const uint32_t n = C.n_ext.v[0];
+    const int buf = it & 1;
+    const float4 *__restrict__ in_a = p.ext_a[buf], *__restrict__ in_b = p.ext_b[buf], *__restrict__ in_c = p.ext_c[buf];
+    const uint4 *__restrict__ in_d = p.ext_d[buf];
+    const uint32_t lane = lane_id();
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    unsigned long long chunk_next = p.cursor[2 * wid], chunk_end = p.cursor[2 * wid + 1]; // warp-uniform
+    bool global_done = false;                                                            // warp-uniform
     uint64_t nodes = 0, tests = 0;
+    uint32_t n_new = 0;
+    uint32_t base = warp_fetch(&C.head_ext.v[0]);
     while (true) {
-        const uint32_t base = warp_fetch(&C.head_ext);
-        if (base >= n)
-            break;
-        const uint32_t idx = base + lane_id();
-        const bool valid = idx < n;
-        uint32_t slot = 0, key = kMatTypes + 1; // key: material type, kMatTypes = miss
-        if (valid) {
-            slot = __ldcs(q + idx);
-            const float4 a = __ldcs(p.ray_o + slot), b = __ldcs(p.ray_d + slot);
-            const V3<float> o(a.x, a.y, a.z), d(b.x, b.y, b.z);
-            float t;
-            uint32_t pi;
-            Pcg rg;
-            rg.s = 0;
-            uint4 x = make_uint4(0, 0, 0, 0);
-            if (p.has_media) { // constant_medium::hit draws from the path's stream
-                x = __ldcs(p.aux + slot);
-                rg.s = uint64_t(x.x) | (uint64_t(x.y) << 32);
+        const bool drain = base >= n;
+        if (drain) {
+            // The queue is done.  Once the global sample counter is exhausted the rest of this
+            // warp's private range would never be asked for: start those paths now.
+            const unsigned long long end = chunk_end < p.total_samples ? chunk_end : p.total_samples;
+            if (chunk_next >= end)
+                break;
+            unsigned long long handed = 0;
+            if (lane == 0)
+                handed = *reinterpret_cast<volatile unsigned long long *>(&p.glob->next_sample);
+            handed = __shfl_sync(kFullMask, handed, 0);
+            if (handed < p.total_samples)
+                break;
+        }
+        uint32_t next_base = 0xffffffffu;
+        if (!drain && lane == 0) // the next chunk's atomic travels while this chunk is traced
+            next_base = atomicAdd(&C.head_ext.v[0], 32u);
+        const uint32_t idx = base + lane;
+        const bool have = !drain && idx < n;
+        uint32_t pix = kInvalidPix, smp = 0xffffffffu; // smp != ~0: this lane started a new path
+        if (have)
+            pix = __float_as_uint(__ldcs(in_c + idx).w);
+        // ---- refill: every empty lane takes the next sample of the warp's private range
+        const bool need = drain || (have && pix == kInvalidPix);
+        const uint32_t m = __ballot_sync(kFullMask, need);
+        bool fresh = false;
+        PathState s;
+        if (m) {
+            const uint32_t cnt = __popc(m), rank = __popc(m & ((1u << lane) - 1u));
+            unsigned long long avail = chunk_end - chunk_next;
+            unsigned long long id;
+            if (avail >= cnt || drain || global_done) {
+                id = rank < avail ? chunk_next + rank : ~0ull;
+                chunk_next += cnt < avail ? cnt : avail;
+            } else {
+                unsigned long long nb = 0;
+                if (lane == 0)
+                    nb = atomicAdd(&p.glob->next_sample, (unsigned long long)kWfChunk);
+                nb = __shfl_sync(kFullMask, nb, 0);
+                id = rank < avail ? chunk_next + rank : nb + (rank - avail);
+                chunk_next = nb + (cnt - avail);
+                chunk_end = nb + kWfChunk;
+                if (nb >= p.total_samples) {
+                    global_done = true;
+                    chunk_next = chunk_end = p.total_samples;
+                }
+            }
+            if (need && id < p.total_samples) {
+                decode_sample(p, id, pix, smp);
+                new_path(p, pix, smp, s);
+                fresh = true;
+            }
+        }
+        const bool active = fresh || (have && pix != kInvalidPix);
+        uint32_t key = kKeys; // kKeys = nothing to push
+        float4 a = make_float4(0, 0, 0, 0), b = a;
+        float2 e = make_float2(0.f, 0.f);
+        Pcg rg;
+        rg.s = 0;
+        if (active) {
+            if (fresh) {
+                a = pack_a(s);
+                b = pack_b(s);
+                if (MEDIA)
+                    rg = s.rng;
+            } else {
+                a = __ldcs(in_a + idx);
+                b = __ldcs(in_b + idx);
+                if (MEDIA) { // constant_medium::hit draws from the path's stream
+                    const uint4 x = __ldcs(in_d + idx);
+                    rg.s = uint64_t(x.x) | (uint64_t(x.y) << 32);
+                }
             }
             PathDraw draw{&rg};
-            pi = trace<false, COUNT>(g, o, d, a.w, 0.001f, Consts<float>::inf(), __float_as_uint(b.w), draw, t, nodes,
-                                     tests);
-            if (p.has_media)
-                __stcs(p.aux + slot, make_uint4(uint32_t(rg.s), uint32_t(rg.s >> 32), x.z, x.w));
-            __stcs(p.hit + slot, make_float4(t, __uint_as_float(pi), 0.f, 0.f));
+            float t;
+            const uint32_t pi = trace<false, COUNT>(g, V3<float>(a.x, a.y, a.z), V3<float>(b.x, b.y, b.z), a.w, 0.001f,
+                                                    Consts<float>::inf(), __float_as_uint(b.w), draw, t, nodes, tests);
+            e = make_float2(t, __uint_as_float(pi));
             key = kMatTypes;
             if (pi != kNoPrim)
                 key = uint32_t(p.shade.mats[g.prims[pi].type_mat >> PT_MAT_SHIFT].type);
         }
-#pragma unroll
-        for (uint32_t k = 0; k <= kMatTypes; ++k) {
-            if (k < kMatTypes && !((p.mat_mask >> k) & 1u))
-                continue;
-            uint32_t *cnt = k < kMatTypes ? &C.n_mat[k] : &C.n_miss;
-            uint32_t *dst = k < kMatTypes ? p.q_mat + size_t(k) * p.P : p.q_miss;
-            const uint32_t pos = warp_reserve(cnt, key == k);
-            if (key == k)
-                __stcs(dst + pos, slot);
+        // ---- push: the leaders of the equal-key groups reserve in ONE atomic instruction (the
+        // counters share a 128-byte line, so L2 sees a single transaction)
+        const uint32_t peers = __match_any_sync(kFullMask, key);
+        const int leader = __ffs(peers) - 1;
+        uint32_t pos = 0;
+        if (int(lane) == leader && key < uint32_t(kKeys))
+            pos = atomicAdd(&C.key.v[key], uint32_t(__popc(peers)));
+        pos = __shfl_sync(kFullMask, pos, leader) + __popc(peers & ((1u << lane) - 1u));
+        if (active) {
+            float4 c;
+            uint4 d;
+            if (fresh) {
+                c = make_float4(1.f, 1.f, 1.f, __uint_as_float(pix));
+                const Pcg r = MEDIA ? rg : rng_after_camera(p, pix, smp);
+                d = make_uint4(uint32_t(r.s), uint32_t(r.s >> 32), 0u, 0u);
+                ++n_new;
+            } else {
+                c = __ldcs(in_c + idx);
+                d = __ldcs(in_d + idx);
+                if (MEDIA) {
+                    d.x = uint32_t(rg.s);
+                    d.y = uint32_t(rg.s >> 32);
+                }
+            }
+            const size_t o = size_t(key) * p.cap + pos;
+            __stcs(p.hit_a + o, a);
+            __stcs(p.hit_b + o, b);
+            __stcs(p.hit_c + o, c);
+            __stcs(p.hit_d + o, d);
+            __stcs(p.hit_e + o, e);
         }
+        if (drain)
+            base = n; // stay in drain mode until the private range is empty
+        else
+            base = __shfl_sync(kFullMask, next_base, 0);
     }
+    if (lane == 0) {
+        p.cursor[2 * wid] = chunk_next;
+        p.cursor[2 * wid + 1] = chunk_end;
+    }
+    const uint32_t started = __reduce_add_sync(kFullMask, n_new);
+    if (lane == 0 && started)
+        atomicAdd(&p.glob->paths, (unsigned long long)started);
     if (COUNT) {
-        atomicAdd(&p.glob->nodes_visited, (unsigned long long)nodes);
-        atomicAdd(&p.glob->prim_tests, (unsigned long long)tests);
+        const unsigned long long x = warp_sum(nodes), y = warp_sum(tests);
+        if (lane == 0) {
+            atomicAdd(&p.glob->nodes_visited, x);
+            atomicAdd(&p.glob->prim_tests, y);
+        }
     }
 }
 
-// shade_<material>: shade_surface<M> for the paths whose hit landed on material type M.
+// Position of hit queue `q`'s entries in the next extend queue: after the entries of the
+// queues before it.
+__device__ __forceinline__ uint32_t out_base(const Counters &C, int q) {
+    uint32_t b = 0;
+    for (int k = 0; k < q; ++k)
+        b += C.key.v[k];
+    return b;
+}
+
+// shade_<material>: shade_surface<M> for the paths whose hit landed on material type M.  The
+// continued path (or an empty entry where the path ended) goes to a FIXED position of the
+// next extend queue, so nothing here contends: warps stride over the chunks statically.
 template <int M, bool OLD>
 __global__ void __launch_bounds__(128) k_shade(WfParams p, int it) {
     __shared__ FlatSmem sm;
     const GeomView<float> g = stage_scene(p.geom, sm);
     Counters &C = p.ctr[it % 3];
-    Counters &N = p.ctr[(it + 1) % 3];
-    const uint32_t n = C.n_mat[M];
-    const uint32_t *q = p.q_mat + size_t(M) * p.P;
-    uint32_t *q_next = p.q_ext[(it + 1) & 1];
-    while (true) {
-        const uint32_t base = warp_fetch(&C.head_mat[M]);
-        if (base >= n)
-            break;
-        const uint32_t idx = base + lane_id();
+    const uint32_t n = C.key.v[M];
+    const uint32_t base_out = out_base(C, M);
+    const int nb = (it + 1) & 1;
+    const size_t qoff = size_t(M) * p.cap;
+    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5), wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    for (uint32_t first = wid * 32u; first < n; first += n_warps * 32u) {
+        const uint32_t idx = first + lane_id();
         const bool valid = idx < n;
-        uint32_t slot = 0;
         bool alive = false;
         PathState s;
         ShadowReq sh;
         sh.want = false;
         uint32_t sh_pix = 0;
         if (valid) {
-            slot = __ldcs(q + idx);
-            s = load_state(p, slot);
-            const float4 h = __ldcs(p.hit + slot);
+            const size_t o = qoff + idx;
+            const float4 a = __ldcs(p.hit_a + o), b = __ldcs(p.hit_b + o), c = __ldcs(p.hit_c + o);
+            const uint4 d = __ldcs(p.hit_d + o);
+            const float2 e = __ldcs(p.hit_e + o);
+            s = unpack(a, b, c, d);
             sh_pix = s.pix;
-            shade_surface<M, OLD>(p, g, s, h.x, __float_as_uint(h.y), alive, sh);
+            shade_surface<M, OLD>(p, g, s, e.x, __float_as_uint(e.y), alive, sh);
         }
         if (!OLD) {
-            const uint32_t pos = warp_reserve(&C.n_shadow, sh.want);
+            const uint32_t pos = warp_reserve(&C.n_shadow.v[0], sh.want);
             if (sh.want) {
                 __stcs(p.sh_a + pos, make_float4(sh.o.x, sh.o.y, sh.o.z, sh.tmax));
                 __stcs(p.sh_b + pos, make_float4(sh.d.x, sh.d.y, sh.d.z, __uint_as_float(sh_pix)));
                 __stcs(p.sh_c + pos, make_float4(sh.c.x, sh.c.y, sh.c.z, __uint_as_float(sh.origin)));
             }
         }
-        finish_lane(p, N, q_next, valid, alive, slot, s);
+        if (valid) {
+            const uint32_t o = base_out + idx;
+            if (alive) {
+                __stcs(p.ext_a[nb] + o, pack_a(s));
+                __stcs(p.ext_b[nb] + o, pack_b(s));
+                __stcs(p.ext_c[nb] + o, pack_c(s));
+                __stcs(p.ext_d[nb] + o, pack_d(s));
+            } else {
+                __stcs(p.ext_c[nb] + o, make_float4(0.f, 0.f, 0.f, __uint_as_float(kInvalidPix)));
+            }
+        }
     }
 }
 
-__global__ void __launch_bounds__(128) k_miss(WfParams p, int it) {
+// miss: the rays that left the scene add background / environment radiance; their entries of
+// the next extend queue become empty.  SHADE = false when that radiance is identically zero
+// (black background, no environment light): then nothing is read at all.
+template <bool SHADE> __global__ void __launch_bounds__(128) k_miss(WfParams p, int it) {
     Counters &C = p.ctr[it % 3];
-    Counters &N = p.ctr[(it + 1) % 3];
-    const uint32_t n = C.n_miss;
-    uint32_t *q_next = p.q_ext[(it + 1) & 1];
-    while (true) {
-        const uint32_t base = warp_fetch(&C.head_miss);
-        if (base >= n)
-            break;
-        const uint32_t idx = base + lane_id();
-        const bool valid = idx < n;
-        uint32_t slot = 0;
-        PathState s;
-        if (valid) {
-            slot = __ldcs(p.q_miss + idx);
-            s = load_state(p, slot);
+    const uint32_t n = C.key.v[kMatTypes];
+    const uint32_t base_out = out_base(C, kMatTypes);
+    const int nb = (it + 1) & 1;
+    const size_t qoff = size_t(kMatTypes) * p.cap;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        p.ctr[(it + 1) % 3].n_ext.v[0] = base_out + n;
+        atomicAdd(&p.glob->rays_closest, (unsigned long long)(base_out + n));
+    }
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += stride) {
+        if (SHADE) {
+            const size_t o = qoff + idx;
+            const PathState s = unpack(__ldcs(p.hit_a + o), __ldcs(p.hit_b + o), __ldcs(p.hit_c + o), __ldcs(p.hit_d + o));
             miss_surface(p, s);
         }
-        finish_lane(p, N, q_next, valid, false, slot, s);
+        __stcs(p.ext_c[nb] + base_out + idx, make_float4(0.f, 0.f, 0.f, __uint_as_float(kInvalidPix)));
     }
 }
 
@@ -692,14 +826,15 @@ __global__ void __launch_bounds__(128) k_connect(WfParams p, int it) {
     __shared__ FlatSmem sm;
     const GeomView<float> g = stage_scene(p.geom, sm);
     Counters &C = p.ctr[it % 3];
-    const uint32_t n = C.n_shadow;
+    const uint32_t n = C.n_shadow.v[0];
     if (blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(&p.glob->rays_shadow, (unsigned long long)n);
     uint64_t nodes = 0, tests = 0;
-    while (true) {
-        const uint32_t base = warp_fetch(&C.head_shadow);
-        if (base >= n)
-            break;
+    uint32_t base = warp_fetch(&C.head_shadow.v[0]);
+    while (base < n) {
+        uint32_t next_base = 0;
+        if (lane_id() == 0)
+            next_base = atomicAdd(&C.head_shadow.v[0], 32u);
         const uint32_t idx = base + lane_id();
         if (idx < n) {
             const float4 a = __ldcs(p.sh_a + idx), b = __ldcs(p.sh_b + idx), c = __ldcs(p.sh_c + idx);
@@ -709,10 +844,14 @@ __global__ void __launch_bounds__(128) k_connect(WfParams p, int it) {
                                       rg, nodes, tests))
                 accum_add(p.accum, __float_as_uint(b.w), V3<float>(c.x, c.y, c.z));
         }
+        base = __shfl_sync(kFullMask, next_base, 0);
     }
     if (COUNT) {
-        atomicAdd(&p.glob->nodes_visited, (unsigned long long)nodes);
-        atomicAdd(&p.glob->prim_tests, (unsigned long long)tests);
+        const unsigned long long x = warp_sum(nodes), y = warp_sum(tests);
+        if (lane_id() == 0) {
+            atomicAdd(&p.glob->nodes_visited, x);
+            atomicAdd(&p.glob->prim_tests, y);
+        }
     }
 }
 
@@ -855,7 +994,8 @@ template <class K> int blocks_per_sm(K kernel, int threads) {
 // Device memory of the path pool; kept across renders on a context.
 struct WavefrontPool {
     uint32_t P = 0;
-    DeviceBuffer ray_o, ray_d, thr, hit, aux, q_ext0, q_ext1, q_mat, q_miss, sh_a, sh_b, sh_c, ctr, glob;
+    uint32_t cap = 0, n_cursor = 0;
+    DeviceBuffer ext[2][4], hit[5], sh_a, sh_b, sh_c, cursor, ctr, glob;
     uint32_t *h_live = nullptr; // pinned: extend-queue length probes
     Globals *h_glob = nullptr;  // pinned
     cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -881,25 +1021,27 @@ struct WavefrontPool {
         ctr.alloc(3 * sizeof(Counters));
         glob.alloc(sizeof(Globals));
     }
-    void ensure(uint32_t want) {
+    // want = resident paths, warps = warps of one k_extend launch (each owns a private sample range)
+    void ensure(uint32_t want, uint32_t warps) {
         ensure_common();
-        if (want == P)
+        if (want == P && warps == n_cursor)
             return;
         P = 0;
-        const size_t n = want;
-        ray_o.alloc(n * 16);
-        ray_d.alloc(n * 16);
-        thr.alloc(n * 16);
-        hit.alloc(n * 16);
-        aux.alloc(n * 16);
-        q_ext0.alloc(n * 4);
-        q_ext1.alloc(n * 4);
-        q_mat.alloc(n * 4 * kMatTypes);
-        q_miss.alloc(n * 4);
+        // the final drain of the private sample ranges can add up to warps * kWfChunk paths
+        const size_t n = size_t(want) + size_t(warps) * kWfChunk + 32;
+        for (auto &q : ext)
+            for (auto &arr : q)
+                arr.alloc(n * 16);
+        for (int k = 0; k < 4; ++k)
+            hit[k].alloc(n * 16 * kKeys);
+        hit[4].alloc(n * 8 * kKeys);
         sh_a.alloc(n * 16);
         sh_b.alloc(n * 16);
         sh_c.alloc(n * 16);
+        cursor.alloc(size_t(warps) * 16);
         P = want;
+        cap = uint32_t(n);
+        n_cursor = warps;
     }
     ~WavefrontPool() {
         if (h_live)
@@ -951,6 +1093,8 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
     W.cam = sc.host.f32.camera;
     pool.ensure_common();
     uint32_t P = 0;
+    const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
+    const int wf_grid = sms * 8; // 8 resident CTAs of 128 threads per SM
     if (!fused) {
         P = rp.pool_paths > 0 ? uint32_t(rp.pool_paths) : (1u << 21);
         P = (P + 31u) & ~31u;
@@ -958,19 +1102,23 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
             P = uint32_t((total + 31ull) & ~31ull);
         if (P < 32)
             P = 32;
-        pool.ensure(P);
-        W.ray_o = pool.ray_o.as<float4>();
-        W.ray_d = pool.ray_d.as<float4>();
-        W.thr = pool.thr.as<float4>();
-        W.hit = pool.hit.as<float4>();
-        W.aux = pool.aux.as<uint4>();
-        W.q_ext[0] = pool.q_ext0.as<uint32_t>();
-        W.q_ext[1] = pool.q_ext1.as<uint32_t>();
-        W.q_mat = pool.q_mat.as<uint32_t>();
-        W.q_miss = pool.q_miss.as<uint32_t>();
+        pool.ensure(P, uint32_t(wf_grid) * 4u);
+        for (int b = 0; b < 2; ++b) {
+            W.ext_a[b] = pool.ext[b][0].as<float4>();
+            W.ext_b[b] = pool.ext[b][1].as<float4>();
+            W.ext_c[b] = pool.ext[b][2].as<float4>();
+            W.ext_d[b] = pool.ext[b][3].as<uint4>();
+        }
+        W.hit_a = pool.hit[0].as<float4>();
+        W.hit_b = pool.hit[1].as<float4>();
+        W.hit_c = pool.hit[2].as<float4>();
+        W.hit_d = pool.hit[3].as<uint4>();
+        W.hit_e = pool.hit[4].as<float2>();
         W.sh_a = pool.sh_a.as<float4>();
         W.sh_b = pool.sh_b.as<float4>();
         W.sh_c = pool.sh_c.as<float4>();
+        W.cursor = pool.cursor.as<unsigned long long>();
+        W.cap = pool.cap;
     }
     W.ctr = pool.ctr.as<Counters>();
     W.glob = pool.glob.as<Globals>();
@@ -998,14 +1146,13 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
     const bool count = (rp.flags & RTB_RENDER_COUNT_VISITS) != 0;
     const bool time_dom = (rp.flags & RTB_RENDER_TIME_EXTEND) != 0;
     size_t n_ext_events = 0;
-    const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
 
     uint64_t launches = 0;
     int it = 0;
     bool cancelled = false;
     RTB_CUDA(cudaEventRecord(pool.ev_begin, st));
     RTB_CUDA(cudaMemsetAsync(d_accum, 0, size_t(npix) * sizeof(float4), st));
-    k_clear<<<1, 128, 0, st>>>(W.ctr, W.glob);
+    k_clear<<<1, 256, 0, st>>>(W.ctr, W.glob);
     ++launches;
 
     if (fused) {
@@ -1047,12 +1194,16 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
             }
         }
     } else {
-        const int grid = sms * 8; // 8 resident CTAs of 128 threads per SM
-        k_generate<<<sms * 4, 256, 0, st>>>(W);
+        const int grid = wf_grid;
+        k_init<<<sms * 4, 256, 0, st>>>(W, P, pool.n_cursor);
         ++launches;
         RTB_CUDA(cudaGetLastError());
+        // radiance of a ray that leaves the scene is identically zero: k_miss only empties entries
+        const bool miss_shades = W.bg[0] != 0.f || W.bg[1] != 0.f || W.bg[2] != 0.f ||
+                                 (rp.integrator >= RTB_INTEGRATOR_DIRECT && W.shade.n_infinite_lights > 0);
+        const bool media = W.has_media != 0;
         constexpr int kBatch = 4; // iterations between two host-side liveness probes
-        int probe = 0;
+        int probe = 0, zero_probes = 0;
         bool done = total == 0;
         int pending[2] = {-1, -1}; // probe slots in flight
         while (!done) {
@@ -1063,10 +1214,17 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
                         RTB_CUDA(cudaEventRecord(pool.ext_event(n_ext_events++), st));
                 };
                 mark();
-                if (count)
-                    k_extend<true><<<grid, 128, 0, st>>>(W, it);
-                else
-                    k_extend<false><<<grid, 128, 0, st>>>(W, it);
+                if (count) {
+                    if (media)
+                        k_extend<true, true><<<grid, 128, 0, st>>>(W, it);
+                    else
+                        k_extend<true, false><<<grid, 128, 0, st>>>(W, it);
+                } else {
+                    if (media)
+                        k_extend<false, true><<<grid, 128, 0, st>>>(W, it);
+                    else
+                        k_extend<false, false><<<grid, 128, 0, st>>>(W, it);
+                }
                 mark();
                 ++launches;
                 for (int m = 0; m < kMatTypes; ++m)
@@ -1078,7 +1236,10 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
                         ++launches;
                     }
                 mark();
-                k_miss<<<grid, 128, 0, st>>>(W, it);
+                if (miss_shades)
+                    k_miss<true><<<grid, 128, 0, st>>>(W, it);
+                else
+                    k_miss<false><<<grid, 128, 0, st>>>(W, it);
                 ++launches;
                 mark();
                 if (nee) {
@@ -1092,16 +1253,19 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
             }
             RTB_CUDA(cudaGetLastError());
             // length of the NEXT extend queue, read back without stalling the pipeline: the
-            // host only waits for the probe of the PREVIOUS batch
+            // host only waits for the probe of the PREVIOUS batch.  An empty queue ends the
+            // render once it has been seen twice in a row: the extend that found it empty
+            // may still have started the last samples of the warps' private ranges.
             const int slot = probe & 1;
-            RTB_CUDA(cudaMemcpyAsync(&pool.h_live[slot], &W.ctr[it % 3].n_ext, sizeof(uint32_t),
+            RTB_CUDA(cudaMemcpyAsync(&pool.h_live[slot], &W.ctr[it % 3].n_ext.v[0], sizeof(uint32_t),
                                      cudaMemcpyDeviceToHost, st));
             RTB_CUDA(cudaEventRecord(pool.ev[slot], st));
             pending[slot] = it;
             const int prev = (probe + 1) & 1;
             if (pending[prev] >= 0) {
                 RTB_CUDA(cudaEventSynchronize(pool.ev[prev]));
-                if (pool.h_live[prev] == 0)
+                zero_probes = pool.h_live[prev] == 0 ? zero_probes + 1 : 0;
+                if (zero_probes >= 2)
                     done = true;
             }
             ++probe;
@@ -1109,9 +1273,10 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
                 cancelled = true;
                 break;
             }
-            // every slot is busy on every iteration until the samples run out, so the last
+            // every entry is busy on every iteration until the samples run out, so the last
             // sample starts no later than iteration total*max_depth/P; the tail adds max_depth
-            if ((unsigned long long)it > total * (unsigned long long)rp.max_depth / P + rp.max_depth + 4 * kBatch)
+            if ((unsigned long long)it >
+                total * (unsigned long long)rp.max_depth / P + 2ull * rp.max_depth + 16 * kBatch)
                 throw std::runtime_error("wavefront: iteration bound exceeded (internal error)");
         }
     }
@@ -1124,10 +1289,8 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
         std::memset(stats, 0, sizeof(*stats));
         if (rp.max_depth <= 0)
             stats->paths = n_samples;
-        else if (fused)
-            stats->paths = pool.h_glob->paths;
         else
-            stats->paths = pool.h_glob->next_sample < total ? pool.h_glob->next_sample : total;
+            stats->paths = pool.h_glob->paths;
         stats->rays_closest = pool.h_glob->rays_closest;
         stats->rays_shadow = pool.h_glob->rays_shadow;
         stats->nodes_visited = pool.h_glob->nodes_visited;

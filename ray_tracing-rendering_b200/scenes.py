@@ -98,6 +98,49 @@ class SceneBuilder:
     def yz_rect(self, y0, y1, z0, z1, k, mat, chain=-1):
         return self._prim(P_YZ, mat, [y0, y1, z0, z1, k], chain)
 
+    def moving_sphere(self, c0, c1, t0, t1, r, mat, chain=-1):     # moving_sphere.h:10-17
+        return self._prim(P_MSPHERE, mat, [c0[0], c0[1], c0[2], c1[0], c1[1], c1[2], t0, t1, r], chain)
+
+    def constant_medium(self, boundary_prim, density, c):          # constant_medium.h:28-53
+        """The boundary primitive must already exist; pass flags=BOUNDARY_ONLY when it is not
+        itself a member of the world."""
+        m = self._mat(T_ISOTROPIC, (self.solid(c), -1, -1, -1))
+        i = self._prim(P_MEDIUM, m, [-1.0 / density])
+        self.prims[i]["aux0"], self.prims[i]["aux1"] = boundary_prim, 1
+        return i
+
+    def image_missing(self):                                       # texture.h:96-110 (file not found)
+        im = np.zeros(1, abi.IMAGE)[0]
+        self.images.append(im)
+        t = np.zeros(1, abi.TEXTURE)[0]
+        t["type"] = 2
+        t["even"] = t["odd"] = t["perlin"] = -1
+        t["image"] = len(self.images) - 1
+        self.texs.append(t)
+        return len(self.texs) - 1
+
+    def noise(self, scale, rng):                                   # texture.h:148-163, perlin.h:10-20,62-78
+        pl = np.zeros(1, abi.PERLIN)[0]
+        for i in range(256):
+            v = np.array([rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(-1, 1)])
+            pl["ranvec"][i] = (1.0 / math.sqrt(float(v @ v))) * v
+        for name in ("perm_x", "perm_y", "perm_z"):
+            perm = list(range(256))
+            for i in range(255, 0, -1):
+                tgt = rng.randint(0, i)
+                perm[i], perm[tgt] = perm[tgt], perm[i]
+            pl[name] = perm
+        self.perlins.append(pl)
+        t = np.zeros(1, abi.TEXTURE)[0]
+        t["type"] = 3
+        t["even"] = t["odd"] = t["image"] = -1
+        t["perlin"], t["scale"] = len(self.perlins) - 1, scale
+        self.texs.append(t)
+        return len(self.texs) - 1
+
+    def lambertian_tex(self, tex):
+        return self._mat(T_LAMBERTIAN, (tex, -1, -1, -1))
+
     def box(self, p0, p1, mat, chain=-1):            # box.h:31-47: six rects, this order
         self.xy_rect(p0[0], p1[0], p0[1], p1[1], p1[2], mat, chain)
         self.xy_rect(p0[0], p1[0], p0[1], p1[1], p0[2], mat, chain)
@@ -197,6 +240,12 @@ class XorShift32:
         self.s = np.uint32(s)
         return s * 2.3283064365386963e-10
 
+    def uniform(self, lo, hi):                       # random_double(min, max), rtweekend.h:37-40
+        return lo + (hi - lo) * self.next()
+
+    def randint(self, lo, hi):                       # random_int, rtweekend.h:48-50
+        return int(self.uniform(lo, hi + 1))
+
     def block(self, n):
         out = np.empty(n)
         s = int(self.s)
@@ -268,7 +317,79 @@ def sphere_field(half_extent: int = 500, width: int = 3840, height: int = 2160, 
                            "materials": mats, "textures": texs, "lights": lights})
 
 
-BUILDERS = {7: lambda: cornell_box(False), 21: lambda: cornell_box(True), 23: mis_comparison}
+def final_scene(seed: int = 1) -> bytes:
+    """scene 9 (final_scene, scenes.cpp:221-290 + case 9, :1595-1604): 400 boxes of random height,
+    the rect light, a moving sphere, glass / metal spheres, two constant media (one inside a glass
+    boundary that is also a world member, one filling a 5000-radius boundary), the earth sphere
+    (earthmap.jpg is absent from the reference repo => cyan, texture.h:96-110), a Perlin sphere
+    and 1000 small spheres under rotate_y(15)+translate.  The reference draws from an RNG seeded
+    by the thread id; here the same xorshift32 starts from `seed`."""
+    rng = XorShift32(seed)
+    b = SceneBuilder()
+    ground = b.lambertian((0.48, 0.83, 0.53))
+    for i in range(20):
+        for j in range(20):
+            w = 100.0
+            x0, z0 = -1000.0 + i * w, -1000.0 + j * w
+            y1 = rng.uniform(1, 101)
+            b.box((x0, 0.0, z0), (x0 + w, y1, z0 + w), ground)
+    b.xz_rect(123, 423, 147, 412, 554, b.diffuse_light((7, 7, 7)))
+    b.moving_sphere((400, 400, 200), (430, 400, 200), 0, 1, 50, b.lambertian((0.7, 0.3, 0.1)))
+    b.sphere((260, 150, 45), 50, b.dielectric(1.5))
+    b.sphere((0, 150, 145), 50, b.metal((0.8, 0.8, 0.9), 1.0))
+    glass = b.dielectric(1.5)
+    boundary = b.sphere((360, 150, 145), 70, glass)               # world member AND medium boundary
+    inner = b.sphere((360, 150, 145), 70, glass)
+    b.prims[inner]["flags"] = 1
+    b.constant_medium(inner, 0.2, (0.2, 0.4, 0.9))
+    fog = b.sphere((0, 0, 0), 5000, b.dielectric(1.5))
+    b.prims[fog]["flags"] = 1
+    b.constant_medium(fog, 0.0001, (1, 1, 1))
+    b.sphere((400, 200, 400), 100, b.lambertian_tex(b.image_missing()))
+    b.sphere((220, 280, 300), 80, b.lambertian_tex(b.noise(0.1, rng)))
+    white = b.lambertian((.73, .73, .73))
+    ch = b.chain([("translate", (-100, 270, 395)), ("rotate_y", 15)])
+    for _ in range(1000):
+        b.sphere((rng.uniform(0, 165), rng.uniform(0, 165), rng.uniform(0, 165)), 10, white, ch)
+    return b.finish(9, 800, 1.0, 500, (0, 0, 0), (478, 278, -600), (278, 278, 0), 40.0)
+
+
+def synthetic_hdr(width: int = 2048, height: int = 1024, seed: int = 1) -> np.ndarray:
+    """The synthetic equirectangular environment of C4-env: vertical sky gradient
+    0.2 -> 1.0, one 32x32-texel sun at radiance 5e3, +-5 % xorshift32 noise.  (H, W, 3) float32."""
+    v = np.linspace(1.0, 0.2, height, dtype=np.float64)[:, None, None]     # row 0 = zenith
+    img = np.broadcast_to(v, (height, width, 3)).copy()
+    s = np.uint32(seed)
+    n = height * width
+    # vectorised xorshift32 stream: one independent lane per row keeps this O(W) python steps
+    lanes = (np.arange(height, dtype=np.uint64) * 2654435761 + int(s)) & 0xFFFFFFFF
+    lanes = np.where(lanes == 0, 1, lanes).astype(np.uint64)
+    noise = np.empty((height, width))
+    for x in range(width):
+        lanes ^= (lanes << np.uint64(13)) & np.uint64(0xFFFFFFFF)
+        lanes ^= lanes >> np.uint64(17)
+        lanes ^= (lanes << np.uint64(5)) & np.uint64(0xFFFFFFFF)
+        noise[:, x] = lanes * 2.3283064365386963e-10
+    img *= (0.95 + 0.1 * noise)[:, :, None]
+    y0, x0 = height // 4, (3 * width) // 8
+    img[y0:y0 + 32, x0:x0 + 32, :] = 5.0e3
+    del n
+    return img.astype(np.float32)
+
+
+def hdr_demo(width: int = 1920, env: np.ndarray = None, spp: int = 200) -> bytes:
+    """scene 24 (hdr_demo_scene, scenes.cpp:658-683 + case 24, :1783-1794) at `width` x 16:9 with
+    an environment light; env=None reproduces the reference's missing-file behaviour (white)."""
+    b = SceneBuilder()
+    b.sphere((-4, 1, 0), 1.0, b.metal((0.9, 0.9, 0.9), 0.0))
+    b.sphere((0, 1, 0), 1.0, b.pbr((1.0, 0.71, 0.29), 0.2, 1.0))
+    b.sphere((4, 1, 0), 1.0, b.dielectric(1.5))
+    b.env_light(env)
+    return b.finish(24, width, 16.0 / 9.0, spp, (0, 0, 0), (0, 3, 10), (0, 1, 0), 30.0)
+
+
+BUILDERS = {7: lambda: cornell_box(False), 21: lambda: cornell_box(True), 23: mis_comparison, 9: final_scene,
+            24: lambda: hdr_demo(800, None)}
 
 
 def select_scene(scene_id: int) -> bytes:
