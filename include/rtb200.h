@@ -103,6 +103,9 @@ typedef struct rtb_render_stats {
     /* with RTB_RENDER_TIME_EXTEND on the wavefront schedule: CUDA-event time per stage, summed
      * over the iterations: [0] extend, [1] shade (all material kernels), [2] miss, [3] connect */
     double stage_ms[4];
+    /* only with RTB_RENDER_COUNT_VISITS on the wavefront schedule: the most BVH nodes any single
+     * closest-hit ray visited (the longest traversal sets the tail of an extend launch) */
+    uint64_t max_nodes_per_ray;
 } rtb_render_stats;
 
 typedef struct rtb_scene_stats {

@@ -12,7 +12,8 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librtb200.so")
+# RTB200_LIBRARY selects another build of the same library (kernel-tuning experiments)
+LIB_PATH = os.environ.get("RTB200_LIBRARY") or os.path.join(_HERE, "librtb200.so")
 
 RTB_OK = 0
 STATUS_NAMES = {0: "RTB_OK", -1: "RTB_ERR_INVALID_ARGUMENT", -2: "RTB_ERR_NO_DEVICE",
@@ -42,7 +43,8 @@ class RenderStats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("rays_closest", C.c_uint64), ("rays_shadow", C.c_uint64),
                 ("nodes_visited", C.c_uint64), ("prim_tests", C.c_uint64), ("iterations", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("device_ms", C.c_double), ("extend_ms", C.c_double),
-                ("extend_launches", C.c_uint64), ("schedule", C.c_int32), ("reserved", C.c_int32), ("stage_ms", C.c_double * 4)]
+                ("extend_launches", C.c_uint64), ("schedule", C.c_int32), ("reserved", C.c_int32), ("stage_ms", C.c_double * 4),
+                ("max_nodes_per_ray", C.c_uint64)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_}

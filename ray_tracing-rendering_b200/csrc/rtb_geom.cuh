@@ -378,21 +378,117 @@ RTB_HD Node32 load_node(const Node32 *nodes, uint32_t i) {
 #endif
 }
 
+// ---- traversal stacks ------------------------------------------------------------------------
+// The traversal is written against a small stack interface so that kernels can keep the stack
+// in shared memory while host instantiations (tests/hostcheck) and simple kernels use a plain
+// array.  A push beyond the capacity is dropped (the builder caps the tree depth below it).
+struct LocalStack {
+    uint32_t s[kStackDepth];
+    int sp = 0;
+    RTB_HD void push(uint32_t x) {
+        if (sp < kStackDepth)
+            s[sp++] = x;
+    }
+    RTB_HD uint32_t pop() { return s[--sp]; }
+    RTB_HD bool empty() const { return sp == 0; }
+};
+
+#ifdef __CUDACC__
+// Per-thread stack in shared memory, level-major: level L of thread T lives at word
+// L * STRIDE + T of the block's stack array, so the 32 lanes of a warp always touch 32
+// different banks whatever their stack depths are.  Local memory would route every push/pop
+// through the L1 that the BVH node fetches are fighting over.  The first kSmemStackDepth
+// levels are in shared memory; deeper ones (rare: a near-first descent consumes the top of a
+// tall tree first) go to `spill`, a local array owned by the caller.  The members are three
+// scalars (shared-space address, depth, pointer) so the object itself stays in registers.
+constexpr int kSmemStackDepth = 24;
+template <int STRIDE> struct SmemStack {
+    uint32_t saddr; // shared-window address of this thread's level 0
+    int sp;
+    uint32_t *spill; // kStackDepth - kSmemStackDepth words
+    __device__ __forceinline__ SmemStack(uint32_t *thread_base, uint32_t *spill_words)
+        : sp(0), spill(spill_words) {
+        // opaque move: keeps the address in a register instead of being re-derived from
+        // %tid / the shared window base (two S2R) at every push and pop
+        asm volatile("mov.u32 %0, %1;" : "=r"(saddr) : "r"(uint32_t(__cvta_generic_to_shared(thread_base))));
+    }
+    __device__ __forceinline__ void push(uint32_t x) {
+        if (sp < kSmemStackDepth)
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr + uint32_t(sp) * (STRIDE * 4u)), "r"(x) : "memory");
+        else if (sp < kStackDepth)
+            spill[sp - kSmemStackDepth] = x;
+        else
+            return;
+        ++sp;
+    }
+    __device__ __forceinline__ uint32_t pop() {
+        --sp;
+        uint32_t x;
+        if (sp < kSmemStackDepth)
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(saddr + uint32_t(sp) * (STRIDE * 4u)) : "memory");
+        else
+            x = spill[sp - kSmemStackDepth];
+        return x;
+    }
+    __device__ __forceinline__ bool empty() const { return sp == 0; }
+};
+#endif
+
+// The ray as the slab test wants it.  Production (float, ROBUST): t = lo * idir + ood with
+// ood = -(o * idir), one FMA per plane, |idir| capped so that ood stays finite for axis-parallel rays.
+// Validation: the reference's (lo - o) * idir (aabb.h:33-36).
+#ifndef RTB_SLAB_FMA
+#define RTB_SLAB_FMA 1
+#endif
+template <class R, bool ROBUST> struct SlabRay {
+    V3<R> idir, ood;
+    RTB_HD void set(V3<R> o, V3<R> d) {
+        if (RTB_SLAB_FMA && ROBUST && sizeof(R) == 4) {
+            const R eps = R(1e-18);
+            const R dx = fabs_(d.x) < eps ? (d.x < 0 ? -eps : eps) : d.x;
+            const R dy = fabs_(d.y) < eps ? (d.y < 0 ? -eps : eps) : d.y;
+            const R dz = fabs_(d.z) < eps ? (d.z < 0 ? -eps : eps) : d.z;
+            idir = V3<R>(R(1) / dx, R(1) / dy, R(1) / dz);
+            ood = V3<R>(-(o.x * idir.x), -(o.y * idir.y), -(o.z * idir.z));
+        } else {
+            idir = safe_inv(d);
+            ood = o;
+        }
+    }
+    RTB_HD R plane(R v, R id, R oo) const {
+        if (RTB_SLAB_FMA && ROBUST && sizeof(R) == 4)
+            return fma_(v, id, oo);
+        return (v - oo) * id;
+    }
+    // entry / exit distance of a box clipped to [t_min, t_max]; hit when near <= far
+    RTB_HD bool box(const Node32 &n, R t_min, R t_max, R &t_near) const {
+        const R x0 = plane(R(n.lo[0]), idir.x, ood.x), x1 = plane(R(n.hi[0]), idir.x, ood.x);
+        const R y0 = plane(R(n.lo[1]), idir.y, ood.y), y1 = plane(R(n.hi[1]), idir.y, ood.y);
+        const R z0 = plane(R(n.lo[2]), idir.z, ood.z), z1 = plane(R(n.hi[2]), idir.z, ood.z);
+        const R tn = fmax_(fmax_(fmin_(x0, x1), fmin_(y0, y1)), fmax_(fmin_(z0, z1), t_min));
+        const R tf = fmin_(fmin_(fmax_(x0, x1), fmax_(y0, y1)), fmin_(fmax_(z0, z1), t_max));
+        t_near = tn;
+        return tn <= tf;
+    }
+};
+
 // Closest hit (ANY = false) or first hit (ANY = true) of the world-space ray through the
 // two-level BVH.  Returns the SORTED primitive index or kNoPrim, and t.
 //   origin_prim : sorted index of the primitive the ray leaves (ROBUST only).
 //   rng         : callable returning R uniform in (0,1) — drawn once per medium test, as
 //                 constant_medium::hit does (constant_medium.h:85).
+//   stack       : LocalStack or SmemStack, empty on entry.
 // "while-while" form: the inner loop only descends (one 64-byte child-pair fetch and two slab
-// tests per step, nearer child first), leaves are processed between descents, so the lanes of
-// a warp spend most of their time in the same loop.
-template <class R, bool ANY, bool ROBUST, class Rng>
+// tests per step, nearer child first, no data-dependent branches besides the loop itself),
+// leaves are processed between descents, so the lanes of a warp spend most of their time in
+// the same loop.
+template <class R, bool ANY, bool ROBUST, class Rng, class Stack>
 RTB_HD uint32_t traverse(const GeomView<R> &g, V3<R> o, V3<R> d, R time, R t_min, R t_max, uint32_t origin_prim,
-                         Rng &rng, R &t_hit, uint64_t *n_nodes, uint64_t *n_tests) {
-    uint32_t stack[kStackDepth];
-    int sp = 0;
+                         Rng &rng, R &t_hit, uint64_t *n_nodes, uint64_t *n_tests, Stack &stack) {
     uint32_t best = kNoPrim;
-    V3<R> co = o, cd = d, cid = safe_inv(d); // current-level ray
+    V3<R> co = o, cd = d; // current-level ray
+    SlabRay<R, ROBUST> sr;
+    sr.set(o, d);
     uint32_t cur = g.root_ref;
     while (true) {
         while (!(cur & kLeafFlag)) { // descend
@@ -400,39 +496,37 @@ RTB_HD uint32_t traverse(const GeomView<R> &g, V3<R> o, V3<R> d, R time, R t_min
             if (n_nodes)
                 *n_nodes += 2;
             R e0, e1;
-            const bool h0 = slab(c0, co, cid, t_min, t_max, e0);
-            const bool h1 = slab(c1, co, cid, t_min, t_max, e1);
-            if (h0 & h1) {
-                const bool swap = e1 < e0;
-                if (sp < kStackDepth)
-                    stack[sp++] = swap ? c0.ref : c1.ref;
-                cur = swap ? c1.ref : c0.ref;
-            } else if (h0 | h1) {
-                cur = h0 ? c0.ref : c1.ref;
-            } else {
-                if (sp == 0) {
+            const bool h0 = sr.box(c0, t_min, t_max, e0);
+            const bool h1 = sr.box(c1, t_min, t_max, e1);
+            const bool first1 = h1 & (!h0 | (e1 < e0)); // child 1 is the one to enter next
+            const uint32_t near = first1 ? c1.ref : c0.ref, far = first1 ? c0.ref : c1.ref;
+            if (h0 & h1)
+                stack.push(far);
+            cur = near;
+            if (!(h0 | h1)) {
+                if (stack.empty()) {
                     t_hit = t_max;
                     return best;
                 }
-                cur = stack[--sp];
+                cur = stack.pop();
             }
         }
         bool entered = false;
         if (cur == kSentinelRef) { // leaving the instance: back to the world ray
             co = o;
             cd = d;
-            cid = safe_inv(d);
+            sr.set(o, d);
         } else if (cur != kEmptyRef) {
             const uint32_t first = cur & kLeafFirstMask, last = first + ((cur >> 27) & 15u) + 1u;
+            V3<R> cid = safe_inv(cd);
             for (uint32_t i = first; i < last; ++i) {
                 const PrimT<R> p = g.prims[i];
                 const uint32_t type = p.type_mat & PT_TYPE_MASK;
                 if (type == PT_INSTANCE) {
                     // builder guarantee: an instance is alone in its leaf, top level only
-                    if (sp < kStackDepth)
-                        stack[sp++] = kSentinelRef;
+                    stack.push(kSentinelRef);
                     enter_instance<R, ROBUST>(g, int(p.aux2), co, cd);
-                    cid = safe_inv(cd);
+                    sr.set(co, cd);
                     cur = p.aux; // the bottom-level tree's root ref
                     entered = true;
                     break;
@@ -467,12 +561,19 @@ RTB_HD uint32_t traverse(const GeomView<R> &g, V3<R> o, V3<R> d, R time, R t_min
         }
         if (entered)
             continue;
-        if (sp == 0) {
+        if (stack.empty()) {
             t_hit = t_max;
             return best;
         }
-        cur = stack[--sp];
+        cur = stack.pop();
     }
+}
+// with a stack of its own in local memory
+template <class R, bool ANY, bool ROBUST, class Rng>
+RTB_HD uint32_t traverse(const GeomView<R> &g, V3<R> o, V3<R> d, R time, R t_min, R t_max, uint32_t origin_prim,
+                         Rng &rng, R &t_hit, uint64_t *n_nodes, uint64_t *n_tests) {
+    LocalStack stack;
+    return traverse<R, ANY, ROBUST>(g, o, d, time, t_min, t_max, origin_prim, rng, t_hit, n_nodes, n_tests, stack);
 }
 
 // Lockstep traversal for small scenes (the Cornell-box class: a few dozen primitives).

@@ -75,6 +75,8 @@ RTB_HD float rsqrt_(float x) {
 }
 RTB_HD float sqrt_(float x) { return sqrtf(x); }
 RTB_HD double sqrt_(double x) { return sqrt(x); }
+RTB_HD float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+RTB_HD double fma_(double a, double b, double c) { return fma(a, b, c); }
 RTB_HD float fabs_(float x) { return fabsf(x); }
 RTB_HD double fabs_(double x) { return fabs(x); }
 RTB_HD float fmin_(float a, float b) { return fminf(a, b); }

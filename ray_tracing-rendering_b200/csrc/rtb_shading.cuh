@@ -68,7 +68,7 @@ template <class R, class G> RTB_HD V3<R> random_unit_vector(G &g) {
 }
 // uniform in the unit ball == the rejection loop of vec3.h:226-233
 template <class R, class G> RTB_HD V3<R> random_in_unit_sphere(G &g) {
-    const R rad = cbrt_(g.next());
+    const R rad = cbrt_(g.next_open()); // (0,1): the rejection loop never returns the centre itself
     return rad * random_unit_vector<R>(g);
 }
 // uniform in the unit disk == vec3.h:250-257

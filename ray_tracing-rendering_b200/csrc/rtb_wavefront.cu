@@ -56,6 +56,9 @@ namespace {
 constexpr int kMatTypes = RTB_MAT_TYPE_COUNT; // 6
 constexpr uint32_t kFullMask = 0xffffffffu;
 
+#ifndef RTB_EXTEND_MIN_BLOCKS
+#define RTB_EXTEND_MIN_BLOCKS 5 // resident CTAs per SM k_extend is compiled for (register budget 65536 / (128 * N))
+#endif
 constexpr int kKeys = kMatTypes + 1;          // hit queues: one per material type + [kMatTypes] = miss
 constexpr uint32_t kInvalidPix = 0xffffffffu; // c.w of an empty queue entry
 constexpr uint32_t kWfChunk = 128;            // samples a warp of k_extend reserves per global atomic
@@ -80,6 +83,7 @@ struct Globals {
     unsigned long long nodes_visited;
     unsigned long long prim_tests;
     unsigned long long paths;
+    unsigned long long max_nodes_per_ray;
 };
 
 struct WfParams {
@@ -165,38 +169,8 @@ struct FlatSmem {
     int32_t prim_chain[kFlatMaxPrims];
 };
 
-// Cooperative copy by the whole block; returns a view whose tables live in shared memory.
-// When the scene is not flat the global view is returned unchanged.
-__device__ __forceinline__ GeomView<float> stage_scene(const GeomView<float> &g, FlatSmem &sm) {
-    if (!g.flat)
-        return g;
-    const int n4 = g.n_prims * int(sizeof(PrimT<float>) / 16);
-    const float4 *src = reinterpret_cast<const float4 *>(g.prims);
-    float4 *dst = reinterpret_cast<float4 *>(sm.prims);
-    for (int i = threadIdx.x; i < n4; i += blockDim.x)
-        dst[i] = __ldg(src + i);
-    for (int i = threadIdx.x; i < g.n_prims; i += blockDim.x)
-        sm.prim_chain[i] = g.prim_chain[i];
-    for (int i = threadIdx.x; i < kFlatMaxOps; i += blockDim.x)
-        if (i < g.n_ops)
-            sm.ops[i] = g.ops[i];
-    for (int i = threadIdx.x; i < kFlatMaxChains; i += blockDim.x)
-        if (i < g.n_chains) {
-            sm.chains[i] = g.chains[i];
-            sm.affine[i] = g.affine[i];
-        }
-    __syncthreads();
-    GeomView<float> s = g;
-    s.prims = sm.prims;
-    s.ops = sm.ops;
-    s.chains = sm.chains;
-    s.affine = sm.affine;
-    s.prim_chain = sm.prim_chain;
-    return s;
-}
-
-// The same for kernels that only run on flat scenes: without the global/shared merge above
-// the compiler can prove the tables are in shared memory and emits LDS instead of generic LD.
+// Cooperative copy by the whole block of the fused kernel; the returned view's tables live in
+// shared memory (and the compiler can prove it: LDS, not generic LD).
 __device__ __forceinline__ GeomView<float> stage_scene_flat(const GeomView<float> &g, FlatSmem &sm) {
     const int n4 = g.n_prims * int(sizeof(PrimT<float>) / 16);
     const float4 *src = reinterpret_cast<const float4 *>(g.prims);
@@ -234,16 +208,27 @@ __device__ __forceinline__ GeomView<float> stage_scene_flat(const GeomView<float
 }
 
 // FLAT_ONLY: the caller only ever runs on flat scenes (fused kernel) — the BVH code and its
-// stack are not even compiled in.
+// stack are not even compiled in.  Otherwise `stack_base` is the calling thread's column of
+// the block's shared-memory traversal stack (kSmemStackDepth x blockDim.x words).
+constexpr int kWfBlock = 128; // threads per block of every wavefront kernel
+#ifndef RTB_SMEM_STACK
+#define RTB_SMEM_STACK 0
+#endif
 template <bool ANY, bool COUNT, bool FLAT_ONLY = false, class Rng>
 __device__ __forceinline__ uint32_t trace(const GeomView<float> &g, V3<float> o, V3<float> d, float time,
                                           float t_min, float t_max, uint32_t origin, Rng &rng, float &t,
-                                          uint64_t &nodes, uint64_t &tests) {
+                                          uint64_t &nodes, uint64_t &tests, uint32_t *stack_base = nullptr) {
     if (FLAT_ONLY || g.flat)
         return traverse_flat<float, ANY, true>(g, o, d, time, t_min, t_max, origin, rng, t,
                                                COUNT ? &nodes : nullptr, COUNT ? &tests : nullptr);
+#if RTB_SMEM_STACK
+    uint32_t spill[kStackDepth - kSmemStackDepth];
+    SmemStack<kWfBlock> stack(stack_base, spill);
+#else
+    LocalStack stack;
+#endif
     return traverse<float, ANY, true>(g, o, d, time, t_min, t_max, origin, rng, t, COUNT ? &nodes : nullptr,
-                                      COUNT ? &tests : nullptr);
+                                      COUNT ? &tests : nullptr, stack);
 }
 
 // ---- path state ----------------------------------------------------------------------------
@@ -511,6 +496,11 @@ __device__ __forceinline__ void shade_surface(const WfParams &p, const GeomView<
     s.depth += 1;
     if (int(s.depth) >= p.max_depth)
         alive = false;
+    // fp32 guard: a degenerate continuation (zero or non-finite direction / origin) would make
+    // every slab test pass and drag a NaN through up to max_depth full-tree traversals
+    const float chk = fabsf(s.o.x) + fabsf(s.o.y) + fabsf(s.o.z) + fabsf(s.d.x) + fabsf(s.d.y) + fabsf(s.d.z);
+    if (!(chk < Consts<float>::inf()) || (s.d.x == 0.f && s.d.y == 0.f && s.d.z == 0.f))
+        alive = false;
 }
 
 // The ray left the scene: background for integrators 0-2 (e.g. rr_path_integrator.h:30-33),
@@ -541,12 +531,14 @@ struct PathDraw { // RNG adaptor handed to the traversal for constant_medium tes
 // time 0 regardless of the path's time (direct_light_integrator.h:115).
 template <bool COUNT, bool FLAT_ONLY = false>
 __device__ __forceinline__ bool shadow_visible(const GeomView<float> &g, V3<float> o, V3<float> d, float tmax,
-                                               uint32_t origin, Pcg &rng, uint64_t &nodes, uint64_t &tests) {
+                                               uint32_t origin, Pcg &rng, uint64_t &nodes, uint64_t &tests,
+                                               uint32_t *stack_base = nullptr) {
     // t_min is 0.001 along the UNIT direction; the stored direction may be the unnormalised segment
     const float len = isfinite(tmax) ? length(d) : 1.0f;
     PathDraw draw{&rng};
     float t;
-    return trace<true, COUNT, FLAT_ONLY>(g, o, d, 0.0f, 0.001f / len, tmax, origin, draw, t, nodes, tests) == kNoPrim;
+    return trace<true, COUNT, FLAT_ONLY>(g, o, d, 0.0f, 0.001f / len, tmax, origin, draw, t, nodes, tests, stack_base) ==
+           kNoPrim;
 }
 
 // ---- (A) wavefront kernels -------------------------------------------------------------------
@@ -560,6 +552,7 @@ __global__ void k_clear(Counters *ctr, Globals *glob) {
     if (threadIdx.x == 0) {
         glob->next_sample = 0;
         glob->rays_closest = glob->rays_shadow = glob->nodes_visited = glob->prim_tests = glob->paths = 0;
+        glob->max_nodes_per_ray = 0;
     }
 }
 
@@ -581,9 +574,9 @@ __global__ void __launch_bounds__(256) k_init(WfParams p, uint32_t n0, uint32_t 
 // rr_path_integrator.h:29), everything under bvh_node::hit and the pixel loop of
 // renderer.h:66-80.
 template <bool COUNT, bool MEDIA>
-__global__ void __launch_bounds__(128, 6) k_extend(WfParams p, int it) {
-    __shared__ FlatSmem sm;
-    const GeomView<float> g = stage_scene(p.geom, sm);
+__global__ void __launch_bounds__(kWfBlock, RTB_EXTEND_MIN_BLOCKS) k_extend(WfParams p, int it) {
+    __shared__ uint32_t s_stack[kSmemStackDepth * kWfBlock];
+    const GeomView<float> &g = p.geom;
     Counters &C = p.ctr[it % 3];
     if (blockIdx.x == 0)
         for (uint32_t i = threadIdx.x; i < sizeof(Counters) / 4; i += blockDim.x)
@@ -596,7 +589,7 @@ __global__ void __launch_bounds__(128, 6) k_extend(WfParams p, int it) {
     const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     unsigned long long chunk_next = p.cursor[2 * wid], chunk_end = p.cursor[2 * wid + 1]; // warp-uniform
     bool global_done = false;                                                            // warp-uniform
-    uint64_t nodes = 0, tests = 0;
+    uint64_t nodes = 0, tests = 0, max_nodes = 0;
     uint32_t n_new = 0;
     uint32_t base = warp_fetch(&C.head_ext.v[0]);
     while (true) {
@@ -675,8 +668,13 @@ __global__ void __launch_bounds__(128, 6) k_extend(WfParams p, int it) {
             }
             PathDraw draw{&rg};
             float t;
+            const uint64_t nodes_before = nodes;
             const uint32_t pi = trace<false, COUNT>(g, V3<float>(a.x, a.y, a.z), V3<float>(b.x, b.y, b.z), a.w, 0.001f,
-                                                    Consts<float>::inf(), __float_as_uint(b.w), draw, t, nodes, tests);
+                                                    Consts<float>::inf(), __float_as_uint(b.w), draw, t, nodes, tests,
+                                                    s_stack + threadIdx.x);
+            if (COUNT && nodes - nodes_before > max_nodes)
+                max_nodes = nodes - nodes_before;
+
             e = make_float2(t, __uint_as_float(pi));
             key = kMatTypes;
             if (pi != kNoPrim)
@@ -731,6 +729,7 @@ __global__ void __launch_bounds__(128, 6) k_extend(WfParams p, int it) {
             atomicAdd(&p.glob->nodes_visited, x);
             atomicAdd(&p.glob->prim_tests, y);
         }
+        atomicMax(&p.glob->max_nodes_per_ray, (unsigned long long)max_nodes);
     }
 }
 
@@ -747,9 +746,8 @@ __device__ __forceinline__ uint32_t out_base(const Counters &C, int q) {
 // continued path (or an empty entry where the path ended) goes to a FIXED position of the
 // next extend queue, so nothing here contends: warps stride over the chunks statically.
 template <int M, bool OLD>
-__global__ void __launch_bounds__(128) k_shade(WfParams p, int it) {
-    __shared__ FlatSmem sm;
-    const GeomView<float> g = stage_scene(p.geom, sm);
+__global__ void __launch_bounds__(kWfBlock) k_shade(WfParams p, int it) {
+    const GeomView<float> &g = p.geom;
     Counters &C = p.ctr[it % 3];
     const uint32_t n = C.key.v[M];
     const uint32_t base_out = out_base(C, M);
@@ -822,9 +820,9 @@ template <bool SHADE> __global__ void __launch_bounds__(128) k_miss(WfParams p, 
 // connect: any-hit test of the shadow rays queued by shade; unoccluded ones add their
 // (already weighted) contribution.
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_connect(WfParams p, int it) {
-    __shared__ FlatSmem sm;
-    const GeomView<float> g = stage_scene(p.geom, sm);
+__global__ void __launch_bounds__(kWfBlock, RTB_EXTEND_MIN_BLOCKS) k_connect(WfParams p, int it) {
+    __shared__ uint32_t s_stack[kSmemStackDepth * kWfBlock];
+    const GeomView<float> &g = p.geom;
     Counters &C = p.ctr[it % 3];
     const uint32_t n = C.n_shadow.v[0];
     if (blockIdx.x == 0 && threadIdx.x == 0)
@@ -841,7 +839,7 @@ __global__ void __launch_bounds__(128) k_connect(WfParams p, int it) {
             // media on a shadow ray draw from a stream keyed by the queue entry
             Pcg rg = pcg_seed((uint64_t(__float_as_uint(a.x)) << 32) ^ __float_as_uint(b.y), p.seed ^ idx);
             if (shadow_visible<COUNT>(g, V3<float>(a.x, a.y, a.z), V3<float>(b.x, b.y, b.z), a.w, __float_as_uint(c.w),
-                                      rg, nodes, tests))
+                                      rg, nodes, tests, s_stack + threadIdx.x))
                 accum_add(p.accum, __float_as_uint(b.w), V3<float>(c.x, c.y, c.z));
         }
         base = __shfl_sync(kFullMask, next_base, 0);
@@ -1295,6 +1293,7 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
         stats->rays_shadow = pool.h_glob->rays_shadow;
         stats->nodes_visited = pool.h_glob->nodes_visited;
         stats->prim_tests = pool.h_glob->prim_tests;
+        stats->max_nodes_per_ray = pool.h_glob->max_nodes_per_ray;
         stats->iterations = uint64_t(it);
         stats->kernel_launches = launches;
         stats->device_ms = ms;

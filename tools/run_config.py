@@ -47,7 +47,8 @@ def main():
         if a.time:
             line += f" stage_ms {[round(x, 2) for x in st['stage_ms']]} extend_ms {st['extend_ms']:.2f}"
         if a.count:
-            line += (f" nodes/ray {st['nodes_visited'] / max(rays, 1):.2f} prims/ray {st['prim_tests'] / max(rays, 1):.2f}")
+            line += (f" nodes/ray {st['nodes_visited'] / max(rays, 1):.2f} prims/ray {st['prim_tests'] / max(rays, 1):.2f} "
+                     f"max nodes/ray {st['max_nodes_per_ray']}")
         print(line, flush=True)
 
 
