@@ -84,7 +84,8 @@ typedef struct rtb_render_params {
 enum rtb_render_flags {
     RTB_RENDER_COUNT_VISITS = 1, /* also count BVH nodes visited / primitive tests (slower) */
     RTB_RENDER_TIME_EXTEND = 2,  /* bracket every launch of the dominant kernel with CUDA events (extend_ms) */
-    RTB_RENDER_FORCE_WAVEFRONT = 4 /* use the wavefront schedule even where the fused one applies */
+    RTB_RENDER_FORCE_WAVEFRONT = 4, /* use the wavefront schedule even where the fused one applies */
+    RTB_RENDER_FORCE_FUSED = 8      /* use the fused schedule wherever the scene fits shared memory */
 };
 
 typedef struct rtb_render_stats {

@@ -22,6 +22,7 @@ STATUS_NAMES = {0: "RTB_OK", -1: "RTB_ERR_INVALID_ARGUMENT", -2: "RTB_ERR_NO_DEV
 RENDER_COUNT_VISITS = 1
 RENDER_TIME_EXTEND = 2
 RENDER_FORCE_WAVEFRONT = 4
+RENDER_FORCE_FUSED = 8
 OPT_FLAT_TRAVERSAL, OPT_FUSED_SCHEDULE = 1, 2
 
 # Every symbol include/rtb200.h declares (tests check the library exports them all).

@@ -211,6 +211,7 @@ int rtb_scene_upload(rtb_context *ctx, const void *blob, uint64_t nbytes) {
         sc->device_bytes = bytes;
         RTB_CUDA(cudaStreamSynchronize(s));
         ctx->scene = std::move(sc);
+        ++ctx->scene_serial;
     });
 }
 

@@ -123,6 +123,7 @@ struct rtb_context {
     cudaStream_t stream = nullptr;
     std::string last_error;
     std::unique_ptr<rtb::DeviceScene> scene;
+    uint64_t scene_serial = 0;          // bumped by every rtb_scene_upload (keys per-scene decisions)
     rtb::WavefrontPool *pool = nullptr; // owned; freed by wavefront_release
     rtb::DeviceBuffer accum;            // float4 accumulators of the last rtb_render
     int accum_w = 0, accum_h = 0;

@@ -546,10 +546,11 @@ __device__ __forceinline__ bool shadow_visible(const GeomView<float> &g, V3<floa
 // written with st.global.cs (evict-first), so that the streaming path state does not push
 // the BVH nodes and primitive records out of the 126 MB L2.
 
+// glob == nullptr: only the queue counters (start of a later segment of the same render)
 __global__ void k_clear(Counters *ctr, Globals *glob) {
     for (uint32_t i = threadIdx.x; i < 3 * sizeof(Counters) / 4; i += blockDim.x)
         reinterpret_cast<uint32_t *>(ctr)[i] = 0;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && glob) {
         glob->next_sample = 0;
         glob->rays_closest = glob->rays_shadow = glob->nodes_visited = glob->prim_tests = glob->paths = 0;
         glob->max_nodes_per_ray = 0;
@@ -558,14 +559,14 @@ __global__ void k_clear(Counters *ctr, Globals *glob) {
 
 // Initial state: n0 empty entries in extend queue 0 (k_extend fills them with camera samples),
 // every warp's private sample range empty.
-__global__ void __launch_bounds__(256) k_init(WfParams p, uint32_t n0, uint32_t n_cursor) {
+__global__ void __launch_bounds__(256) k_init(WfParams p, int it, uint32_t n0, uint32_t n_cursor) {
     const uint32_t stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
     for (uint32_t i = t0; i < n0; i += stride)
-        p.ext_c[0][i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(kInvalidPix));
+        p.ext_c[it & 1][i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(kInvalidPix));
     for (uint32_t i = t0; i < 2 * n_cursor; i += stride)
         p.cursor[i] = 0ull;
     if (t0 == 0)
-        p.ctr[0].n_ext.v[0] = n0;
+        p.ctr[it % 3].n_ext.v[0] = n0;
 }
 
 // extend: closest hit for every queued path; an empty entry is first refilled with the next
@@ -1022,7 +1023,7 @@ struct WavefrontPool {
     // want = resident paths, warps = warps of one k_extend launch (each owns a private sample range)
     void ensure(uint32_t want, uint32_t warps) {
         ensure_common();
-        if (want == P && warps == n_cursor)
+        if (want <= P && warps == n_cursor) // grow-only: reallocating ~2 GB costs tens of milliseconds
             return;
         P = 0;
         // the final drain of the private sample ranges can add up to warps * kWfChunk paths
@@ -1082,7 +1083,6 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
     GeomView<float> geom = sc.geom<float>();
     if (ctx->opt_flat == 0)
         geom.flat = 0;
-    const bool fused = geom.flat && ctx->opt_fused != 0 && !(rp.flags & RTB_RENDER_FORCE_WAVEFRONT);
 
     WfParams W;
     std::memset(&W, 0, sizeof(W));
@@ -1090,38 +1090,11 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
     W.shade = sc.shade<float>();
     W.cam = sc.host.f32.camera;
     pool.ensure_common();
-    uint32_t P = 0;
     const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
     const int wf_grid = sms * 8; // 8 resident CTAs of 128 threads per SM
-    if (!fused) {
-        P = rp.pool_paths > 0 ? uint32_t(rp.pool_paths) : (1u << 21);
-        P = (P + 31u) & ~31u;
-        if ((unsigned long long)P > total)
-            P = uint32_t((total + 31ull) & ~31ull);
-        if (P < 32)
-            P = 32;
-        pool.ensure(P, uint32_t(wf_grid) * 4u);
-        for (int b = 0; b < 2; ++b) {
-            W.ext_a[b] = pool.ext[b][0].as<float4>();
-            W.ext_b[b] = pool.ext[b][1].as<float4>();
-            W.ext_c[b] = pool.ext[b][2].as<float4>();
-            W.ext_d[b] = pool.ext[b][3].as<uint4>();
-        }
-        W.hit_a = pool.hit[0].as<float4>();
-        W.hit_b = pool.hit[1].as<float4>();
-        W.hit_c = pool.hit[2].as<float4>();
-        W.hit_d = pool.hit[3].as<uint4>();
-        W.hit_e = pool.hit[4].as<float2>();
-        W.sh_a = pool.sh_a.as<float4>();
-        W.sh_b = pool.sh_b.as<float4>();
-        W.sh_c = pool.sh_c.as<float4>();
-        W.cursor = pool.cursor.as<unsigned long long>();
-        W.cap = pool.cap;
-    }
     W.ctr = pool.ctr.as<Counters>();
     W.glob = pool.glob.as<Globals>();
     W.accum = d_accum;
-    W.P = P;
     W.width = rp.width;
     W.height = rp.height;
     W.spp = rp.spp;
@@ -1143,20 +1116,17 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
     const bool nee = rp.integrator >= RTB_INTEGRATOR_DIRECT && !sc.host.f32.lights.empty();
     const bool count = (rp.flags & RTB_RENDER_COUNT_VISITS) != 0;
     const bool time_dom = (rp.flags & RTB_RENDER_TIME_EXTEND) != 0;
+    const bool simple = (W.mat_mask & ~((1u << RTB_MAT_LAMBERTIAN) | (1u << RTB_MAT_DIFFUSE_LIGHT))) == 0;
     size_t n_ext_events = 0;
 
     uint64_t launches = 0;
     int it = 0;
     bool cancelled = false;
-    RTB_CUDA(cudaEventRecord(pool.ev_begin, st));
-    RTB_CUDA(cudaMemsetAsync(d_accum, 0, size_t(npix) * sizeof(float4), st));
-    k_clear<<<1, 256, 0, st>>>(W.ctr, W.glob);
-    ++launches;
 
-    if (fused) {
+    // ---- the two schedules, each over the local samples [begin, end) --------------------------
+    auto run_fused = [&](unsigned long long begin, unsigned long long end) {
         // One persistent kernel per window of samples (windows keep rtb_cancel responsive).
         // pick the instantiation once: (legacy vs BSDF API) x (counting) x (simple material set)
-        const bool simple = (W.mat_mask & ~((1u << RTB_MAT_LAMBERTIAN) | (1u << RTB_MAT_DIFFUSE_LIGHT))) == 0;
         void (*kern)(WfParams) = nullptr;
         {
             void (*table[2][2][2])(WfParams) = {
@@ -1169,9 +1139,11 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
         const int bps = blocks_per_sm(kern, 128);
         const int grid = sms * bps;
         const unsigned long long window = 1ull << 26;
-        for (unsigned long long begin = 0; begin < total; begin += window) {
-            W.window_end = std::min(total, begin + window);
-            k_set_next_sample<<<1, 1, 0, st>>>(W.glob, begin);
+        int in_flight = 0;
+        for (unsigned long long b0 = begin; b0 < end && !cancelled; b0 += window) {
+            W.total_samples = total;
+            W.window_end = std::min(end, b0 + window);
+            k_set_next_sample<<<1, 1, 0, st>>>(W.glob, b0);
             if (time_dom)
                 RTB_CUDA(cudaEventRecord(pool.ext_event(n_ext_events++), st));
             kern<<<grid, 128, 0, st>>>(W);
@@ -1179,22 +1151,57 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
                 RTB_CUDA(cudaEventRecord(pool.ext_event(n_ext_events++), st));
             launches += 2;
             ++it;
+            ++in_flight;
             RTB_CUDA(cudaGetLastError());
-            if (begin + window < total) { // keep at most two windows in flight
-                const int slot = it & 1;
+            if (b0 + window < end) { // keep at most two windows in flight
+                const int slot = in_flight & 1;
                 RTB_CUDA(cudaEventRecord(pool.ev[slot], st));
-                if (it >= 2)
+                if (in_flight >= 2)
                     RTB_CUDA(cudaEventSynchronize(pool.ev[slot ^ 1]));
             }
-            if (ctx->cancel.load(std::memory_order_relaxed)) {
+            if (ctx->cancel.load(std::memory_order_relaxed))
                 cancelled = true;
-                break;
-            }
         }
-    } else {
+    };
+
+    auto run_wavefront = [&](unsigned long long begin, unsigned long long end, bool first_segment) {
+        const unsigned long long seg = end - begin;
+        uint32_t P = rp.pool_paths > 0 ? uint32_t(rp.pool_paths) : (1u << 21);
+        P = (P + 31u) & ~31u;
+        if ((unsigned long long)P > seg)
+            P = uint32_t((seg + 31ull) & ~31ull);
+        if (P < 32)
+            P = 32;
+        // always at least the default pool, so that a small first render (a preview) is not
+        // followed by a reallocation inside the next, full-size one
+        pool.ensure(std::max(P, 1u << 21), uint32_t(wf_grid) * 4u);
+        for (int b = 0; b < 2; ++b) {
+            W.ext_a[b] = pool.ext[b][0].as<float4>();
+            W.ext_b[b] = pool.ext[b][1].as<float4>();
+            W.ext_c[b] = pool.ext[b][2].as<float4>();
+            W.ext_d[b] = pool.ext[b][3].as<uint4>();
+        }
+        W.hit_a = pool.hit[0].as<float4>();
+        W.hit_b = pool.hit[1].as<float4>();
+        W.hit_c = pool.hit[2].as<float4>();
+        W.hit_d = pool.hit[3].as<uint4>();
+        W.hit_e = pool.hit[4].as<float2>();
+        W.sh_a = pool.sh_a.as<float4>();
+        W.sh_b = pool.sh_b.as<float4>();
+        W.sh_c = pool.sh_c.as<float4>();
+        W.cursor = pool.cursor.as<unsigned long long>();
+        W.cap = pool.cap;
+        W.P = P;
+        W.total_samples = end; // k_extend hands out samples [next_sample, total_samples)
+        W.window_end = end;
         const int grid = wf_grid;
-        k_init<<<sms * 4, 256, 0, st>>>(W, P, pool.n_cursor);
-        ++launches;
+        if (!first_segment) {
+            k_clear<<<1, 256, 0, st>>>(W.ctr, nullptr);
+            ++launches;
+        }
+        k_set_next_sample<<<1, 1, 0, st>>>(W.glob, begin);
+        k_init<<<sms * 4, 256, 0, st>>>(W, it, P, pool.n_cursor);
+        launches += 2;
         RTB_CUDA(cudaGetLastError());
         // radiance of a ray that leaves the scene is identically zero: k_miss only empties entries
         const bool miss_shades = W.bg[0] != 0.f || W.bg[1] != 0.f || W.bg[2] != 0.f ||
@@ -1202,7 +1209,8 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
         const bool media = W.has_media != 0;
         constexpr int kBatch = 4; // iterations between two host-side liveness probes
         int probe = 0, zero_probes = 0;
-        bool done = total == 0;
+        const int it0 = it;
+        bool done = seg == 0;
         int pending[2] = {-1, -1}; // probe slots in flight
         while (!done) {
             for (int b = 0; b < kBatch; ++b, ++it) {
@@ -1272,12 +1280,34 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
                 break;
             }
             // every entry is busy on every iteration until the samples run out, so the last
-            // sample starts no later than iteration total*max_depth/P; the tail adds max_depth
-            if ((unsigned long long)it >
-                total * (unsigned long long)rp.max_depth / P + 2ull * rp.max_depth + 16 * kBatch)
+            // sample starts no later than iteration seg*max_depth/P; the tail adds max_depth
+            if ((unsigned long long)(it - it0) >
+                seg * (unsigned long long)rp.max_depth / P + 2ull * rp.max_depth + 16 * kBatch)
                 throw std::runtime_error("wavefront: iteration bound exceeded (internal error)");
         }
+    };
+
+    // ---- which schedule ------------------------------------------------------------------
+    // Not shared-memory sized: wavefront.  Small scenes: the fused kernel, except where every
+    // bounce runs next-event estimation against area / delta lights on a mixed material set —
+    // there the divergent Cook-Torrance + MIS shading and the partially filled inline shadow
+    // rays cost more than the queues, and the material-sorted wavefront wins.  Measured on B200
+    // (fused vs wavefront): C1 30 vs 55 ms, C3 69 vs 87 ms, C4-env 44 vs 55 ms, C4 17.4 vs 6.6 ms.
+    const bool can_fuse = geom.flat && ctx->opt_fused != 0 && !(rp.flags & RTB_RENDER_FORCE_WAVEFRONT);
+    const bool finite_lights = int(sc.host.f32.lights.size()) > sc.host.n_infinite_lights;
+    const bool prefer_wavefront = !simple && nee && finite_lights;
+    int schedule = 0;
+    RTB_CUDA(cudaEventRecord(pool.ev_begin, st));
+    RTB_CUDA(cudaMemsetAsync(d_accum, 0, size_t(npix) * sizeof(float4), st));
+    k_clear<<<1, 256, 0, st>>>(W.ctr, W.glob);
+    ++launches;
+    if (can_fuse && (!prefer_wavefront || (rp.flags & RTB_RENDER_FORCE_FUSED))) {
+        schedule = 1;
+        run_fused(0, total);
+    } else {
+        run_wavefront(0, total, true);
     }
+    const bool fused = schedule == 1;
     RTB_CUDA(cudaMemcpyAsync(pool.h_glob, W.glob, sizeof(Globals), cudaMemcpyDeviceToHost, st));
     RTB_CUDA(cudaEventRecord(pool.ev_end, st));
     RTB_CUDA(cudaStreamSynchronize(st));

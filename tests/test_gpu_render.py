@@ -142,13 +142,13 @@ def test_resolve_rgb8_matches_reference_conversion(gpu_ctx, golden):
 
 @pytest.mark.parametrize("sid,integrator", [(7, 1), (21, 4), (23, 4), (23, 3), (8, 1)])
 def test_fused_and_wavefront_schedules_agree(gpu_ctx, golden, binding, sid, integrator):
-    """Small scenes run the fused persistent kernel by default; the wavefront schedule is the
+    """Small scenes can run the fused persistent kernel; the wavefront schedule is the
     same stage functions behind HBM queues.  Both consume the per-sample RNG stream in the
     same order, so without media they trace exactly the same paths."""
     g = golden(sid)
     gpu_ctx.upload_scene(g.blob)
     w, h, spp = 96, 96, 64
-    a, sa = gpu_ctx.render(gpu_ctx.params(w, h, spp, integrator, seed=21))
+    a, sa = gpu_ctx.render(gpu_ctx.params(w, h, spp, integrator, seed=21, flags=binding.RENDER_FORCE_FUSED))
     b, sb = gpu_ctx.render(gpu_ctx.params(w, h, spp, integrator, seed=21, flags=binding.RENDER_FORCE_WAVEFRONT))
     assert sa["schedule"] == 1 and sb["schedule"] == 0
     assert sa["paths"] == sb["paths"] == w * h * spp

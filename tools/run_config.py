@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--spp", type=int, default=0)
     ap.add_argument("--pool", type=int, default=0)
     ap.add_argument("--wavefront", action="store_true")
+    ap.add_argument("--fused", action="store_true")
     ap.add_argument("--time", action="store_true")
     ap.add_argument("--count", action="store_true")
     ap.add_argument("--reps", type=int, default=1)
@@ -32,7 +33,7 @@ def main():
     spp = a.spp or cfg.spp
     ctx = pkg.Context(0)
     ctx.upload_scene(cfg.blob())
-    flags = (binding.RENDER_FORCE_WAVEFRONT if a.wavefront else 0) | (binding.RENDER_TIME_EXTEND if a.time else 0) \
+    flags = (binding.RENDER_FORCE_WAVEFRONT if a.wavefront else 0) | (binding.RENDER_FORCE_FUSED if a.fused else 0) | (binding.RENDER_TIME_EXTEND if a.time else 0) \
         | (binding.RENDER_COUNT_VISITS if a.count else 0)
     for _ in range(a.warm):
         ctx.render(ctx.params(cfg.width, cfg.height, min(spp, 2), cfg.integrator, cfg.depth, pool_paths=a.pool))
