@@ -1,12 +1,14 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the path-integration hot path.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--config C1..C5] [--spp S]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[0], the configuration the metric is quoted on): scene07
-Cornell box, 600x600, 400 spp, depth 50, integrator 1 (Russian roulette).  One STEP is one
-full render of that configuration per GPU (144 M camera paths, ~470 M rays).
+Default workload (BASELINE.json configs[0], the configuration the metric is quoted on): C1 =
+scene07 Cornell box, 600x600, 400 spp, depth 50, integrator 1 (Russian roulette).  One STEP is
+one full render of that configuration per GPU (144 M camera paths, ~470 M rays).  --config
+selects another BASELINE configuration (ray_tracing-rendering_b200/configs.py); --spp reduces
+the samples per pixel of a step (stated in config.workload; cost is linear in spp).
 
 native arm      value   Mpaths/s with the scene resident in HBM: K steps bracketed by CUDA events
                         (barrier + synchronize on both sides, max over ranks); with N > 1 ranks
@@ -37,6 +39,19 @@ PKG = "ray_tracing-rendering_b200"
 
 W, H, SPP, DEPTH, INTEGRATOR, SCENE = 600, 600, 400, 50, 1, 7
 WORKLOAD = "scene07 Cornell box 600x600 spp=400 kMaxDepth=50 integrator 1 (Russian roulette)"
+CONFIG = "C1"
+
+
+def select_config(name, spp):
+    """Points the module-level workload description at a BASELINE configuration."""
+    global W, H, SPP, DEPTH, INTEGRATOR, SCENE, WORKLOAD, CONFIG
+    cfg = importlib.import_module(PKG + ".configs").get(name)
+    W, H, SPP, DEPTH, INTEGRATOR, SCENE, CONFIG = cfg.width, cfg.height, cfg.spp, cfg.depth, cfg.integrator, cfg.scene_id, name
+    WORKLOAD = cfg.workload
+    if spp and spp != cfg.spp:
+        SPP = spp
+        WORKLOAD += f" [step reduced to spp={spp} of {cfg.spp}]"
+    return cfg
 
 
 class ClockSampler(threading.Thread):
@@ -76,6 +91,8 @@ def cpu_reference(steps, warmup, budget_s):
     reference compiled from /root/reference (oracle/_ref, Renderer::render untouched); where that
     library did not travel, kind "port" = the CPU restatement oracle/port on the same scene."""
     from oracle import refbind
+    if SCENE < 0:
+        raise RuntimeError("synthetic configuration: the reference has no such scene to time")
     if refbind.available():
         t_probe, _, _, _ = refbind.render_timed(SCENE, INTEGRATOR, W, 8, DEPTH)
         per_step = budget_s / max(steps + warmup, 1)
@@ -93,7 +110,7 @@ def cpu_reference(steps, warmup, budget_s):
         if not portbind.available():
             raise RuntimeError("neither oracle/_ref/libref_oracle.so nor oracle/liboracle_port.so is built")
         scenes = importlib.import_module(PKG + ".scenes")
-        sc = portbind.PortScene(scenes.select_scene(SCENE))
+        sc = portbind.PortScene(importlib.import_module(PKG + ".configs").get(CONFIG).blob())
         _, _, _, t_probe = sc.render_linear(INTEGRATOR, W, H, 2, DEPTH, want_images=False)
         per_step = budget_s / max(steps + warmup, 1)
         spp = int(max(1, min(SPP, per_step / max(t_probe / 2, 1e-3))))
@@ -116,7 +133,7 @@ def run_reference(args, rank):
     out = {"metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-           "config": {"workload": WORKLOAD, "integrator": INTEGRATOR, "width": W, "height": H, "spp": SPP},
+           "config": {"workload": WORKLOAD, "name": CONFIG, "integrator": INTEGRATOR, "width": W, "height": H, "spp": SPP},
            "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
@@ -137,7 +154,7 @@ def run_native(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = pkg.Context(local_rank)
-    blob = scenes.select_scene(SCENE)       # the product's own builder; no reference code involved
+    blob = importlib.import_module(PKG + ".configs").get(CONFIG).blob()   # the product's own builder; no reference code
     ctx.upload_scene(blob)
     stream = torch.cuda.Stream(dev)          # kernels, events and the NCCL reduce all run on this stream
     accum = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
@@ -200,41 +217,64 @@ def run_native(args, rank, local_rank, world):
     ms, tot, clocks = timed(step)
     ms_e2e, tot_e2e, _ = timed(step_e2e)
 
-    # roofline of the dominant kernel (extend): per-launch CUDA-event durations measured live,
-    # algorithmic bytes from the same kernel's counting variant on the same workload
+    # roofline of the dominant kernel: per-launch CUDA-event durations measured live (on the
+    # stream the kernels run on), algorithmic bytes from the same kernel's counting variant
     st_t = ctx.render_device(params(binding.RENDER_TIME_EXTEND, seed=77), accum.data_ptr(), stream.cuda_stream)
-    cp = ctx.params(W, H, 16, INTEGRATOR, DEPTH, 3, 77, 0, 1, 0, binding.RENDER_COUNT_VISITS)
+    cp = ctx.params(W, H, min(SPP, 16), INTEGRATOR, DEPTH, 3, 77, 0, 1, 0, binding.RENDER_COUNT_VISITS)
     st_c = ctx.render_device(cp, accum.data_ptr(), stream.cuda_stream)
-    n_node = st_c["nodes_visited"] / st_c["rays_closest"]
-    n_prim = st_c["prim_tests"] / st_c["rays_closest"]
+    fused = st_t.get("schedule") == 1
+    rays_c = st_c["rays_closest"] + st_c["rays_shadow"]
+    n_node = st_c["nodes_visited"] / rays_c
+    n_prim = st_c["prim_tests"] / rays_c
     b_ray = 32.0 * n_node + 32.0 * n_prim + 48.0
-    rays_per_launch = st_t["rays_closest"] / max(st_t["extend_launches"], 1)
+    # fused: the one kernel traces closest-hit AND shadow rays; wavefront: k_extend traces the closest-hit rays
+    rays_dom = st_t["rays_closest"] + (st_t["rays_shadow"] if fused else 0)
+    rays_per_launch = rays_dom / max(st_t["extend_launches"], 1)
     us_per_launch = 1e3 * st_t["extend_ms"] / max(st_t["extend_launches"], 1)
-    achieved = b_ray * st_t["rays_closest"] / (st_t["extend_ms"] * 1e-3) / 1e9
+    achieved = b_ray * rays_dom / (st_t["extend_ms"] * 1e-3) / 1e9
     peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         pass
-    traffic = None
+    traffic, micro = None, {}
     try:
         with open(os.path.join(ROOT, "profiles", "extend_traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            traffic = json.load(f).get(CONFIG, {}).get("dram_bytes_per_launch")
     except Exception:
         pass
-    dominant = "k_fused (trace + shade + regenerate, scene in shared memory)" if st_t.get("schedule") == 1 else "k_extend"
+    try:
+        with open(os.path.join(ROOT, "profiles", "microbench.json")) as f:
+            micro = json.load(f)
+    except Exception:
+        pass
+    # secondary figure for the cache-resident scenes: algorithmic flops per ray
+    # F_ray = 24 n_node + 30 n_sphere + 10 n_rect + F_shade against the measured FP32 FMA rate
+    ptypes = importlib.import_module(PKG + ".abi").parse_blob(blob)["prims"]["type"]
+    frac_sphere = float((ptypes <= 1).mean()) if len(ptypes) else 0.0
+    f_prim = 30.0 * frac_sphere + 10.0 * (1.0 - frac_sphere)
+    f_ray = 24.0 * n_node + f_prim * n_prim + 60.0
+    grays = rays_dom / (st_t["extend_ms"] * 1e-3) / 1e9
+    fp32_peak = micro.get("fp32_fma_tflops")
+    dominant = "k_fused (trace + shade + regenerate, scene in shared memory)" if fused else "k_extend (closest hit + refill + material sort)"
+    note = ("the scene is shared-memory resident: the dominant kernel keeps path state in registers and is "
+            "instruction-issue bound, not HBM bound; the algorithmic bytes of SURVEY 8(d) over the kernel time are "
+            "reported against the HBM peak as the contract asks and can exceed it because those bytes never leave the SM"
+            if fused else
+            "BVH traversal is divergence / issue bound (ncu: ~16 of 32 lanes active, 55 % issue slots, L2 hit 50-67 %); "
+            "algorithmic bytes per SURVEY 8(d): 32 B per node visited + 32 B per primitive tested + 48 B per ray")
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "bytes_per_ray": b_ray, "nodes_per_ray": n_node, "prims_per_ray": n_prim,
                 "rays_per_launch": rays_per_launch, "us_per_launch": us_per_launch,
                 "extend_share_of_step": st_t["extend_ms"] / st_t["device_ms"],
-                "grays_per_s_in_kernel": st_t["rays_closest"] / (st_t["extend_ms"] * 1e-3) / 1e9,
-                "note": "scene07 is 18 primitives (1 KB): the dominant kernel reads it from shared memory and "
-                        "keeps path state in registers, so it is issue-bound, not HBM-bound; the algorithmic "
-                        "bytes of SURVEY 8(d) (32 B per instance entry + 32 B per primitive test + 48 B per ray) "
-                        "over the kernel time are reported against the HBM peak as the contract asks, and can "
-                        "exceed it because those bytes never leave the SM"}
+                "grays_per_s_in_kernel": grays,
+                "stage_ms": st_t.get("stage_ms"),
+                "fp32": {"flops_per_ray": f_ray, "achieved_tflops": grays * f_ray / 1e3, "peak_tflops": fp32_peak,
+                         "frac": (grays * f_ray / 1e3 / fp32_peak) if fp32_peak else None,
+                         "peak_source": "tools/microbench (profiles/microbench.json), FMA = 2 flops"},
+                "note": note}
 
     cpu = None
     if rank == 0 and world == 1:
@@ -251,13 +291,15 @@ def run_native(args, rank, local_rank, world):
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic", "impl": "native",
                "mrays_per_s": tot[1] / secs / 1e6,
-               "config": {"workload": WORKLOAD, "integrator": INTEGRATOR, "width": W, "height": H,
+               "config": {"workload": WORKLOAD, "name": CONFIG, "integrator": INTEGRATOR, "width": W, "height": H,
                           "spp_per_gpu": SPP, "paths_per_step_per_gpu": W * H * SPP, "parallelism": f"spp-split x{world}",
                           "collective": "one NCCL SUM-reduce of the float4 accumulators per step" if world > 1 else "none",
-                          "schedule": "fused" if st_t.get("schedule") == 1 else "wavefront",
-                          "l2": "no L2 flush needed: the fused schedule keeps the 1 KB scene in shared memory and "
-                                "path state in registers; every step writes all 5.8 MB of accumulators with "
-                                "atomics after a memset (wavefront schedule: the 0.2 GB path pool exceeds L2)"},
+                          "schedule": "fused" if fused else "wavefront",
+                          "l2": ("no L2 flush needed: the fused schedule keeps the scene in shared memory and path "
+                                 "state in registers; every step rewrites all accumulators with atomics after a memset"
+                                 if fused else
+                                 "no extra flush: every wavefront iteration streams the 2 Mi-entry queues (>= 0.3 GB "
+                                 "read + written, evict-first) through the 126 MB L2")},
                "e2e": {"value": tot_e2e[0] / (ms_e2e * 1e-3) / 1e6, "unit": "Mpaths/s",
                        "h2d_bytes_per_step": len(blob), "d2h_bytes_per_step": W * H * 16,
                        "ms_per_step": ms_e2e / args.steps},
@@ -274,7 +316,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--config", default="C1")
+    ap.add_argument("--spp", type=int, default=0)
     args = ap.parse_args()
+    select_config(args.config, args.spp)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
