@@ -63,13 +63,14 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None   # the timed region (samples outside it are dropped)
 
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
+                self.rows.append([time.time()] + [c.strip() for c in line.split(",")])
         except Exception:
             pass
 
@@ -77,12 +78,16 @@ class ClockSampler(threading.Thread):
         if self.proc:
             self.proc.terminate()
         self.join(2)
-        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
-        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        rows = [r[1:] for r in self.rows if self.t0 is None or self.t0 <= r[0] <= (self.t1 or r[0])]
+        if not rows and self.rows:   # region shorter than one sampling period: the sample closest to it
+            mid = 0.5 * ((self.t0 or 0) + (self.t1 or 0))
+            rows = [min(self.rows, key=lambda r: abs(r[0] - mid))[1:]]
+        sm = sorted(float(r[1]) for r in rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v == "Active"})
+        reasons = sorted({n for r in rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v == "Active"})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(rows)}
 
 
 def cpu_reference(steps, warmup, budget_s):
@@ -152,6 +157,8 @@ def run_native(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # keep stdout to the ONE JSON line: NCCL's version banner goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     ctx = pkg.Context(local_rank)
     blob = importlib.import_module(PKG + ".configs").get(CONFIG).blob()   # the product's own builder; no reference code
@@ -159,7 +166,9 @@ def run_native(args, rank, local_rank, world):
     stream = torch.cuda.Stream(dev)          # kernels, events and the NCCL reduce all run on this stream
     accum = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
     host = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
-    total_spp = SPP * world                # weak scaling: every rank renders SPP samples per pixel
+    # weak scaling (default): every rank renders SPP samples per pixel; strong: SPP in total
+    strong = args.scaling == "strong"
+    total_spp = SPP if strong else SPP * world
 
     def params(flags=0, seed=1):
         off, stride, _ = dmod.rank_split(total_spp, rank, world)
@@ -189,13 +198,14 @@ def run_native(args, rank, local_rank, world):
         return st
 
     def timed(fn):
+        sampler = ClockSampler(local_rank)   # started before the warm-up: nvidia-smi takes a while to come up
+        sampler.start()
         for i in range(args.warmup):
             fn(1000 + i)
         sync()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         agg = {"paths": 0, "rays": 0, "launches": 0}
+        sampler.t0 = time.time()
         e0.record(stream)
         for i in range(args.steps):
             st = fn(i + 1)
@@ -204,6 +214,7 @@ def run_native(args, rank, local_rank, world):
             agg["launches"] += st["kernel_launches"]
         e1.record(stream)
         sync()
+        sampler.t1 = time.time()
         clocks = sampler.stop()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         tot = torch.tensor([agg["paths"], agg["rays"], agg["launches"]], dtype=torch.float64, device=dev)
@@ -288,11 +299,12 @@ def run_native(args, rank, local_rank, world):
         secs = ms * 1e-3
         out = {"metric": "Mpaths/s", "value": tot[0] / secs / 1e6, "unit": "Mpaths/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+               "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic", "impl": "native",
                "mrays_per_s": tot[1] / secs / 1e6,
                "config": {"workload": WORKLOAD, "name": CONFIG, "integrator": INTEGRATOR, "width": W, "height": H,
-                          "spp_per_gpu": SPP, "paths_per_step_per_gpu": W * H * SPP, "parallelism": f"spp-split x{world}",
+                          "spp_per_gpu": total_spp / world, "paths_per_step_per_gpu": W * H * total_spp // world,
+                          "parallelism": f"spp-split x{world}",
                           "collective": "one NCCL SUM-reduce of the float4 accumulators per step" if world > 1 else "none",
                           "schedule": "fused" if fused else "wavefront",
                           "l2": ("no L2 flush needed: the fused schedule keeps the scene in shared memory and path "
@@ -318,6 +330,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--config", default="C1")
     ap.add_argument("--spp", type=int, default=0)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     args = ap.parse_args()
     select_config(args.config, args.spp)
     rank = int(os.environ.get("RANK", "0"))
