@@ -19,6 +19,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <exception>
 #include <mutex>
@@ -133,7 +134,13 @@ template <class F> inline void parallel_for(size_t n, size_t grain, unsigned thr
         std::rethrow_exception(err);
 }
 
+// RTB200_BUILD_THREADS overrides the thread count (tests compare trees across counts).
 inline unsigned builder_threads() {
+    if (const char *e = std::getenv("RTB200_BUILD_THREADS")) {
+        const int v = std::atoi(e);
+        if (v >= 1)
+            return unsigned(std::min(v, 64));
+    }
     const unsigned hc = std::thread::hardware_concurrency();
     return std::min(std::max(hc, 1u), 32u);
 }

@@ -82,6 +82,8 @@ def hostcheck():
     L.hc_scene_create.argtypes = [C.c_char_p, C.c_uint64, C.c_int]
     L.hc_scene_destroy.argtypes = [C.c_void_p]
     L.hc_scene_info.argtypes = [C.c_void_p, C.c_void_p]
+    L.hc_scene_tree_hash.restype = C.c_uint64
+    L.hc_scene_tree_hash.argtypes = [C.c_void_p]
     L.hc_trace_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
     L.hc_bsdf_eval.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
     L.hc_bsdf_sample.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_void_p]

@@ -198,6 +198,20 @@ void hc_scene_info(void *h, int64_t sizes[3]) {
     sizes[2] = H->n_instances;
 }
 
+// FNV-1a over the node array and the leaf order: equal iff the trees are identical
+uint64_t hc_scene_tree_hash(void *h) {
+    auto *H = static_cast<HostScene *>(h);
+    uint64_t x = 1469598103934665603ull;
+    auto mix = [&](const void *p, size_t n) {
+        const unsigned char *b = static_cast<const unsigned char *>(p);
+        for (size_t i = 0; i < n; ++i)
+            x = (x ^ b[i]) * 1099511628211ull;
+    };
+    mix(H->nodes.data(), H->nodes.size() * sizeof(Node32));
+    mix(H->prim_orig.data(), H->prim_orig.size() * sizeof(H->prim_orig[0]));
+    return x;
+}
+
 // precision 64: the validation arithmetic (reference operation order, no self-hit
 // logic); 32: the production arithmetic.  stats = {nodes visited, primitive tests}.
 void hc_trace_batch(void *h, const rtb_ray *rays, uint64_t n, int precision, rtb_hit *hits,

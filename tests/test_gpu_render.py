@@ -164,3 +164,53 @@ def test_large_scenes_use_the_wavefront_schedule(gpu_ctx, golden):
     gpu_ctx.upload_scene(golden(9).blob)
     _, st = gpu_ctx.render(gpu_ctx.params(64, 64, 8, 1))
     assert st["schedule"] == 0 and st["iterations"] > 4
+
+
+@pytest.mark.gpu
+def test_wavefront_result_does_not_depend_on_the_pool_size(gpu_ctx, golden, binding):
+    """A sample's random stream is keyed by (pixel, sample), so the set of paths — and, without
+    media, every ray — is the same however many paths are resident: tiny pools exercise the
+    refill of empty queue entries and the final drain of the warps' private sample ranges."""
+    gpu_ctx.upload_scene(golden(1).blob)          # random spheres: BVH scene, no media
+    w, h, spp = 80, 45, 24
+    ref = None
+    for pool in (0, 1000, 4096, 65536):
+        acc, st = gpu_ctx.render(gpu_ctx.params(w, h, spp, 1, seed=5, pool_paths=pool,
+                                                flags=binding.RENDER_FORCE_WAVEFRONT))
+        assert st["schedule"] == 0 and st["paths"] == w * h * spp
+        assert np.isfinite(acc).all()
+        if ref is None:
+            ref = (acc.copy(), st)
+        else:
+            assert st["rays_closest"] == ref[1]["rays_closest"]
+            assert np.allclose(acc[..., :3], ref[0][..., :3], rtol=2e-4, atol=1e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,spp", [(7, 5, 3), (2, 2, 1), (33, 2, 2), (64, 64, 1)])
+def test_wavefront_small_and_ragged_jobs(gpu_ctx, golden, binding, w, h, spp):
+    """Fewer samples than one warp / than the pool, sample counts that are no multiple of 32."""
+    gpu_ctx.upload_scene(golden(1).blob)
+    for integrator in (1, 4):
+        acc, st = gpu_ctx.render(gpu_ctx.params(w, h, spp, integrator, seed=3, flags=binding.RENDER_FORCE_WAVEFRONT))
+        assert st["paths"] == w * h * spp and st["rays_closest"] >= w * h * spp
+        assert np.isfinite(acc).all() and (acc[..., :3] >= 0).all()
+    # max_depth 0: nothing is traced
+    acc, st = gpu_ctx.render(gpu_ctx.params(w, h, spp, 1, max_depth=0, flags=binding.RENDER_FORCE_WAVEFRONT))
+    assert st["rays_closest"] == 0 and not acc[..., :3].any()
+
+
+@pytest.mark.gpu
+def test_no_degenerate_rays_survive(gpu_ctx, golden, binding):
+    """fp32 guard: a zero-length scatter direction (possible once per ~2^24 isotropic draws) used
+    to turn into a NaN ray that passed every slab test and walked the whole tree for up to 50
+    bounces.  With media in the scene, no ray may visit a large part of the tree and the image
+    must be finite."""
+    gpu_ctx.upload_scene(golden(9).blob)
+    n_nodes = gpu_ctx.scene_stats()["n_nodes"]
+    worst = 0
+    for seed in range(1, 5):
+        acc, st = gpu_ctx.render(gpu_ctx.params(400, 400, 24, 1, seed=seed, flags=binding.RENDER_COUNT_VISITS))
+        assert np.isfinite(acc).all()
+        worst = max(worst, st["max_nodes_per_ray"])
+    assert 0 < worst < n_nodes // 4, (worst, n_nodes)

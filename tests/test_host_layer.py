@@ -106,3 +106,22 @@ def test_reference_shaped_api_on_the_gpu(tmp_path):
     assert kv["png"] == ["1"]
     sig = open("/tmp/rtb_host_api_test.png", "rb").read(8)
     assert sig == bytes([137, 80, 78, 71, 13, 10, 26, 10])
+
+
+def test_bvh_builder_is_deterministic_across_thread_counts(hostcheck, monkeypatch):
+    """The multi-threaded binned-SAH builder numbers nodes serially per level, so the tree (and
+    with it every traversal count) must not depend on how many threads built it."""
+    import ctypes as C
+    import importlib
+    scenes = importlib.import_module(PKG + ".scenes")
+    blob = scenes.sphere_field(half_extent=100, width=64, height=36, spp=1)   # 40,000 spheres
+    hashes = []
+    for threads in ("1", "3", "8"):
+        monkeypatch.setenv("RTB200_BUILD_THREADS", threads)
+        h = hostcheck.hc_scene_create(blob, len(blob), 4)
+        assert h
+        sizes = (C.c_int64 * 3)()
+        hostcheck.hc_scene_info(h, sizes)
+        hashes.append((hostcheck.hc_scene_tree_hash(h), sizes[0], sizes[1]))
+        hostcheck.hc_scene_destroy(h)
+    assert hashes[0] == hashes[1] == hashes[2] and hashes[0][1] > 40000
