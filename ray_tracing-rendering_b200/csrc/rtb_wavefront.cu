@@ -56,6 +56,16 @@ namespace {
 constexpr int kMatTypes = RTB_MAT_TYPE_COUNT; // 6
 constexpr uint32_t kFullMask = 0xffffffffu;
 
+// Resident CTAs per SM k_fused is compiled for (register budget 65536 / (128 * N)): the kernel is
+// bound by dependent-issue latency, so occupancy pays until spills take over.  Measured on B200,
+// C1 (legacy-API instantiation): 4 -> 30.4 ms, 6 -> 27.8, 7 -> 26.3, 8 -> 25.3, 10 -> 28.8, 12 -> 40.6;
+// C3 (BSDF-API instantiation): 4 -> 68.7 ms, 6 -> 60.9, 7 -> 61.0, 8 -> 63.2, 10 -> 81.2.
+#ifndef RTB_FUSED_MIN_BLOCKS_OLD
+#define RTB_FUSED_MIN_BLOCKS_OLD 8
+#endif
+#ifndef RTB_FUSED_MIN_BLOCKS_NEW
+#define RTB_FUSED_MIN_BLOCKS_NEW 7
+#endif
 #ifndef RTB_EXTEND_MIN_BLOCKS
 #define RTB_EXTEND_MIN_BLOCKS 5 // resident CTAs per SM k_extend is compiled for (register budget 65536 / (128 * N))
 #endif
@@ -862,7 +872,7 @@ constexpr uint32_t kSampleChunk = 256; // samples a warp reserves per atomic
 // other four shade_surface instantiations are left out, which halves the kernel's code size
 // (the profile of the general kernel showed instruction-cache misses).
 template <bool OLD, bool COUNT, bool SIMPLE>
-__global__ void __launch_bounds__(128, 4) k_fused(WfParams p) {
+__global__ void __launch_bounds__(128, OLD ? RTB_FUSED_MIN_BLOCKS_OLD : RTB_FUSED_MIN_BLOCKS_NEW) k_fused(WfParams p) {
     __shared__ FlatSmem sm;
     const GeomView<float> g = stage_scene_flat(p.geom, sm);
     PathState s;
