@@ -107,6 +107,11 @@ typedef struct rtb_render_stats {
     /* only with RTB_RENDER_COUNT_VISITS on the wavefront schedule: the most BVH nodes any single
      * closest-hit ray visited (the longest traversal sets the tail of an extend launch) */
     uint64_t max_nodes_per_ray;
+    /* only with RTB_RENDER_COUNT_VISITS on the wavefront schedule: nodes visited by closest-hit
+     * rays, and the sum over 32-ray chunks of the LONGEST ray's node count.  Their ratio / 32 is
+     * the lane utilisation a chunk-synchronous traversal can reach at best. */
+    uint64_t extend_nodes;
+    uint64_t extend_chunk_max_nodes;
 } rtb_render_stats;
 
 typedef struct rtb_scene_stats {

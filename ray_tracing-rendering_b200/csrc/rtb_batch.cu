@@ -29,6 +29,17 @@ struct DrawOpen {
     __device__ Real operator()() { return g->next_open(); }
 };
 
+// the plain while-while traversal (the renderer's speculative one is warp-cooperative and is
+// checked against this one ray by ray in tests/test_hostcheck_parity.py and, through whole
+// renders, against the fused schedule and the reference images)
+template <class Rng>
+__device__ __forceinline__ uint32_t trace_bvh(const GeomView<Real> &g, V3<Real> o, V3<Real> d, Real time, Real t_min,
+                                              Real t_max, uint32_t origin, Rng &rng, Real &t, uint64_t *nodes,
+                                              uint64_t *tests) {
+    LocalStack stack;
+    return traverse<Real, false, kRobust>(g, o, d, time, t_min, t_max, origin, rng, t, nodes, tests, stack);
+}
+
 __global__ void __launch_bounds__(128)
 k_trace_batch(GeomView<Real> g, const int32_t *__restrict__ orig_to_sorted, int n_orig,
               const rtb_ray *__restrict__ rays, uint64_t n, rtb_hit *__restrict__ hits,
@@ -51,8 +62,8 @@ k_trace_batch(GeomView<Real> g, const int32_t *__restrict__ orig_to_sorted, int 
             (kRobust && g.flat)
                 ? traverse_flat<Real, false, kRobust>(g, o, d, Real(q.time), Real(q.t_min), Real(q.t_max), origin,
                                                       draw, t, visits ? &nodes : nullptr, visits ? &tests : nullptr)
-                : traverse<Real, false, kRobust>(g, o, d, Real(q.time), Real(q.t_min), Real(q.t_max), origin,
-                                                 draw, t, visits ? &nodes : nullptr, visits ? &tests : nullptr);
+                : trace_bvh(g, o, d, Real(q.time), Real(q.t_min), Real(q.t_max), origin, draw, t,
+                            visits ? &nodes : nullptr, visits ? &tests : nullptr);
         rtb_hit h;
         h.t = 0;
         h.p[0] = h.p[1] = h.p[2] = 0;

@@ -182,6 +182,8 @@ inline BuildResult build_bvh(const std::vector<BuildItem> &items, int max_leaf, 
         if (count < 1 || count > uint32_t(kMaxLeafPrims) || first > kLeafFirstMask - 2)
             throw std::runtime_error("bvh: leaf does not fit the node reference encoding");
         nd.ref = kLeafFlag | ((count - 1) << 27) | first;
+        if (count == 1 && items[idx[t.begin]].solitary)
+            nd.ref |= kLeafInstanceFlag;
         nd.count = count;
     };
     if (n == 0) { // empty tree: the root is a leaf over nothing

@@ -78,11 +78,12 @@ struct ChainAffine {
 // 32-byte BVH node: its own bounds plus a self-describing reference `ref`:
 //   interior  ref = index of its first child; the two children are adjacent (a 64-byte
 //                   aligned pair), so one step of the traversal is one 64-byte fetch;
-//   leaf      ref = kLeafFlag | (count-1) << 27 | first   -> primitives [first, first+count).
+//   leaf      ref = kLeafFlag | (count-1) << 27 | [kLeafInstanceFlag] | first   -> primitives [first, first+count).
 // The traversal keeps only refs on its stack and never re-reads a node to learn what it is.
 // `count` repeats the leaf size (0 for interior nodes) for tools that inspect the tree.
 constexpr uint32_t kLeafFlag = 0x80000000u;
-constexpr uint32_t kLeafFirstMask = 0x07ffffffu;
+constexpr uint32_t kLeafFirstMask = 0x03ffffffu;    // 64 Mi primitive records
+constexpr uint32_t kLeafInstanceFlag = 0x04000000u; // the leaf's single item is an instance record
 constexpr int kMaxLeafPrims = 16;
 constexpr uint32_t kEmptyRef = 0xffffffffu;    // a tree without primitives
 constexpr uint32_t kSentinelRef = 0xfffffffeu; // stack marker: "leave the instance"
@@ -391,6 +392,7 @@ struct LocalStack {
     }
     RTB_HD uint32_t pop() { return s[--sp]; }
     RTB_HD bool empty() const { return sp == 0; }
+    RTB_HD void clear() { sp = 0; }
 };
 
 #ifdef __CUDACC__
@@ -431,6 +433,7 @@ template <int STRIDE> struct SmemStack {
         return x;
     }
     __device__ __forceinline__ bool empty() const { return sp == 0; }
+    __device__ __forceinline__ void clear() { sp = 0; }
 };
 #endif
 

@@ -66,6 +66,9 @@ constexpr uint32_t kFullMask = 0xffffffffu;
 #ifndef RTB_FUSED_MIN_BLOCKS_NEW
 #define RTB_FUSED_MIN_BLOCKS_NEW 7
 #endif
+#ifndef RTB_SHADE_MIN_BLOCKS
+#define RTB_SHADE_MIN_BLOCKS 1
+#endif
 #ifndef RTB_EXTEND_MIN_BLOCKS
 #define RTB_EXTEND_MIN_BLOCKS 5 // resident CTAs per SM k_extend is compiled for (register budget 65536 / (128 * N))
 #endif
@@ -94,6 +97,7 @@ struct Globals {
     unsigned long long prim_tests;
     unsigned long long paths;
     unsigned long long max_nodes_per_ray;
+    unsigned long long extend_nodes, extend_chunk_max_nodes;
 };
 
 struct WfParams {
@@ -224,19 +228,27 @@ constexpr int kWfBlock = 128; // threads per block of every wavefront kernel
 #ifndef RTB_SMEM_STACK
 #define RTB_SMEM_STACK 0
 #endif
+// Lanes without a ray pass active = false.
 template <bool ANY, bool COUNT, bool FLAT_ONLY = false, class Rng>
-__device__ __forceinline__ uint32_t trace(const GeomView<float> &g, V3<float> o, V3<float> d, float time,
+__device__ __forceinline__ uint32_t trace(const GeomView<float> &g, bool active, V3<float> o, V3<float> d, float time,
                                           float t_min, float t_max, uint32_t origin, Rng &rng, float &t,
                                           uint64_t &nodes, uint64_t &tests, uint32_t *stack_base = nullptr) {
-    if (FLAT_ONLY || g.flat)
+    if (FLAT_ONLY || g.flat) {
+        t = t_max;
+        if (!active)
+            return kNoPrim;
         return traverse_flat<float, ANY, true>(g, o, d, time, t_min, t_max, origin, rng, t,
                                                COUNT ? &nodes : nullptr, COUNT ? &tests : nullptr);
+    }
 #if RTB_SMEM_STACK
     uint32_t spill[kStackDepth - kSmemStackDepth];
     SmemStack<kWfBlock> stack(stack_base, spill);
 #else
     LocalStack stack;
 #endif
+    t = t_max;
+    if (!active)
+        return kNoPrim;
     return traverse<float, ANY, true>(g, o, d, time, t_min, t_max, origin, rng, t, COUNT ? &nodes : nullptr,
                                       COUNT ? &tests : nullptr, stack);
 }
@@ -540,15 +552,15 @@ struct PathDraw { // RNG adaptor handed to the traversal for constant_medium tes
 // (direct_light_integrator.h:115-130, mis_path_integrator.h:209-230).  Shadow rays carry
 // time 0 regardless of the path's time (direct_light_integrator.h:115).
 template <bool COUNT, bool FLAT_ONLY = false>
-__device__ __forceinline__ bool shadow_visible(const GeomView<float> &g, V3<float> o, V3<float> d, float tmax,
-                                               uint32_t origin, Pcg &rng, uint64_t &nodes, uint64_t &tests,
+__device__ __forceinline__ bool shadow_visible(const GeomView<float> &g, bool active, V3<float> o, V3<float> d,
+                                               float tmax, uint32_t origin, Pcg &rng, uint64_t &nodes, uint64_t &tests,
                                                uint32_t *stack_base = nullptr) {
     // t_min is 0.001 along the UNIT direction; the stored direction may be the unnormalised segment
     const float len = isfinite(tmax) ? length(d) : 1.0f;
     PathDraw draw{&rng};
     float t;
-    return trace<true, COUNT, FLAT_ONLY>(g, o, d, 0.0f, 0.001f / len, tmax, origin, draw, t, nodes, tests, stack_base) ==
-           kNoPrim;
+    return trace<true, COUNT, FLAT_ONLY>(g, active, o, d, 0.0f, 0.001f / len, tmax, origin, draw, t, nodes, tests,
+                                         stack_base) == kNoPrim;
 }
 
 // ---- (A) wavefront kernels -------------------------------------------------------------------
@@ -564,6 +576,7 @@ __global__ void k_clear(Counters *ctr, Globals *glob) {
         glob->next_sample = 0;
         glob->rays_closest = glob->rays_shadow = glob->nodes_visited = glob->prim_tests = glob->paths = 0;
         glob->max_nodes_per_ray = 0;
+        glob->extend_nodes = glob->extend_chunk_max_nodes = 0;
     }
 }
 
@@ -600,7 +613,7 @@ __global__ void __launch_bounds__(kWfBlock, RTB_EXTEND_MIN_BLOCKS) k_extend(WfPa
     const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     unsigned long long chunk_next = p.cursor[2 * wid], chunk_end = p.cursor[2 * wid + 1]; // warp-uniform
     bool global_done = false;                                                            // warp-uniform
-    uint64_t nodes = 0, tests = 0, max_nodes = 0;
+    uint64_t nodes = 0, tests = 0, max_nodes = 0, ext_nodes = 0, chunk_max = 0;
     uint32_t n_new = 0;
     uint32_t base = warp_fetch(&C.head_ext.v[0]);
     while (true) {
@@ -659,6 +672,7 @@ __global__ void __launch_bounds__(kWfBlock, RTB_EXTEND_MIN_BLOCKS) k_extend(WfPa
         }
         const bool active = fresh || (have && pix != kInvalidPix);
         uint32_t key = kKeys; // kKeys = nothing to push
+        uint32_t ray_nodes = 0;
         float4 a = make_float4(0, 0, 0, 0), b = a;
         float2 e = make_float2(0.f, 0.f);
         Pcg rg;
@@ -677,19 +691,29 @@ __global__ void __launch_bounds__(kWfBlock, RTB_EXTEND_MIN_BLOCKS) k_extend(WfPa
                     rg.s = uint64_t(x.x) | (uint64_t(x.y) << 32);
                 }
             }
+        }
+        {
             PathDraw draw{&rg};
             float t;
             const uint64_t nodes_before = nodes;
-            const uint32_t pi = trace<false, COUNT>(g, V3<float>(a.x, a.y, a.z), V3<float>(b.x, b.y, b.z), a.w, 0.001f,
-                                                    Consts<float>::inf(), __float_as_uint(b.w), draw, t, nodes, tests,
-                                                    s_stack + threadIdx.x);
-            if (COUNT && nodes - nodes_before > max_nodes)
-                max_nodes = nodes - nodes_before;
-
-            e = make_float2(t, __uint_as_float(pi));
-            key = kMatTypes;
-            if (pi != kNoPrim)
-                key = uint32_t(p.shade.mats[g.prims[pi].type_mat >> PT_MAT_SHIFT].type);
+            const uint32_t pi = trace<false, COUNT>(g, active, V3<float>(a.x, a.y, a.z), V3<float>(b.x, b.y, b.z), a.w,
+                                                    0.001f, Consts<float>::inf(), __float_as_uint(b.w), draw, t, nodes,
+                                                    tests, s_stack + threadIdx.x);
+            if (COUNT) {
+                ray_nodes = uint32_t(nodes - nodes_before);
+                if (ray_nodes > max_nodes)
+                    max_nodes = ray_nodes;
+            }
+            if (active) {
+                e = make_float2(t, __uint_as_float(pi));
+                key = kMatTypes;
+                if (pi != kNoPrim)
+                    key = uint32_t(p.shade.mats[g.prims[pi].type_mat >> PT_MAT_SHIFT].type);
+            }
+        }
+        if (COUNT) {
+            ext_nodes += ray_nodes;
+            chunk_max += __reduce_max_sync(kFullMask, ray_nodes);
         }
         // ---- push: the leaders of the equal-key groups reserve in ONE atomic instruction (the
         // counters share a 128-byte line, so L2 sees a single transaction)
@@ -741,6 +765,11 @@ __global__ void __launch_bounds__(kWfBlock, RTB_EXTEND_MIN_BLOCKS) k_extend(WfPa
             atomicAdd(&p.glob->prim_tests, y);
         }
         atomicMax(&p.glob->max_nodes_per_ray, (unsigned long long)max_nodes);
+        const unsigned long long z = warp_sum(ext_nodes);
+        if (lane == 0) {
+            atomicAdd(&p.glob->extend_nodes, z);
+            atomicAdd(&p.glob->extend_chunk_max_nodes, (unsigned long long)chunk_max);
+        }
     }
 }
 
@@ -757,7 +786,7 @@ __device__ __forceinline__ uint32_t out_base(const Counters &C, int q) {
 // continued path (or an empty entry where the path ended) goes to a FIXED position of the
 // next extend queue, so nothing here contends: warps stride over the chunks statically.
 template <int M, bool OLD>
-__global__ void __launch_bounds__(kWfBlock) k_shade(WfParams p, int it) {
+__global__ void __launch_bounds__(kWfBlock, RTB_SHADE_MIN_BLOCKS) k_shade(WfParams p, int it) {
     const GeomView<float> &g = p.geom;
     Counters &C = p.ctr[it % 3];
     const uint32_t n = C.key.v[M];
@@ -845,14 +874,19 @@ __global__ void __launch_bounds__(kWfBlock, RTB_EXTEND_MIN_BLOCKS) k_connect(WfP
         if (lane_id() == 0)
             next_base = atomicAdd(&C.head_shadow.v[0], 32u);
         const uint32_t idx = base + lane_id();
-        if (idx < n) {
-            const float4 a = __ldcs(p.sh_a + idx), b = __ldcs(p.sh_b + idx), c = __ldcs(p.sh_c + idx);
-            // media on a shadow ray draw from a stream keyed by the queue entry
-            Pcg rg = pcg_seed((uint64_t(__float_as_uint(a.x)) << 32) ^ __float_as_uint(b.y), p.seed ^ idx);
-            if (shadow_visible<COUNT>(g, V3<float>(a.x, a.y, a.z), V3<float>(b.x, b.y, b.z), a.w, __float_as_uint(c.w),
-                                      rg, nodes, tests, s_stack + threadIdx.x))
-                accum_add(p.accum, __float_as_uint(b.w), V3<float>(c.x, c.y, c.z));
+        const bool active = idx < n;
+        float4 a = make_float4(0.f, 0.f, 0.f, 1.f), b = make_float4(1.f, 0.f, 0.f, 0.f), c = b;
+        if (active) {
+            a = __ldcs(p.sh_a + idx);
+            b = __ldcs(p.sh_b + idx);
+            c = __ldcs(p.sh_c + idx);
         }
+        // media on a shadow ray draw from a stream keyed by the queue entry
+        Pcg rg = pcg_seed((uint64_t(__float_as_uint(a.x)) << 32) ^ __float_as_uint(b.y), p.seed ^ idx);
+        const bool vis = shadow_visible<COUNT>(g, active, V3<float>(a.x, a.y, a.z), V3<float>(b.x, b.y, b.z), a.w,
+                                               __float_as_uint(c.w), rg, nodes, tests, s_stack + threadIdx.x);
+        if (active && vis)
+            accum_add(p.accum, __float_as_uint(b.w), V3<float>(c.x, c.y, c.z));
         base = __shfl_sync(kFullMask, next_base, 0);
     }
     if (COUNT) {
@@ -914,7 +948,7 @@ __global__ void __launch_bounds__(128, OLD ? RTB_FUSED_MIN_BLOCKS_OLD : RTB_FUSE
         if (alive) {
             PathDraw draw{&s.rng};
             float t;
-            const uint32_t pi = trace<false, COUNT, true>(g, s.o, s.d, s.time, 0.001f, Consts<float>::inf(),
+            const uint32_t pi = trace<false, COUNT, true>(g, true, s.o, s.d, s.time, 0.001f, Consts<float>::inf(),
                                                           s.origin_prim, draw, t, nodes, tests);
             ++n_closest;
             if (pi == kNoPrim) {
@@ -942,7 +976,7 @@ __global__ void __launch_bounds__(128, OLD ? RTB_FUSED_MIN_BLOCKS_OLD : RTB_FUSE
                 if (!OLD && sh.want) {
                     ++n_shadow;
                     Pcg rg = s.rng; // a copy: the shadow test must not advance the path's stream
-                    if (shadow_visible<COUNT, true>(g, sh.o, sh.d, sh.tmax, sh.origin, rg, nodes, tests))
+                    if (shadow_visible<COUNT, true>(g, true, sh.o, sh.d, sh.tmax, sh.origin, rg, nodes, tests))
                         accum_add(p.accum, pix, sh.c);
                 }
             }
@@ -1334,6 +1368,8 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
         stats->nodes_visited = pool.h_glob->nodes_visited;
         stats->prim_tests = pool.h_glob->prim_tests;
         stats->max_nodes_per_ray = pool.h_glob->max_nodes_per_ray;
+        stats->extend_nodes = pool.h_glob->extend_nodes;
+        stats->extend_chunk_max_nodes = pool.h_glob->extend_chunk_max_nodes;
         stats->iterations = uint64_t(it);
         stats->kernel_launches = launches;
         stats->device_ms = ms;

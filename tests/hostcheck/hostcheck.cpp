@@ -69,12 +69,13 @@ void trace_batch(HostScene &H, const rtb_ray *rays, uint64_t n, rtb_hit *hits, u
         if (ROBUST && q.origin_prim >= 0 && q.origin_prim < int(H.orig_to_sorted.size()))
             origin = uint32_t(H.orig_to_sorted[q.origin_prim]);
         R t;
+        LocalStack stack;
         const uint32_t pi =
             use_flat && g.flat
                 ? traverse_flat<R, false, ROBUST>(g, o, d, R(q.time), R(q.t_min), R(q.t_max), origin, draw, t,
                                                   &stats[0], &stats[1])
                 : traverse<R, false, ROBUST>(g, o, d, R(q.time), R(q.t_min), R(q.t_max), origin, draw, t,
-                                             &stats[0], &stats[1]);
+                                             &stats[0], &stats[1], stack);
         rtb_hit &h = hits[i];
         std::memset(&h, 0, sizeof(h));
         h.prim = -1;

@@ -49,7 +49,8 @@ def main():
             line += f" stage_ms {[round(x, 2) for x in st['stage_ms']]} extend_ms {st['extend_ms']:.2f}"
         if a.count:
             line += (f" nodes/ray {st['nodes_visited'] / max(rays, 1):.2f} prims/ray {st['prim_tests'] / max(rays, 1):.2f} "
-                     f"max nodes/ray {st['max_nodes_per_ray']}")
+                     f"max nodes/ray {st['max_nodes_per_ray']} chunk-sync lane utilisation bound "
+                     f"{st['extend_nodes'] / max(32 * st['extend_chunk_max_nodes'], 1):.3f}")
         print(line, flush=True)
 
 
