@@ -139,7 +139,14 @@ RTB_API const char *rtb_last_error(const rtb_context *ctx);
  *   RTB_OPT_FLAT_TRAVERSAL  scenes of <= 64 primitive records are traversed in lockstep from
  *                           shared memory instead of through the BVH;
  *   RTB_OPT_FUSED_SCHEDULE  such scenes are rendered by the fused persistent kernel. */
-enum rtb_option { RTB_OPT_FLAT_TRAVERSAL = 1, RTB_OPT_FUSED_SCHEDULE = 2 };
+enum rtb_option {
+    RTB_OPT_FLAT_TRAVERSAL = 1,
+    RTB_OPT_FUSED_SCHEDULE = 2,
+    /* BVH builder knobs, applied by the NEXT rtb_scene_upload: largest leaf (1..16, default 4) and
+     * the SAH cost of one traversal step in percent of one primitive test (default 100) */
+    RTB_OPT_BVH_MAX_LEAF = 3,
+    RTB_OPT_BVH_TRAVERSAL_COST_PCT = 4
+};
 RTB_API int rtb_set_option(rtb_context *ctx, int option, int64_t value);
 
 /* ---- scene ---------------------------------------------------------------------------- */

@@ -154,8 +154,9 @@ inline unsigned builder_threads() {
 // the root, where a level has fewer tasks than threads, the passes over one task's range are
 // split across the threads instead.  Node numbering is assigned serially per level, so the
 // tree is identical for any thread count.
+// `trav_cost`: cost of one traversal step in units of one primitive test (SAH termination).
 inline BuildResult build_bvh(const std::vector<BuildItem> &items, int max_leaf, uint32_t first_offset,
-                             uint32_t node_offset) {
+                             uint32_t node_offset, double trav_cost = 1.0) {
     constexpr int kBins = 16;
     constexpr int kMaxDepth = 40;
     max_leaf = std::min(std::max(max_leaf, 1), kMaxLeafPrims);
@@ -308,7 +309,7 @@ inline BuildResult build_bvh(const std::vector<BuildItem> &items, int max_leaf, 
         const double leaf_cost = B.b.area() * cnt;
         const bool can_leaf = cnt <= uint32_t(max_leaf) && !B.solitary;
         // traversal step ~ one primitive test
-        if (can_leaf && (best_axis < 0 || best_cost + B.b.area() >= leaf_cost)) {
+        if (can_leaf && (best_axis < 0 || best_cost + trav_cost * B.b.area() >= leaf_cost)) {
             make_leaf(t, B.b);
             return d;
         }

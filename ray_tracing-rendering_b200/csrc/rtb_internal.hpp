@@ -131,6 +131,8 @@ struct rtb_context {
     int sm_count = 0;
     int opt_flat = 1;  // RTB_OPT_FLAT_TRAVERSAL
     int opt_fused = 1; // RTB_OPT_FUSED_SCHEDULE
+    int opt_max_leaf = 4;        // RTB_OPT_BVH_MAX_LEAF
+    int opt_trav_cost_pct = 100; // RTB_OPT_BVH_TRAVERSAL_COST_PCT
 };
 
 namespace rtb {

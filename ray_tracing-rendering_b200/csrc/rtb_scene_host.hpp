@@ -260,7 +260,7 @@ inline bool texture_reads_uv(const rtb::SceneView &S, int tex, int depth = 0) {
 }
 
 // max_leaf: primitives per BVH leaf.
-inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4) {
+inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double trav_cost = 1.0) {
     using namespace detail;
     S.validate();
     HostScene H;
@@ -370,7 +370,7 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4) {
         int inst; // instance index, or -1
     };
     std::vector<Slot> slots;
-    BuildResult tlas = build_bvh(top, max_leaf, 0, 0);
+    BuildResult tlas = build_bvh(top, max_leaf, 0, 0, trav_cost);
     for (uint32_t id : tlas.order)
         slots.push_back(id < uint32_t(np) ? Slot{int(id), -1} : Slot{-1, int(id) - np});
     H.nodes = tlas.nodes;
@@ -381,7 +381,7 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4) {
         size_t gi = 0;
         for (auto &kv : groups) {
             const uint32_t node_off = uint32_t(H.nodes.size());
-            BuildResult b = build_bvh(kv.second, max_leaf, uint32_t(slots.size()), node_off);
+            BuildResult b = build_bvh(kv.second, max_leaf, uint32_t(slots.size()), node_off, trav_cost);
             blas_first[gi] = uint32_t(slots.size());
             blas_count[gi] = uint32_t(b.order.size());
             blas_root[gi++] = b.nodes[0].ref; // the instance record carries the root REF
@@ -466,6 +466,21 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4) {
         f.fuzz = float(m.fuzz);
         d.ir = m.ir;
         f.ir = float(m.ir);
+        // bake solid-colour textures into the record (see mat_tex in rtb_shading.cuh); metal and
+        // dielectric keep color / fuzz / ir for their own parameters
+        auto solid = [&](int t) { return t >= 0 && S.textures()[t].type == RTB_TEX_SOLID; };
+        if (m.type != RTB_MAT_METAL && m.type != RTB_MAT_DIELECTRIC && solid(m.tex[0])) {
+            set3(d.color, S.textures()[m.tex[0]].color);
+            set3(f.color, S.textures()[m.tex[0]].color);
+            d.flags = f.flags = flags |= 2;
+        }
+        if (m.type == RTB_MAT_PBR && solid(m.tex[1]) && solid(m.tex[2])) {
+            d.fuzz = S.textures()[m.tex[1]].color[0];
+            d.ir = S.textures()[m.tex[2]].color[0];
+            f.fuzz = float(d.fuzz);
+            f.ir = float(d.ir);
+            d.flags = f.flags = flags |= 4;
+        }
         H.f64.mats.push_back(d);
         H.f32.mats.push_back(f);
     }

@@ -93,7 +93,7 @@ template <class R, class G> RTB_HD V3<R> random_cosine_direction(G &g) {
 template <class R> struct MatT {
     int32_t type;   // rtb_material_type
     int32_t tex[4]; // albedo/emit, roughness, metallic, normal map
-    int32_t flags;  // bit0: some texture of this material reads u,v
+    int32_t flags;  // bit0: some texture of this material reads u,v; bits 1,2: baked solid textures (mat_tex)
     R color[3];     // metal albedo
     R fuzz;
     R ir;
@@ -257,6 +257,21 @@ template <class R> RTB_HD R ggx_smith(V3<R> N, V3<R> V, V3<R> L, R roughness) {
 }
 
 // PBRMaterial's shading normal, material.h:247-262 (tangent frame from world up)
+// Texture slot k of a material.  Solid-colour textures are baked into the material record at
+// upload (flags bit 1: slot 0 lives in color[]; bit 2: the PBR roughness / metallic scalars live
+// in fuzz / ir), which removes one dependent random gather per hit from the shade kernels (with
+// one material and one texture record per sphere, C5's tables are far larger than any cache).
+template <class R>
+RTB_HD V3<R> mat_tex(const ShadeView<R> &S, const MatT<R> &m, int k, const RecT<R> &rec) {
+    if (k == 0 && (m.flags & 2))
+        return V3<R>(m.color[0], m.color[1], m.color[2]);
+    if (k == 1 && (m.flags & 4))
+        return V3<R>(m.fuzz, m.fuzz, m.fuzz);
+    if (k == 2 && (m.flags & 4))
+        return V3<R>(m.ir, m.ir, m.ir);
+    return tex_value(S, m.tex[k], rec.u, rec.v, rec.p);
+}
+
 template <class R>
 RTB_HD V3<R> pbr_normal(const ShadeView<R> &S, const MatT<R> &m, const RecT<R> &rec) {
     V3<R> N = rec.normal;
@@ -267,7 +282,7 @@ RTB_HD V3<R> pbr_normal(const ShadeView<R> &S, const MatT<R> &m, const RecT<R> &
         else
             ax0 = unit_vector(cross(N, V3<R>(0, 1, 0)));
         const V3<R> ax1 = cross(N, ax0);
-        const V3<R> c = tex_value(S, m.tex[3], rec.u, rec.v, rec.p);
+        const V3<R> c = mat_tex(S, m, 3, rec);
         const V3<R> local_n = unit_vector(c * R(2) - V3<R>(1, 1, 1)); // texture.h:19-22
         N = unit_vector(local_n.x * ax0 + local_n.y * ax1 + local_n.z * N);
     }
@@ -286,7 +301,7 @@ RTB_HD R mat_pdf(const ShadeView<R> &S, const MatT<R> &m, const RecT<R> &rec, V3
         const V3<R> N = pbr_normal(S, m, rec);
         if (dot(N, wi) <= 0)
             return 0;
-        R rough = tex_value(S, m.tex[1], rec.u, rec.v, rec.p).x;
+        R rough = mat_tex(S, m, 1, rec).x;
         rough = clamp_(rough, R(0.01), R(1));
         const R pdf_diff = dot(N, wi) / pi;
         const V3<R> H = unit_vector(wo + wi);
@@ -305,16 +320,16 @@ RTB_HD V3<R> mat_eval(const ShadeView<R> &S, const MatT<R> &m, const RecT<R> &re
                       V3<R> wi) {
     const R pi = Consts<R>::pi();
     if (m.type == 0)
-        return tex_value(S, m.tex[0], rec.u, rec.v, rec.p) / pi;
+        return mat_tex(S, m, 0, rec) / pi;
     if (m.type == 4) {
         const V3<R> N = pbr_normal(S, m, rec);
         const R NdotL = dot(N, wi);
         const R NdotV = dot(N, wo);
         if (NdotL <= 0 || NdotV <= 0)
             return V3<R>(0, 0, 0);
-        R rough = tex_value(S, m.tex[1], rec.u, rec.v, rec.p).x;
-        const R metal = tex_value(S, m.tex[2], rec.u, rec.v, rec.p).x;
-        const V3<R> base = tex_value(S, m.tex[0], rec.u, rec.v, rec.p);
+        R rough = mat_tex(S, m, 1, rec).x;
+        const R metal = mat_tex(S, m, 2, rec).x;
+        const V3<R> base = mat_tex(S, m, 0, rec);
         rough = clamp_(rough, R(0.01), R(1));
         const V3<R> H = unit_vector(wo + wi);
         const V3<R> one(1, 1, 1);
@@ -339,14 +354,14 @@ RTB_HD V3<R> mat_eval(const ShadeView<R> &S, const MatT<R> &m, const RecT<R> &re
 template <class R>
 RTB_HD V3<R> mat_emitted_old(const ShadeView<R> &S, const MatT<R> &m, const RecT<R> &rec) {
     if (m.type == 3)
-        return tex_value(S, m.tex[0], rec.u, rec.v, rec.p);
+        return mat_tex(S, m, 0, rec);
     return V3<R>(0, 0, 0);
 }
 // material::emitted(rec,wo) — front face only (material.h:224-229)
 template <class R>
 RTB_HD V3<R> mat_emitted_new(const ShadeView<R> &S, const MatT<R> &m, const RecT<R> &rec) {
     if (m.type == 3 && rec.front_face)
-        return tex_value(S, m.tex[0], rec.u, rec.v, rec.p);
+        return mat_tex(S, m, 0, rec);
     return V3<R>(0, 0, 0);
 }
 
@@ -362,7 +377,7 @@ RTB_HD bool mat_sample(const ShadeView<R> &S, const MatT<R> &m, const RecT<R> &r
             dir = rec.normal;
         bs.wi = unit_vector(dir);
         bs.pdf = dot(rec.normal, bs.wi) / pi;
-        bs.f = tex_value(S, m.tex[0], rec.u, rec.v, rec.p) / pi;
+        bs.f = mat_tex(S, m, 0, rec) / pi;
         bs.is_specular = false;
         return true;
     }
@@ -391,7 +406,7 @@ RTB_HD bool mat_sample(const ShadeView<R> &S, const MatT<R> &m, const RecT<R> &r
     }
     case 4: { // PBRMaterial, material.h:245-308
         const V3<R> N = pbr_normal(S, m, rec);
-        R rough = tex_value(S, m.tex[1], rec.u, rec.v, rec.p).x;
+        R rough = mat_tex(S, m, 1, rec).x;
         rough = clamp_(rough, R(0.01), R(1));
         if (g.next() < R(0.5)) {
             Onb<R> uvw;
@@ -446,7 +461,7 @@ RTB_HD bool mat_scatter(const ShadeView<R> &S, const MatT<R> &m, const RecT<R> &
         if (near_zero(dir))
             dir = rec.normal;
         dout = dir;
-        atten = tex_value(S, m.tex[0], rec.u, rec.v, rec.p);
+        atten = mat_tex(S, m, 0, rec);
         return true;
     }
     case 1: { // material.h:133-140
@@ -470,7 +485,7 @@ RTB_HD bool mat_scatter(const ShadeView<R> &S, const MatT<R> &m, const RecT<R> &
     }
     case 5: // isotropic, constant_medium.h:19-24
         dout = random_in_unit_sphere<R>(g);
-        atten = tex_value(S, m.tex[0], rec.u, rec.v, rec.p);
+        atten = mat_tex(S, m, 0, rec);
         return true;
     default: // diffuse_light (material.h:231-234), PBRMaterial (no override)
         return false;

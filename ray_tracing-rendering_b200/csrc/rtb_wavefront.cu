@@ -691,12 +691,10 @@ __global__ void __launch_bounds__(kWfBlock, RTB_EXTEND_MIN_BLOCKS) k_extend(WfPa
                     rg.s = uint64_t(x.x) | (uint64_t(x.y) << 32);
                 }
             }
-        }
-        {
             PathDraw draw{&rg};
             float t;
             const uint64_t nodes_before = nodes;
-            const uint32_t pi = trace<false, COUNT>(g, active, V3<float>(a.x, a.y, a.z), V3<float>(b.x, b.y, b.z), a.w,
+            const uint32_t pi = trace<false, COUNT>(g, true, V3<float>(a.x, a.y, a.z), V3<float>(b.x, b.y, b.z), a.w,
                                                     0.001f, Consts<float>::inf(), __float_as_uint(b.w), draw, t, nodes,
                                                     tests, s_stack + threadIdx.x);
             if (COUNT) {
@@ -704,12 +702,10 @@ __global__ void __launch_bounds__(kWfBlock, RTB_EXTEND_MIN_BLOCKS) k_extend(WfPa
                 if (ray_nodes > max_nodes)
                     max_nodes = ray_nodes;
             }
-            if (active) {
-                e = make_float2(t, __uint_as_float(pi));
-                key = kMatTypes;
-                if (pi != kNoPrim)
-                    key = uint32_t(p.shade.mats[g.prims[pi].type_mat >> PT_MAT_SHIFT].type);
-            }
+            e = make_float2(t, __uint_as_float(pi));
+            key = kMatTypes;
+            if (pi != kNoPrim)
+                key = uint32_t(p.shade.mats[g.prims[pi].type_mat >> PT_MAT_SHIFT].type);
         }
         if (COUNT) {
             ext_nodes += ray_nodes;
@@ -874,19 +870,14 @@ __global__ void __launch_bounds__(kWfBlock, RTB_EXTEND_MIN_BLOCKS) k_connect(WfP
         if (lane_id() == 0)
             next_base = atomicAdd(&C.head_shadow.v[0], 32u);
         const uint32_t idx = base + lane_id();
-        const bool active = idx < n;
-        float4 a = make_float4(0.f, 0.f, 0.f, 1.f), b = make_float4(1.f, 0.f, 0.f, 0.f), c = b;
-        if (active) {
-            a = __ldcs(p.sh_a + idx);
-            b = __ldcs(p.sh_b + idx);
-            c = __ldcs(p.sh_c + idx);
+        if (idx < n) {
+            const float4 a = __ldcs(p.sh_a + idx), b = __ldcs(p.sh_b + idx), c = __ldcs(p.sh_c + idx);
+            // media on a shadow ray draw from a stream keyed by the queue entry
+            Pcg rg = pcg_seed((uint64_t(__float_as_uint(a.x)) << 32) ^ __float_as_uint(b.y), p.seed ^ idx);
+            if (shadow_visible<COUNT>(g, true, V3<float>(a.x, a.y, a.z), V3<float>(b.x, b.y, b.z), a.w,
+                                      __float_as_uint(c.w), rg, nodes, tests, s_stack + threadIdx.x))
+                accum_add(p.accum, __float_as_uint(b.w), V3<float>(c.x, c.y, c.z));
         }
-        // media on a shadow ray draw from a stream keyed by the queue entry
-        Pcg rg = pcg_seed((uint64_t(__float_as_uint(a.x)) << 32) ^ __float_as_uint(b.y), p.seed ^ idx);
-        const bool vis = shadow_visible<COUNT>(g, active, V3<float>(a.x, a.y, a.z), V3<float>(b.x, b.y, b.z), a.w,
-                                               __float_as_uint(c.w), rg, nodes, tests, s_stack + threadIdx.x);
-        if (active && vis)
-            accum_add(p.accum, __float_as_uint(b.w), V3<float>(c.x, c.y, c.z));
         base = __shfl_sync(kFullMask, next_base, 0);
     }
     if (COUNT) {
