@@ -36,7 +36,8 @@ template <class Rng>
 __device__ __forceinline__ uint32_t trace_bvh(const GeomView<Real> &g, V3<Real> o, V3<Real> d, Real time, Real t_min,
                                               Real t_max, uint32_t origin, Rng &rng, Real &t, uint64_t *nodes,
                                               uint64_t *tests) {
-    LocalStack stack;
+    uint32_t storage[kStackDepth];
+    LocalStack stack(storage);
     return traverse<Real, false, kRobust>(g, o, d, time, t_min, t_max, origin, rng, t, nodes, tests, stack);
 }
 

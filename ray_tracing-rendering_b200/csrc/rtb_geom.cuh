@@ -383,9 +383,13 @@ RTB_HD Node32 load_node(const Node32 *nodes, uint32_t i) {
 // The traversal is written against a small stack interface so that kernels can keep the stack
 // in shared memory while host instantiations (tests/hostcheck) and simple kernels use a plain
 // array.  A push beyond the capacity is dropped (the builder caps the tree depth below it).
+// The storage is a separate array and the object holds only two scalars (pointer, depth): kept
+// together in one struct the dynamically indexed array drags the depth counter into local
+// memory too, and every push / pop then pays a dependent local load for it.
 struct LocalStack {
-    uint32_t s[kStackDepth];
-    int sp = 0;
+    uint32_t *s;
+    int sp;
+    RTB_HD explicit LocalStack(uint32_t *storage) : s(storage), sp(0) {}
     RTB_HD void push(uint32_t x) {
         if (sp < kStackDepth)
             s[sp++] = x;
@@ -575,7 +579,8 @@ RTB_HD uint32_t traverse(const GeomView<R> &g, V3<R> o, V3<R> d, R time, R t_min
 template <class R, bool ANY, bool ROBUST, class Rng>
 RTB_HD uint32_t traverse(const GeomView<R> &g, V3<R> o, V3<R> d, R time, R t_min, R t_max, uint32_t origin_prim,
                          Rng &rng, R &t_hit, uint64_t *n_nodes, uint64_t *n_tests) {
-    LocalStack stack;
+    uint32_t storage[kStackDepth];
+    LocalStack stack(storage);
     return traverse<R, ANY, ROBUST>(g, o, d, time, t_min, t_max, origin_prim, rng, t_hit, n_nodes, n_tests, stack);
 }
 

@@ -244,7 +244,8 @@ __device__ __forceinline__ uint32_t trace(const GeomView<float> &g, bool active,
     uint32_t spill[kStackDepth - kSmemStackDepth];
     SmemStack<kWfBlock> stack(stack_base, spill);
 #else
-    LocalStack stack;
+    uint32_t storage[kStackDepth];
+    LocalStack stack(storage);
 #endif
     t = t_max;
     if (!active)

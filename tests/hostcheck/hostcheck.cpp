@@ -69,7 +69,8 @@ void trace_batch(HostScene &H, const rtb_ray *rays, uint64_t n, rtb_hit *hits, u
         if (ROBUST && q.origin_prim >= 0 && q.origin_prim < int(H.orig_to_sorted.size()))
             origin = uint32_t(H.orig_to_sorted[q.origin_prim]);
         R t;
-        LocalStack stack;
+        uint32_t storage[kStackDepth];
+        LocalStack stack(storage);
         const uint32_t pi =
             use_flat && g.flat
                 ? traverse_flat<R, false, ROBUST>(g, o, d, R(q.time), R(q.t_min), R(q.t_max), origin, draw, t,
