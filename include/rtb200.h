@@ -145,7 +145,9 @@ enum rtb_option {
     /* BVH builder knobs, applied by the NEXT rtb_scene_upload: largest leaf (1..16, default 4) and
      * the SAH cost of one traversal step in percent of one primitive test (default 100) */
     RTB_OPT_BVH_MAX_LEAF = 3,
-    RTB_OPT_BVH_TRAVERSAL_COST_PCT = 4
+    RTB_OPT_BVH_TRAVERSAL_COST_PCT = 4,
+    /* node order: 0 = level order, 1 = sibling pairs depth-first (left subtree right after its pair) */
+    RTB_OPT_BVH_LAYOUT_DFS = 5
 };
 RTB_API int rtb_set_option(rtb_context *ctx, int option, int64_t value);
 

@@ -174,6 +174,8 @@ int rtb_set_option(rtb_context *ctx, int option, int64_t value) {
         ctx->opt_max_leaf = int(value);
     else if (option == RTB_OPT_BVH_TRAVERSAL_COST_PCT)
         ctx->opt_trav_cost_pct = int(value);
+    else if (option == RTB_OPT_BVH_LAYOUT_DFS)
+        ctx->opt_layout_dfs = value != 0;
     else
         return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_set_option: unknown option");
     return RTB_OK;
@@ -188,7 +190,7 @@ int rtb_scene_upload(rtb_context *ctx, const void *blob, uint64_t nbytes) {
         std::unique_ptr<DeviceScene> sc(new DeviceScene());
         try {
             SceneView view(blob, nbytes);
-            sc->host = build_host_scene(view, ctx->opt_max_leaf, 0.01 * ctx->opt_trav_cost_pct);
+            sc->host = build_host_scene(view, ctx->opt_max_leaf, 0.01 * ctx->opt_trav_cost_pct, ctx->opt_layout_dfs != 0);
         } catch (const CudaError &) {
             throw;
         } catch (const std::exception &e) {

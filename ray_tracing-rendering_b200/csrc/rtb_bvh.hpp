@@ -156,7 +156,7 @@ inline unsigned builder_threads() {
 // tree is identical for any thread count.
 // `trav_cost`: cost of one traversal step in units of one primitive test (SAH termination).
 inline BuildResult build_bvh(const std::vector<BuildItem> &items, int max_leaf, uint32_t first_offset,
-                             uint32_t node_offset, double trav_cost = 1.0) {
+                             uint32_t node_offset, double trav_cost = 1.0, bool layout_dfs = false) {
     constexpr int kBins = 16;
     constexpr int kMaxDepth = 40;
     max_leaf = std::min(std::max(max_leaf, 1), kMaxLeafPrims);
@@ -357,6 +357,37 @@ inline BuildResult build_bvh(const std::vector<BuildItem> &items, int max_leaf, 
     out.order.resize(n);
     for (uint32_t i = 0; i < n; ++i)
         out.order[i] = items[idx[i]].id;
+    if (layout_dfs && out.nodes.size() > 2) {
+        // Re-number the sibling pairs depth-first (pair, left subtree, right subtree): the pair a
+        // descent needs next is then usually the 64 bytes right after the current one, instead of
+        // twice as far down the array as in level order.
+        std::vector<Node32> dfs(out.nodes.size());
+        dfs[0] = out.nodes[0];
+        dfs[1] = out.nodes[1];
+        uint32_t next_pair = 2;
+        struct Fix {
+            uint32_t at; // index in dfs[] of the interior node whose ref is to be set
+            uint32_t old_pair;
+        };
+        std::vector<Fix> stack;
+        if (!(dfs[0].ref & kLeafFlag))
+            stack.push_back({0, dfs[0].ref - node_offset});
+        while (!stack.empty()) {
+            const Fix f = stack.back();
+            stack.pop_back();
+            const uint32_t at = next_pair;
+            next_pair += 2;
+            dfs[at] = out.nodes[f.old_pair];
+            dfs[at + 1] = out.nodes[f.old_pair + 1];
+            dfs[f.at].ref = node_offset + at;
+            // push right first so that the left subtree is laid out immediately after its pair
+            if (!(dfs[at + 1].ref & kLeafFlag))
+                stack.push_back({at + 1, dfs[at + 1].ref - node_offset});
+            if (!(dfs[at].ref & kLeafFlag))
+                stack.push_back({at, dfs[at].ref - node_offset});
+        }
+        out.nodes.swap(dfs);
+    }
     return out;
 }
 

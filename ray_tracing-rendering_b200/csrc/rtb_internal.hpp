@@ -133,6 +133,7 @@ struct rtb_context {
     int opt_fused = 1; // RTB_OPT_FUSED_SCHEDULE
     int opt_max_leaf = 4;        // RTB_OPT_BVH_MAX_LEAF
     int opt_trav_cost_pct = 100; // RTB_OPT_BVH_TRAVERSAL_COST_PCT
+    int opt_layout_dfs = 0;      // RTB_OPT_BVH_LAYOUT_DFS
 };
 
 namespace rtb {

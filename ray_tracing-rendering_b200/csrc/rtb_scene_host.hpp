@@ -260,7 +260,8 @@ inline bool texture_reads_uv(const rtb::SceneView &S, int tex, int depth = 0) {
 }
 
 // max_leaf: primitives per BVH leaf.
-inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double trav_cost = 1.0) {
+inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double trav_cost = 1.0,
+                                  bool layout_dfs = false) {
     using namespace detail;
     S.validate();
     HostScene H;
@@ -370,7 +371,7 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double t
         int inst; // instance index, or -1
     };
     std::vector<Slot> slots;
-    BuildResult tlas = build_bvh(top, max_leaf, 0, 0, trav_cost);
+    BuildResult tlas = build_bvh(top, max_leaf, 0, 0, trav_cost, layout_dfs);
     for (uint32_t id : tlas.order)
         slots.push_back(id < uint32_t(np) ? Slot{int(id), -1} : Slot{-1, int(id) - np});
     H.nodes = tlas.nodes;
@@ -381,7 +382,7 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double t
         size_t gi = 0;
         for (auto &kv : groups) {
             const uint32_t node_off = uint32_t(H.nodes.size());
-            BuildResult b = build_bvh(kv.second, max_leaf, uint32_t(slots.size()), node_off, trav_cost);
+            BuildResult b = build_bvh(kv.second, max_leaf, uint32_t(slots.size()), node_off, trav_cost, layout_dfs);
             blas_first[gi] = uint32_t(slots.size());
             blas_count[gi] = uint32_t(b.order.size());
             blas_root[gi++] = b.nodes[0].ref; // the instance record carries the root REF
