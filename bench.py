@@ -171,8 +171,10 @@ def run_native(args, rank, local_rank, world):
     total_spp = SPP if strong else SPP * world
 
     def params(flags=0, seed=1):
-        off, stride, _ = dmod.rank_split(total_spp, rank, world)
-        return ctx.params(W, H, total_spp, INTEGRATOR, DEPTH, 3, seed, off, stride, 0, flags)
+        # samples of every pixel are split across the ranks; rows too when spp < ranks (plan_split)
+        pl = dmod.plan_split(total_spp, H, rank, world)
+        return ctx.params(W, H, total_spp, INTEGRATOR, DEPTH, 3, seed, pl["sample_offset"], pl["sample_stride"], 0,
+                          flags, pl["row_offset"], pl["row_stride"])
 
     def sync():
         torch.cuda.synchronize(dev)

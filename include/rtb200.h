@@ -79,6 +79,11 @@ typedef struct rtb_render_params {
     uint64_t seed;
     int32_t pool_paths; /* paths resident on the device at once; 0 = default */
     int32_t flags;      /* RTB_RENDER_* */
+    /* Image split (the tile queue of renderer.h:40-94 across GPUs): this call renders the rows j
+     * of the image with j % row_stride == row_offset (stride 0 or 1 = all rows); pixels of other
+     * rows stay zero in the accumulators.  Combines freely with the sample split. */
+    int32_t row_offset;
+    int32_t row_stride;
 } rtb_render_params;
 
 enum rtb_render_flags {

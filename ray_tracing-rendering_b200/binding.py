@@ -37,7 +37,8 @@ class RenderParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("spp", C.c_int32),
                 ("max_depth", C.c_int32), ("rr_start_depth", C.c_int32), ("integrator", C.c_int32),
                 ("sample_offset", C.c_int32), ("sample_stride", C.c_int32), ("seed", C.c_uint64),
-                ("pool_paths", C.c_int32), ("flags", C.c_int32)]
+                ("pool_paths", C.c_int32), ("flags", C.c_int32), ("row_offset", C.c_int32),
+                ("row_stride", C.c_int32)]
 
 
 class RenderStats(C.Structure):
@@ -163,9 +164,9 @@ class Context:
     # ---- render
     @staticmethod
     def params(width, height, spp, integrator, max_depth=50, rr_start_depth=3, seed=1,
-               sample_offset=0, sample_stride=1, pool_paths=0, flags=0) -> RenderParams:
+               sample_offset=0, sample_stride=1, pool_paths=0, flags=0, row_offset=0, row_stride=1) -> RenderParams:
         return RenderParams(width, height, spp, max_depth, rr_start_depth, integrator, sample_offset,
-                            sample_stride, seed, pool_paths, flags)
+                            sample_stride, seed, pool_paths, flags, row_offset, row_stride)
 
     def render(self, params: RenderParams, out=None):
         """Host-buffer render: returns (accum[h, w, 4] float32 linear SUMS, stats dict)."""

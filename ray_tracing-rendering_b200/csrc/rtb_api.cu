@@ -71,6 +71,9 @@ int check_params(rtb_context *ctx, const rtb_render_params *p) {
     if (p->sample_stride < 0 || p->sample_offset < 0 ||
         (p->sample_stride > 0 && p->sample_offset >= p->sample_stride))
         return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "render: need 0 <= sample_offset < sample_stride");
+    if (p->row_stride < 0 || p->row_offset < 0 || (p->row_stride > 0 && p->row_offset >= p->row_stride) ||
+        (p->row_stride == 0 && p->row_offset != 0))
+        return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "render: need 0 <= row_offset < row_stride");
     if (p->pool_paths < 0)
         return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "render: pool_paths must be >= 0");
     if (!ctx->scene)

@@ -119,7 +119,8 @@ struct WfParams {
     uint32_t P;
     int32_t width, height, spp, max_depth, rr_start, integrator;
     int32_t sample_offset, sample_stride;
-    uint32_t npix;
+    int32_t row_offset, row_stride; // this call's rows: row_offset + k * row_stride
+    uint32_t npix;                  // pixels this call renders = width * (its rows)
     unsigned long long total_samples; // samples this call renders = npix * local spp
     unsigned long long window_end;    // fused schedule: samples [next_sample, window_end) this launch
     uint64_t seed;
@@ -308,6 +309,10 @@ __device__ __forceinline__ void decode_sample(const WfParams &p, unsigned long l
         pix = uint32_t(g - (unsigned long long)k * p.npix);
     }
     smp = uint32_t(p.sample_offset) + k * uint32_t(p.sample_stride);
+    if (p.row_stride > 1) { // pix counts the pixels of this call's rows: map to the image
+        const uint32_t jl = pix / uint32_t(p.width), i = pix - jl * uint32_t(p.width);
+        pix = (uint32_t(p.row_offset) + jl * uint32_t(p.row_stride)) * uint32_t(p.width) + i;
+    }
 }
 __device__ __forceinline__ Pcg sample_stream(const WfParams &p, uint32_t pix, uint32_t smp) {
     return pcg_seed((unsigned long long)pix * uint32_t(p.spp) + smp, p.seed);
@@ -1107,7 +1112,10 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
         ctx->pool = new WavefrontPool();
     WavefrontPool &pool = *ctx->pool;
 
-    const uint32_t npix = uint32_t(rp.width) * uint32_t(rp.height);
+    const uint32_t npix_image = uint32_t(rp.width) * uint32_t(rp.height);
+    const int row_stride = rp.row_stride > 0 ? rp.row_stride : 1;
+    const int my_rows = rp.row_offset < rp.height ? (rp.height - rp.row_offset + row_stride - 1) / row_stride : 0;
+    const uint32_t npix = uint32_t(rp.width) * uint32_t(my_rows);
     const int stride = rp.sample_stride > 0 ? rp.sample_stride : 1;
     const int offset = rp.sample_offset;
     const int local_spp = offset < rp.spp ? (rp.spp - offset + stride - 1) / stride : 0;
@@ -1139,6 +1147,8 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
     W.integrator = rp.integrator;
     W.sample_offset = offset;
     W.sample_stride = stride;
+    W.row_offset = rp.row_offset;
+    W.row_stride = row_stride;
     W.npix = npix;
     W.total_samples = total;
     W.window_end = total;
@@ -1334,7 +1344,7 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
     const bool prefer_wavefront = !simple && nee && finite_lights;
     int schedule = 0;
     RTB_CUDA(cudaEventRecord(pool.ev_begin, st));
-    RTB_CUDA(cudaMemsetAsync(d_accum, 0, size_t(npix) * sizeof(float4), st));
+    RTB_CUDA(cudaMemsetAsync(d_accum, 0, size_t(npix_image) * sizeof(float4), st));
     k_clear<<<1, 256, 0, st>>>(W.ctr, W.glob);
     ++launches;
     if (can_fuse && (!prefer_wavefront || (rp.flags & RTB_RENDER_FORCE_FUSED))) {

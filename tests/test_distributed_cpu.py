@@ -67,3 +67,20 @@ def test_two_rank_reduce_matches_single_rank():
         assert p.exitcode == 0
     want = fake_accumulators(range(spp), w, h)
     assert np.allclose(got, want, rtol=1e-5, atol=1e-5)
+
+
+def test_plan_split_covers_every_sample_of_every_pixel_once():
+    d = importlib.import_module(PKG + ".distributed")
+    for spp, height, world in ((400, 600, 8), (1, 64, 8), (2, 10, 8), (3, 7, 6), (16, 5, 4), (5, 9, 1)):
+        seen = np.zeros((height, spp), int)
+        for rank in range(world):
+            pl = d.plan_split(spp, height, rank, world)
+            assert pl["sample_stride"] * pl["row_stride"] == world
+            rows = d.local_rows(height, pl["row_offset"], pl["row_stride"])
+            smp = np.arange(pl["sample_offset"], spp, pl["sample_stride"])
+            seen[np.ix_(rows, smp)] += 1
+        assert (seen == 1).all(), (spp, height, world)
+    pl = d.plan_split(400, 600, 3, 8)
+    assert pl == {"sample_offset": 3, "sample_stride": 8, "row_offset": 0, "row_stride": 1}   # enough samples: no row split
+    with pytest.raises(ValueError):
+        d.plan_split(1, 2, 0, 8)
