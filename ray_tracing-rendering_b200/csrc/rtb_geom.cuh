@@ -489,7 +489,9 @@ template <class R, bool ROBUST> struct SlabRay {
 // tests per step, nearer child first, no data-dependent branches besides the loop itself),
 // leaves are processed between descents, so the lanes of a warp spend most of their time in
 // the same loop.
-template <class R, bool ANY, bool ROBUST, class Rng, class Stack>
+// MEDIA = false: the caller knows the scene holds no constant_medium, so that code (two boundary
+// walks, a log) is not compiled into its kernel at all.
+template <class R, bool ANY, bool ROBUST, class Rng, class Stack, bool MEDIA = true>
 RTB_HD uint32_t traverse(const GeomView<R> &g, V3<R> o, V3<R> d, R time, R t_min, R t_max, uint32_t origin_prim,
                          Rng &rng, R &t_hit, uint64_t *n_nodes, uint64_t *n_tests, Stack &stack) {
     uint32_t best = kNoPrim;
@@ -542,7 +544,7 @@ RTB_HD uint32_t traverse(const GeomView<R> &g, V3<R> o, V3<R> d, R time, R t_min
                     ++*n_tests;
                 R t;
                 bool h;
-                if (type == PT_MEDIUM) {
+                if (MEDIA && type == PT_MEDIUM) {
                     h = hit_medium<R, ROBUST>(g, p, co, cd, time, t_min, t_max, rng(), t);
                     if (p.type_mat & PT_DUP_LEAF) {
                         // second visit of a one-object bvh_node (bvh.h:46-47): t_max has

@@ -230,7 +230,7 @@ constexpr int kWfBlock = 128; // threads per block of every wavefront kernel
 #define RTB_SMEM_STACK 0
 #endif
 // Lanes without a ray pass active = false.
-template <bool ANY, bool COUNT, bool FLAT_ONLY = false, class Rng>
+template <bool ANY, bool COUNT, bool FLAT_ONLY = false, bool MEDIA = true, class Rng>
 __device__ __forceinline__ uint32_t trace(const GeomView<float> &g, bool active, V3<float> o, V3<float> d, float time,
                                           float t_min, float t_max, uint32_t origin, Rng &rng, float &t,
                                           uint64_t &nodes, uint64_t &tests, uint32_t *stack_base = nullptr) {
@@ -251,8 +251,9 @@ __device__ __forceinline__ uint32_t trace(const GeomView<float> &g, bool active,
     t = t_max;
     if (!active)
         return kNoPrim;
-    return traverse<float, ANY, true>(g, o, d, time, t_min, t_max, origin, rng, t, COUNT ? &nodes : nullptr,
-                                      COUNT ? &tests : nullptr, stack);
+    return traverse<float, ANY, true, Rng, decltype(stack), MEDIA>(g, o, d, time, t_min, t_max, origin, rng, t,
+                                                                   COUNT ? &nodes : nullptr, COUNT ? &tests : nullptr,
+                                                                   stack);
 }
 
 // ---- path state ----------------------------------------------------------------------------
@@ -557,7 +558,7 @@ struct PathDraw { // RNG adaptor handed to the traversal for constant_medium tes
 // Visibility of one NEE sample: scene.hit(shadow_ray, 0.001, dist - 0.001)
 // (direct_light_integrator.h:115-130, mis_path_integrator.h:209-230).  Shadow rays carry
 // time 0 regardless of the path's time (direct_light_integrator.h:115).
-template <bool COUNT, bool FLAT_ONLY = false>
+template <bool COUNT, bool FLAT_ONLY = false, bool MEDIA = true>
 __device__ __forceinline__ bool shadow_visible(const GeomView<float> &g, bool active, V3<float> o, V3<float> d,
                                                float tmax, uint32_t origin, Pcg &rng, uint64_t &nodes, uint64_t &tests,
                                                uint32_t *stack_base = nullptr) {
@@ -565,8 +566,8 @@ __device__ __forceinline__ bool shadow_visible(const GeomView<float> &g, bool ac
     const float len = isfinite(tmax) ? length(d) : 1.0f;
     PathDraw draw{&rng};
     float t;
-    return trace<true, COUNT, FLAT_ONLY>(g, active, o, d, 0.0f, 0.001f / len, tmax, origin, draw, t, nodes, tests,
-                                         stack_base) == kNoPrim;
+    return trace<true, COUNT, FLAT_ONLY, MEDIA>(g, active, o, d, 0.0f, 0.001f / len, tmax, origin, draw, t, nodes, tests,
+                                                stack_base) == kNoPrim;
 }
 
 // ---- (A) wavefront kernels -------------------------------------------------------------------
@@ -700,9 +701,10 @@ __global__ void __launch_bounds__(kWfBlock, RTB_EXTEND_MIN_BLOCKS) k_extend(WfPa
             PathDraw draw{&rg};
             float t;
             const uint64_t nodes_before = nodes;
-            const uint32_t pi = trace<false, COUNT>(g, true, V3<float>(a.x, a.y, a.z), V3<float>(b.x, b.y, b.z), a.w,
-                                                    0.001f, Consts<float>::inf(), __float_as_uint(b.w), draw, t, nodes,
-                                                    tests, s_stack + threadIdx.x);
+            const uint32_t pi = trace<false, COUNT, false, MEDIA>(g, true, V3<float>(a.x, a.y, a.z),
+                                                                  V3<float>(b.x, b.y, b.z), a.w, 0.001f,
+                                                                  Consts<float>::inf(), __float_as_uint(b.w), draw, t,
+                                                                  nodes, tests, s_stack + threadIdx.x);
             if (COUNT) {
                 ray_nodes = uint32_t(nodes - nodes_before);
                 if (ray_nodes > max_nodes)
@@ -861,7 +863,7 @@ template <bool SHADE> __global__ void __launch_bounds__(128) k_miss(WfParams p, 
 
 // connect: any-hit test of the shadow rays queued by shade; unoccluded ones add their
 // (already weighted) contribution.
-template <bool COUNT>
+template <bool COUNT, bool MEDIA>
 __global__ void __launch_bounds__(kWfBlock, RTB_EXTEND_MIN_BLOCKS) k_connect(WfParams p, int it) {
     __shared__ uint32_t s_stack[kSmemStackDepth * kWfBlock];
     const GeomView<float> &g = p.geom;
@@ -880,7 +882,7 @@ __global__ void __launch_bounds__(kWfBlock, RTB_EXTEND_MIN_BLOCKS) k_connect(WfP
             const float4 a = __ldcs(p.sh_a + idx), b = __ldcs(p.sh_b + idx), c = __ldcs(p.sh_c + idx);
             // media on a shadow ray draw from a stream keyed by the queue entry
             Pcg rg = pcg_seed((uint64_t(__float_as_uint(a.x)) << 32) ^ __float_as_uint(b.y), p.seed ^ idx);
-            if (shadow_visible<COUNT>(g, true, V3<float>(a.x, a.y, a.z), V3<float>(b.x, b.y, b.z), a.w,
+            if (shadow_visible<COUNT, false, MEDIA>(g, true, V3<float>(a.x, a.y, a.z), V3<float>(b.x, b.y, b.z), a.w,
                                       __float_as_uint(c.w), rg, nodes, tests, s_stack + threadIdx.x))
                 accum_add(p.accum, __float_as_uint(b.w), V3<float>(c.x, c.y, c.z));
         }
@@ -1295,10 +1297,17 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
                 ++launches;
                 mark();
                 if (nee) {
-                    if (count)
-                        k_connect<true><<<grid, 128, 0, st>>>(W, it);
-                    else
-                        k_connect<false><<<grid, 128, 0, st>>>(W, it);
+                    if (count) {
+                        if (media)
+                            k_connect<true, true><<<grid, 128, 0, st>>>(W, it);
+                        else
+                            k_connect<true, false><<<grid, 128, 0, st>>>(W, it);
+                    } else {
+                        if (media)
+                            k_connect<false, true><<<grid, 128, 0, st>>>(W, it);
+                        else
+                            k_connect<false, false><<<grid, 128, 0, st>>>(W, it);
+                    }
                     ++launches;
                 }
                 mark();
