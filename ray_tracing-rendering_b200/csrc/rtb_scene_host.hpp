@@ -43,6 +43,7 @@ struct HostScene {
     rtb_globals globals{};
     int n_infinite_lights = 0;
     uint32_t mat_type_mask = 0; // bit t set: some primitive uses a material of type t
+    bool textured_lambertian = false; // some lambertian in use has a non-solid (noise / image / checker) albedo
     bool has_media = false;
     int n_instances = 0;
     int n_top_items = 0; // primitives + instance records of the top level = prims[0 .. n_top_items)
@@ -332,6 +333,11 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double t
         if (P[i].flags & RTB_PRIM_BOUNDARY_ONLY)
             continue;
         H.mat_type_mask |= 1u << S.materials()[P[i].material].type;
+        {
+            const rtb_material &pm = S.materials()[P[i].material];
+            if (pm.type == RTB_MAT_LAMBERTIAN && pm.tex[0] >= 0 && S.textures()[pm.tex[0]].type != RTB_TEX_SOLID)
+                H.textured_lambertian = true;
+        }
         if (P[i].type == RTB_PRIM_MEDIUM)
             H.has_media = true;
         if (P[i].type == RTB_PRIM_MEDIUM && chain_moves(P[i].chain))

@@ -16,14 +16,14 @@
 //     c  float4  throughput.rgb, pixel index (0xffffffff = empty entry)
 //     d  uint4   rng state (2 x u32), depth | specular_bounce << 16, prev_bsdf_pdf
 //     e  float2  t, primitive index                        (hit queues only)
-//   Queues: q_ext[2] (double buffered: paths that need a closest-hit ray), q_hit[7] (hits
-//   sorted by material type, [6] = rays that left the scene), the shadow-ray queue.
+//   Queues: q_ext[2] (double buffered: paths that need a closest-hit ray), q_hit[8] (hits
+//   sorted by material type, [6] = textured lambertians, [7] = rays that left the scene), the shadow-ray queue.
 //   One iteration = k_extend -> k_shade<M> (x present material types) -> k_miss -> k_connect.
 //     k_extend  persistent warps pull 32-entry chunks (next chunk's atomic issued before the
 //               current trace); an EMPTY entry is refilled with the next camera sample from
 //               the warp's private sample range (one global atomic per 128 samples); the hit
 //               is pushed to its material queue with ONE multi-lane atomic per chunk: the
-//               leaders of the __match_any groups add to the 7 counters of one 128-byte line
+//               leaders of the __match_any groups add to the 8 counters of one 128-byte line
 //               in a single instruction, which L2 serves as one transaction.
 //     k_shade / k_miss  no atomics on the path: chunk c of material queue M maps to the fixed
 //               position base_M + c*32 + lane of the next extend queue (base_M = entries of
@@ -72,7 +72,12 @@ constexpr uint32_t kFullMask = 0xffffffffu;
 #ifndef RTB_EXTEND_MIN_BLOCKS
 #define RTB_EXTEND_MIN_BLOCKS 5 // resident CTAs per SM k_extend is compiled for (register budget 65536 / (128 * N))
 #endif
-constexpr int kKeys = kMatTypes + 1;          // hit queues: one per material type + [kMatTypes] = miss
+// hit queues: one per material type, one for lambertians whose albedo is a procedural / image
+// texture (Perlin turbulence is ~100x a solid colour: mixed into the plain lambertian queue it
+// left 10 of 32 lanes active in that shade kernel on scene09), one for rays that left the scene
+constexpr int kTexturedKey = kMatTypes;
+constexpr int kMissKey = kMatTypes + 1;
+constexpr int kKeys = kMatTypes + 2;
 constexpr uint32_t kInvalidPix = 0xffffffffu; // c.w of an empty queue entry
 constexpr uint32_t kWfChunk = 128;            // samples a warp of k_extend reserves per global atomic
 
@@ -81,7 +86,7 @@ struct alignas(128) CounterLine {
     uint32_t v[32];
 };
 struct Counters {
-    CounterLine key;         // v[k]: entries of hit queue k (7 counters, ONE line: pushed with one multi-lane atomic)
+    CounterLine key;         // v[k]: entries of hit queue k (8 counters, ONE line: pushed with one multi-lane atomic)
     CounterLine head_ext;    // work-distribution cursor of k_extend
     CounterLine n_shadow;    // entries of the shadow queue
     CounterLine head_shadow; // work-distribution cursor of k_connect
@@ -711,9 +716,13 @@ __global__ void __launch_bounds__(kWfBlock, RTB_EXTEND_MIN_BLOCKS) k_extend(WfPa
                     max_nodes = ray_nodes;
             }
             e = make_float2(t, __uint_as_float(pi));
-            key = kMatTypes;
-            if (pi != kNoPrim)
-                key = uint32_t(p.shade.mats[g.prims[pi].type_mat >> PT_MAT_SHIFT].type);
+            key = kMissKey;
+            if (pi != kNoPrim) {
+                const MatT<float> &hm = p.shade.mats[g.prims[pi].type_mat >> PT_MAT_SHIFT];
+                key = uint32_t(hm.type);
+                if (key == RTB_MAT_LAMBERTIAN && !(hm.flags & 2))
+                    key = kTexturedKey;
+            }
         }
         if (COUNT) {
             ext_nodes += ray_nodes;
@@ -790,13 +799,13 @@ __device__ __forceinline__ uint32_t out_base(const Counters &C, int q) {
 // continued path (or an empty entry where the path ended) goes to a FIXED position of the
 // next extend queue, so nothing here contends: warps stride over the chunks statically.
 template <int M, bool OLD>
-__global__ void __launch_bounds__(kWfBlock, RTB_SHADE_MIN_BLOCKS) k_shade(WfParams p, int it) {
+__global__ void __launch_bounds__(kWfBlock, RTB_SHADE_MIN_BLOCKS) k_shade(WfParams p, int it, int q) {
     const GeomView<float> &g = p.geom;
     Counters &C = p.ctr[it % 3];
-    const uint32_t n = C.key.v[M];
-    const uint32_t base_out = out_base(C, M);
+    const uint32_t n = C.key.v[q];
+    const uint32_t base_out = out_base(C, q);
     const int nb = (it + 1) & 1;
-    const size_t qoff = size_t(M) * p.cap;
+    const size_t qoff = size_t(q) * p.cap;
     const uint32_t n_warps = gridDim.x * (blockDim.x >> 5), wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     for (uint32_t first = wid * 32u; first < n; first += n_warps * 32u) {
         const uint32_t idx = first + lane_id();
@@ -842,10 +851,10 @@ __global__ void __launch_bounds__(kWfBlock, RTB_SHADE_MIN_BLOCKS) k_shade(WfPara
 // (black background, no environment light): then nothing is read at all.
 template <bool SHADE> __global__ void __launch_bounds__(128) k_miss(WfParams p, int it) {
     Counters &C = p.ctr[it % 3];
-    const uint32_t n = C.key.v[kMatTypes];
-    const uint32_t base_out = out_base(C, kMatTypes);
+    const uint32_t n = C.key.v[kMissKey];
+    const uint32_t base_out = out_base(C, kMissKey);
     const int nb = (it + 1) & 1;
-    const size_t qoff = size_t(kMatTypes) * p.cap;
+    const size_t qoff = size_t(kMissKey) * p.cap;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         p.ctr[(it + 1) % 3].n_ext.v[0] = base_out + n;
         atomicAdd(&p.glob->rays_closest, (unsigned long long)(base_out + n));
@@ -1014,14 +1023,15 @@ __global__ void k_resolve_rgb8(const float4 *__restrict__ accum, int w, int h, f
     }
 }
 
-template <bool OLD> void launch_shade(int mtype, const WfParams &P, int it, int grid, cudaStream_t st) {
+// queue q holds hits on material type mtype (q == mtype, or kTexturedKey for textured lambertians)
+template <bool OLD> void launch_shade(int mtype, int q, const WfParams &P, int it, int grid, cudaStream_t st) {
     switch (mtype) {
-    case 0: k_shade<0, OLD><<<grid, 128, 0, st>>>(P, it); break;
-    case 1: k_shade<1, OLD><<<grid, 128, 0, st>>>(P, it); break;
-    case 2: k_shade<2, OLD><<<grid, 128, 0, st>>>(P, it); break;
-    case 3: k_shade<3, OLD><<<grid, 128, 0, st>>>(P, it); break;
-    case 4: k_shade<4, OLD><<<grid, 128, 0, st>>>(P, it); break;
-    default: k_shade<5, OLD><<<grid, 128, 0, st>>>(P, it); break;
+    case 0: k_shade<0, OLD><<<grid, 128, 0, st>>>(P, it, q); break;
+    case 1: k_shade<1, OLD><<<grid, 128, 0, st>>>(P, it, q); break;
+    case 2: k_shade<2, OLD><<<grid, 128, 0, st>>>(P, it, q); break;
+    case 3: k_shade<3, OLD><<<grid, 128, 0, st>>>(P, it, q); break;
+    case 4: k_shade<4, OLD><<<grid, 128, 0, st>>>(P, it, q); break;
+    default: k_shade<5, OLD><<<grid, 128, 0, st>>>(P, it, q); break;
     }
 }
 
@@ -1281,14 +1291,16 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
                 }
                 mark();
                 ++launches;
-                for (int m = 0; m < kMatTypes; ++m)
-                    if ((W.mat_mask >> m) & 1u) {
-                        if (old_api)
-                            launch_shade<true>(m, W, it, grid, st);
-                        else
-                            launch_shade<false>(m, W, it, grid, st);
-                        ++launches;
-                    }
+                for (int q = 0; q <= kTexturedKey; ++q) {
+                    const int m = q == kTexturedKey ? int(RTB_MAT_LAMBERTIAN) : q;
+                    if (q == kTexturedKey ? !sc.host.textured_lambertian : !((W.mat_mask >> m) & 1u))
+                        continue;
+                    if (old_api)
+                        launch_shade<true>(m, q, W, it, grid, st);
+                    else
+                        launch_shade<false>(m, q, W, it, grid, st);
+                    ++launches;
+                }
                 mark();
                 if (miss_shades)
                     k_miss<true><<<grid, 128, 0, st>>>(W, it);
