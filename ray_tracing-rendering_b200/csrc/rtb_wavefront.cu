@@ -103,6 +103,7 @@ struct Globals {
     unsigned long long paths;
     unsigned long long max_nodes_per_ray;
     unsigned long long extend_nodes, extend_chunk_max_nodes;
+    unsigned long long overflow; // != 0: a queue push fell outside its capacity (internal error, checked by the host)
 };
 
 struct WfParams {
@@ -589,6 +590,7 @@ __global__ void k_clear(Counters *ctr, Globals *glob) {
         glob->rays_closest = glob->rays_shadow = glob->nodes_visited = glob->prim_tests = glob->paths = 0;
         glob->max_nodes_per_ray = 0;
         glob->extend_nodes = glob->extend_chunk_max_nodes = 0;
+        glob->overflow = 0;
     }
 }
 
@@ -682,7 +684,7 @@ __global__ void __launch_bounds__(kWfBlock, RTB_EXTEND_MIN_BLOCKS) k_extend(WfPa
                 fresh = true;
             }
         }
-        const bool active = fresh || (have && pix != kInvalidPix);
+        bool active = fresh || (have && pix != kInvalidPix);
         uint32_t key = kKeys; // kKeys = nothing to push
         uint32_t ray_nodes = 0;
         float4 a = make_float4(0, 0, 0, 0), b = a;
@@ -736,6 +738,10 @@ __global__ void __launch_bounds__(kWfBlock, RTB_EXTEND_MIN_BLOCKS) k_extend(WfPa
         if (int(lane) == leader && key < uint32_t(kKeys))
             pos = atomicAdd(&C.key.v[key], uint32_t(__popc(peers)));
         pos = __shfl_sync(kFullMask, pos, leader) + __popc(peers & ((1u << lane) - 1u));
+        if (active && pos >= p.cap) { // cannot happen while the capacity bound of WavefrontPool::ensure holds
+            atomicExch(&p.glob->overflow, 1ull);
+            active = false;
+        }
         if (active) {
             float4 c;
             uint4 d;
@@ -826,6 +832,10 @@ __global__ void __launch_bounds__(kWfBlock, RTB_SHADE_MIN_BLOCKS) k_shade(WfPara
         }
         if (!OLD) {
             const uint32_t pos = warp_reserve(&C.n_shadow.v[0], sh.want);
+            if (sh.want && pos >= p.cap) {
+                atomicExch(&p.glob->overflow, 2ull);
+                sh.want = false;
+            }
             if (sh.want) {
                 __stcs(p.sh_a + pos, make_float4(sh.o.x, sh.o.y, sh.o.z, sh.tmax));
                 __stcs(p.sh_b + pos, make_float4(sh.d.x, sh.d.y, sh.d.z, __uint_as_float(sh_pix)));
@@ -1415,6 +1425,8 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
         }
         stats->schedule = fused ? 1 : 0;
     }
+    if (pool.h_glob->overflow)
+        throw std::runtime_error("wavefront: queue overflow (internal error " + std::to_string(pool.h_glob->overflow) + ")");
     if (cancelled)
         throw std::runtime_error("cancelled");
 }
