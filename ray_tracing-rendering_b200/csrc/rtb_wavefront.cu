@@ -57,14 +57,20 @@ constexpr int kMatTypes = RTB_MAT_TYPE_COUNT; // 6
 constexpr uint32_t kFullMask = 0xffffffffu;
 
 // Resident CTAs per SM k_fused is compiled for (register budget 65536 / (128 * N)): the kernel is
-// bound by dependent-issue latency, so occupancy pays until spills take over.  Measured on B200,
-// C1 (legacy-API instantiation): 4 -> 30.4 ms, 6 -> 27.8, 7 -> 26.3, 8 -> 25.3, 10 -> 28.8, 12 -> 40.6;
-// C3 (BSDF-API instantiation): 4 -> 68.7 ms, 6 -> 60.9, 7 -> 61.0, 8 -> 63.2, 10 -> 81.2.
+// bound by dependent-issue latency, so occupancy pays until spills take over.  Measured on B200
+// with the generic lockstep traversal, C1 (legacy-API instantiation): 4 -> 30.4 ms, 6 -> 27.8,
+// 7 -> 26.3, 8 -> 25.3, 10 -> 28.8, 12 -> 40.6; C3 (BSDF-API): 4 -> 68.7 ms, 6 -> 60.9, 7 -> 61.0,
+// 8 -> 63.2, 10 -> 81.2.  With the typed traversal (fewer, leaner instructions, more live values):
+// C1 6 -> 20.4 ms, 7 -> 19.7, 8 -> 20.3; C3 6 -> 43.0, 7 -> 47.1, 8 -> 51.3.
+#ifndef RTB_FLAT_UNROLL
+#define RTB_FLAT_UNROLL 1
+#endif
+constexpr int kFlatUnroll = RTB_FLAT_UNROLL; // unroll factor of the typed rect loops of k_fused
 #ifndef RTB_FUSED_MIN_BLOCKS_OLD
-#define RTB_FUSED_MIN_BLOCKS_OLD 8
+#define RTB_FUSED_MIN_BLOCKS_OLD 7
 #endif
 #ifndef RTB_FUSED_MIN_BLOCKS_NEW
-#define RTB_FUSED_MIN_BLOCKS_NEW 7
+#define RTB_FUSED_MIN_BLOCKS_NEW 6
 #endif
 #ifndef RTB_SHADE_MIN_BLOCKS
 #define RTB_SHADE_MIN_BLOCKS 1
@@ -235,6 +241,166 @@ constexpr int kWfBlock = 128; // threads per block of every wavefront kernel
 #ifndef RTB_SMEM_STACK
 #define RTB_SMEM_STACK 0
 #endif
+// ---- typed lockstep traversal of the fused kernel ------------------------------------------------
+// The generic traverse_flat() dispatches on the primitive type per primitive: measured on C1
+// (ncu source view) that is ~42 instructions per rect test, 12 of them arithmetic — a jump-table
+// switch, two type checks, the origin check and a BSSY/BSYNC pair around every test.  For the
+// fused kernel the block digests the scene once into typed lists per SPACE (the world, then
+// every instance): axis-aligned rects grouped by axis, each loop with compile-time axes and one
+// branch-free predicate per rect; everything else (spheres, media) stays on the generic path.
+// The set of primitives tested is the same, only the order inside a space changes (which could
+// matter only for hits at bit-identical t).
+struct FlatFast {
+    struct Space {
+        int16_t first[4]; // rects of this space: [first[a], first[a+1]) has constant axis a (0 = yz, 1 = xz, 2 = xy)
+        int16_t other_first, other_end; // indices into `other`
+        int16_t sph_first, sph_end;     // indices into `sph`
+        int16_t chain;                  // wrapper chain of the instance, -1 for the world
+        int16_t pad;
+    };
+    float4 ra[kFlatMaxPrims]; // k, a0, a1, b0
+    float2 rb[kFlatMaxPrims]; // b1, primitive index (bits)
+    float4 sph[kFlatMaxPrims]; // centre, radius
+    int16_t sph_id[kFlatMaxPrims];
+    int16_t other[kFlatMaxPrims];
+    Space space[kFlatMaxChains + 1];
+    int32_t n_spaces;
+};
+
+// Built by thread 0 from the staged (shared-memory) primitive table; the caller syncs afterwards.
+__device__ inline void build_flat_fast(const GeomView<float> &g, FlatFast &ff) {
+    int n_rect = 0, n_other = 0, n_sph = 0, n_spaces = 0;
+    auto add_space = [&](uint32_t begin, uint32_t end, int chain, bool top_level) {
+        FlatFast::Space &sp = ff.space[n_spaces++];
+        sp.chain = int16_t(chain);
+        sp.pad = 0;
+        const uint32_t axis_type[3] = {PT_YZ, PT_XZ, PT_XY}; // constant axis 0, 1, 2
+        for (int a = 0; a < 3; ++a) {
+            sp.first[a] = int16_t(n_rect);
+            for (uint32_t i = begin; i < end; ++i) {
+                const PrimT<float> p = g.prims[i];
+                if ((p.type_mat & PT_TYPE_MASK) != axis_type[a])
+                    continue;
+                ff.ra[n_rect] = make_float4(p.d[4], p.d[0], p.d[1], p.d[2]);
+                ff.rb[n_rect] = make_float2(p.d[3], __uint_as_float(i));
+                ++n_rect;
+            }
+        }
+        sp.first[3] = int16_t(n_rect);
+        sp.other_first = int16_t(n_other);
+        sp.sph_first = int16_t(n_sph);
+        for (uint32_t i = begin; i < end; ++i) {
+            const PrimT<float> p = g.prims[i];
+            const uint32_t type = p.type_mat & PT_TYPE_MASK;
+            if (type == PT_XY || type == PT_XZ || type == PT_YZ || (top_level && type == PT_INSTANCE))
+                continue;
+            if (type == PT_SPHERE) {
+                ff.sph[n_sph] = make_float4(p.d[0], p.d[1], p.d[2], p.d[3]);
+                ff.sph_id[n_sph++] = int16_t(i);
+            } else {
+                ff.other[n_other++] = int16_t(i);
+            }
+        }
+        sp.other_end = int16_t(n_other);
+        sp.sph_end = int16_t(n_sph);
+    };
+    const uint32_t n_top = uint32_t(g.n_top);
+    add_space(0, n_top, -1, true);
+    for (uint32_t i = 0; i < n_top && n_spaces <= kFlatMaxChains; ++i) {
+        const PrimT<float> p = g.prims[i];
+        if ((p.type_mat & PT_TYPE_MASK) != PT_INSTANCE)
+            continue;
+        const uint32_t first = uint32_t(p.d[0]);
+        add_space(first, first + uint32_t(p.d[1]), int(p.aux2), false);
+    }
+    ff.n_spaces = n_spaces;
+}
+
+// Closest hit of the rects [first, last) whose constant axis is AX (in-plane axes A, B).
+template <int AX, int A, int B, bool COUNT>
+__device__ __forceinline__ void flat_rects(const FlatFast &ff, int first, int last, V3<float> o, V3<float> d,
+                                           float idir_ax, float t_min, float &t_max, uint32_t origin, uint32_t &best,
+                                           uint64_t &tests) {
+#pragma unroll kFlatUnroll
+    for (int i = first; i < last; ++i) {
+        const float4 ra = ff.ra[i];
+        const float2 rb = ff.rb[i];
+        const float t = (ra.x - o[AX]) * idir_ax; // the arithmetic of hit_rect(), bit for bit
+        const float a = fmaf(t, d[A], o[A]);
+        const float b = fmaf(t, d[B], o[B]);
+        const uint32_t id = __float_as_uint(rb.y);
+        const bool ok = (t >= t_min) & (t <= t_max) & (a >= ra.y) & (a <= ra.z) & (b >= ra.w) & (b <= rb.x) & (id != origin);
+        best = ok ? id : best;
+        t_max = ok ? t : t_max;
+    }
+    if (COUNT)
+        tests += uint64_t(last - first);
+}
+
+template <bool ANY, bool COUNT, class Rng>
+__device__ __forceinline__ uint32_t traverse_flat_fast(const GeomView<float> &g, const FlatFast &ff, V3<float> o,
+                                                       V3<float> d, float time, float t_min, float t_max,
+                                                       uint32_t origin, Rng &rng, float &t_hit, uint64_t &nodes,
+                                                       uint64_t &tests) {
+    uint32_t best = kNoPrim;
+    const int n_spaces = ff.n_spaces;
+    for (int s = 0; s < n_spaces; ++s) {
+        const FlatFast::Space sp = ff.space[s];
+        V3<float> lo = o, ld = d;
+        if (sp.chain >= 0) {
+            enter_instance<float, true>(g, sp.chain, lo, ld);
+            if (COUNT)
+                ++nodes; // one "node" = one instance entry (ray transform)
+        }
+        const V3<float> lid = safe_inv(ld);
+        flat_rects<0, 1, 2, COUNT>(ff, sp.first[0], sp.first[1], lo, ld, lid.x, t_min, t_max, origin, best, tests);
+        flat_rects<1, 0, 2, COUNT>(ff, sp.first[1], sp.first[2], lo, ld, lid.y, t_min, t_max, origin, best, tests);
+        flat_rects<2, 0, 1, COUNT>(ff, sp.first[2], sp.first[3], lo, ld, lid.z, t_min, t_max, origin, best, tests);
+#pragma unroll 1
+        for (int k = sp.sph_first; k < sp.sph_end; ++k) {
+            const float4 c = ff.sph[k];
+            const uint32_t i = uint32_t(ff.sph_id[k]);
+            float t;
+            if (hit_sphere<float, true>(V3<float>(c.x, c.y, c.z), c.w, lo, ld, t_min, t_max, i == origin, t)) {
+                best = i;
+                t_max = t;
+            }
+        }
+        if (COUNT)
+            tests += uint64_t(sp.sph_end - sp.sph_first);
+#pragma unroll 1
+        for (int k = sp.other_first; k < sp.other_end; ++k) { // moving spheres, media
+            const uint32_t i = uint32_t(ff.other[k]);
+            const PrimT<float> p = g.prims[i];
+            const uint32_t type = p.type_mat & PT_TYPE_MASK;
+            if (COUNT)
+                ++tests;
+            float t;
+            bool h;
+            if (type == PT_MEDIUM) {
+                h = hit_medium<float, true>(g, p, lo, ld, time, t_min, t_max, rng(), t);
+                if (p.type_mat & PT_DUP_LEAF) {
+                    float t2;
+                    if (hit_medium<float, true>(g, p, lo, ld, time, t_min, h ? t : t_max, rng(), t2)) {
+                        h = true;
+                        t = t2;
+                    }
+                }
+            } else {
+                h = hit_simple<float, true>(g, p, type, lo, ld, lid, time, t_min, t_max, i == origin, t);
+            }
+            if (h) {
+                best = i;
+                t_max = t;
+            }
+        }
+        if (ANY && best != kNoPrim)
+            break;
+    }
+    t_hit = t_max;
+    return best;
+}
+
 // Lanes without a ray pass active = false.
 template <bool ANY, bool COUNT, bool FLAT_ONLY = false, bool MEDIA = true, class Rng>
 __device__ __forceinline__ uint32_t trace(const GeomView<float> &g, bool active, V3<float> o, V3<float> d, float time,
@@ -926,7 +1092,11 @@ constexpr uint32_t kSampleChunk = 256; // samples a warp reserves per atomic
 template <bool OLD, bool COUNT, bool SIMPLE>
 __global__ void __launch_bounds__(128, OLD ? RTB_FUSED_MIN_BLOCKS_OLD : RTB_FUSED_MIN_BLOCKS_NEW) k_fused(WfParams p) {
     __shared__ FlatSmem sm;
+    __shared__ FlatFast ff;
     const GeomView<float> g = stage_scene_flat(p.geom, sm);
+    if (threadIdx.x == 0)
+        build_flat_fast(g, ff);
+    __syncthreads();
     PathState s;
     bool alive = false, exhausted = false;
     unsigned long long chunk_next = 0, chunk_end = 0; // warp-uniform: this warp's private sample range
@@ -966,8 +1136,8 @@ __global__ void __launch_bounds__(128, OLD ? RTB_FUSED_MIN_BLOCKS_OLD : RTB_FUSE
         if (alive) {
             PathDraw draw{&s.rng};
             float t;
-            const uint32_t pi = trace<false, COUNT, true>(g, true, s.o, s.d, s.time, 0.001f, Consts<float>::inf(),
-                                                          s.origin_prim, draw, t, nodes, tests);
+            const uint32_t pi = traverse_flat_fast<false, COUNT>(g, ff, s.o, s.d, s.time, 0.001f, Consts<float>::inf(),
+                                                                 s.origin_prim, draw, t, nodes, tests);
             ++n_closest;
             if (pi == kNoPrim) {
                 miss_surface(p, s);
@@ -994,7 +1164,12 @@ __global__ void __launch_bounds__(128, OLD ? RTB_FUSED_MIN_BLOCKS_OLD : RTB_FUSE
                 if (!OLD && sh.want) {
                     ++n_shadow;
                     Pcg rg = s.rng; // a copy: the shadow test must not advance the path's stream
-                    if (shadow_visible<COUNT, true>(g, true, sh.o, sh.d, sh.tmax, sh.origin, rg, nodes, tests))
+                    // t_min is 0.001 along the UNIT direction; sh.d may be the unnormalised segment
+                    const float len = isfinite(sh.tmax) ? length(sh.d) : 1.0f;
+                    PathDraw sdraw{&rg};
+                    float st;
+                    if (traverse_flat_fast<true, COUNT>(g, ff, sh.o, sh.d, 0.0f, 0.001f / len, sh.tmax, sh.origin, sdraw,
+                                                        st, nodes, tests) == kNoPrim)
                         accum_add(p.accum, pix, sh.c);
                 }
             }
