@@ -256,8 +256,18 @@ struct FlatFast {
         int16_t other_first, other_end; // indices into `other`
         int16_t sph_first, sph_end;     // indices into `sph`
         int16_t chain;                  // wrapper chain of the instance, -1 for the world
-        int16_t pad;
+        int16_t box;                    // >= 0: the space is exactly one `box` (box.h): index into `box`
     };
+    // The six rects of a box (box.h:31-47) as one slab test.  face[s]: primitive index of the face
+    // x = lo, x = hi, y = lo, y = hi, z = lo, z = hi; slot[r]: the same map backwards for the
+    // primitives first .. first + 5.
+    struct Box {
+        float lo[3], hi[3];
+        uint32_t first;
+        int16_t face[6];
+        int16_t slot[6];
+    };
+    Box box[kFlatMaxChains];
     float4 ra[kFlatMaxPrims]; // k, a0, a1, b0
     float2 rb[kFlatMaxPrims]; // b1, primitive index (bits)
     float4 sph[kFlatMaxPrims]; // centre, radius
@@ -269,11 +279,66 @@ struct FlatFast {
 
 // Built by thread 0 from the staged (shared-memory) primitive table; the caller syncs afterwards.
 __device__ inline void build_flat_fast(const GeomView<float> &g, FlatFast &ff) {
-    int n_rect = 0, n_other = 0, n_sph = 0, n_spaces = 0;
+    int n_rect = 0, n_other = 0, n_sph = 0, n_spaces = 0, n_box = 0;
+    // six rects, two per axis, that close up into one axis-aligned box?
+    auto as_box = [&](uint32_t begin, uint32_t end, FlatFast::Box &bx) -> bool {
+        if (end - begin != 6)
+            return false;
+        int cnt[3] = {0, 0, 0};
+        bx.first = begin;
+        for (uint32_t i = begin; i < end; ++i) {
+            const PrimT<float> p = g.prims[i];
+            const uint32_t type = p.type_mat & PT_TYPE_MASK;
+            const int ax = type == PT_YZ ? 0 : type == PT_XZ ? 1 : type == PT_XY ? 2 : -1;
+            if (ax < 0 || cnt[ax] >= 2)
+                return false;
+            // in-plane extents: YZ -> (y, z), XZ -> (x, z), XY -> (x, y)
+            const int A = ax == 0 ? 1 : 0, B = ax == 2 ? 1 : 2;
+            if (cnt[ax] == 0) {
+                bx.lo[ax] = p.d[4];
+                bx.face[2 * ax] = int16_t(i);
+            } else {
+                bx.hi[ax] = p.d[4];
+                bx.face[2 * ax + 1] = int16_t(i);
+                if (bx.hi[ax] < bx.lo[ax]) {
+                    const float tf = bx.lo[ax];
+                    bx.lo[ax] = bx.hi[ax];
+                    bx.hi[ax] = tf;
+                    const int16_t ti = bx.face[2 * ax];
+                    bx.face[2 * ax] = bx.face[2 * ax + 1];
+                    bx.face[2 * ax + 1] = ti;
+                }
+            }
+            ++cnt[ax];
+            (void)A;
+            (void)B;
+        }
+        if (cnt[0] != 2 || cnt[1] != 2 || cnt[2] != 2 || !(bx.lo[0] < bx.hi[0]) || !(bx.lo[1] < bx.hi[1]) ||
+            !(bx.lo[2] < bx.hi[2]))
+            return false;
+        for (uint32_t i = begin; i < end; ++i) { // every face must span exactly the other two extents
+            const PrimT<float> p = g.prims[i];
+            const uint32_t type = p.type_mat & PT_TYPE_MASK;
+            const int ax = type == PT_YZ ? 0 : type == PT_XZ ? 1 : 2;
+            const int A = ax == 0 ? 1 : 0, B = ax == 2 ? 1 : 2;
+            if (p.d[0] != bx.lo[A] || p.d[1] != bx.hi[A] || p.d[2] != bx.lo[B] || p.d[3] != bx.hi[B])
+                return false;
+        }
+        for (int s6 = 0; s6 < 6; ++s6)
+            bx.slot[uint32_t(bx.face[s6]) - begin] = int16_t(s6);
+        return true;
+    };
     auto add_space = [&](uint32_t begin, uint32_t end, int chain, bool top_level) {
         FlatFast::Space &sp = ff.space[n_spaces++];
         sp.chain = int16_t(chain);
-        sp.pad = 0;
+        sp.box = -1;
+        if (!top_level && n_box < kFlatMaxChains && as_box(begin, end, ff.box[n_box])) {
+            sp.box = int16_t(n_box++);
+            sp.first[0] = sp.first[1] = sp.first[2] = sp.first[3] = int16_t(n_rect);
+            sp.other_first = sp.other_end = int16_t(n_other);
+            sp.sph_first = sp.sph_end = int16_t(n_sph);
+            return;
+        }
         const uint32_t axis_type[3] = {PT_YZ, PT_XZ, PT_XY}; // constant axis 0, 1, 2
         for (int a = 0; a < 3; ++a) {
             sp.first[a] = int16_t(n_rect);
@@ -337,6 +402,42 @@ __device__ __forceinline__ void flat_rects(const FlatFast &ff, int first, int la
         tests += uint64_t(last - first);
 }
 
+// All six faces of a box at once.  The plane distances are the rect test's own
+// (k - o) * idir, so a hit has the same t bit for bit; which FACE is hit is decided by the slab
+// ordering instead of the in-rectangle tests, which can differ from the rect-by-rect answer only
+// for rays within rounding distance of a box edge.
+template <bool COUNT>
+__device__ __forceinline__ void flat_box(const FlatFast::Box &bx, V3<float> o, V3<float> d, V3<float> idir, float t_min,
+                                         float &t_max, uint32_t origin, uint32_t &best, uint64_t &tests) {
+    const float tx0 = (bx.lo[0] - o.x) * idir.x, tx1 = (bx.hi[0] - o.x) * idir.x;
+    const float ty0 = (bx.lo[1] - o.y) * idir.y, ty1 = (bx.hi[1] - o.y) * idir.y;
+    const float tz0 = (bx.lo[2] - o.z) * idir.z, tz1 = (bx.hi[2] - o.z) * idir.z;
+    const float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fminf(tz0, tz1));
+    const float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fmaxf(tz0, tz1));
+    if (COUNT)
+        tests += 6;
+    float cand;
+    bool ok;
+    const uint32_t rel = origin - bx.first;
+    if (rel < 6u) {
+        // the ray starts ON this box: heading outward it cannot meet a convex box again; heading
+        // inward (a transmitted ray) it leaves through the far side
+        const int slot = bx.slot[rel], ax = slot >> 1;
+        const float dn = ax == 0 ? d.x : ax == 1 ? d.y : d.z;
+        const bool inward = (slot & 1) ? dn < 0.f : dn > 0.f;
+        cand = tf;
+        ok = inward & (cand >= t_min) & (cand <= t_max);
+    } else {
+        cand = tn >= t_min ? tn : tf;
+        ok = (tn <= tf) & (cand >= t_min) & (cand <= t_max);
+    }
+    if (ok) {
+        const int slot = cand == tx0 ? 0 : cand == tx1 ? 1 : cand == ty0 ? 2 : cand == ty1 ? 3 : cand == tz0 ? 4 : 5;
+        best = uint32_t(bx.face[slot]);
+        t_max = cand;
+    }
+}
+
 template <bool ANY, bool COUNT, class Rng>
 __device__ __forceinline__ uint32_t traverse_flat_fast(const GeomView<float> &g, const FlatFast &ff, V3<float> o,
                                                        V3<float> d, float time, float t_min, float t_max,
@@ -353,6 +454,12 @@ __device__ __forceinline__ uint32_t traverse_flat_fast(const GeomView<float> &g,
                 ++nodes; // one "node" = one instance entry (ray transform)
         }
         const V3<float> lid = safe_inv(ld);
+        if (sp.box >= 0) {
+            flat_box<COUNT>(ff.box[sp.box], lo, ld, lid, t_min, t_max, origin, best, tests);
+            if (ANY && best != kNoPrim)
+                break;
+            continue;
+        }
         flat_rects<0, 1, 2, COUNT>(ff, sp.first[0], sp.first[1], lo, ld, lid.x, t_min, t_max, origin, best, tests);
         flat_rects<1, 0, 2, COUNT>(ff, sp.first[1], sp.first[2], lo, ld, lid.y, t_min, t_max, origin, best, tests);
         flat_rects<2, 0, 1, COUNT>(ff, sp.first[2], sp.first[3], lo, ld, lid.z, t_min, t_max, origin, best, tests);

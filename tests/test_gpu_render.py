@@ -152,10 +152,18 @@ def test_fused_and_wavefront_schedules_agree(gpu_ctx, golden, binding, sid, inte
     b, sb = gpu_ctx.render(gpu_ctx.params(w, h, spp, integrator, seed=21, flags=binding.RENDER_FORCE_WAVEFRONT))
     assert sa["schedule"] == 1 and sb["schedule"] == 0
     assert sa["paths"] == sb["paths"] == w * h * spp
-    if sid != 8:  # cornell_smoke: shadow/extension rays through media draw different random numbers
+    if sid == 23:  # no boxes, no media: identical paths, ray for ray
         assert sa["rays_closest"] == sb["rays_closest"] and sa["rays_shadow"] == sb["rays_shadow"]
         assert np.allclose(a[..., :3], b[..., :3], rtol=2e-4, atol=1e-3)
-    else:
+    elif sid != 8:
+        # The fused kernel tests a `box` as one slab test, the wavefront as six rects: same t for
+        # the same face, but a ray within rounding distance of a box edge may pick the other face,
+        # after which that one path differs.  Almost every pixel is still identical.
+        assert abs(sa["rays_closest"] - sb["rays_closest"]) <= 2e-4 * sb["rays_closest"]
+        same = np.isclose(a[..., :3], b[..., :3], rtol=2e-4, atol=1e-3).all(axis=-1)
+        assert same.mean() > 0.998
+        assert np.allclose(a[..., :3].mean(axis=(0, 1)), b[..., :3].mean(axis=(0, 1)), rtol=2e-3)
+    else:  # cornell_smoke: shadow/extension rays through media draw different random numbers
         assert abs(sa["rays_closest"] - sb["rays_closest"]) < 0.01 * sb["rays_closest"]
         assert np.allclose(a[..., :3].mean(axis=(0, 1)), b[..., :3].mean(axis=(0, 1)), rtol=0.02)
 
