@@ -44,12 +44,15 @@ RTB_HD uint64_t mix64(uint64_t z) { // splitmix64 finaliser
     z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
     return z ^ (z >> 31);
 }
-RTB_HD Pcg pcg_seed(uint64_t sample_index, uint64_t seed) {
+// seed_mixed = mix64(seed): the same for every sample of a render, so the renderer mixes it once
+// on the host
+RTB_HD Pcg pcg_seed_premixed(uint64_t sample_index, uint64_t seed_mixed) {
     Pcg r;
-    r.s = mix64(sample_index * 0x9e3779b97f4a7c15ULL + mix64(seed));
+    r.s = mix64(sample_index * 0x9e3779b97f4a7c15ULL + seed_mixed);
     r.next_u32();
     return r;
 }
+RTB_HD Pcg pcg_seed(uint64_t sample_index, uint64_t seed) { return pcg_seed_premixed(sample_index, mix64(seed)); }
 
 template <class R> struct RngT {
     Pcg g;

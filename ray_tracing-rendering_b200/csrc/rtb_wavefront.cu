@@ -136,6 +136,7 @@ struct WfParams {
     unsigned long long total_samples; // samples this call renders = npix * local spp
     unsigned long long window_end;    // fused schedule: samples [next_sample, window_end) this launch
     uint64_t seed;
+    uint64_t seed_mixed; // mix64(seed)
     float bg[3];
     uint32_t mat_mask;
     int32_t has_media;
@@ -595,7 +596,7 @@ __device__ __forceinline__ void decode_sample(const WfParams &p, unsigned long l
     }
 }
 __device__ __forceinline__ Pcg sample_stream(const WfParams &p, uint32_t pix, uint32_t smp) {
-    return pcg_seed((unsigned long long)pix * uint32_t(p.spp) + smp, p.seed);
+    return pcg_seed_premixed((unsigned long long)pix * uint32_t(p.spp) + smp, p.seed_mixed);
 }
 
 // renderer.h:72-75: one camera sample.
@@ -1457,6 +1458,7 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
     W.total_samples = total;
     W.window_end = total;
     W.seed = rp.seed;
+    W.seed_mixed = mix64(rp.seed);
     for (int k = 0; k < 3; ++k)
         W.bg[k] = float(sc.host.globals.background[k]);
     W.mat_mask = sc.host.mat_type_mask;
