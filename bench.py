@@ -157,9 +157,20 @@ def run_native(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # keep stdout to the ONE JSON line: NCCL's version banner goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        # keep stdout to the ONE JSON line: NCCL prints its version banner to fd 1 when the
+        # communicator comes up, so fd 1 points at stderr until the first collective is through
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     ctx = pkg.Context(local_rank)
     blob = importlib.import_module(PKG + ".configs").get(CONFIG).blob()   # the product's own builder; no reference code
     ctx.upload_scene(blob)
