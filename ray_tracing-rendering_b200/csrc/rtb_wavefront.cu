@@ -1300,6 +1300,60 @@ __global__ void __launch_bounds__(128, OLD ? RTB_FUSED_MIN_BLOCKS_OLD : RTB_FUSE
 
 __global__ void k_set_next_sample(Globals *glob, unsigned long long v) { glob->next_sample = v; }
 
+// Parity layer 1 for the fused kernel's own traversal: the rays of rtb_trace_batch through
+// traverse_flat_fast (typed lists, box slab tests), records through the same make_record.
+struct FlatDraw {
+    Pcg *g;
+    __device__ float operator()() { return g->next_open(); }
+};
+__global__ void __launch_bounds__(128) k_trace_fast_batch(GeomView<float> geom, const int32_t *__restrict__ orig_to_sorted,
+                                                          int n_orig, const rtb_ray *__restrict__ rays, uint64_t n,
+                                                          rtb_hit *__restrict__ hits, unsigned long long *visits) {
+    __shared__ FlatSmem sm;
+    __shared__ FlatFast ff;
+    const GeomView<float> g = stage_scene_flat(geom, sm);
+    if (threadIdx.x == 0)
+        build_flat_fast(g, ff);
+    __syncthreads();
+    uint64_t nodes = 0, tests = 0;
+    for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
+        const rtb_ray q = rays[i];
+        const V3<float> o{float(q.o[0]), float(q.o[1]), float(q.o[2])}, d{float(q.d[0]), float(q.d[1]), float(q.d[2])};
+        uint32_t origin = kNoPrim;
+        if (q.origin_prim >= 0 && q.origin_prim < n_orig)
+            origin = uint32_t(orig_to_sorted[q.origin_prim]);
+        Pcg rg = pcg_seed(i, 0x51ed270b);
+        FlatDraw draw{&rg};
+        float t;
+        const uint32_t pi = traverse_flat_fast<false, true>(g, ff, o, d, float(q.time), float(q.t_min), float(q.t_max),
+                                                            origin, draw, t, nodes, tests);
+        rtb_hit h;
+        std::memset(&h, 0, sizeof(h));
+        h.prim = -1;
+        h.material = -1;
+        if (pi != kNoPrim) {
+            const RecT<float> rec = make_record<float, true, true>(g, pi, o, d, float(q.time), t);
+            h.t = rec.t;
+            h.p[0] = rec.p.x;
+            h.p[1] = rec.p.y;
+            h.p[2] = rec.p.z;
+            h.normal[0] = rec.normal.x;
+            h.normal[1] = rec.normal.y;
+            h.normal[2] = rec.normal.z;
+            h.u = rec.u;
+            h.v = rec.v;
+            h.prim = g.prim_orig[pi];
+            h.front_face = rec.front_face ? 1 : 0;
+            h.material = int32_t(g.prims[pi].type_mat >> PT_MAT_SHIFT);
+        }
+        hits[i] = h;
+    }
+    if (visits) {
+        atomicAdd(&visits[0], (unsigned long long)nodes);
+        atomicAdd(&visits[1], (unsigned long long)tests);
+    }
+}
+
 // renderer.h:126-140 + render_buffer.h:35-55: sqrt(sum/spp), clamp, (uchar)(x*255), y flip.
 __global__ void k_resolve_rgb8(const float4 *__restrict__ accum, int w, int h, float inv_spp,
                                uint8_t *__restrict__ rgb8) {
@@ -1713,6 +1767,18 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
         throw std::runtime_error("wavefront: queue overflow (internal error " + std::to_string(pool.h_glob->overflow) + ")");
     if (cancelled)
         throw std::runtime_error("cancelled");
+}
+
+void launch_trace_fast_batch(rtb_context *ctx, const rtb_ray *d_rays, uint64_t n, rtb_hit *d_hits,
+                             unsigned long long *d_visits) {
+    const DeviceScene &sc = *ctx->scene;
+    const GeomView<float> g = sc.geom<float>();
+    if (!g.flat)
+        throw std::runtime_error("precision 33 (the fused kernel's typed traversal) needs a scene of <= 64 primitive records");
+    const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
+    k_trace_fast_batch<<<sms * 4, 128, 0, ctx->stream>>>(g, sc.orig_to_sorted.as<int32_t>(),
+                                                         int(sc.host.orig_to_sorted.size()), d_rays, n, d_hits, d_visits);
+    RTB_CUDA(cudaGetLastError());
 }
 
 void launch_resolve_rgb8(rtb_context *ctx, const float4 *d_accum, int w, int h, int spp, uint8_t *d_rgb8,
