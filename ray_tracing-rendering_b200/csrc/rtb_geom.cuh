@@ -326,13 +326,40 @@ RTB_HD bool hit_medium(const GeomView<R> &g, const PrimT<R> &p, V3<R> o, V3<R> d
                        R t_max, R xi, R &t_out) {
     const R inf = Consts<R>::inf();
     R t1, t2;
-    if (!hit_boundary<R, ROBUST>(g, p.aux, p.aux2, o, d, time, -inf, inf, t1))
-        return false;
-    // ROBUST: 1e-4 is below one fp32 ulp once |t1| > ~800 (a ray deep inside a large
-    // boundary), which would return the entry point again; step by a few ulps instead
-    const R step = ROBUST ? fmax_(R(0.0001), fabs_(t1) * R(1e-6)) : R(0.0001);
-    if (!hit_boundary<R, ROBUST>(g, p.aux, p.aux2, o, d, time, t1 + step, inf, t2))
-        return false;
+    bool have = false;
+    if (ROBUST && p.aux2 == 1u && g.prim_chain[p.aux] < 0) {
+        const PrimT<R> b = g.prims[p.aux];
+        if ((b.type_mat & PT_TYPE_MASK) == PT_SPHERE) {
+            // A single untransformed sphere as boundary (both media of scene09): the two
+            // boundary->hit() calls are the two roots of ONE quadratic (the arithmetic of
+            // hit_sphere's ROBUST branch), instead of two walks over the boundary list.
+            const V3<R> oc = o - V3<R>(b.d[0], b.d[1], b.d[2]);
+            const R a = length_squared(d), half_b = dot(oc, d), inv_a = R(1) / a;
+            const V3<R> l = oc - (half_b * inv_a) * d;
+            const R disc = b.d[3] * b.d[3] - length_squared(l);
+            if (disc < 0)
+                return false;
+            const R cc = length_squared(oc) - b.d[3] * b.d[3];
+            const R sq = sqrt_(a * disc);
+            const R q = -half_b + (half_b > 0 ? -sq : sq);
+            const R r0 = q * inv_a, r1 = (q != 0) ? cc / q : r0;
+            t1 = fmin_(r0, r1);
+            t2 = fmax_(r0, r1);
+            const R step = fmax_(R(0.0001), fabs_(t1) * R(1e-6));
+            if (!(t2 >= t1 + step)) // the second hit() starts at t1 + step
+                return false;
+            have = true;
+        }
+    }
+    if (!have) {
+        if (!hit_boundary<R, ROBUST>(g, p.aux, p.aux2, o, d, time, -inf, inf, t1))
+            return false;
+        // ROBUST: 1e-4 is below one fp32 ulp once |t1| > ~800 (a ray deep inside a large
+        // boundary), which would return the entry point again; step by a few ulps instead
+        const R step = ROBUST ? fmax_(R(0.0001), fabs_(t1) * R(1e-6)) : R(0.0001);
+        if (!hit_boundary<R, ROBUST>(g, p.aux, p.aux2, o, d, time, t1 + step, inf, t2))
+            return false;
+    }
     if (t1 < t_min)
         t1 = t_min;
     if (t2 > t_max)
