@@ -518,7 +518,14 @@ template <class R, bool ROBUST> struct SlabRay {
 // the same loop.
 // MEDIA = false: the caller knows the scene holds no constant_medium, so that code (two boundary
 // walks, a log) is not compiled into its kernel at all.
-template <class R, bool ANY, bool ROBUST, class Rng, class Stack, bool MEDIA = true>
+// INST = true: instance entry / exit (a ray transform each) is handled in the leaf phase, with the
+// warp converged.  INST = false: inside the descent loop, recognised from the ref alone
+// (kLeafInstanceFlag, kSentinelRef), so the leaf phase only ever tests primitives.  Both shapes
+// give the same hits on any scene; which one is faster was MEASURED on B200: scenes with
+// instances prefer the leaf-phase shape (C2 extend 40.1 vs 41.9 ms), scenes without — where the
+// extra branches never execute — run faster with the leaner leaf phase of the other (C5 extend +
+// connect 72.3 vs 75.5 ms).  The renderer picks by whether the scene has instances.
+template <class R, bool ANY, bool ROBUST, class Rng, class Stack, bool MEDIA = true, bool INST = true>
 RTB_HD uint32_t traverse(const GeomView<R> &g, V3<R> o, V3<R> d, R time, R t_min, R t_max, uint32_t origin_prim,
                          Rng &rng, R &t_hit, uint64_t *n_nodes, uint64_t *n_tests, Stack &stack) {
     uint32_t best = kNoPrim;
@@ -527,28 +534,53 @@ RTB_HD uint32_t traverse(const GeomView<R> &g, V3<R> o, V3<R> d, R time, R t_min
     sr.set(o, d);
     uint32_t cur = g.root_ref;
     while (true) {
-        while (!(cur & kLeafFlag)) { // descend
-            const Node32 c0 = load_node(g.nodes, cur), c1 = load_node(g.nodes, cur + 1);
-            if (n_nodes)
-                *n_nodes += 2;
-            R e0, e1;
-            const bool h0 = sr.box(c0, t_min, t_max, e0);
-            const bool h1 = sr.box(c1, t_min, t_max, e1);
-            const bool first1 = h1 & (!h0 | (e1 < e0)); // child 1 is the one to enter next
-            const uint32_t near = first1 ? c1.ref : c0.ref, far = first1 ? c0.ref : c1.ref;
-            if (h0 & h1)
-                stack.push(far);
-            cur = near;
-            if (!(h0 | h1)) {
-                if (stack.empty()) {
-                    t_hit = t_max;
-                    return best;
+        while (true) {
+            if (!(cur & kLeafFlag)) { // descend
+                const Node32 c0 = load_node(g.nodes, cur), c1 = load_node(g.nodes, cur + 1);
+                if (n_nodes)
+                    *n_nodes += 2;
+                R e0, e1;
+                const bool h0 = sr.box(c0, t_min, t_max, e0);
+                const bool h1 = sr.box(c1, t_min, t_max, e1);
+                const bool first1 = h1 & (!h0 | (e1 < e0)); // child 1 is the one to enter next
+                const uint32_t near = first1 ? c1.ref : c0.ref, far = first1 ? c0.ref : c1.ref;
+                if (h0 & h1)
+                    stack.push(far);
+                cur = near;
+                if (!(h0 | h1)) {
+                    if (stack.empty()) {
+                        t_hit = t_max;
+                        return best;
+                    }
+                    cur = stack.pop();
                 }
-                cur = stack.pop();
+                continue;
             }
+            if (!INST) { // instance entry / exit inside the descent
+                if (cur == kSentinelRef) { // leaving the instance: back to the world ray
+                    co = o;
+                    cd = d;
+                    sr.set(o, d);
+                    if (stack.empty()) {
+                        t_hit = t_max;
+                        return best;
+                    }
+                    cur = stack.pop();
+                    continue;
+                }
+                if ((cur & kLeafInstanceFlag) && cur != kEmptyRef) {
+                    const PrimT<R> p = g.prims[cur & kLeafFirstMask];
+                    stack.push(kSentinelRef);
+                    enter_instance<R, ROBUST>(g, int(p.aux2), co, cd);
+                    sr.set(co, cd);
+                    cur = p.aux; // the bottom-level tree's root ref
+                    continue;
+                }
+            }
+            break; // a leaf
         }
         bool entered = false;
-        if (cur == kSentinelRef) { // leaving the instance: back to the world ray
+        if (INST && cur == kSentinelRef) { // leaving the instance: back to the world ray
             co = o;
             cd = d;
             sr.set(o, d);
@@ -558,7 +590,7 @@ RTB_HD uint32_t traverse(const GeomView<R> &g, V3<R> o, V3<R> d, R time, R t_min
             for (uint32_t i = first; i < last; ++i) {
                 const PrimT<R> p = g.prims[i];
                 const uint32_t type = p.type_mat & PT_TYPE_MASK;
-                if (type == PT_INSTANCE) {
+                if (INST && type == PT_INSTANCE) {
                     // builder guarantee: an instance is alone in its leaf, top level only
                     stack.push(kSentinelRef);
                     enter_instance<R, ROBUST>(g, int(p.aux2), co, cd);

@@ -510,7 +510,7 @@ __device__ __forceinline__ uint32_t traverse_flat_fast(const GeomView<float> &g,
 }
 
 // Lanes without a ray pass active = false.
-template <bool ANY, bool COUNT, bool FLAT_ONLY = false, bool MEDIA = true, class Rng>
+template <bool ANY, bool COUNT, bool FLAT_ONLY = false, bool MEDIA = true, bool INST = true, class Rng>
 __device__ __forceinline__ uint32_t trace(const GeomView<float> &g, bool active, V3<float> o, V3<float> d, float time,
                                           float t_min, float t_max, uint32_t origin, Rng &rng, float &t,
                                           uint64_t &nodes, uint64_t &tests, uint32_t *stack_base = nullptr) {
@@ -531,9 +531,9 @@ __device__ __forceinline__ uint32_t trace(const GeomView<float> &g, bool active,
     t = t_max;
     if (!active)
         return kNoPrim;
-    return traverse<float, ANY, true, Rng, decltype(stack), MEDIA>(g, o, d, time, t_min, t_max, origin, rng, t,
-                                                                   COUNT ? &nodes : nullptr, COUNT ? &tests : nullptr,
-                                                                   stack);
+    return traverse<float, ANY, true, Rng, decltype(stack), MEDIA, INST>(g, o, d, time, t_min, t_max, origin, rng, t,
+                                                                         COUNT ? &nodes : nullptr,
+                                                                         COUNT ? &tests : nullptr, stack);
 }
 
 // ---- path state ----------------------------------------------------------------------------
@@ -838,7 +838,7 @@ struct PathDraw { // RNG adaptor handed to the traversal for constant_medium tes
 // Visibility of one NEE sample: scene.hit(shadow_ray, 0.001, dist - 0.001)
 // (direct_light_integrator.h:115-130, mis_path_integrator.h:209-230).  Shadow rays carry
 // time 0 regardless of the path's time (direct_light_integrator.h:115).
-template <bool COUNT, bool FLAT_ONLY = false, bool MEDIA = true>
+template <bool COUNT, bool FLAT_ONLY = false, bool MEDIA = true, bool INST = true>
 __device__ __forceinline__ bool shadow_visible(const GeomView<float> &g, bool active, V3<float> o, V3<float> d,
                                                float tmax, uint32_t origin, Pcg &rng, uint64_t &nodes, uint64_t &tests,
                                                uint32_t *stack_base = nullptr) {
@@ -846,8 +846,8 @@ __device__ __forceinline__ bool shadow_visible(const GeomView<float> &g, bool ac
     const float len = isfinite(tmax) ? length(d) : 1.0f;
     PathDraw draw{&rng};
     float t;
-    return trace<true, COUNT, FLAT_ONLY, MEDIA>(g, active, o, d, 0.0f, 0.001f / len, tmax, origin, draw, t, nodes, tests,
-                                                stack_base) == kNoPrim;
+    return trace<true, COUNT, FLAT_ONLY, MEDIA, INST>(g, active, o, d, 0.0f, 0.001f / len, tmax, origin, draw, t, nodes,
+                                                      tests, stack_base) == kNoPrim;
 }
 
 // ---- (A) wavefront kernels -------------------------------------------------------------------
@@ -885,7 +885,7 @@ __global__ void __launch_bounds__(256) k_init(WfParams p, int it, uint32_t n0, u
 // (or the miss queue).  Replaces scene.hit(current_ray, 0.001, infinity, rec) (e.g.
 // rr_path_integrator.h:29), everything under bvh_node::hit and the pixel loop of
 // renderer.h:66-80.
-template <bool COUNT, bool MEDIA>
+template <bool COUNT, bool MEDIA, bool INST>
 __global__ void __launch_bounds__(kWfBlock, RTB_EXTEND_MIN_BLOCKS) k_extend(WfParams p, int it) {
     __shared__ uint32_t s_stack[kSmemStackDepth * kWfBlock];
     const GeomView<float> &g = p.geom;
@@ -982,7 +982,7 @@ __global__ void __launch_bounds__(kWfBlock, RTB_EXTEND_MIN_BLOCKS) k_extend(WfPa
             PathDraw draw{&rg};
             float t;
             const uint64_t nodes_before = nodes;
-            const uint32_t pi = trace<false, COUNT, false, MEDIA>(g, true, V3<float>(a.x, a.y, a.z),
+            const uint32_t pi = trace<false, COUNT, false, MEDIA, INST>(g, true, V3<float>(a.x, a.y, a.z),
                                                                   V3<float>(b.x, b.y, b.z), a.w, 0.001f,
                                                                   Consts<float>::inf(), __float_as_uint(b.w), draw, t,
                                                                   nodes, tests, s_stack + threadIdx.x);
@@ -1156,7 +1156,7 @@ template <bool SHADE> __global__ void __launch_bounds__(128) k_miss(WfParams p, 
 
 // connect: any-hit test of the shadow rays queued by shade; unoccluded ones add their
 // (already weighted) contribution.
-template <bool COUNT, bool MEDIA>
+template <bool COUNT, bool MEDIA, bool INST>
 __global__ void __launch_bounds__(kWfBlock, RTB_EXTEND_MIN_BLOCKS) k_connect(WfParams p, int it) {
     __shared__ uint32_t s_stack[kSmemStackDepth * kWfBlock];
     const GeomView<float> &g = p.geom;
@@ -1175,7 +1175,7 @@ __global__ void __launch_bounds__(kWfBlock, RTB_EXTEND_MIN_BLOCKS) k_connect(WfP
             const float4 a = __ldcs(p.sh_a + idx), b = __ldcs(p.sh_b + idx), c = __ldcs(p.sh_c + idx);
             // media on a shadow ray draw from a stream keyed by the queue entry
             Pcg rg = pcg_seed((uint64_t(__float_as_uint(a.x)) << 32) ^ __float_as_uint(b.y), p.seed ^ idx);
-            if (shadow_visible<COUNT, false, MEDIA>(g, true, V3<float>(a.x, a.y, a.z), V3<float>(b.x, b.y, b.z), a.w,
+            if (shadow_visible<COUNT, false, MEDIA, INST>(g, true, V3<float>(a.x, a.y, a.z), V3<float>(b.x, b.y, b.z), a.w,
                                       __float_as_uint(c.w), rg, nodes, tests, s_stack + threadIdx.x))
                 accum_add(p.accum, __float_as_uint(b.w), V3<float>(c.x, c.y, c.z));
         }
@@ -1613,6 +1613,7 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
         const bool miss_shades = W.bg[0] != 0.f || W.bg[1] != 0.f || W.bg[2] != 0.f ||
                                  (rp.integrator >= RTB_INTEGRATOR_DIRECT && W.shade.n_infinite_lights > 0);
         const bool media = W.has_media != 0;
+        const bool inst = sc.host.n_instances > 0; // instance code is compiled out of the kernels otherwise
         constexpr int kBatch = 4; // iterations between two host-side liveness probes
         int probe = 0, zero_probes = 0;
         const int it0 = it;
@@ -1626,16 +1627,14 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
                         RTB_CUDA(cudaEventRecord(pool.ext_event(n_ext_events++), st));
                 };
                 mark();
-                if (count) {
-                    if (media)
-                        k_extend<true, true><<<grid, 128, 0, st>>>(W, it);
-                    else
-                        k_extend<true, false><<<grid, 128, 0, st>>>(W, it);
-                } else {
-                    if (media)
-                        k_extend<false, true><<<grid, 128, 0, st>>>(W, it);
-                    else
-                        k_extend<false, false><<<grid, 128, 0, st>>>(W, it);
+                {
+                    typedef void (*ExtendKernel)(WfParams, int);
+                    static const ExtendKernel table[2][2][2] = {
+                        {{k_extend<false, false, false>, k_extend<false, false, true>},
+                         {k_extend<false, true, false>, k_extend<false, true, true>}},
+                        {{k_extend<true, false, false>, k_extend<true, false, true>},
+                         {k_extend<true, true, false>, k_extend<true, true, true>}}};
+                    table[count ? 1 : 0][media ? 1 : 0][inst ? 1 : 0]<<<grid, 128, 0, st>>>(W, it);
                 }
                 mark();
                 ++launches;
@@ -1657,17 +1656,13 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
                 ++launches;
                 mark();
                 if (nee) {
-                    if (count) {
-                        if (media)
-                            k_connect<true, true><<<grid, 128, 0, st>>>(W, it);
-                        else
-                            k_connect<true, false><<<grid, 128, 0, st>>>(W, it);
-                    } else {
-                        if (media)
-                            k_connect<false, true><<<grid, 128, 0, st>>>(W, it);
-                        else
-                            k_connect<false, false><<<grid, 128, 0, st>>>(W, it);
-                    }
+                    typedef void (*ConnectKernel)(WfParams, int);
+                    static const ConnectKernel table[2][2][2] = {
+                        {{k_connect<false, false, false>, k_connect<false, false, true>},
+                         {k_connect<false, true, false>, k_connect<false, true, true>}},
+                        {{k_connect<true, false, false>, k_connect<true, false, true>},
+                         {k_connect<true, true, false>, k_connect<true, true, true>}}};
+                    table[count ? 1 : 0][media ? 1 : 0][inst ? 1 : 0]<<<grid, 128, 0, st>>>(W, it);
                     ++launches;
                 }
                 mark();
