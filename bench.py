@@ -323,7 +323,7 @@ def run_native(args, rank, local_rank, world):
                           "l2": ("no L2 flush needed: the fused schedule keeps the scene in shared memory and path "
                                  "state in registers; every step rewrites all accumulators with atomics after a memset"
                                  if fused else
-                                 "no extra flush: every wavefront iteration streams the 2 Mi-entry queues (>= 0.3 GB "
+                                 "no extra flush: every wavefront iteration streams the 8 Mi-entry queues (>= 1 GB "
                                  "read + written, evict-first) through the 126 MB L2")},
                "e2e": {"value": tot_e2e[0] / (ms_e2e * 1e-3) / 1e6, "unit": "Mpaths/s",
                        "h2d_bytes_per_step": len(blob), "d2h_bytes_per_step": W * H * 16,
