@@ -1083,7 +1083,7 @@ __device__ __forceinline__ uint32_t out_base(const Counters &C, int q) {
 // continued path (or an empty entry where the path ended) goes to a FIXED position of the
 // next extend queue, so nothing here contends: warps stride over the chunks statically.
 template <int M, bool OLD>
-__global__ void __launch_bounds__(kWfBlock, RTB_SHADE_MIN_BLOCKS) k_shade(WfParams p, int it, int q) {
+__device__ __forceinline__ void shade_queue(const WfParams &p, int it, int q) {
     const GeomView<float> &g = p.geom;
     Counters &C = p.ctr[it % 3];
     const uint32_t n = C.key.v[q];
@@ -1108,7 +1108,7 @@ __global__ void __launch_bounds__(kWfBlock, RTB_SHADE_MIN_BLOCKS) k_shade(WfPara
             sh_pix = s.pix;
             shade_surface<M, OLD>(p, g, s, e.x, __float_as_uint(e.y), alive, sh);
         }
-        if (!OLD) {
+        if (!OLD && (M == RTB_MAT_LAMBERTIAN || M == RTB_MAT_PBR)) { // the only materials with a non-zero eval()
             const uint32_t pos = warp_reserve(&C.n_shadow.v[0], sh.want);
             if (sh.want && pos >= p.cap) {
                 atomicExch(&p.glob->overflow, 2ull);
@@ -1132,6 +1132,23 @@ __global__ void __launch_bounds__(kWfBlock, RTB_SHADE_MIN_BLOCKS) k_shade(WfPara
             }
         }
     }
+}
+template <int M, bool OLD>
+__global__ void __launch_bounds__(kWfBlock, RTB_SHADE_MIN_BLOCKS) k_shade(WfParams p, int it, int q) {
+    shade_queue<M, OLD>(p, it, q);
+}
+// The cheap, usually sparsely hit material types (metal, dielectric, emitter, isotropic) in ONE
+// launch, queue after queue: each still runs its own shade_surface<M> over its own queue, so
+// nothing diverges, but three launches (and their tails) per iteration are saved.
+template <bool OLD> __global__ void __launch_bounds__(kWfBlock, RTB_SHADE_MIN_BLOCKS) k_shade_minor(WfParams p, int it) {
+    if ((p.mat_mask >> RTB_MAT_METAL) & 1u)
+        shade_queue<RTB_MAT_METAL, OLD>(p, it, RTB_MAT_METAL);
+    if ((p.mat_mask >> RTB_MAT_DIELECTRIC) & 1u)
+        shade_queue<RTB_MAT_DIELECTRIC, OLD>(p, it, RTB_MAT_DIELECTRIC);
+    if ((p.mat_mask >> RTB_MAT_DIFFUSE_LIGHT) & 1u)
+        shade_queue<RTB_MAT_DIFFUSE_LIGHT, OLD>(p, it, RTB_MAT_DIFFUSE_LIGHT);
+    if ((p.mat_mask >> RTB_MAT_ISOTROPIC) & 1u)
+        shade_queue<RTB_MAT_ISOTROPIC, OLD>(p, it, RTB_MAT_ISOTROPIC);
 }
 
 // miss: the rays that left the scene add background / environment radiance; their entries of
@@ -1618,6 +1635,8 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
                                  (rp.integrator >= RTB_INTEGRATOR_DIRECT && W.shade.n_infinite_lights > 0);
         const bool media = W.has_media != 0;
         const bool inst = sc.host.n_instances > 0; // instance code is compiled out of the kernels otherwise
+        const uint32_t minor_mask = (1u << RTB_MAT_METAL) | (1u << RTB_MAT_DIELECTRIC) | (1u << RTB_MAT_DIFFUSE_LIGHT) |
+                                    (1u << RTB_MAT_ISOTROPIC);
         constexpr int kBatch = 4; // iterations between two host-side liveness probes
         int probe = 0, zero_probes = 0;
         const int it0 = it;
@@ -1642,14 +1661,23 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
                 }
                 mark();
                 ++launches;
-                for (int q = 0; q <= kTexturedKey; ++q) {
+                for (int q = 0; q <= kTexturedKey; ++q) { // the two expensive types get their own launches
                     const int m = q == kTexturedKey ? int(RTB_MAT_LAMBERTIAN) : q;
+                    if (m != RTB_MAT_LAMBERTIAN && m != RTB_MAT_PBR)
+                        continue;
                     if (q == kTexturedKey ? !sc.host.textured_lambertian : !((W.mat_mask >> m) & 1u))
                         continue;
                     if (old_api)
                         launch_shade<true>(m, q, W, it, grid, st);
                     else
                         launch_shade<false>(m, q, W, it, grid, st);
+                    ++launches;
+                }
+                if (W.mat_mask & minor_mask) {
+                    if (old_api)
+                        k_shade_minor<true><<<grid, 128, 0, st>>>(W, it);
+                    else
+                        k_shade_minor<false><<<grid, 128, 0, st>>>(W, it);
                     ++launches;
                 }
                 mark();
