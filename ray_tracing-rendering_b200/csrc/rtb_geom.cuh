@@ -542,12 +542,12 @@ RTB_HD uint32_t traverse(const GeomView<R> &g, V3<R> o, V3<R> d, R time, R t_min
                 R e0, e1;
                 const bool h0 = sr.box(c0, t_min, t_max, e0);
                 const bool h1 = sr.box(c1, t_min, t_max, e1);
-                const bool first1 = h1 & (!h0 | (e1 < e0)); // child 1 is the one to enter next
+                const bool first1 = h1 && (!h0 || (e1 < e0)); // child 1 is the one to enter next
                 const uint32_t near = first1 ? c1.ref : c0.ref, far = first1 ? c0.ref : c1.ref;
-                if (h0 & h1)
+                if (h0 && h1)
                     stack.push(far);
                 cur = near;
-                if (!(h0 | h1)) {
+                if (!h0 && !h1) {
                     if (stack.empty()) {
                         t_hit = t_max;
                         return best;
