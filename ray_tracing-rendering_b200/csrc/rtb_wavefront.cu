@@ -1565,7 +1565,7 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
         }
         const int bps = blocks_per_sm(kern, 128);
         const int grid = sms * bps;
-        const unsigned long long window = 1ull << 26;
+        const unsigned long long window = 1ull << 28; // ~30 ms of work on C1: bounds the latency of rtb_cancel
         int in_flight = 0;
         for (unsigned long long b0 = begin; b0 < end && !cancelled; b0 += window) {
             W.total_samples = total;
