@@ -161,17 +161,6 @@ __device__ __forceinline__ uint32_t warp_reserve(uint32_t *counter, bool want) {
     base = __shfl_sync(kFullMask, base, leader);
     return base + __popc(m & ((1u << lane_id()) - 1u));
 }
-__device__ __forceinline__ unsigned long long warp_reserve64(unsigned long long *counter, bool want) {
-    const uint32_t m = __ballot_sync(kFullMask, want);
-    if (m == 0)
-        return 0;
-    const int leader = __ffs(m) - 1;
-    unsigned long long base = 0;
-    if (int(lane_id()) == leader)
-        base = atomicAdd(counter, (unsigned long long)__popc(m));
-    base = __shfl_sync(kFullMask, base, leader);
-    return base + __popc(m & ((1u << lane_id()) - 1u));
-}
 // Persistent-thread work fetch: the warp takes the next 32 queue entries.
 __device__ __forceinline__ uint32_t warp_fetch(uint32_t *head) {
     uint32_t base = 0;
@@ -891,7 +880,11 @@ __global__ void __launch_bounds__(256) k_init(WfParams p, int it, uint32_t n0, u
 // renderer.h:66-80.
 template <bool COUNT, bool MEDIA, bool INST>
 __global__ void __launch_bounds__(kWfBlock, RTB_EXTEND_MIN_BLOCKS) k_extend(WfParams p, int it) {
+#if RTB_SMEM_STACK
     __shared__ uint32_t s_stack[kSmemStackDepth * kWfBlock];
+#else
+    uint32_t *const s_stack = nullptr; // the traversal stack lives in local memory (measured faster)
+#endif
     const GeomView<float> &g = p.geom;
     Counters &C = p.ctr[it % 3];
     if (blockIdx.x == 0)
@@ -1179,7 +1172,11 @@ template <bool SHADE> __global__ void __launch_bounds__(128) k_miss(WfParams p, 
 // (already weighted) contribution.
 template <bool COUNT, bool MEDIA, bool INST>
 __global__ void __launch_bounds__(kWfBlock, RTB_EXTEND_MIN_BLOCKS) k_connect(WfParams p, int it) {
+#if RTB_SMEM_STACK
     __shared__ uint32_t s_stack[kSmemStackDepth * kWfBlock];
+#else
+    uint32_t *const s_stack = nullptr; // the traversal stack lives in local memory (measured faster)
+#endif
     const GeomView<float> &g = p.geom;
     Counters &C = p.ctr[it % 3];
     const uint32_t n = C.n_shadow.v[0];
