@@ -32,15 +32,19 @@ struct DrawOpen {
 // the plain while-while traversal (the renderer's speculative one is warp-cooperative and is
 // checked against this one ray by ray in tests/test_hostcheck_parity.py and, through whole
 // renders, against the fused schedule and the reference images)
-template <class Rng>
+// INST: the traversal shape the renderer uses for this scene (instances handled in the leaf phase
+// when the scene has any, inside the descent otherwise; see traverse() in rtb_geom.cuh)
+template <bool INST, class Rng>
 __device__ __forceinline__ uint32_t trace_bvh(const GeomView<Real> &g, V3<Real> o, V3<Real> d, Real time, Real t_min,
                                               Real t_max, uint32_t origin, Rng &rng, Real &t, uint64_t *nodes,
                                               uint64_t *tests) {
     uint32_t storage[kStackDepth];
     LocalStack stack(storage);
-    return traverse<Real, false, kRobust>(g, o, d, time, t_min, t_max, origin, rng, t, nodes, tests, stack);
+    return traverse<Real, false, kRobust, Rng, LocalStack, true, INST>(g, o, d, time, t_min, t_max, origin, rng, t, nodes,
+                                                                        tests, stack);
 }
 
+template <bool INST>
 __global__ void __launch_bounds__(128)
 k_trace_batch(GeomView<Real> g, const int32_t *__restrict__ orig_to_sorted, int n_orig,
               const rtb_ray *__restrict__ rays, uint64_t n, rtb_hit *__restrict__ hits,
@@ -63,7 +67,7 @@ k_trace_batch(GeomView<Real> g, const int32_t *__restrict__ orig_to_sorted, int 
             (kRobust && g.flat)
                 ? traverse_flat<Real, false, kRobust>(g, o, d, Real(q.time), Real(q.t_min), Real(q.t_max), origin,
                                                       draw, t, visits ? &nodes : nullptr, visits ? &tests : nullptr)
-                : trace_bvh(g, o, d, Real(q.time), Real(q.t_min), Real(q.t_max), origin, draw, t,
+                : trace_bvh<INST>(g, o, d, Real(q.time), Real(q.t_min), Real(q.t_max), origin, draw, t,
                             visits ? &nodes : nullptr, visits ? &tests : nullptr);
         rtb_hit h;
         h.t = 0;
@@ -226,9 +230,13 @@ void launch_trace_batch<Real>(rtb_context *ctx, const rtb_ray *d_rays, uint64_t 
     GeomView<Real> gv = sc.geom<Real>();
     if (ctx->opt_flat == 0)
         gv.flat = 0;
-    k_trace_batch<<<grid_for(ctx, n, 128), 128, 0, ctx->stream>>>(
-        gv, sc.orig_to_sorted.as<int32_t>(), int(sc.host.orig_to_sorted.size()), d_rays, n,
-        d_hits, d_visits);
+    // fp32: the renderer's choice of traversal shape; fp64 validation: always the leaf-phase shape
+    if (kRobust && sc.host.n_instances == 0)
+        k_trace_batch<false><<<grid_for(ctx, n, 128), 128, 0, ctx->stream>>>(
+            gv, sc.orig_to_sorted.as<int32_t>(), int(sc.host.orig_to_sorted.size()), d_rays, n, d_hits, d_visits);
+    else
+        k_trace_batch<true><<<grid_for(ctx, n, 128), 128, 0, ctx->stream>>>(
+            gv, sc.orig_to_sorted.as<int32_t>(), int(sc.host.orig_to_sorted.size()), d_rays, n, d_hits, d_visits);
     RTB_CUDA(cudaGetLastError());
 }
 template <>

@@ -57,7 +57,8 @@ template <class R> ShadeView<R> shade_view(HostScene &H) {
 }
 
 template <class R, bool ROBUST>
-void trace_batch(HostScene &H, const rtb_ray *rays, uint64_t n, rtb_hit *hits, uint64_t stats[2], bool use_flat) {
+void trace_batch(HostScene &H, const rtb_ray *rays, uint64_t n, rtb_hit *hits, uint64_t stats[2], bool use_flat,
+                 bool inst_in_descent = false) {
     const GeomView<R> g = geom_view<R>(H);
     RngT<R> rng;
     rng.g = pcg_seed(1, 2);
@@ -75,6 +76,9 @@ void trace_batch(HostScene &H, const rtb_ray *rays, uint64_t n, rtb_hit *hits, u
             use_flat && g.flat
                 ? traverse_flat<R, false, ROBUST>(g, o, d, R(q.time), R(q.t_min), R(q.t_max), origin, draw, t,
                                                   &stats[0], &stats[1])
+            : inst_in_descent
+                ? traverse<R, false, ROBUST, decltype(draw), LocalStack, true, false>(
+                      g, o, d, R(q.time), R(q.t_min), R(q.t_max), origin, draw, t, &stats[0], &stats[1], stack)
                 : traverse<R, false, ROBUST>(g, o, d, R(q.time), R(q.t_min), R(q.t_max), origin, draw, t,
                                              &stats[0], &stats[1], stack);
         rtb_hit &h = hits[i];
@@ -220,12 +224,14 @@ void hc_trace_batch(void *h, const rtb_ray *rays, uint64_t n, int precision, rtb
                     uint64_t stats[2]) {
     auto *H = static_cast<HostScene *>(h);
     uint64_t local[2] = {0, 0};
-    // 64: fp64 through the BVH; 65: fp64 lockstep; 32: fp32 as the renderer traces this scene
-    // (lockstep when it is small); 33: fp32 forced through the BVH
-    if (precision == 64 || precision == 65)
-        trace_batch<double, false>(*H, rays, n, hits, local, precision == 65);
+    // 64: fp64 through the BVH; 65: fp64 lockstep; 66: fp64 through the BVH with instance entry /
+    // exit inside the descent (the traversal shape of instance-free scenes, valid on any scene);
+    // 32: fp32 as the renderer traces this scene (lockstep when it is small); 33: fp32 forced
+    // through the BVH; 34: the same with instance entry / exit inside the descent
+    if (precision >= 64)
+        trace_batch<double, false>(*H, rays, n, hits, local, precision == 65, precision == 66);
     else
-        trace_batch<float, true>(*H, rays, n, hits, local, precision == 32);
+        trace_batch<float, true>(*H, rays, n, hits, local, precision == 32, precision == 34);
     if (stats) {
         stats[0] = local[0];
         stats[1] = local[1];

@@ -107,3 +107,25 @@ def test_node_and_primitive_records_are_32_bytes(hostcheck, scenes, golden):
     hostcheck.hc_scene_info(scenes(7), _ptr(info))
     assert info[1] == 18 + 2 and info[2] == 2  # 18 rects + 2 instance records, 2 bottom-level trees
     assert info[0] % 2 == 0                    # sibling pairs stay 64-byte aligned
+
+
+@pytest.mark.parametrize("sid", GOLDEN_SCENES)
+def test_both_traversal_shapes_give_the_same_hits(hostcheck, scenes, golden, abi, sid):
+    """traverse() handles instance entry / exit either in the leaf phase or inside the descent
+    loop (the renderer picks by scene); both must return the same primitive at the same t, bit
+    for bit, in both precisions, on scenes with and without instances — and so the second shape
+    is bit-exact against the reference in fp64 as well."""
+    g = golden(sid)
+    T = abi.parse_blob(g.blob)
+    rays, ref = g["rays"], g["hits"]
+    a64, sa = trace(hostcheck, scenes(sid), rays, 64, abi)
+    b64, sb = trace(hostcheck, scenes(sid), rays, 66, abi)
+    mask = parity.deterministic_mask(T, ref, a64) & parity.deterministic_mask(T, ref, b64)
+    assert parity.trace_mismatches(ref, b64, mask) == 0
+    assert np.array_equal(a64["prim"][mask], b64["prim"][mask]) and np.array_equal(a64["t"][mask], b64["t"][mask])
+    assert sa[0] == sb[0] or T["prims"]["type"].max() >= 5      # same node visits (media draws shift them)
+    seg = parity.to_segment_form(rays)
+    a32, _ = trace(hostcheck, scenes(sid), seg, 33, abi)
+    b32, _ = trace(hostcheck, scenes(sid), seg, 34, abi)
+    mask &= parity.deterministic_mask(T, ref, a32) & parity.deterministic_mask(T, ref, b32)
+    assert np.array_equal(a32["prim"][mask], b32["prim"][mask]) and np.array_equal(a32["t"][mask], b32["t"][mask])
