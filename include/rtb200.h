@@ -199,6 +199,9 @@ RTB_API int rtb_resolve_rgb8(rtb_context *ctx, int32_t spp, uint8_t *rgb8_host);
  * precision 32: the production fp32 traversal the wavefront uses.
  * precision 33 (rtb_trace_batch only, scenes of <= 64 primitive records): the fused kernel's own
  *   typed lockstep traversal (rects grouped by axis, box instances as slab tests).
+ * precision 35 (same restriction): as 33, with the hit records of planar primitives taken from the
+ *   fused kernel's per-primitive plane digest (p, normal, front_face; u = v = 0) instead of the
+ *   wrapper-chain replay.
  * visits (optional, 2 x uint64): BVH nodes visited, primitive tests. */
 RTB_API int rtb_trace_batch(rtb_context *ctx, const rtb_ray *rays, uint64_t n, int precision, rtb_hit *hits,
                     uint64_t *visits);

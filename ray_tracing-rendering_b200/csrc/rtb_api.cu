@@ -322,7 +322,7 @@ int rtb_resolve_rgb8(rtb_context *ctx, int32_t spp, uint8_t *rgb8_host) {
 
 int rtb_trace_batch(rtb_context *ctx, const rtb_ray *rays, uint64_t n, int precision, rtb_hit *hits,
                     uint64_t *visits) {
-    const int rc = check_batch(ctx, rays, hits, n, precision == 33 ? 32 : precision);
+    const int rc = check_batch(ctx, rays, hits, n, precision == 33 || precision == 35 ? 32 : precision);
     if (rc != RTB_OK)
         return rc;
     return guarded(ctx, [&] {
@@ -337,8 +337,8 @@ int rtb_trace_batch(rtb_context *ctx, const rtb_ray *rays, uint64_t n, int preci
             run_batch(ctx, rays, n, hits, [&](const rtb_ray *di, rtb_hit *dout) {
                 if (precision == 64)
                     launch_trace_batch<double>(ctx, di, n, dout, dv);
-                else if (precision == 33)
-                    launch_trace_fast_batch(ctx, di, n, dout, dv);
+                else if (precision == 33 || precision == 35)
+                    launch_trace_fast_batch(ctx, di, n, dout, dv, precision == 35);
                 else
                     launch_trace_batch<float>(ctx, di, n, dout, dv);
             });

@@ -827,6 +827,101 @@ RTB_HD RecT<R> make_record(const GeomView<R> &g, uint32_t pi, V3<R> o, V3<R> d, 
     return rec;
 }
 
+// ---- hit record of a planar primitive, digested once per scene ---------------------------------
+// make_record() replays the wrapper chain op by op for every hit (two loops with a kind switch,
+// a type switch, two divisions for u,v).  For an axis-aligned rect none of that depends on the
+// ray: the chain maps the rect's plane to ONE world-space plane n.x = k, and what the reverse
+// pass leaves in `normal` / `front_face` is a fixed function of the signs of d.v for at most two
+// per-primitive vectors v.  Every translate / rotate_y wrapper re-runs set_face_normal with ITS
+// ray against the normal as it stands (hittable.h:59,153), so
+//   * the final normal is +-n with the sign the OUTERMOST such wrapper picks: it opposes
+//     v_last = that wrapper's ray direction pulled back to the world.  For translate that is the
+//     world direction itself (v_last = n); rotate_y tests its object-space ray against the
+//     normal it has already rotated out (hittable.h:142-153), i.e. v_last = n turned once more;
+//   * front_face says whether the normal that wrapper RECEIVED already opposed its ray: the signs
+//     chosen by the outermost wrapper and by the one below it (or by the leaf: v_prev = n) agree;
+//   * flip_face (hittable.h:168) only toggles front_face, so only flips above the outermost
+//     translate / rotate_y survive.
+// fp32 production only (the fused kernel); u,v are not produced, so materials whose textures read
+// them stay on make_record().
+struct PlaneRec {
+    float n[3], k;  // world-space normal of the leaf's "outward" axis; plane n.x = k
+    float vl[3];    // v_last
+    uint32_t mode;  // bit 0: surviving flips (parity); bit 1: the chain has a translate / rotate_y
+    float vp[3];    // v_prev
+    uint32_t valid; // 0: not a planar primitive (or its chain is too long): use make_record()
+};
+
+template <class R> RTB_HD void build_plane_rec(const GeomView<R> &g, uint32_t pi, PlaneRec &out) {
+    out = PlaneRec{};
+    const PrimT<R> p = g.prims[pi];
+    const uint32_t type = p.type_mat & PT_TYPE_MASK;
+    if (type != PT_XY && type != PT_XZ && type != PT_YZ)
+        return;
+    const int AX = type == PT_XY ? 2 : (type == PT_XZ ? 1 : 0);
+    V3<R> n(0, 0, 0), q(0, 0, 0);
+    n.set(AX, R(1));
+    q.set(AX, p.d[4]);
+    auto turn = [](const XfOp<R> &op, V3<R> v) { // the reverse pass of make_record() for rotate_y
+        return V3<R>(op.b * v.x + op.a * v.z, v.y, -op.a * v.x + op.b * v.z);
+    };
+    uint32_t flips = 0;
+    int last = -1, prev = -1, first = 0; // outermost and second-outermost translate / rotate_y
+    const int chain = g.prim_chain[pi];
+    if (chain >= 0) {
+        const ChainRec c = g.chains[chain];
+        if (c.count > kMaxChainOps)
+            return;
+        first = c.first;
+        for (int i = c.count - 1; i >= 0; --i) {
+            const XfOp<R> op = g.ops[first + i];
+            if (op.kind == 0) {
+                q = V3<R>(q.x + op.a, q.y + op.b, q.z + op.c);
+            } else if (op.kind == 1) {
+                q = turn(op, q);
+                n = turn(op, n);
+            }
+            if (op.kind == 0 || op.kind == 1) {
+                prev = last;
+                last = i;
+                flips = 0;
+            } else {
+                flips ^= 1u;
+            }
+        }
+    }
+    auto stage_vec = [&](int i) {
+        if (i < 0)
+            return n;
+        const XfOp<R> op = g.ops[first + i];
+        return op.kind == 1 ? turn(op, n) : n;
+    };
+    const V3<R> vl = stage_vec(last), vp = stage_vec(prev);
+    for (int k = 0; k < 3; ++k) {
+        out.n[k] = float(n[k]);
+        out.vl[k] = float(vl[k]);
+        out.vp[k] = float(vp[k]);
+    }
+    out.k = float(dot(n, q));
+    out.mode = flips | (last >= 0 ? 2u : 0u);
+    out.valid = 1;
+}
+
+template <class R> RTB_HD RecT<R> plane_record(const PlaneRec &pl, V3<R> o, V3<R> d, R t) {
+    const V3<R> n(R(pl.n[0]), R(pl.n[1]), R(pl.n[2]));
+    RecT<R> rec;
+    rec.t = t;
+    rec.u = 0;
+    rec.v = 0;
+    const V3<R> p = o + t * d;
+    rec.p = p - (dot(n, p) - R(pl.k)) * n; // back onto the plane (exact for an axis-aligned normal)
+    const bool a_last = dot(d, V3<R>(R(pl.vl[0]), R(pl.vl[1]), R(pl.vl[2]))) < 0;
+    const bool a_prev = dot(d, V3<R>(R(pl.vp[0]), R(pl.vp[1]), R(pl.vp[2]))) < 0;
+    rec.normal = a_last ? n : -n;
+    rec.front_face = ((pl.mode & 2u) ? a_prev == a_last : a_last) != ((pl.mode & 1u) != 0);
+    return rec;
+}
+
 } // namespace rtb
 
 #endif // RTB_GEOM_CUH

@@ -159,7 +159,7 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &p, float4 *d_ac
                       rtb_render_stats *stats);
 void wavefront_release(rtb_context *ctx);
 void launch_trace_fast_batch(rtb_context *ctx, const rtb_ray *d_rays, uint64_t n, rtb_hit *d_hits,
-                             unsigned long long *d_visits);
+                             unsigned long long *d_visits, bool plane_records);
 void launch_resolve_rgb8(rtb_context *ctx, const float4 *d_accum, int w, int h, int spp, uint8_t *d_rgb8,
                          cudaStream_t stream);
 

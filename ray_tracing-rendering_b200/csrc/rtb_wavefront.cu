@@ -137,6 +137,7 @@ struct WfParams {
     int32_t sample_offset, sample_stride;
     int32_t row_offset, row_stride; // this call's rows: row_offset + k * row_stride
     uint32_t npix;                  // pixels this call renders = width * (its rows)
+    uint32_t inv_npix, inv_width;   // recip32(npix), recip32(width): see div_u32
     unsigned long long total_samples; // samples this call renders = npix * local spp
     unsigned long long window_end;    // fused schedule: samples [next_sample, window_end) this launch
     uint64_t seed;
@@ -269,6 +270,7 @@ struct FlatFast {
     int16_t other[kFlatMaxPrims];
     Space space[kFlatMaxChains + 1];
     int32_t n_spaces;
+    PlaneRec plane[kFlatMaxPrims]; // shading input of planar primitives (build_plane_rec, one thread per primitive)
 };
 
 // Built by thread 0 from the staged (shared-memory) primitive table; the caller syncs afterwards.
@@ -432,7 +434,9 @@ __device__ __forceinline__ void flat_box(const FlatFast::Box &bx, V3<float> o, V
     }
 }
 
-template <bool ANY, bool COUNT, class Rng>
+// RECTS_ONLY: the host checked that the scene holds nothing but axis-aligned rects (all_planar),
+// so the sphere / moving sphere / medium loops are not compiled into the kernel's hot loop.
+template <bool ANY, bool COUNT, bool RECTS_ONLY = false, class Rng>
 __device__ __forceinline__ uint32_t traverse_flat_fast(const GeomView<float> &g, const FlatFast &ff, V3<float> o,
                                                        V3<float> d, float time, float t_min, float t_max,
                                                        uint32_t origin, Rng &rng, float &t_hit, uint64_t &nodes,
@@ -457,6 +461,11 @@ __device__ __forceinline__ uint32_t traverse_flat_fast(const GeomView<float> &g,
         flat_rects<0, 1, 2, COUNT>(ff, sp.first[0], sp.first[1], lo, ld, lid.x, t_min, t_max, origin, best, tests);
         flat_rects<1, 0, 2, COUNT>(ff, sp.first[1], sp.first[2], lo, ld, lid.y, t_min, t_max, origin, best, tests);
         flat_rects<2, 0, 1, COUNT>(ff, sp.first[2], sp.first[3], lo, ld, lid.z, t_min, t_max, origin, best, tests);
+        if (RECTS_ONLY) {
+            if (ANY && best != kNoPrim)
+                break;
+            continue;
+        }
 #pragma unroll 1
         for (int k = sp.sph_first; k < sp.sph_end; ++k) {
             const float4 c = ff.sph[k];
@@ -571,20 +580,33 @@ __device__ __forceinline__ PathState unpack(float4 a, float4 b, float4 c, uint4 
     return s;
 }
 
+// n / d and n % d for a divisor known at launch: inv = floor(2^32 / d) (0xffffffff for d = 1)
+// puts umulhi(n, inv) at floor(n / d) or one below it, so one conditional step finishes the job:
+// 5 instructions instead of the ~20 of the general 32-bit division, on a path every regenerated
+// lane walks.
+inline uint32_t recip32(uint32_t d) { return d <= 1 ? 0xffffffffu : uint32_t((1ull << 32) / d); }
+__device__ __forceinline__ uint32_t div_u32(uint32_t n, uint32_t d, uint32_t inv, uint32_t &rem) {
+    uint32_t q = __umulhi(n, inv);
+    uint32_t r = n - q * d;
+    const bool more = r >= d;
+    rem = more ? r - d : r;
+    return more ? q + 1 : q;
+}
+
 // Local sample index g -> (pixel, sample-in-pixel) in sample-major order, so concurrently
 // resident paths belong to different pixels and consecutive indices are neighbouring pixels.
 __device__ __forceinline__ void decode_sample(const WfParams &p, unsigned long long g, uint32_t &pix, uint32_t &smp) {
     uint32_t k;
-    if (p.total_samples <= 0xffffffffull) { // 32-bit divide: ~5x cheaper than the 64-bit one
-        k = uint32_t(g) / p.npix;
-        pix = uint32_t(g) - k * p.npix;
+    if (p.total_samples <= 0xffffffffull) { // 32-bit: ~5x cheaper than the 64-bit divide
+        k = div_u32(uint32_t(g), p.npix, p.inv_npix, pix);
     } else {
         k = uint32_t(g / p.npix);
         pix = uint32_t(g - (unsigned long long)k * p.npix);
     }
     smp = uint32_t(p.sample_offset) + k * uint32_t(p.sample_stride);
     if (p.row_stride > 1) { // pix counts the pixels of this call's rows: map to the image
-        const uint32_t jl = pix / uint32_t(p.width), i = pix - jl * uint32_t(p.width);
+        uint32_t i;
+        const uint32_t jl = div_u32(pix, uint32_t(p.width), p.inv_width, i);
         pix = (uint32_t(p.row_offset) + jl * uint32_t(p.row_stride)) * uint32_t(p.width) + i;
     }
 }
@@ -597,7 +619,8 @@ __device__ __forceinline__ void new_path(const WfParams &p, uint32_t pix, uint32
     s.rng = sample_stream(p, pix, smp);
     RngT<float> r;
     r.g = s.rng;
-    const uint32_t i = pix % uint32_t(p.width), j = pix / uint32_t(p.width);
+    uint32_t i;
+    const uint32_t j = div_u32(pix, uint32_t(p.width), p.inv_width, i);
     const float u = (float(i) + r.next()) / float(p.width - 1);
     const float v = (float(j) + r.next()) / float(p.height - 1);
     camera_ray(p.cam, u, v, r, s.o, s.d, s.time);
@@ -655,14 +678,24 @@ __device__ float all_lights_pdf(const WfParams &p, V3<float> o, V3<float> d) {
 // 2/3/4 (sample/eval/pdf + one-sided emitted(rec,wo), NEE, MIS).  Updates the path in
 // place (next ray, throughput, depth, rng), adds emission to the image, and returns the
 // NEE sample (if any) for the caller to test for visibility.
-template <int M, bool OLD>
+template <int M, bool OLD, bool ALL_PLANAR = false>
 __device__ __forceinline__ void shade_surface(const WfParams &p, const GeomView<float> &g, PathState &s, float t,
-                                              uint32_t pi, bool &alive, ShadowReq &sh) {
+                                              uint32_t pi, bool &alive, ShadowReq &sh, const PlaneRec *plane = nullptr) {
     sh.want = false;
     MatT<float> m = p.shade.mats[g.prims[pi].type_mat >> PT_MAT_SHIFT];
     m.type = M; // compile-time constant: prunes the per-type switches
-    const RecT<float> rec = (m.flags & 1) ? make_record<float, true, true>(g, pi, s.o, s.d, s.time, t)
-                                          : make_record<float, true, false>(g, pi, s.o, s.d, s.time, t);
+    // `plane` (fused kernel): the per-primitive digest of planar primitives in shared memory.
+    // ALL_PLANAR: the host checked that every primitive has one and that every albedo / emission
+    // texture is a solid colour baked into the material record, so neither make_record() nor
+    // tex_value() is compiled in.
+    if (ALL_PLANAR)
+        m.flags = 2;
+    RecT<float> rec;
+    if (ALL_PLANAR || (plane != nullptr && !(m.flags & 1) && plane[pi].valid))
+        rec = plane_record<float>(plane[pi], s.o, s.d, t);
+    else
+        rec = (m.flags & 1) ? make_record<float, true, true>(g, pi, s.o, s.d, s.time, t)
+                            : make_record<float, true, false>(g, pi, s.o, s.d, s.time, t);
     RngT<float> rng;
     rng.g = s.rng;
     alive = true;
@@ -807,10 +840,13 @@ __device__ __forceinline__ void shade_surface(const WfParams &p, const GeomView<
 
 // The ray left the scene: background for integrators 0-2 (e.g. rr_path_integrator.h:30-33),
 // environment lights for 3/4 (direct_light_integrator.h:35-48, mis_path_integrator.h:37-67).
+// OLD: the caller is instantiated for the legacy-API integrators 0 / 1 only, which never look at
+// environment lights: that code (acos / atan2, fp64 table look-ups) is left out of the kernel.
+template <bool OLD = false>
 __device__ __forceinline__ void miss_surface(const WfParams &p, const PathState &s) {
     const V3<float> bg(p.bg[0], p.bg[1], p.bg[2]);
     V3<float> L = s.T * bg;
-    if (p.integrator >= RTB_INTEGRATOR_DIRECT && p.shade.n_infinite_lights > 0) {
+    if (!OLD && p.integrator >= RTB_INTEGRATOR_DIRECT && p.shade.n_infinite_lights > 0) {
         V3<float> env(0, 0, 0);
         for (int i = 0; i < p.shade.n_lights; ++i)
             if (p.shade.lights[i].type == RTB_LIGHT_ENV)
@@ -1212,16 +1248,21 @@ __global__ void __launch_bounds__(kWfBlock, RTB_EXTEND_MIN_BLOCKS) k_connect(WfP
 
 constexpr uint32_t kSampleChunk = 256; // samples a warp reserves per atomic
 
-// SIMPLE: the scene only uses lambertian and diffuse_light materials (the Cornell boxes): the
+// SIMPLE >= 1: the scene only uses lambertian and diffuse_light materials (the Cornell boxes): the
 // other four shade_surface instantiations are left out, which halves the kernel's code size
-// (the profile of the general kernel showed instruction-cache misses).
-template <bool OLD, bool COUNT, bool SIMPLE>
+// (the profile of the general kernel showed instruction-cache misses).  SIMPLE == 2: in addition
+// every primitive is an axis-aligned rect and every texture a solid colour: hit records come from
+// the per-primitive plane digest only (ALL_PLANAR), the traversal holds the rect and box loops
+// only (RECTS_ONLY) and no texture code is compiled in.
+template <bool OLD, bool COUNT, int SIMPLE>
 __global__ void __launch_bounds__(128, OLD ? RTB_FUSED_MIN_BLOCKS_OLD : RTB_FUSED_MIN_BLOCKS_NEW) k_fused(WfParams p) {
     __shared__ FlatSmem sm;
     __shared__ FlatFast ff;
     const GeomView<float> g = stage_scene_flat(p.geom, sm);
     if (threadIdx.x == 0)
         build_flat_fast(g, ff);
+    if (int(threadIdx.x) < g.n_prims)
+        build_plane_rec(g, threadIdx.x, ff.plane[threadIdx.x]);
     __syncthreads();
     PathState s;
     bool alive = false, exhausted = false;
@@ -1262,11 +1303,11 @@ __global__ void __launch_bounds__(128, OLD ? RTB_FUSED_MIN_BLOCKS_OLD : RTB_FUSE
         if (alive) {
             PathDraw draw{&s.rng};
             float t;
-            const uint32_t pi = traverse_flat_fast<false, COUNT>(g, ff, s.o, s.d, s.time, 0.001f, Consts<float>::inf(),
+            const uint32_t pi = traverse_flat_fast<false, COUNT, SIMPLE == 2>(g, ff, s.o, s.d, s.time, 0.001f, Consts<float>::inf(),
                                                                  s.origin_prim, draw, t, nodes, tests);
             ++n_closest;
             if (pi == kNoPrim) {
-                miss_surface(p, s);
+                miss_surface<OLD>(p, s);
                 alive = false;
             } else {
                 ShadowReq sh;
@@ -1274,17 +1315,17 @@ __global__ void __launch_bounds__(128, OLD ? RTB_FUSED_MIN_BLOCKS_OLD : RTB_FUSE
                 const int mtype = p.shade.mats[g.prims[pi].type_mat >> PT_MAT_SHIFT].type;
                 if (SIMPLE) {
                     if (mtype == 0)
-                        shade_surface<0, OLD>(p, g, s, t, pi, alive, sh);
+                        shade_surface<0, OLD, SIMPLE == 2>(p, g, s, t, pi, alive, sh, ff.plane);
                     else
-                        shade_surface<3, OLD>(p, g, s, t, pi, alive, sh);
+                        shade_surface<3, OLD, SIMPLE == 2>(p, g, s, t, pi, alive, sh, ff.plane);
                 } else {
                     switch (mtype) {
-                    case 0: shade_surface<0, OLD>(p, g, s, t, pi, alive, sh); break;
-                    case 1: shade_surface<1, OLD>(p, g, s, t, pi, alive, sh); break;
-                    case 2: shade_surface<2, OLD>(p, g, s, t, pi, alive, sh); break;
-                    case 3: shade_surface<3, OLD>(p, g, s, t, pi, alive, sh); break;
-                    case 4: shade_surface<4, OLD>(p, g, s, t, pi, alive, sh); break;
-                    default: shade_surface<5, OLD>(p, g, s, t, pi, alive, sh); break;
+                    case 0: shade_surface<0, OLD>(p, g, s, t, pi, alive, sh, ff.plane); break;
+                    case 1: shade_surface<1, OLD>(p, g, s, t, pi, alive, sh, ff.plane); break;
+                    case 2: shade_surface<2, OLD>(p, g, s, t, pi, alive, sh, ff.plane); break;
+                    case 3: shade_surface<3, OLD>(p, g, s, t, pi, alive, sh, ff.plane); break;
+                    case 4: shade_surface<4, OLD>(p, g, s, t, pi, alive, sh, ff.plane); break;
+                    default: shade_surface<5, OLD>(p, g, s, t, pi, alive, sh, ff.plane); break;
                     }
                 }
                 if (!OLD && sh.want) {
@@ -1294,7 +1335,7 @@ __global__ void __launch_bounds__(128, OLD ? RTB_FUSED_MIN_BLOCKS_OLD : RTB_FUSE
                     const float len = isfinite(sh.tmax) ? length(sh.d) : 1.0f;
                     PathDraw sdraw{&rg};
                     float st;
-                    if (traverse_flat_fast<true, COUNT>(g, ff, sh.o, sh.d, 0.0f, 0.001f / len, sh.tmax, sh.origin, sdraw,
+                    if (traverse_flat_fast<true, COUNT, SIMPLE == 2>(g, ff, sh.o, sh.d, 0.0f, 0.001f / len, sh.tmax, sh.origin, sdraw,
                                                         st, nodes, tests) == kNoPrim)
                         accum_add(p.accum, pix, sh.c);
                 }
@@ -1326,12 +1367,15 @@ struct FlatDraw {
 };
 __global__ void __launch_bounds__(128) k_trace_fast_batch(GeomView<float> geom, const int32_t *__restrict__ orig_to_sorted,
                                                           int n_orig, const rtb_ray *__restrict__ rays, uint64_t n,
-                                                          rtb_hit *__restrict__ hits, unsigned long long *visits) {
+                                                          rtb_hit *__restrict__ hits, unsigned long long *visits,
+                                                          bool plane_records) {
     __shared__ FlatSmem sm;
     __shared__ FlatFast ff;
     const GeomView<float> g = stage_scene_flat(geom, sm);
     if (threadIdx.x == 0)
         build_flat_fast(g, ff);
+    if (int(threadIdx.x) < g.n_prims)
+        build_plane_rec(g, threadIdx.x, ff.plane[threadIdx.x]);
     __syncthreads();
     uint64_t nodes = 0, tests = 0;
     for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
@@ -1350,7 +1394,10 @@ __global__ void __launch_bounds__(128) k_trace_fast_batch(GeomView<float> geom, 
         h.prim = -1;
         h.material = -1;
         if (pi != kNoPrim) {
-            const RecT<float> rec = make_record<float, true, true>(g, pi, o, d, float(q.time), t);
+            // planar primitives: the record the fused kernel shades from (no u,v)
+            const RecT<float> rec = plane_records && ff.plane[pi].valid
+                                        ? plane_record<float>(ff.plane[pi], o, d, t)
+                                        : make_record<float, true, true>(g, pi, o, d, float(q.time), t);
             h.t = rec.t;
             h.p[0] = rec.p.x;
             h.p[1] = rec.p.y;
@@ -1527,6 +1574,8 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
     W.row_offset = rp.row_offset;
     W.row_stride = row_stride;
     W.npix = npix;
+    W.inv_npix = recip32(npix);
+    W.inv_width = recip32(uint32_t(rp.width));
     W.total_samples = total;
     W.window_end = total;
     W.seed = rp.seed;
@@ -1541,6 +1590,16 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
     const bool count = (rp.flags & RTB_RENDER_COUNT_VISITS) != 0;
     const bool time_dom = (rp.flags & RTB_RENDER_TIME_EXTEND) != 0;
     const bool simple = (W.mat_mask & ~((1u << RTB_MAT_LAMBERTIAN) | (1u << RTB_MAT_DIFFUSE_LIGHT))) == 0;
+    // every primitive has a plane digest (build_plane_rec) and every material a baked solid colour?
+    bool all_planar = simple && sc.host.flat_ok;
+    for (size_t i = 0; all_planar && i < sc.host.f32.prims.size(); ++i) {
+        const uint32_t type = sc.host.f32.prims[i].type_mat & PT_TYPE_MASK;
+        const int chain = sc.host.prim_chain[i];
+        all_planar = type == PT_INSTANCE || ((type == PT_XY || type == PT_XZ || type == PT_YZ) &&
+                                             (chain < 0 || sc.host.chains[size_t(chain)].count <= kMaxChainOps));
+    }
+    for (size_t i = 0; all_planar && i < sc.host.f32.mats.size(); ++i)
+        all_planar = (sc.host.f32.mats[i].flags & 3) == 2; // solid colour, baked (mat_tex)
     size_t n_ext_events = 0;
 
     uint64_t launches = 0;
@@ -1553,12 +1612,12 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
         // pick the instantiation once: (legacy vs BSDF API) x (counting) x (simple material set)
         void (*kern)(WfParams) = nullptr;
         {
-            void (*table[2][2][2])(WfParams) = {
-                {{k_fused<false, false, false>, k_fused<false, false, true>},
-                 {k_fused<false, true, false>, k_fused<false, true, true>}},
-                {{k_fused<true, false, false>, k_fused<true, false, true>},
-                 {k_fused<true, true, false>, k_fused<true, true, true>}}};
-            kern = table[old_api ? 1 : 0][count ? 1 : 0][simple ? 1 : 0];
+            void (*table[2][2][3])(WfParams) = {
+                {{k_fused<false, false, 0>, k_fused<false, false, 1>, k_fused<false, false, 2>},
+                 {k_fused<false, true, 0>, k_fused<false, true, 1>, k_fused<false, true, 2>}},
+                {{k_fused<true, false, 0>, k_fused<true, false, 1>, k_fused<true, false, 2>},
+                 {k_fused<true, true, 0>, k_fused<true, true, 1>, k_fused<true, true, 2>}}};
+            kern = table[old_api ? 1 : 0][count ? 1 : 0][all_planar ? 2 : simple ? 1 : 0];
         }
         const int bps = blocks_per_sm(kern, 128);
         const int grid = sms * bps;
@@ -1794,14 +1853,15 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
 }
 
 void launch_trace_fast_batch(rtb_context *ctx, const rtb_ray *d_rays, uint64_t n, rtb_hit *d_hits,
-                             unsigned long long *d_visits) {
+                             unsigned long long *d_visits, bool plane_records) {
     const DeviceScene &sc = *ctx->scene;
     const GeomView<float> g = sc.geom<float>();
     if (!g.flat)
-        throw std::runtime_error("precision 33 (the fused kernel's typed traversal) needs a scene of <= 64 primitive records");
+        throw std::runtime_error("precision 33 / 35 (the fused kernel's typed traversal) needs a scene of <= 64 primitive records");
     const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
     k_trace_fast_batch<<<sms * 4, 128, 0, ctx->stream>>>(g, sc.orig_to_sorted.as<int32_t>(),
-                                                         int(sc.host.orig_to_sorted.size()), d_rays, n, d_hits, d_visits);
+                                                         int(sc.host.orig_to_sorted.size()), d_rays, n, d_hits, d_visits,
+                                                         plane_records);
     RTB_CUDA(cudaGetLastError());
 }
 

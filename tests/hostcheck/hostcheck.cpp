@@ -58,7 +58,7 @@ template <class R> ShadeView<R> shade_view(HostScene &H) {
 
 template <class R, bool ROBUST>
 void trace_batch(HostScene &H, const rtb_ray *rays, uint64_t n, rtb_hit *hits, uint64_t stats[2], bool use_flat,
-                 bool inst_in_descent = false) {
+                 bool inst_in_descent = false, bool plane_records = false) {
     const GeomView<R> g = geom_view<R>(H);
     RngT<R> rng;
     rng.g = pcg_seed(1, 2);
@@ -87,7 +87,15 @@ void trace_batch(HostScene &H, const rtb_ray *rays, uint64_t n, rtb_hit *hits, u
         h.material = -1;
         if (pi == kNoPrim)
             continue;
-        const RecT<R> rec = make_record<R, ROBUST, true>(g, pi, o, d, R(q.time), t);
+        RecT<R> rec;
+        PlaneRec pl;
+        pl.valid = 0;
+        if (plane_records) // the fused kernel's digest of planar primitives (u,v are not produced)
+            build_plane_rec(g, pi, pl);
+        if (pl.valid)
+            rec = plane_record<R>(pl, o, d, t);
+        else
+            rec = make_record<R, ROBUST, true>(g, pi, o, d, R(q.time), t);
         h.t = rec.t;
         h.p[0] = rec.p.x; h.p[1] = rec.p.y; h.p[2] = rec.p.z;
         h.normal[0] = rec.normal.x; h.normal[1] = rec.normal.y; h.normal[2] = rec.normal.z;
@@ -227,11 +235,13 @@ void hc_trace_batch(void *h, const rtb_ray *rays, uint64_t n, int precision, rtb
     // 64: fp64 through the BVH; 65: fp64 lockstep; 66: fp64 through the BVH with instance entry /
     // exit inside the descent (the traversal shape of instance-free scenes, valid on any scene);
     // 32: fp32 as the renderer traces this scene (lockstep when it is small); 33: fp32 forced
-    // through the BVH; 34: the same with instance entry / exit inside the descent
+    // through the BVH; 34: the same with instance entry / exit inside the descent; 35: as 32 with
+    // the records of planar primitives from plane_record() (the fused kernel's shading input)
     if (precision >= 64)
         trace_batch<double, false>(*H, rays, n, hits, local, precision == 65, precision == 66);
     else
-        trace_batch<float, true>(*H, rays, n, hits, local, precision == 32, precision == 34);
+        trace_batch<float, true>(*H, rays, n, hits, local, precision == 32 || precision == 35, precision == 34,
+                                 precision == 35);
     if (stats) {
         stats[0] = local[0];
         stats[1] = local[1];

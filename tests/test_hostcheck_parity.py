@@ -129,3 +129,29 @@ def test_both_traversal_shapes_give_the_same_hits(hostcheck, scenes, golden, abi
     b32, _ = trace(hostcheck, scenes(sid), seg, 34, abi)
     mask &= parity.deterministic_mask(T, ref, a32) & parity.deterministic_mask(T, ref, b32)
     assert np.array_equal(a32["prim"][mask], b32["prim"][mask]) and np.array_equal(a32["t"][mask], b32["t"][mask])
+
+
+@pytest.mark.parametrize("sid", GOLDEN_SCENES)
+def test_plane_records_match_the_reference_records(hostcheck, scenes, golden, abi, sid):
+    """The fused kernel shades planar primitives from plane_record() (one world-space plane per
+    rect, digested once) instead of replaying the wrapper chain in make_record(): the normal and
+    front_face must be the reference's own (hit_record after every wrapper), the point within
+    fp32 rounding of it."""
+    g = golden(sid)
+    T = abi.parse_blob(g.blob)
+    rays, ref = g["rays"], g["hits"]
+    seg = parity.to_segment_form(rays)
+    a, _ = trace(hostcheck, scenes(sid), seg, 32, abi)
+    b, _ = trace(hostcheck, scenes(sid), seg, 35, abi)
+    assert np.array_equal(a["prim"], b["prim"]) and np.array_equal(a["t"], b["t"])
+    hit = (ref["prim"] >= 0) & (b["prim"] == ref["prim"]) & parity.deterministic_mask(T, ref, b)
+    planar = hit & np.isin(T["prims"]["type"][np.maximum(ref["prim"], 0)], (2, 3, 4))
+    if not planar.any():
+        pytest.skip("no planar primitives in this fixture")
+    scale = np.maximum(1.0, np.abs(ref["p"][planar]).max())
+    grazing = np.abs(np.einsum("ij,ij->i", ref["normal"][planar], rays["d"][planar])) < \
+        1e-5 * np.linalg.norm(rays["d"][planar], axis=1)
+    for got in (a, b):
+        assert np.abs(got["p"][planar] - ref["p"][planar]).max() <= 4e-6 * scale
+        assert np.abs(got["normal"][planar] - ref["normal"][planar])[~grazing].max() <= 2e-6
+        assert np.array_equal(got["front_face"][planar][~grazing], ref["front_face"][planar][~grazing])
