@@ -1241,6 +1241,10 @@ class Renderer {
             m_integrator->set_max_depth(depth);
     }
     void set_seed(uint64_t seed) { m_seed = seed; }
+    // Progressive preview: how many sample passes the render is cut into (0 = automatic, about
+    // 2^28 samples per pass; 1 = one call).  target_buffer is refreshed after every pass.
+    void set_preview_passes(int passes) { m_preview_passes = passes; }
+    int passes_done() const { return m_passes_done; }
     void cancel() { // renderer.h:113 — safe from another thread
         m_is_rendering = false;
         if (m_ctx)
@@ -1270,23 +1274,58 @@ class Renderer {
         p.max_depth = m_integrator->max_depth();
         p.rr_start_depth = m_integrator->rr_start_depth();
         p.integrator = m_integrator->id();
-        p.sample_offset = 0;
-        p.sample_stride = 1;
         p.seed = m_seed;
-        std::vector<float> acc(size_t(w) * h * 4);
-        const int rc = rtb_render(m_ctx, &p, acc.data(), &m_stats);
-        if (rc != RTB_OK && rc != RTB_ERR_CANCELLED) {
-            m_is_rendering = false;
-            rtb::check(rc, m_ctx, "rtb_render");
+        // The reference's worker threads fill target_buffer tile by tile while the UI thread polls
+        // it every 33 ms (main.cpp:119-126).  Here the image fills in sample PASSES: pass k renders
+        // the samples s = k (mod passes) of every pixel (the same split the multi-GPU driver uses;
+        // a sample's random stream depends on (pixel, s, seed) only, so the passes add up to exactly
+        // the one-call sample set) and the buffer shows sqrt(mean so far) after each.
+        int passes = m_preview_passes;
+        if (passes <= 0) { // automatic: about 2^28 samples (tens of ms on a B200) per pass
+            const unsigned long long total = (unsigned long long)w * h * (unsigned long long)std::max(p.spp, 1);
+            passes = int(std::min<unsigned long long>((total + (1ull << 28) - 1) >> 28, 64));
         }
-        if (rc == RTB_OK) // renderer.h:126-140
-            for (int j = 0; j < h; ++j)
+        passes = std::max(1, std::min(passes, std::max(p.spp, 1)));
+        p.sample_stride = passes;
+        std::vector<float> acc(size_t(w) * h * 4), sum;
+        rtb_render_stats total_stats{};
+        int samples_done = 0;
+        m_passes_done = 0;
+        for (int pass = 0; pass < passes && m_is_rendering; ++pass) {
+            p.sample_offset = pass;
+            const int rc = rtb_render(m_ctx, &p, acc.data(), &m_stats);
+            if (rc == RTB_ERR_CANCELLED)
+                break;
+            if (rc != RTB_OK) {
+                m_is_rendering = false;
+                rtb::check(rc, m_ctx, "rtb_render");
+            }
+            samples_done += (p.spp - pass + passes - 1) / passes;
+            total_stats.paths += m_stats.paths;
+            total_stats.rays_closest += m_stats.rays_closest;
+            total_stats.rays_shadow += m_stats.rays_shadow;
+            total_stats.iterations += m_stats.iterations;
+            total_stats.kernel_launches += m_stats.kernel_launches;
+            total_stats.device_ms += m_stats.device_ms;
+            total_stats.schedule = m_stats.schedule;
+            const float *show = acc.data();
+            if (passes > 1) {
+                if (sum.empty())
+                    sum.assign(acc.size(), 0.f);
+                for (size_t i = 0; i < acc.size(); ++i)
+                    sum[i] += acc[i];
+                show = sum.data();
+            }
+            const double scale = 1.0 / std::max(samples_done, 1);
+            for (int j = 0; j < h; ++j) // renderer.h:126-140
                 for (int i = 0; i < w; ++i) {
-                    const float *a = &acc[(size_t(j) * w + i) * 4];
-                    const double scale = 1.0 / p.spp;
+                    const float *a = &show[(size_t(j) * w + i) * 4];
                     target_buffer.set_pixel(i, j, color(clamp(sqrt(scale * a[0]), 0.0, 1.0), clamp(sqrt(scale * a[1]), 0.0, 1.0),
                                                         clamp(sqrt(scale * a[2]), 0.0, 1.0)));
                 }
+            m_passes_done = pass + 1;
+        }
+        m_stats = total_stats;
         const std::chrono::duration<double> elapsed = std::chrono::high_resolution_clock::now() - start;
         m_is_rendering = false;
         std::cout << "Rendering finished in " << elapsed.count() << " seconds." << std::endl; // renderer.h:100
@@ -1300,6 +1339,8 @@ class Renderer {
     rtb_render_stats m_stats{};
     int m_device = 0;
     uint64_t m_seed = 1;
+    int m_preview_passes = 0;
+    std::atomic<int> m_passes_done{0};
 };
 
 #endif // RTB_HOST_HPP

@@ -3,6 +3,7 @@
 // Prints "key value..." lines that tests/test_host_layer.py checks.
 #include "rtb_scenes.hpp"
 
+#include <cmath>
 #include <cstdio>
 
 int main() {
@@ -55,6 +56,16 @@ int main() {
                     sum[k] += px[k] * px[k]; // undo the sqrt: mean of clamped linear values
         std::printf("render %.6f %.6f %.6f %d\n", sum[0] / 4096, sum[1] / 4096, sum[2] / 4096, int(renderer.is_rendering()));
         std::printf("png %d\n", int(buf.save_to_png("/tmp/rtb_host_api_test.png")));
+        // progressive preview: four sample passes add up to the one-call image (same sample set)
+        RenderBuffer buf4(64, 64);
+        renderer.set_preview_passes(4);
+        renderer.render(c.world, cam, c.background, buf4, c.lights);
+        double worst = 0;
+        for (int j = 0; j < 64; ++j)
+            for (int i = 0; i < 64; ++i)
+                for (int k = 0; k < 3; ++k)
+                    worst = std::max(worst, std::fabs(buf.get_data()[j][i][k] - buf4.get_data()[j][i][k]));
+        std::printf("passes %d %.3g %llu\n", renderer.passes_done(), worst, (unsigned long long)renderer.last_stats().paths);
         return 0;
     } catch (const std::exception &e) {
         std::printf("exception %s\n", e.what());

@@ -280,3 +280,34 @@ def test_fused_kernel_traversal_on_a_million_rays(gpu_ctx, up, golden, abi):
     assert differ2.mean() < 1e-4, differ2.sum()
     ok2 = (f2["prim"] == g2["prim"]) & (f2["prim"] >= 0)
     assert np.array_equal(f2["t"][ok2], g2["t"][ok2])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sid", [7, 21, 23, 8, 17, 24])
+def test_fused_kernel_plane_records_match_reference_records(gpu_ctx, up, golden, abi, sid):
+    """The fused kernel shades planar primitives from its per-primitive plane digest (precision
+    35) instead of replaying the wrapper chain: same primitive and t as precision 33, the
+    reference's own normal and front_face (the rotate_y / flip_face quirks included), the
+    reference's point within fp32 rounding."""
+    g = golden(sid)
+    T = abi.parse_blob(g.blob)
+    ctx = up(sid)
+    ref, rays64 = g["hits"], g["rays"]
+    rays = parity.to_segment_form(rays64)
+    a, b = ctx.trace(rays, 33), ctx.trace(rays, 35)
+    assert np.array_equal(a["prim"], b["prim"]) and np.array_equal(a["t"], b["t"])
+    hit = (ref["prim"] >= 0) & (b["prim"] == ref["prim"]) & parity.deterministic_mask(T, ref, b)
+    planar = hit & np.isin(T["prims"]["type"][np.maximum(ref["prim"], 0)], (2, 3, 4))
+    if not planar.any():
+        pytest.skip("no planar primitives in this fixture")
+    scale = np.maximum(1.0, np.abs(ref["p"][planar]).max())
+    grazing = np.abs(np.einsum("ij,ij->i", ref["normal"][planar], rays64["d"][planar])) < \
+        1e-5 * np.linalg.norm(rays64["d"][planar], axis=1)
+    assert np.abs(b["p"][planar] - ref["p"][planar]).max() <= 4e-6 * scale
+    assert np.abs(b["normal"][planar] - ref["normal"][planar])[~grazing].max() <= 2e-6
+    assert np.array_equal(b["front_face"][planar][~grazing], ref["front_face"][planar][~grazing])
+    assert np.array_equal(b["material"][planar], ref["material"][planar])
+    # non-planar hits keep the generic record
+    other = hit & ~planar & (a["prim"] == b["prim"])
+    for f in ("p", "normal", "front_face", "u", "v"):
+        assert np.array_equal(a[f][other], b[f][other]), f

@@ -104,6 +104,8 @@ def test_reference_shaped_api_on_the_gpu(tmp_path):
     # mean of the CLAMPED linear image (the emitter saturates at 1): ~0.094, red > green > blue
     assert 0.07 < rend[0] < 0.13 and rend[0] > rend[1] > rend[2] and kv["render"][3] == "0"
     assert kv["png"] == ["1"]
+    # four preview passes: same samples, the image agrees up to float summation order
+    assert kv["passes"][0] == "4" and float(kv["passes"][1]) < 1e-4 and int(kv["passes"][2]) == 64 * 64 * 256
     sig = open("/tmp/rtb_host_api_test.png", "rb").read(8)
     assert sig == bytes([137, 80, 78, 71, 13, 10, 26, 10])
 
