@@ -850,7 +850,11 @@ struct PlaneRec {
     uint32_t mode;  // bit 0: surviving flips (parity); bit 1: the chain has a translate / rotate_y
     float vp[3];    // v_prev
     uint32_t valid; // 0: not a planar primitive (or its chain is too long): use make_record()
+    // filled by the fused kernel for scenes it shades from this record alone (solid colours only)
+    float color[3];
+    int32_t mat_type;
 };
+static_assert(sizeof(PlaneRec) == 64, "PlaneRec is four 16-byte vectors");
 
 template <class R> RTB_HD void build_plane_rec(const GeomView<R> &g, uint32_t pi, PlaneRec &out) {
     out = PlaneRec{};

@@ -33,10 +33,20 @@ struct Pcg {
         const uint32_t r = uint32_t(old >> 59u);
         return (x >> r) | (x << ((32u - r) & 31u));
     }
+    // The float draws take the TOP 24 bits of the LCG state directly (the bits with the longest
+    // period; the XSH-RR permutation exists to make the LOW bits usable, which a 24-bit float draw
+    // never touches): 5 instructions per draw instead of 12 on a path that is instruction-issue
+    // bound (ncu source view of k_fused on the Cornell box: 10 % of all issued instructions were
+    // next_u32()).  Integer draws keep the permuted output.
+    RTB_HD uint32_t next_top24() {
+        const uint64_t old = s;
+        s = old * 6364136223846793005ULL + 1442695040888963407ULL;
+        return uint32_t(old >> 40u);
+    }
     // uniform in [0,1), 24 bits
-    RTB_HD float next_f() { return float(next_u32() >> 8) * (1.0f / 16777216.0f); }
+    RTB_HD float next_f() { return float(next_top24()) * (1.0f / 16777216.0f); }
     // uniform in (0,1): safe argument for log()
-    RTB_HD float next_open() { return (float(next_u32() >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+    RTB_HD float next_open() { return (float(next_top24()) + 0.5f) * (1.0f / 16777216.0f); }
 };
 
 RTB_HD uint64_t mix64(uint64_t z) { // splitmix64 finaliser

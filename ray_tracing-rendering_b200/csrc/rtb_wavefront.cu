@@ -72,6 +72,9 @@ constexpr int kFlatUnroll = RTB_FLAT_UNROLL; // unroll factor of the typed rect 
 #ifndef RTB_FUSED_MIN_BLOCKS_NEW
 #define RTB_FUSED_MIN_BLOCKS_NEW 6
 #endif
+#ifndef RTB_FUSED_MIN_BLOCKS_NEW_PLANAR
+#define RTB_FUSED_MIN_BLOCKS_NEW_PLANAR 8 // the all-planar BSDF-API kernel (C3 6 -> 23.98 ms, 7 -> 22.95, 8 -> 22.68)
+#endif
 #ifndef RTB_SHADE_MIN_BLOCKS
 #define RTB_SHADE_MIN_BLOCKS 1
 #endif
@@ -246,25 +249,37 @@ constexpr int kWfBlock = 128; // threads per block of every wavefront kernel
 // The set of primitives tested is the same, only the order inside a space changes (which could
 // matter only for hits at bit-identical t).
 struct FlatFast {
-    struct Space {
-        int16_t first[4]; // rects of this space: [first[a], first[a+1]) has constant axis a (0 = yz, 1 = xz, 2 = xy)
-        int16_t other_first, other_end; // indices into `other`
-        int16_t sph_first, sph_end;     // indices into `sph`
-        int16_t chain;                  // wrapper chain of the instance, -1 for the world
-        int16_t box;                    // >= 0: the space is exactly one `box` (box.h): index into `box`
+    // All fields are 32-bit and the records 16-byte aligned: one LDS.128 brings a whole record,
+    // nothing is unpacked (the first version held int16 fields: the ncu source view showed ~30
+    // instructions per space spent on loading and sign-extending them).
+    struct alignas(16) Space {
+        int32_t first[4]; // rects of this space: [first[a], first[a+1]) has constant axis a (0 = yz, 1 = xz, 2 = xy)
+        int32_t chain;    // wrapper chain of the instance, -1 for the world
+        int32_t box;      // >= 0: the space is exactly one `box` (box.h): index into `box`
+        int32_t sph_first, sph_end;     // indices into `sph`
+        int32_t other_first, other_end; // indices into `other`
+        int32_t pad[2];
     };
     // The six rects of a box (box.h:31-47) as one slab test.  face[s]: primitive index of the face
     // x = lo, x = hi, y = lo, y = hi, z = lo, z = hi; slot[r]: the same map backwards for the
-    // primitives first .. first + 5.
-    struct Box {
-        float lo[3], hi[3];
+    // primitives first .. first + 5.  The instance's folded transform travels with the box.
+    struct alignas(16) Box {
+        float xf[4];  // ChainAffine: c, s, bx, bz
+        float lo[3];
+        float by;     // ChainAffine: by
+        float hi[3];
         uint32_t first;
-        int16_t face[6];
-        int16_t slot[6];
+        int32_t face[6];
+        int32_t slot[6];
+    };
+    struct alignas(16) Rect {
+        float k, a0, a1, b0; // plane, in-plane extents
+        float b1;
+        uint32_t id;         // primitive index
+        float pad[2];
     };
     Box box[kFlatMaxChains];
-    float4 ra[kFlatMaxPrims]; // k, a0, a1, b0
-    float2 rb[kFlatMaxPrims]; // b1, primitive index (bits)
+    Rect rect[kFlatMaxPrims];
     float4 sph[kFlatMaxPrims]; // centre, radius
     int16_t sph_id[kFlatMaxPrims];
     int16_t other[kFlatMaxPrims];
@@ -292,15 +307,15 @@ __device__ inline void build_flat_fast(const GeomView<float> &g, FlatFast &ff) {
             const int A = ax == 0 ? 1 : 0, B = ax == 2 ? 1 : 2;
             if (cnt[ax] == 0) {
                 bx.lo[ax] = p.d[4];
-                bx.face[2 * ax] = int16_t(i);
+                bx.face[2 * ax] = int32_t(i);
             } else {
                 bx.hi[ax] = p.d[4];
-                bx.face[2 * ax + 1] = int16_t(i);
+                bx.face[2 * ax + 1] = int32_t(i);
                 if (bx.hi[ax] < bx.lo[ax]) {
                     const float tf = bx.lo[ax];
                     bx.lo[ax] = bx.hi[ax];
                     bx.hi[ax] = tf;
-                    const int16_t ti = bx.face[2 * ax];
+                    const int32_t ti = bx.face[2 * ax];
                     bx.face[2 * ax] = bx.face[2 * ax + 1];
                     bx.face[2 * ax + 1] = ti;
                 }
@@ -321,35 +336,46 @@ __device__ inline void build_flat_fast(const GeomView<float> &g, FlatFast &ff) {
                 return false;
         }
         for (int s6 = 0; s6 < 6; ++s6)
-            bx.slot[uint32_t(bx.face[s6]) - begin] = int16_t(s6);
+            bx.slot[uint32_t(bx.face[s6]) - begin] = s6;
         return true;
     };
     auto add_space = [&](uint32_t begin, uint32_t end, int chain, bool top_level) {
         FlatFast::Space &sp = ff.space[n_spaces++];
-        sp.chain = int16_t(chain);
+        sp.chain = chain;
         sp.box = -1;
         if (!top_level && n_box < kFlatMaxChains && as_box(begin, end, ff.box[n_box])) {
-            sp.box = int16_t(n_box++);
-            sp.first[0] = sp.first[1] = sp.first[2] = sp.first[3] = int16_t(n_rect);
-            sp.other_first = sp.other_end = int16_t(n_other);
-            sp.sph_first = sp.sph_end = int16_t(n_sph);
+            const ChainAffine a = g.affine[chain];
+            FlatFast::Box &bx = ff.box[n_box];
+            bx.xf[0] = a.c;
+            bx.xf[1] = a.s;
+            bx.xf[2] = a.bx;
+            bx.xf[3] = a.bz;
+            bx.by = a.by;
+            sp.box = n_box++;
+            sp.first[0] = sp.first[1] = sp.first[2] = sp.first[3] = n_rect;
+            sp.other_first = sp.other_end = n_other;
+            sp.sph_first = sp.sph_end = n_sph;
             return;
         }
         const uint32_t axis_type[3] = {PT_YZ, PT_XZ, PT_XY}; // constant axis 0, 1, 2
         for (int a = 0; a < 3; ++a) {
-            sp.first[a] = int16_t(n_rect);
+            sp.first[a] = n_rect;
             for (uint32_t i = begin; i < end; ++i) {
                 const PrimT<float> p = g.prims[i];
                 if ((p.type_mat & PT_TYPE_MASK) != axis_type[a])
                     continue;
-                ff.ra[n_rect] = make_float4(p.d[4], p.d[0], p.d[1], p.d[2]);
-                ff.rb[n_rect] = make_float2(p.d[3], __uint_as_float(i));
-                ++n_rect;
+                FlatFast::Rect &r = ff.rect[n_rect++];
+                r.k = p.d[4];
+                r.a0 = p.d[0];
+                r.a1 = p.d[1];
+                r.b0 = p.d[2];
+                r.b1 = p.d[3];
+                r.id = i;
             }
         }
-        sp.first[3] = int16_t(n_rect);
-        sp.other_first = int16_t(n_other);
-        sp.sph_first = int16_t(n_sph);
+        sp.first[3] = n_rect;
+        sp.other_first = n_other;
+        sp.sph_first = n_sph;
         for (uint32_t i = begin; i < end; ++i) {
             const PrimT<float> p = g.prims[i];
             const uint32_t type = p.type_mat & PT_TYPE_MASK;
@@ -362,8 +388,8 @@ __device__ inline void build_flat_fast(const GeomView<float> &g, FlatFast &ff) {
                 ff.other[n_other++] = int16_t(i);
             }
         }
-        sp.other_end = int16_t(n_other);
-        sp.sph_end = int16_t(n_sph);
+        sp.other_end = n_other;
+        sp.sph_end = n_sph;
     };
     const uint32_t n_top = uint32_t(g.n_top);
     add_space(0, n_top, -1, true);
@@ -382,10 +408,11 @@ template <int AX, int A, int B, bool COUNT>
 __device__ __forceinline__ void flat_rects(const FlatFast &ff, int first, int last, V3<float> o, V3<float> d,
                                            float idir_ax, float t_min, float &t_max, uint32_t origin, uint32_t &best,
                                            uint64_t &tests) {
+    const FlatFast::Rect *r = ff.rect + first, *const r_end = ff.rect + last;
 #pragma unroll kFlatUnroll
-    for (int i = first; i < last; ++i) {
-        const float4 ra = ff.ra[i];
-        const float2 rb = ff.rb[i];
+    for (; r != r_end; ++r) {
+        const float4 ra = *reinterpret_cast<const float4 *>(&r->k); // k, a0, a1, b0
+        const float2 rb = *reinterpret_cast<const float2 *>(&r->b1); // b1, id
         const float t = (ra.x - o[AX]) * idir_ax; // the arithmetic of hit_rect(), bit for bit
         const float a = fmaf(t, d[A], o[A]);
         const float b = fmaf(t, d[B], o[B]);
@@ -403,18 +430,25 @@ __device__ __forceinline__ void flat_rects(const FlatFast &ff, int first, int la
 // ordering instead of the in-rectangle tests, which can differ from the rect-by-rect answer only
 // for rays within rounding distance of a box edge.
 template <bool COUNT>
-__device__ __forceinline__ void flat_box(const FlatFast::Box &bx, V3<float> o, V3<float> d, V3<float> idir, float t_min,
-                                         float &t_max, uint32_t origin, uint32_t &best, uint64_t &tests) {
-    const float tx0 = (bx.lo[0] - o.x) * idir.x, tx1 = (bx.hi[0] - o.x) * idir.x;
-    const float ty0 = (bx.lo[1] - o.y) * idir.y, ty1 = (bx.hi[1] - o.y) * idir.y;
-    const float tz0 = (bx.lo[2] - o.z) * idir.z, tz1 = (bx.hi[2] - o.z) * idir.z;
+__device__ __forceinline__ void flat_box(const FlatFast::Box &bx, V3<float> wo, V3<float> wd, float t_min, float &t_max,
+                                         uint32_t origin, uint32_t &best, uint64_t &tests) {
+    // the ray in the box's object space: the arithmetic of enter_instance<float, true>
+    const float4 xf = *reinterpret_cast<const float4 *>(bx.xf);
+    const float4 lob = *reinterpret_cast<const float4 *>(bx.lo);
+    const V3<float> o(xf.x * wo.x - xf.y * wo.z + xf.z, wo.y + lob.w, xf.y * wo.x + xf.x * wo.z + xf.w);
+    const V3<float> d(xf.x * wd.x - xf.y * wd.z, wd.y, xf.y * wd.x + xf.x * wd.z);
+    const V3<float> idir = safe_inv(d);
+    const float4 hif = *reinterpret_cast<const float4 *>(bx.hi); // hi, first
+    const float tx0 = (lob.x - o.x) * idir.x, tx1 = (hif.x - o.x) * idir.x;
+    const float ty0 = (lob.y - o.y) * idir.y, ty1 = (hif.y - o.y) * idir.y;
+    const float tz0 = (lob.z - o.z) * idir.z, tz1 = (hif.z - o.z) * idir.z;
     const float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fminf(tz0, tz1));
     const float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fmaxf(tz0, tz1));
     if (COUNT)
         tests += 6;
     float cand;
     bool ok;
-    const uint32_t rel = origin - bx.first;
+    const uint32_t rel = origin - __float_as_uint(hif.w);
     if (rel < 6u) {
         // the ray starts ON this box: heading outward it cannot meet a convex box again; heading
         // inward (a transmitted ray) it leaves through the far side
@@ -445,19 +479,21 @@ __device__ __forceinline__ uint32_t traverse_flat_fast(const GeomView<float> &g,
     const int n_spaces = ff.n_spaces;
     for (int s = 0; s < n_spaces; ++s) {
         const FlatFast::Space sp = ff.space[s];
-        V3<float> lo = o, ld = d;
-        if (sp.chain >= 0) {
-            enter_instance<float, true>(g, sp.chain, lo, ld);
+        if (sp.box >= 0) {
             if (COUNT)
                 ++nodes; // one "node" = one instance entry (ray transform)
-        }
-        const V3<float> lid = safe_inv(ld);
-        if (sp.box >= 0) {
-            flat_box<COUNT>(ff.box[sp.box], lo, ld, lid, t_min, t_max, origin, best, tests);
+            flat_box<COUNT>(ff.box[sp.box], o, d, t_min, t_max, origin, best, tests);
             if (ANY && best != kNoPrim)
                 break;
             continue;
         }
+        V3<float> lo = o, ld = d;
+        if (sp.chain >= 0) {
+            enter_instance<float, true>(g, sp.chain, lo, ld);
+            if (COUNT)
+                ++nodes;
+        }
+        const V3<float> lid = safe_inv(ld);
         flat_rects<0, 1, 2, COUNT>(ff, sp.first[0], sp.first[1], lo, ld, lid.x, t_min, t_max, origin, best, tests);
         flat_rects<1, 0, 2, COUNT>(ff, sp.first[1], sp.first[2], lo, ld, lid.y, t_min, t_max, origin, best, tests);
         flat_rects<2, 0, 1, COUNT>(ff, sp.first[2], sp.first[3], lo, ld, lid.z, t_min, t_max, origin, best, tests);
@@ -682,14 +718,21 @@ template <int M, bool OLD, bool ALL_PLANAR = false>
 __device__ __forceinline__ void shade_surface(const WfParams &p, const GeomView<float> &g, PathState &s, float t,
                                               uint32_t pi, bool &alive, ShadowReq &sh, const PlaneRec *plane = nullptr) {
     sh.want = false;
-    MatT<float> m = p.shade.mats[g.prims[pi].type_mat >> PT_MAT_SHIFT];
-    m.type = M; // compile-time constant: prunes the per-type switches
     // `plane` (fused kernel): the per-primitive digest of planar primitives in shared memory.
     // ALL_PLANAR: the host checked that every primitive has one and that every albedo / emission
-    // texture is a solid colour baked into the material record, so neither make_record() nor
-    // tex_value() is compiled in.
-    if (ALL_PLANAR)
+    // texture is a solid colour, which the kernel copied into the digest: neither make_record()
+    // nor tex_value() is compiled in and shading reads no global table.
+    MatT<float> m;
+    if (ALL_PLANAR) {
+        m = MatT<float>{};
         m.flags = 2;
+        m.color[0] = plane[pi].color[0];
+        m.color[1] = plane[pi].color[1];
+        m.color[2] = plane[pi].color[2];
+    } else {
+        m = p.shade.mats[g.prims[pi].type_mat >> PT_MAT_SHIFT];
+    }
+    m.type = M; // compile-time constant: prunes the per-type switches
     RecT<float> rec;
     if (ALL_PLANAR || (plane != nullptr && !(m.flags & 1) && plane[pi].valid))
         rec = plane_record<float>(plane[pi], s.o, s.d, t);
@@ -1255,19 +1298,30 @@ constexpr uint32_t kSampleChunk = 256; // samples a warp reserves per atomic
 // the per-primitive plane digest only (ALL_PLANAR), the traversal holds the rect and box loops
 // only (RECTS_ONLY) and no texture code is compiled in.
 template <bool OLD, bool COUNT, int SIMPLE>
-__global__ void __launch_bounds__(128, OLD ? RTB_FUSED_MIN_BLOCKS_OLD : RTB_FUSED_MIN_BLOCKS_NEW) k_fused(WfParams p) {
+__global__ void __launch_bounds__(128, OLD ? RTB_FUSED_MIN_BLOCKS_OLD : (SIMPLE == 2 ? RTB_FUSED_MIN_BLOCKS_NEW_PLANAR : RTB_FUSED_MIN_BLOCKS_NEW))
+    k_fused(WfParams p) {
     __shared__ FlatSmem sm;
     __shared__ FlatFast ff;
     const GeomView<float> g = stage_scene_flat(p.geom, sm);
     if (threadIdx.x == 0)
         build_flat_fast(g, ff);
-    if (int(threadIdx.x) < g.n_prims)
-        build_plane_rec(g, threadIdx.x, ff.plane[threadIdx.x]);
+    if (int(threadIdx.x) < g.n_prims) {
+        PlaneRec &pl = ff.plane[threadIdx.x];
+        build_plane_rec(g, threadIdx.x, pl);
+        if ((g.prims[threadIdx.x].type_mat & PT_TYPE_MASK) != PT_INSTANCE) {
+            const MatT<float> m = p.shade.mats[g.prims[threadIdx.x].type_mat >> PT_MAT_SHIFT];
+            pl.color[0] = m.color[0];
+            pl.color[1] = m.color[1];
+            pl.color[2] = m.color[2];
+            pl.mat_type = m.type;
+        }
+    }
     __syncthreads();
     PathState s;
     bool alive = false, exhausted = false;
     unsigned long long chunk_next = 0, chunk_end = 0; // warp-uniform: this warp's private sample range
-    uint64_t n_closest = 0, n_shadow = 0, n_paths = 0, nodes = 0, tests = 0;
+    uint32_t n_closest = 0, n_shadow = 0, n_paths = 0; // per thread and launch (a launch is <= 2^28 samples)
+    uint64_t nodes = 0, tests = 0;
     while (true) {
         // regeneration: every idle lane takes the next sample of the warp's chunk
         const bool need = !alive && !exhausted;
@@ -1312,7 +1366,7 @@ __global__ void __launch_bounds__(128, OLD ? RTB_FUSED_MIN_BLOCKS_OLD : RTB_FUSE
             } else {
                 ShadowReq sh;
                 const uint32_t pix = s.pix;
-                const int mtype = p.shade.mats[g.prims[pi].type_mat >> PT_MAT_SHIFT].type;
+                const int mtype = SIMPLE == 2 ? ff.plane[pi].mat_type : p.shade.mats[g.prims[pi].type_mat >> PT_MAT_SHIFT].type;
                 if (SIMPLE) {
                     if (mtype == 0)
                         shade_surface<0, OLD, SIMPLE == 2>(p, g, s, t, pi, alive, sh, ff.plane);

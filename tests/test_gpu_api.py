@@ -79,7 +79,7 @@ def test_empty_and_ragged_batches(gpu_ctx, golden, binding):
 
 def test_cancel_from_another_thread(gpu_ctx, golden, binding):
     gpu_ctx.upload_scene(golden(7).blob)
-    p = gpu_ctx.params(600, 600, 4000, 0, seed=1)   # ~1.5 s of work
+    p = gpu_ctx.params(600, 600, 60000, 0, seed=1)   # 21.6 G samples: seconds of work even at > 10 Gpaths/s
     res = {}
 
     def run():
@@ -90,7 +90,7 @@ def test_cancel_from_another_thread(gpu_ctx, golden, binding):
             res["status"] = e.status
     t = threading.Thread(target=run)
     t.start()
-    time.sleep(0.2)
+    time.sleep(0.1)
     gpu_ctx.cancel()
     t.join(60)
     assert res.get("status") == -6
