@@ -255,7 +255,7 @@ struct FlatFast {
     struct alignas(16) Space {
         int32_t first[4]; // rects of this space: [first[a], first[a+1]) has constant axis a (0 = yz, 1 = xz, 2 = xy)
         int32_t chain;    // wrapper chain of the instance, -1 for the world
-        int32_t box;      // >= 0: the space is exactly one `box` (box.h): index into `box`
+        int32_t box;      // unused (box instances live in FlatFast::box only)
         int32_t sph_first, sph_end;     // indices into `sph`
         int32_t other_first, other_end; // indices into `other`
         int32_t pad[2];
@@ -284,7 +284,8 @@ struct FlatFast {
     int16_t sph_id[kFlatMaxPrims];
     int16_t other[kFlatMaxPrims];
     Space space[kFlatMaxChains + 1];
-    int32_t n_spaces;
+    int32_t n_spaces; // the world, then every instance that is not a plain box
+    int32_t n_box;    // instances that are exactly one `box`: tested after the spaces
     PlaneRec plane[kFlatMaxPrims]; // shading input of planar primitives (build_plane_rec, one thread per primitive)
 };
 
@@ -340,23 +341,20 @@ __device__ inline void build_flat_fast(const GeomView<float> &g, FlatFast &ff) {
         return true;
     };
     auto add_space = [&](uint32_t begin, uint32_t end, int chain, bool top_level) {
-        FlatFast::Space &sp = ff.space[n_spaces++];
-        sp.chain = chain;
-        sp.box = -1;
         if (!top_level && n_box < kFlatMaxChains && as_box(begin, end, ff.box[n_box])) {
+            // a box instance is not a space of its own: the traversal walks ff.box after the spaces
             const ChainAffine a = g.affine[chain];
-            FlatFast::Box &bx = ff.box[n_box];
+            FlatFast::Box &bx = ff.box[n_box++];
             bx.xf[0] = a.c;
             bx.xf[1] = a.s;
             bx.xf[2] = a.bx;
             bx.xf[3] = a.bz;
             bx.by = a.by;
-            sp.box = n_box++;
-            sp.first[0] = sp.first[1] = sp.first[2] = sp.first[3] = n_rect;
-            sp.other_first = sp.other_end = n_other;
-            sp.sph_first = sp.sph_end = n_sph;
             return;
         }
+        FlatFast::Space &sp = ff.space[n_spaces++];
+        sp.chain = chain;
+        sp.box = -1;
         const uint32_t axis_type[3] = {PT_YZ, PT_XZ, PT_XY}; // constant axis 0, 1, 2
         for (int a = 0; a < 3; ++a) {
             sp.first[a] = n_rect;
@@ -401,6 +399,7 @@ __device__ inline void build_flat_fast(const GeomView<float> &g, FlatFast &ff) {
         add_space(first, first + uint32_t(p.d[1]), int(p.aux2), false);
     }
     ff.n_spaces = n_spaces;
+    ff.n_box = n_box;
 }
 
 // Closest hit of the rects [first, last) whose constant axis is AX (in-plane axes A, B).
@@ -429,7 +428,7 @@ __device__ __forceinline__ void flat_rects(const FlatFast &ff, int first, int la
 // (k - o) * idir, so a hit has the same t bit for bit; which FACE is hit is decided by the slab
 // ordering instead of the in-rectangle tests, which can differ from the rect-by-rect answer only
 // for rays within rounding distance of a box edge.
-template <bool COUNT>
+template <bool ANY, bool COUNT>
 __device__ __forceinline__ void flat_box(const FlatFast::Box &bx, V3<float> wo, V3<float> wd, float t_min, float &t_max,
                                          uint32_t origin, uint32_t &best, uint64_t &tests) {
     // the ray in the box's object space: the arithmetic of enter_instance<float, true>
@@ -461,7 +460,9 @@ __device__ __forceinline__ void flat_box(const FlatFast::Box &bx, V3<float> wo, 
         cand = tn >= t_min ? tn : tf;
         ok = (tn <= tf) & (cand >= t_min) & (cand <= t_max);
     }
-    if (ok) {
+    if (ANY) { // a shadow ray only asks WHETHER: which face is not worked out
+        best = ok ? __float_as_uint(hif.w) : best;
+    } else if (ok) {
         const int slot = cand == tx0 ? 0 : cand == tx1 ? 1 : cand == ty0 ? 2 : cand == ty1 ? 3 : cand == tz0 ? 4 : 5;
         best = uint32_t(bx.face[slot]);
         t_max = cand;
@@ -479,14 +480,6 @@ __device__ __forceinline__ uint32_t traverse_flat_fast(const GeomView<float> &g,
     const int n_spaces = ff.n_spaces;
     for (int s = 0; s < n_spaces; ++s) {
         const FlatFast::Space sp = ff.space[s];
-        if (sp.box >= 0) {
-            if (COUNT)
-                ++nodes; // one "node" = one instance entry (ray transform)
-            flat_box<COUNT>(ff.box[sp.box], o, d, t_min, t_max, origin, best, tests);
-            if (ANY && best != kNoPrim)
-                break;
-            continue;
-        }
         V3<float> lo = o, ld = d;
         if (sp.chain >= 0) {
             enter_instance<float, true>(g, sp.chain, lo, ld);
@@ -542,6 +535,14 @@ __device__ __forceinline__ uint32_t traverse_flat_fast(const GeomView<float> &g,
         }
         if (ANY && best != kNoPrim)
             break;
+    }
+    const int n_box = ff.n_box;
+    for (int b = 0; b < n_box; ++b) {
+        if (ANY && best != kNoPrim)
+            break;
+        if (COUNT)
+            ++nodes; // one "node" = one instance entry (ray transform)
+        flat_box<ANY, COUNT>(ff.box[b], o, d, t_min, t_max, origin, best, tests);
     }
     t_hit = t_max;
     return best;
@@ -876,9 +877,10 @@ __device__ __forceinline__ void shade_surface(const WfParams &p, const GeomView<
         alive = false;
     // fp32 guard: a degenerate continuation (zero or non-finite direction / origin) would make
     // every slab test pass and drag a NaN through up to max_depth full-tree traversals
-    const float chk = fabsf(s.o.x) + fabsf(s.o.y) + fabsf(s.o.z) + fabsf(s.d.x) + fabsf(s.d.y) + fabsf(s.d.z);
-    if (!(chk < Consts<float>::inf()) || (s.d.x == 0.f && s.d.y == 0.f && s.d.z == 0.f))
-        alive = false;
+    // (two compares that a NaN fails: no branch)
+    const float sd = fabsf(s.d.x) + fabsf(s.d.y) + fabsf(s.d.z);
+    const float chk = sd + fabsf(s.o.x) + fabsf(s.o.y) + fabsf(s.o.z);
+    alive = alive & (chk < Consts<float>::inf()) & (sd > 0.f);
 }
 
 // The ray left the scene: background for integrators 0-2 (e.g. rr_path_integrator.h:30-33),
