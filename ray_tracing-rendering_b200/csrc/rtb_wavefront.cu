@@ -416,9 +416,21 @@ __device__ __forceinline__ void flat_rects(const FlatFast &ff, int first, int la
         const float a = fmaf(t, d[A], o[A]);
         const float b = fmaf(t, d[B], o[B]);
         const uint32_t id = __float_as_uint(rb.y);
-        const bool ok = (t >= t_min) & (t <= t_max) & (a >= ra.y) & (a <= ra.z) & (b >= ra.w) & (b <= rb.x) & (id != origin);
-        best = ok ? id : best;
-        t_max = ok ? t : t_max;
+        // seven compares folded into ONE predicate chain (setp.and): the compiler's own choice was a
+        // tree of six FSETP + three PLOP3, i.e. three instructions more per rect on an issue-bound
+        // kernel.  Same comparisons, same NaN behaviour (every ordered compare fails).
+        asm("{\n\t.reg .pred p;\n\t"
+            "setp.ge.ftz.f32 p, %2, %4;\n\t"
+            "setp.le.and.ftz.f32 p, %2, %1, p;\n\t"
+            "setp.ge.and.ftz.f32 p, %5, %6, p;\n\t"
+            "setp.le.and.ftz.f32 p, %5, %7, p;\n\t"
+            "setp.ge.and.ftz.f32 p, %8, %9, p;\n\t"
+            "setp.le.and.ftz.f32 p, %8, %10, p;\n\t"
+            "setp.ne.and.u32 p, %11, %3, p;\n\t"
+            "selp.u32 %0, %11, %0, p;\n\t"
+            "selp.f32 %1, %2, %1, p;\n\t}"
+            : "+r"(best), "+f"(t_max)
+            : "f"(t), "r"(origin), "f"(t_min), "f"(a), "f"(ra.y), "f"(ra.z), "f"(b), "f"(ra.w), "f"(rb.x), "r"(id));
     }
     if (COUNT)
         tests += uint64_t(last - first);
@@ -428,7 +440,7 @@ __device__ __forceinline__ void flat_rects(const FlatFast &ff, int first, int la
 // (k - o) * idir, so a hit has the same t bit for bit; which FACE is hit is decided by the slab
 // ordering instead of the in-rectangle tests, which can differ from the rect-by-rect answer only
 // for rays within rounding distance of a box edge.
-template <bool ANY, bool COUNT>
+template <bool COUNT>
 __device__ __forceinline__ void flat_box(const FlatFast::Box &bx, V3<float> wo, V3<float> wd, float t_min, float &t_max,
                                          uint32_t origin, uint32_t &best, uint64_t &tests) {
     // the ray in the box's object space: the arithmetic of enter_instance<float, true>
@@ -445,28 +457,19 @@ __device__ __forceinline__ void flat_box(const FlatFast::Box &bx, V3<float> wo, 
     const float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fmaxf(tz0, tz1));
     if (COUNT)
         tests += 6;
-    float cand;
-    bool ok;
-    const uint32_t rel = origin - __float_as_uint(hif.w);
-    if (rel < 6u) {
-        // the ray starts ON this box: heading outward it cannot meet a convex box again; heading
-        // inward (a transmitted ray) it leaves through the far side
-        const int slot = bx.slot[rel], ax = slot >> 1;
-        const float dn = ax == 0 ? d.x : ax == 1 ? d.y : d.z;
-        const bool inward = (slot & 1) ? dn < 0.f : dn > 0.f;
-        cand = tf;
-        ok = inward & (cand >= t_min) & (cand <= t_max);
-    } else {
-        cand = tn >= t_min ? tn : tf;
-        ok = (tn <= tf) & (cand >= t_min) & (cand <= t_max);
-    }
-    if (ANY) { // a shadow ray only asks WHETHER: which face is not worked out
-        best = ok ? __float_as_uint(hif.w) : best;
-    } else if (ok) {
-        const int slot = cand == tx0 ? 0 : cand == tx1 ? 1 : cand == ty0 ? 2 : cand == ty1 ? 3 : cand == tz0 ? 4 : 5;
-        best = uint32_t(bx.face[slot]);
-        t_max = cand;
-    }
+    // Branch-free (the ncu source view of the branchy version: its two divergent blocks — "the ray
+    // starts on this box" and "which face" — ran at 3 of 32 lanes and made up 13 % of the kernel's
+    // instructions).  A ray that starts ON this box cannot enter it: its only candidate is the far
+    // side tf, and heading outward that far side is the very face it starts on (tf ~ 0), which the
+    // face != origin test rejects; heading inward (a transmitted ray) it leaves through another face.
+    const bool mine = (origin - __float_as_uint(hif.w)) < 6u;
+    const bool enter = !mine & (tn >= t_min);
+    const float cand = enter ? tn : tf;
+    const int slot = cand == tx0 ? 0 : cand == tx1 ? 1 : cand == ty0 ? 2 : cand == ty1 ? 3 : cand == tz0 ? 4 : 5;
+    const uint32_t face = uint32_t(bx.face[slot]);
+    const bool ok = (tn <= tf) & (cand >= t_min) & (cand <= t_max) & (face != origin);
+    best = ok ? face : best;
+    t_max = ok ? cand : t_max;
 }
 
 // RECTS_ONLY: the host checked that the scene holds nothing but axis-aligned rects (all_planar),
@@ -542,7 +545,7 @@ __device__ __forceinline__ uint32_t traverse_flat_fast(const GeomView<float> &g,
             break;
         if (COUNT)
             ++nodes; // one "node" = one instance entry (ray transform)
-        flat_box<ANY, COUNT>(ff.box[b], o, d, t_min, t_max, origin, best, tests);
+        flat_box<COUNT>(ff.box[b], o, d, t_min, t_max, origin, best, tests);
     }
     t_hit = t_max;
     return best;
