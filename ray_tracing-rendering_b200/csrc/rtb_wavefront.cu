@@ -72,6 +72,10 @@ constexpr int kFlatUnroll = RTB_FLAT_UNROLL; // unroll factor of the typed rect 
 #ifndef RTB_FUSED_MIN_BLOCKS_NEW
 #define RTB_FUSED_MIN_BLOCKS_NEW 6
 #endif
+#ifndef RTB_BOX_UNROLL
+#define RTB_BOX_UNROLL 1 // box instances per trip of the box loop of k_fused (2: 66 registers, 7 CTAs/SM, C1 9.18 ms; 1: 55, 9 CTAs, 9.03 ms)
+#endif
+constexpr int kBoxUnroll = RTB_BOX_UNROLL;
 #ifndef RTB_FUSED_MIN_BLOCKS_NEW_PLANAR
 #define RTB_FUSED_MIN_BLOCKS_NEW_PLANAR 8 // the all-planar BSDF-API kernel (C3 6 -> 23.98 ms, 7 -> 22.95, 8 -> 22.68)
 #endif
@@ -465,8 +469,21 @@ __device__ __forceinline__ void flat_box(const FlatFast::Box &bx, V3<float> wo, 
     const bool mine = (origin - __float_as_uint(hif.w)) < 6u;
     const bool enter = !mine & (tn >= t_min);
     const float cand = enter ? tn : tf;
-    const int slot = cand == tx0 ? 0 : cand == tx1 ? 1 : cand == ty0 ? 2 : cand == ty1 ? 3 : cand == tz0 ? 4 : 5;
-    const uint32_t face = uint32_t(bx.face[slot]);
+    // which face: the first of tx0, tx1, ty0, ty1, tz0, tz1 that IS cand.  Written as five
+    // setp / selp pairs over the six face ids (two vector loads): left to the compiler the ?: chain
+    // came back as nested divergent branches plus a dependent shared-memory look-up.
+    const uint4 f03 = *reinterpret_cast<const uint4 *>(bx.face);
+    const uint2 f45 = *reinterpret_cast<const uint2 *>(bx.face + 4);
+    uint32_t face;
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.eq.ftz.f32 p, %1, %6;\n\tselp.u32 %0, %11, %12, p;\n\t"
+        "setp.eq.ftz.f32 p, %1, %5;\n\tselp.u32 %0, %10, %0, p;\n\t"
+        "setp.eq.ftz.f32 p, %1, %4;\n\tselp.u32 %0, %9, %0, p;\n\t"
+        "setp.eq.ftz.f32 p, %1, %3;\n\tselp.u32 %0, %8, %0, p;\n\t"
+        "setp.eq.ftz.f32 p, %1, %2;\n\tselp.u32 %0, %7, %0, p;\n\t}"
+        : "=&r"(face)
+        : "f"(cand), "f"(tx0), "f"(tx1), "f"(ty0), "f"(ty1), "f"(tz0), "r"(f03.x), "r"(f03.y), "r"(f03.z), "r"(f03.w),
+          "r"(f45.x), "r"(f45.y));
     const bool ok = (tn <= tf) & (cand >= t_min) & (cand <= t_max) & (face != origin);
     best = ok ? face : best;
     t_max = ok ? cand : t_max;
@@ -540,6 +557,7 @@ __device__ __forceinline__ uint32_t traverse_flat_fast(const GeomView<float> &g,
             break;
     }
     const int n_box = ff.n_box;
+#pragma unroll kBoxUnroll
     for (int b = 0; b < n_box; ++b) {
         if (ANY && best != kNoPrim)
             break;
