@@ -38,10 +38,13 @@
 //   Cornell-box class of BASELINE configs C1/C3/C4).  There the wavefront's costs are all
 //   overhead: the scene is ~1 KB, so a bounce is a few hundred instructions, far less than
 //   moving 144 B of path state through HBM and three queues.  One persistent kernel
-//   (k_fused) keeps the path state in REGISTERS, traces in lockstep against the
-//   shared-memory scene (traverse_flat), shades through the same shade_surface<M>, tests
-//   the shadow ray inline and regenerates finished lanes from warp-private sample chunks.
-//   The only global traffic is one vector reduction (RED.ADD.v4.f32) per contribution.
+//   (k_fused) keeps the path state in REGISTERS, traces in lockstep against a typed
+//   shared-memory digest of the scene (FlatFast / traverse_flat_fast: rect records by axis, box
+//   instances as slab tests, a plane digest per planar primitive for shading), shades through
+//   the same shade_surface<M>, tests the shadow ray inline and regenerates finished lanes from
+//   warp-private sample chunks.  The only global traffic is one vector reduction
+//   (RED.ADD.v4.f32) per contribution.  The kernel is instruction-issue bound; its history in
+//   executed instructions per 32-ray iteration is in DESIGN.md section 4.
 //
 // accum[H*W] float4: linear radiance SUMS.
 #include "rtb_internal.hpp"
@@ -61,7 +64,9 @@ constexpr uint32_t kFullMask = 0xffffffffu;
 // with the generic lockstep traversal, C1 (legacy-API instantiation): 4 -> 30.4 ms, 6 -> 27.8,
 // 7 -> 26.3, 8 -> 25.3, 10 -> 28.8, 12 -> 40.6; C3 (BSDF-API): 4 -> 68.7 ms, 6 -> 60.9, 7 -> 61.0,
 // 8 -> 63.2, 10 -> 81.2.  With the typed traversal (fewer, leaner instructions, more live values):
-// C1 6 -> 20.4 ms, 7 -> 19.7, 8 -> 20.3; C3 6 -> 43.0, 7 -> 47.1, 8 -> 51.3.
+// C1 6 -> 20.4 ms, 7 -> 19.7, 8 -> 20.3; C3 6 -> 43.0, 7 -> 47.1, 8 -> 51.3.  The all-planar
+// instantiations need 55 (legacy API) / 64 (BSDF API) registers and run 9 / 8 CTAs per SM
+// (C1 9.0 ms; forcing 8 or 10 CTAs: 9.14 / 11.8 ms at an earlier step).
 #ifndef RTB_FLAT_UNROLL
 #define RTB_FLAT_UNROLL 1
 #endif
@@ -259,7 +264,7 @@ struct FlatFast {
     struct alignas(16) Space {
         int32_t first[4]; // rects of this space: [first[a], first[a+1]) has constant axis a (0 = yz, 1 = xz, 2 = xy)
         int32_t chain;    // wrapper chain of the instance, -1 for the world
-        int32_t box;      // unused (box instances live in FlatFast::box only)
+        int32_t reserved; // (box instances are not spaces: they live in FlatFast::box)
         int32_t sph_first, sph_end;     // indices into `sph`
         int32_t other_first, other_end; // indices into `other`
         int32_t pad[2];
@@ -358,7 +363,7 @@ __device__ inline void build_flat_fast(const GeomView<float> &g, FlatFast &ff) {
         }
         FlatFast::Space &sp = ff.space[n_spaces++];
         sp.chain = chain;
-        sp.box = -1;
+        sp.reserved = 0;
         const uint32_t axis_type[3] = {PT_YZ, PT_XZ, PT_XY}; // constant axis 0, 1, 2
         for (int a = 0; a < 3; ++a) {
             sp.first[a] = n_rect;
