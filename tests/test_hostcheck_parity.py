@@ -155,3 +155,62 @@ def test_plane_records_match_the_reference_records(hostcheck, scenes, golden, ab
         assert np.abs(got["p"][planar] - ref["p"][planar]).max() <= 4e-6 * scale
         assert np.abs(got["normal"][planar] - ref["normal"][planar])[~grazing].max() <= 2e-6
         assert np.array_equal(got["front_face"][planar][~grazing], ref["front_face"][planar][~grazing])
+
+
+def test_plane_records_follow_make_record_on_arbitrary_wrapper_chains(hostcheck, abi):
+    """Beyond the reference's own scenes: rects under every order of translate / rotate_y /
+    flip_face the plane digest claims to handle (rotate_y outermost — where the reference tests
+    its object-space ray against the rotated normal — double rotations, flips below and above
+    the moving wrappers).  make_record() replays the chain op by op and is pinned to the
+    reference on the golden fixtures; plane_record() must leave the same normal and front_face."""
+    import importlib
+    scenes = importlib.import_module("ray_tracing-rendering_b200.scenes")
+    chains = [
+        [],
+        [("flip",)],
+        [("translate", (30, -20, 10))],
+        [("rotate_y", 35)],                                   # rotate_y outermost: the quirk shows in the normal
+        [("translate", (30, 5, 10)), ("rotate_y", -25)],       # translate(rotate_y(x)): the Cornell boxes
+        [("rotate_y", 40), ("translate", (12, 3, -7))],        # rotate_y(translate(x))
+        [("rotate_y", 20), ("rotate_y", 50)],
+        [("flip",), ("translate", (1, 2, 3))],                 # flip above a translate survives
+        [("translate", (1, 2, 3)), ("flip",)],                 # flip below is overwritten
+        [("flip",), ("rotate_y", 70), ("flip",), ("translate", (4, 0, 4))],
+        [("translate", (5, 5, 5)), ("rotate_y", 10), ("translate", (-3, 0, 2)), ("rotate_y", -60)],
+    ]
+    b = scenes.SceneBuilder()
+    mat = b.lambertian((.5, .5, .5))
+    n_rect = 0
+    for k, ops in enumerate(chains):
+        c = b.chain(ops) if ops else -1
+        off = 37.0 * k - 200.0                                 # planes of different chains interleave
+        b.xy_rect(-900, 900, -900, 900, off + 7.0, mat, c)
+        b.xz_rect(-900, 900, -900, 900, off - 9.0, mat, c)
+        b.yz_rect(-900, 900, -900, 900, off + 3.0, mat, c)
+        n_rect += 3
+    blob = b.finish(99, 64, 1.0, 1, (0, 0, 0), (0, 0, -10), (0, 0, 0), 40.0)
+    h = hostcheck.hc_scene_create(blob, len(blob), 4)
+    assert h
+    try:
+        rng = np.random.default_rng(11)
+        n = 200_000
+        rays = np.zeros(n, abi.RAY)
+        rays["o"] = rng.uniform(-400, 400, (n, 3))
+        d = rng.normal(size=(n, 3))
+        rays["d"] = d / np.linalg.norm(d, axis=1, keepdims=True) * rng.uniform(0.3, 2.0, (n, 1))
+        rays["t_min"], rays["t_max"], rays["origin_prim"] = 0.001, np.inf, -1
+        a, _ = trace(hostcheck, h, rays, 32, abi)
+        p, _ = trace(hostcheck, h, rays, 35, abi)
+    finally:
+        hostcheck.hc_scene_destroy(h)
+    assert np.array_equal(a["prim"], p["prim"]) and np.array_equal(a["t"], p["t"])
+    hit = a["prim"] >= 0
+    assert hit.sum() > 5000 and len(np.unique(a["prim"][hit])) == n_rect      # every rect of every chain is exercised
+    # away from grazing incidence (where the two evaluation orders may round d.n to different signs)
+    cosine = np.abs(np.einsum("ij,ij->i", a["normal"], rays["d"])) / np.linalg.norm(rays["d"], axis=1)
+    ok = hit & (cosine > 1e-4)
+    assert np.abs(a["normal"][ok] - p["normal"][ok]).max() <= 2e-6
+    assert np.array_equal(a["front_face"][ok], p["front_face"][ok])
+    assert np.abs(a["p"][ok] - p["p"][ok]).max() <= 2e-3
+    # both answers occur for every chain that can produce them (the test is not vacuous)
+    assert 0.05 < a["front_face"][ok].mean() < 0.95
