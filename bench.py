@@ -63,9 +63,33 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.proc = index, [], None
+        self.done, self.nvml = False, False
         self.t0 = self.t1 = None   # the timed region (samples outside it are dropped)
 
     def run(self):
+        # NVML in-process (a sample every ~5 ms: the default C1 timed region is only ~90 ms long, less
+        # than one period of `nvidia-smi -lms 100`, whose start-up alone can outlast the whole run);
+        # the nvidia-smi loop of the recipe is the fallback when NVML cannot be loaded.
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = ((0x8, 5), (0x40, 6), (0x20, 7), (0x4, 8))   # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap -> row columns
+            self.nvml = True
+            while not self.done:
+                t = time.time()
+                r = reasons_fn(h)
+                row = [str(self.index), str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx), "", hex(r), "", "", "", ""]
+                for bit, col in bits:
+                    row[col] = "Active" if r & bit else "Not Active"
+                self.rows.append([t] + row)
+                time.sleep(0.005)
+            return
+        except Exception:
+            if self.rows:
+                return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
@@ -75,6 +99,7 @@ class ClockSampler(threading.Thread):
             pass
 
     def stop(self):
+        self.done = True
         if self.proc:
             self.proc.terminate()
         self.join(2)
@@ -87,7 +112,7 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v == "Active"})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(rows)}
+                "reasons": reasons, "samples": len(rows), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def cpu_reference(steps, warmup, budget_s):
