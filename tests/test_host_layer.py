@@ -127,3 +127,65 @@ def test_bvh_builder_is_deterministic_across_thread_counts(hostcheck, monkeypatc
         hashes.append((hostcheck.hc_scene_tree_hash(h), sizes[0], sizes[1]))
         hostcheck.hc_scene_destroy(h)
     assert hashes[0] == hashes[1] == hashes[2] and hashes[0][1] > 40000
+
+
+@pytest.mark.parametrize("w,h", [(5, 3), (300, 2), (1, 1), (257, 260)])
+def test_png_writer_matches_the_reference_conversion(tmp_path, w, h):
+    """RenderBuffer::save_to_png (host layer, stored-deflate PNG) against the reference's
+    conversion, render_buffer.h:35-55: y flip and (unsigned char)(x * 255); rows longer than one
+    deflate block (65535 bytes) included."""
+    from PIL import Image
+    exe, png = str(tmp_path / "png_writer_test"), str(tmp_path / "out.png")
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, PKG, "host"),
+                           os.path.join(ROOT, "tests", "png_writer_test.cpp"), "-o", exe, "-L" + os.path.join(ROOT, PKG), "-lrtb200",
+                           "-Wl,-rpath," + os.path.join(ROOT, PKG)])
+    subprocess.check_call([exe, png, str(w), str(h)])
+    img = np.asarray(Image.open(png).convert("RGB"))
+    assert img.shape == (h, w, 3)
+    i, j = np.meshgrid(np.arange(w), np.arange(h))
+    buf = np.stack([(i + 0.5) / w, np.where(j == h - 1, 1.0, j / h), ((i * 7 + j * 13) % 256) / 255.0 + 1e-9], axis=-1)
+    want = (buf[::-1] * 255).astype(np.uint8)            # row 0 of the buffer is the bottom row of the image
+    assert np.array_equal(img, want)
+
+
+@pytest.mark.parametrize("w,h", [(64, 32), (7, 5), (33, 33), (2048, 4)])
+def test_hdr_loader_matches_the_reference_stb_loader(tmp_path, w, h):
+    """EnvironmentLight's .hdr reader (host layer) against the reference's own loader: the file is
+    written by the reference's vendored stb_image_write (new-style RLE for widths 8..32767, flat
+    otherwise) and read back by its stbi_loadf (environmental_light.h:121-134), both through
+    oracle/_ref; the host layer must return the same texels bit for bit, and fall back to the
+    reference's empty map for a missing file."""
+    import ctypes as C
+    ref_path = os.path.join(ROOT, "oracle", "_ref", "libref_oracle.so")
+    if not os.path.exists(ref_path):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    ref = C.CDLL(ref_path)
+    ref.stbi_write_hdr.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    ref.stbi_loadf.restype = C.POINTER(C.c_float)
+    ref.stbi_loadf.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]
+    ref.stbi_image_free.argtypes = [C.c_void_p]
+    rng = np.random.default_rng(w * 1000 + h)
+    img = (rng.uniform(0, 1, (h, w, 3)) * 10.0 ** rng.uniform(-3, 4, (h, w, 1))).astype(np.float32)
+    img[0, : w // 2] = img[0, 0]                           # a run, so that the RLE path has something to compress
+    img[h - 1, 0] = 0.0                                     # exponent byte 0
+    hdr = str(tmp_path / "env.hdr")
+    assert ref.stbi_write_hdr(hdr.encode(), w, h, 3, img.ctypes.data_as(C.c_void_p)) == 1
+    rw, rh, rn = C.c_int(), C.c_int(), C.c_int()
+    data = ref.stbi_loadf(hdr.encode(), C.byref(rw), C.byref(rh), C.byref(rn), 0)
+    assert data and (rw.value, rh.value, rn.value) == (w, h, 3)
+    want = np.ctypeslib.as_array(data, shape=(h * w * 3,)).copy()
+    ref.stbi_image_free(data)
+    exe, dump = str(tmp_path / "hdr_loader_test"), str(tmp_path / "texels.bin")
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, PKG, "host"),
+                           os.path.join(ROOT, "tests", "hdr_loader_test.cpp"), "-o", exe, "-L" + os.path.join(ROOT, PKG), "-lrtb200",
+                           "-Wl,-rpath," + os.path.join(ROOT, PKG)])
+    subprocess.check_call([exe, hdr, dump])
+    raw = open(dump, "rb").read()
+    dims = np.frombuffer(raw[:8], np.int32)
+    got = np.frombuffer(raw[8:], np.float32)
+    assert tuple(dims) == (w, h)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # a missing file: width = height = 0, no texels (environmental_light.h:125-130)
+    subprocess.check_call([exe, str(tmp_path / "missing.hdr"), dump], stderr=subprocess.DEVNULL)
+    raw = open(dump, "rb").read()
+    assert tuple(np.frombuffer(raw[:8], np.int32)) == (0, 0) and len(raw) == 8
