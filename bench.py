@@ -287,10 +287,12 @@ def run_native(args, rank, local_rank, world):
             peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         pass
-    traffic, micro = None, {}
+    traffic, micro, ncu_counters = None, {}, None
     try:
         with open(os.path.join(ROOT, "profiles", "extend_traffic.json")) as f:
-            traffic = json.load(f).get(CONFIG, {}).get("dram_bytes_per_launch")
+            captured = json.load(f).get(CONFIG, {})
+        traffic = captured.get("dram_bytes_per_launch")
+        ncu_counters = captured.get("ncu")   # which limit binds, from the committed ncu capture of this kernel
     except Exception:
         pass
     try:
@@ -319,7 +321,7 @@ def run_native(args, rank, local_rank, world):
                 "rays_per_launch": rays_per_launch, "us_per_launch": us_per_launch,
                 "extend_share_of_step": st_t["extend_ms"] / st_t["device_ms"],
                 "grays_per_s_in_kernel": grays,
-                "stage_ms": st_t.get("stage_ms"),
+                "stage_ms": st_t.get("stage_ms"), "ncu": ncu_counters,
                 "fp32": {"flops_per_ray": f_ray, "achieved_tflops": grays * f_ray / 1e3, "peak_tflops": fp32_peak,
                          "frac": (grays * f_ray / 1e3 / fp32_peak) if fp32_peak else None,
                          "peak_source": "tools/microbench (profiles/microbench.json), FMA = 2 flops"},
