@@ -9,6 +9,9 @@
 // (librtb200.so) contains no host execution path and fails loudly without a GPU.
 #include "rtb200_types.h"
 #include "rtb_scene_host.hpp"
+#include "rtb_wide.cuh"
+
+#include <map>
 
 #include <cstdio>
 #include <cstring>
@@ -56,10 +59,20 @@ template <class R> ShadeView<R> shade_view(HostScene &H) {
     return s;
 }
 
+// the 4-wide tree of a scene (rtb_wide.cuh), built on first use
+std::map<const HostScene *, WideTree> g_wide;
+const WideTree &wide_of(HostScene &H) {
+    auto it = g_wide.find(&H);
+    if (it == g_wide.end())
+        it = g_wide.emplace(&H, build_wide(H.nodes, H.root_ref, H.f32.prims.data(), H.f32.prims.size())).first;
+    return it->second;
+}
+
 template <class R, bool ROBUST>
 void trace_batch(HostScene &H, const rtb_ray *rays, uint64_t n, rtb_hit *hits, uint64_t stats[2], bool use_flat,
-                 bool inst_in_descent = false, bool plane_records = false) {
+                 bool inst_in_descent = false, bool plane_records = false, bool wide = false) {
     const GeomView<R> g = geom_view<R>(H);
+    const WideTree *W = wide ? &wide_of(H) : nullptr;
     RngT<R> rng;
     rng.g = pcg_seed(1, 2);
     auto draw = [&]() { return rng.next_open(); };
@@ -73,7 +86,9 @@ void trace_batch(HostScene &H, const rtb_ray *rays, uint64_t n, rtb_hit *hits, u
         uint32_t storage[kStackDepth];
         LocalStack stack(storage);
         const uint32_t pi =
-            use_flat && g.flat
+            wide ? traverse_wide<R, false, ROBUST>(g, W->nodes.data(), W->root_ref, W->prim_root.data(), o, d, R(q.time),
+                                                   R(q.t_min), R(q.t_max), origin, draw, t, &stats[0], &stats[1], stack)
+            : use_flat && g.flat
                 ? traverse_flat<R, false, ROBUST>(g, o, d, R(q.time), R(q.t_min), R(q.t_max), origin, draw, t,
                                                   &stats[0], &stats[1])
             : inst_in_descent
@@ -202,7 +217,17 @@ void *hc_scene_create(const void *blob, uint64_t nbytes, int max_leaf) {
         return nullptr;
     }
 }
-void hc_scene_destroy(void *h) { delete static_cast<HostScene *>(h); }
+void hc_scene_destroy(void *h) {
+    g_wide.erase(static_cast<HostScene *>(h));
+    delete static_cast<HostScene *>(h);
+}
+
+// nodes and occupied child slots of the scene's 4-wide tree
+void hc_wide_info(void *h, uint64_t out[2]) {
+    const WideTree &w = wide_of(*static_cast<HostScene *>(h));
+    out[0] = w.nodes.size();
+    out[1] = w.n_children;
+}
 
 // sizes = {nodes, sorted prims, instances}
 void hc_scene_info(void *h, int64_t sizes[3]) {
@@ -237,7 +262,12 @@ void hc_trace_batch(void *h, const rtb_ray *rays, uint64_t n, int precision, rtb
     // 32: fp32 as the renderer traces this scene (lockstep when it is small); 33: fp32 forced
     // through the BVH; 34: the same with instance entry / exit inside the descent; 35: as 32 with
     // the records of planar primitives from plane_record() (the fused kernel's shading input)
-    if (precision >= 64)
+    // 67 / 37: fp64 / fp32 through the 4-wide tree of rtb_wide.cuh (stats[0] counts 128-byte nodes)
+    if (precision == 67)
+        trace_batch<double, false>(*H, rays, n, hits, local, false, false, false, true);
+    else if (precision == 37)
+        trace_batch<float, true>(*H, rays, n, hits, local, false, false, false, true);
+    else if (precision >= 64)
         trace_batch<double, false>(*H, rays, n, hits, local, precision == 65, precision == 66);
     else
         trace_batch<float, true>(*H, rays, n, hits, local, precision == 32 || precision == 35, precision == 34,

@@ -214,3 +214,29 @@ def test_plane_records_follow_make_record_on_arbitrary_wrapper_chains(hostcheck,
     assert np.abs(a["p"][ok] - p["p"][ok]).max() <= 2e-3
     # both answers occur for every chain that can produce them (the test is not vacuous)
     assert 0.05 < a["front_face"][ok].mean() < 0.95
+
+
+@pytest.mark.parametrize("sid", GOLDEN_SCENES)
+def test_wide_bvh_traversal_gives_the_reference_hits(hostcheck, scenes, golden, abi, sid):
+    """Groundwork for the next round (csrc/rtb_wide.cuh, not yet in librtb200.so): the binary tree
+    collapsed into 128-byte 4-wide nodes and traversed nearest child first must name the
+    reference's primitive at the reference's t, bit for bit in fp64, and agree with the binary
+    fp32 traversal, while fetching fewer nodes per ray."""
+    g = golden(sid)
+    T = abi.parse_blob(g.blob)
+    rays, ref = g["rays"], g["hits"]
+    w64, sw = trace(hostcheck, scenes(sid), rays, 67, abi)
+    b64, sb = trace(hostcheck, scenes(sid), rays, 64, abi)
+    mask = parity.deterministic_mask(T, ref, w64) & parity.deterministic_mask(T, ref, b64)
+    assert mask.mean() > 0.3
+    assert parity.trace_mismatches(ref, w64, mask) == 0
+    seg = parity.to_segment_form(rays)
+    w32, _ = trace(hostcheck, scenes(sid), seg, 37, abi)
+    b32, _ = trace(hostcheck, scenes(sid), seg, 33, abi)
+    m32 = mask & parity.deterministic_mask(T, ref, w32) & parity.deterministic_mask(T, ref, b32)
+    assert np.array_equal(w32["prim"][m32], b32["prim"][m32]) and np.array_equal(w32["t"][m32], b32["t"][m32])
+    info = np.zeros(2, np.uint64)
+    hostcheck.hc_wide_info(scenes(sid), _ptr(info))
+    if info[0] > 4:                                  # a real tree: wider nodes, fewer dependent steps
+        assert info[1] / info[0] > 2.5               # mean arity
+        assert sw[0] < 0.75 * (sb[0] / 2) or T["prims"]["type"].max() >= 5   # 128-byte fetches vs 64-byte pair fetches
