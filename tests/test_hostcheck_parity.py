@@ -240,3 +240,34 @@ def test_wide_bvh_traversal_gives_the_reference_hits(hostcheck, scenes, golden, 
     if info[0] > 4:                                  # a real tree: wider nodes, fewer dependent steps
         assert info[1] / info[0] > 2.5               # mean arity
         assert sw[0] < 0.75 * (sb[0] / 2) or T["prims"]["type"].max() >= 5   # 128-byte fetches vs 64-byte pair fetches
+
+
+def test_wide_bvh_on_a_deep_tree(hostcheck, abi):
+    """The same on a tree with real depth: a 40 x 40 sphere field of the C5 generator (1,600 spheres,
+    no instances), 100,000 random rays from above the ground: binary and 4-wide traversal return
+    the same primitive and the same t bit for bit in fp64 and in fp32."""
+    import importlib
+    scenes = importlib.import_module("ray_tracing-rendering_b200.scenes")
+    blob = scenes.sphere_field(half_extent=20, width=64, height=36, spp=1)
+    h = hostcheck.hc_scene_create(blob, len(blob), 4)
+    assert h
+    try:
+        rng = np.random.default_rng(3)
+        n = 100_000
+        rays = np.zeros(n, abi.RAY)
+        rays["o"] = rng.uniform(-25, 25, (n, 3)) * np.array([1, 0, 1]) + np.array([0, 1, 0]) * rng.uniform(0.05, 6, (n, 1))
+        d = rng.normal(size=(n, 3))
+        rays["d"] = d / np.linalg.norm(d, axis=1, keepdims=True)
+        rays["t_min"], rays["t_max"], rays["origin_prim"] = 0.001, np.inf, -1
+        b64, sb = trace(hostcheck, h, rays, 64, abi)
+        w64, sw = trace(hostcheck, h, rays, 67, abi)
+        b32, _ = trace(hostcheck, h, rays, 33, abi)
+        w32, _ = trace(hostcheck, h, rays, 37, abi)
+        info = np.zeros(2, np.uint64)
+        hostcheck.hc_wide_info(h, _ptr(info))
+    finally:
+        hostcheck.hc_scene_destroy(h)
+    assert (b64["prim"] >= 0).mean() > 0.5
+    assert np.array_equal(b64["prim"], w64["prim"]) and np.array_equal(b64["t"], w64["t"])
+    assert np.array_equal(b32["prim"], w32["prim"]) and np.array_equal(b32["t"], w32["t"])
+    assert info[1] / info[0] > 3.0 and sw[0] < 0.65 * (sb[0] / 2)      # near-full nodes, far fewer dependent steps
