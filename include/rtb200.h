@@ -152,7 +152,10 @@ enum rtb_option {
     RTB_OPT_BVH_MAX_LEAF = 3,
     RTB_OPT_BVH_TRAVERSAL_COST_PCT = 4,
     /* node order: 0 = level order, 1 = sibling pairs depth-first (left subtree right after its pair) */
-    RTB_OPT_BVH_LAYOUT_DFS = 5
+    RTB_OPT_BVH_LAYOUT_DFS = 5,
+    /* 1: trace BVH scenes with round 1's kernels (binary tree, one 32-ray chunk per warp at a time)
+     * instead of the warp-scheduled 4-wide traversal; kept for A/B measurements (default 0) */
+    RTB_OPT_BINARY_TRAVERSAL = 6
 };
 RTB_API int rtb_set_option(rtb_context *ctx, int option, int64_t value);
 
@@ -197,6 +200,9 @@ RTB_API int rtb_resolve_rgb8(rtb_context *ctx, int32_t spp, uint8_t *rgb8_host);
  * precision 64: fp64 validation kernels (reference operation order, no FMA):
  *               t / primitive id bit-exact against the reference.
  * precision 32: the production fp32 traversal the wavefront uses.
+ * precision 34 (rtb_trace_batch only): the renderer's warp-scheduled traversal of the 4-wide BVH
+ *   (windows sorted by octant, lanes refilled as they finish) — the kernel k_extend runs, fed with
+ *   the caller's rays; precision 36: its any-hit form (k_connect): prim >= 0 iff the ray is blocked.
  * precision 33 (rtb_trace_batch only, scenes of <= 64 primitive records): the fused kernel's own
  *   typed lockstep traversal (rects grouped by axis, box instances as slab tests).
  * precision 35 (same restriction): as 33, with the hit records of planar primitives taken from the

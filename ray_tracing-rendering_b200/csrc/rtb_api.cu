@@ -179,6 +179,8 @@ int rtb_set_option(rtb_context *ctx, int option, int64_t value) {
         ctx->opt_trav_cost_pct = int(value);
     else if (option == RTB_OPT_BVH_LAYOUT_DFS)
         ctx->opt_layout_dfs = value != 0;
+    else if (option == RTB_OPT_BINARY_TRAVERSAL)
+        ctx->opt_binary_traversal = value != 0;
     else
         return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_set_option: unknown option");
     return RTB_OK;
@@ -214,6 +216,9 @@ int rtb_scene_upload(rtb_context *ctx, const void *blob, uint64_t nbytes) {
         sc->image_bytes.upload(H.image_bytes, s);
         sc->env_texels.upload(H.env_texels, s);
         sc->env_tables.upload(H.env_tables, s);
+        sc->wide_nodes.upload(H.wide.nodes, s);
+        sc->wide_chain_root.upload(H.wide.chain_root, s);
+        bytes += sc->wide_nodes.bytes() + sc->wide_chain_root.bytes();
         bytes += sc->nodes.bytes() + sc->chains.bytes() + sc->prim_chain.bytes() + sc->prim_orig.bytes() +
                  sc->orig_to_sorted.bytes() + sc->images.bytes() + sc->image_bytes.bytes() +
                  sc->env_texels.bytes() + sc->env_tables.bytes();
@@ -322,7 +327,8 @@ int rtb_resolve_rgb8(rtb_context *ctx, int32_t spp, uint8_t *rgb8_host) {
 
 int rtb_trace_batch(rtb_context *ctx, const rtb_ray *rays, uint64_t n, int precision, rtb_hit *hits,
                     uint64_t *visits) {
-    const int rc = check_batch(ctx, rays, hits, n, precision == 33 || precision == 35 ? 32 : precision);
+    const bool p32 = precision == 33 || precision == 34 || precision == 35 || precision == 36;
+    const int rc = check_batch(ctx, rays, hits, n, p32 ? 32 : precision);
     if (rc != RTB_OK)
         return rc;
     return guarded(ctx, [&] {
@@ -339,12 +345,15 @@ int rtb_trace_batch(rtb_context *ctx, const rtb_ray *rays, uint64_t n, int preci
                     launch_trace_batch<double>(ctx, di, n, dout, dv);
                 else if (precision == 33 || precision == 35)
                     launch_trace_fast_batch(ctx, di, n, dout, dv, precision == 35);
+                else if (precision == 34 || precision == 36)
+                    launch_trace_wide_batch(ctx, di, n, dout, dv, precision == 36);
                 else
                     launch_trace_batch<float>(ctx, di, n, dout, dv);
             });
         if (visits) {
             unsigned long long h[2] = {0, 0};
-            RTB_CUDA(cudaMemcpy(h, dv, sizeof(h), cudaMemcpyDeviceToHost));
+            RTB_CUDA(cudaMemcpyAsync(h, dv, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+            RTB_CUDA(cudaStreamSynchronize(ctx->stream));
             visits[0] = h[0];
             visits[1] = h[1];
         }

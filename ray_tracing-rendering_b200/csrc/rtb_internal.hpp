@@ -5,6 +5,7 @@
 
 #include "rtb200.h"
 #include "rtb_scene_host.hpp"
+#include "rtb_trace.cuh"
 
 #include <atomic>
 #include <cuda_runtime.h>
@@ -71,7 +72,7 @@ struct DeviceScene {
     DeviceTyped<float> f32;
     DeviceTyped<double> f64;
     DeviceBuffer nodes, chains, affine, prim_chain, prim_orig, orig_to_sorted, images, image_bytes, env_texels,
-        env_tables;
+        env_tables, wide_nodes, wide_chain_root;
     size_t device_bytes = 0;
 
     template <class R> const DeviceTyped<R> &typed() const;
@@ -94,6 +95,14 @@ struct DeviceScene {
         g.n_top = host.n_top_items;
         g.flat = host.flat_ok ? 1 : 0;
         return g;
+    }
+    WideView wide() const { // the 4-wide tree of the production traversal (rtb_trace.cuh)
+        WideView w;
+        w.nodes = wide_nodes.as<Vec4f>();
+        w.chain_root = wide_chain_root.as<uint32_t>();
+        w.root_ref = host.wide.root_ref;
+        w.n_nodes = uint32_t(host.wide.nodes.size());
+        return w;
     }
     template <class R> ShadeView<R> shade() const {
         const DeviceTyped<R> &T = typed<R>();
@@ -134,6 +143,7 @@ struct rtb_context {
     int opt_max_leaf = 4;        // RTB_OPT_BVH_MAX_LEAF
     int opt_trav_cost_pct = 100; // RTB_OPT_BVH_TRAVERSAL_COST_PCT
     int opt_layout_dfs = 0;      // RTB_OPT_BVH_LAYOUT_DFS
+    int opt_binary_traversal = 0; // RTB_OPT_BINARY_TRAVERSAL: round 1's per-chunk while-while kernels (A/B measurements)
 };
 
 namespace rtb {
@@ -162,6 +172,9 @@ void launch_trace_fast_batch(rtb_context *ctx, const rtb_ray *d_rays, uint64_t n
                              unsigned long long *d_visits, bool plane_records);
 void launch_resolve_rgb8(rtb_context *ctx, const float4 *d_accum, int w, int h, int spp, uint8_t *d_rgb8,
                          cudaStream_t stream);
+// rtb_trace_batch precision 34 / 36: the renderer's own traversal kernel (closest hit / any hit)
+void launch_trace_wide_batch(rtb_context *ctx, const rtb_ray *d_rays, uint64_t n, rtb_hit *d_hits,
+                             unsigned long long *d_visits, bool any_hit);
 
 } // namespace rtb
 

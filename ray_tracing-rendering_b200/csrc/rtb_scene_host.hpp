@@ -8,10 +8,12 @@
 #include "rtb200_blob.hpp"
 #include "rtb_bvh.hpp"
 #include "rtb_shading.cuh"
+#include "rtb_wide.cuh"
 
 #include <cstring>
 #include <map>
 #include <stdexcept>
+#include <string>
 #include <vector>
 
 namespace rtb {
@@ -31,6 +33,7 @@ struct HostScene {
     TypedTables<float> f32;
     TypedTables<double> f64;
     std::vector<Node32> nodes;
+    WideTree wide; // the same trees collapsed into 128-byte 4-wide nodes (the production traversal's)
     std::vector<ChainRec> chains;
     std::vector<ChainAffine> affine;     // per chain, fp32 production path
     std::vector<int32_t> prim_chain;     // per sorted prim
@@ -578,6 +581,12 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double t
         H.f64.lights.push_back(d);
         H.f32.lights.push_back(f);
     }
+
+    // the production traversal's tree (rtb_trace.cuh)
+    H.wide = build_wide(H.nodes, H.root_ref, H.f32.prims.data(), H.f32.prims.size(), H.chains.size());
+    if (wide_stack_need(H.wide) > kWideStack)
+        throw std::runtime_error("scene: BVH of depth " + std::to_string(H.wide.max_depth) +
+                                 " exceeds the traversal stack (kWideStack)");
 
     H.flat_ok = int(H.prim_orig.size()) <= kFlatMaxPrims && int(S.n_xform_ops()) <= kFlatMaxOps &&
                 int(S.n_chains()) <= kFlatMaxChains;

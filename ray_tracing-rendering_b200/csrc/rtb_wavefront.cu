@@ -130,11 +130,13 @@ struct Globals {
 
 struct WfParams {
     GeomView<float> geom;
+    WideView wide; // the 4-wide tree k_extend_w / k_connect_w walk
     ShadeView<float> shade;
     CameraT<float> cam;
     // wavefront queues (SoA, see the file header)
     float4 *ext_a[2], *ext_b[2], *ext_c[2];
     uint4 *ext_d[2];
+    float2 *ext_e[2];              // k_extend_w: (t, primitive) of an entry until its window is pushed
     float4 *hit_a, *hit_b, *hit_c; // kKeys queues of `cap` entries each, queue k at offset k * cap
     uint4 *hit_d;
     float2 *hit_e;
@@ -1315,6 +1317,351 @@ __global__ void __launch_bounds__(kWfBlock, RTB_EXTEND_MIN_BLOCKS) k_connect(WfP
     }
 }
 
+// ---- (A') the warp-scheduled 4-wide traversal (rtb_trace.cuh) behind extend and connect ------------
+// Same queues and the same stage contract as k_extend / k_connect above, which remain selectable
+// (RTB_OPT_BINARY_TRAVERSAL) for A/B measurements.  A warp reserves a WINDOW of queue entries,
+// starts camera samples in its empty entries (one global atomic per window), sorts the window by
+// direction octant and walks it with lanes refilled as they finish; when the window's last ray is
+// done the warp pushes all its hits into the material queues with ONE multi-lane atomic.
+#ifndef RTB_TRACE_MIN_BLOCKS
+#define RTB_TRACE_MIN_BLOCKS 3 // resident CTAs of 256 threads per SM the traversal kernels are compiled for
+#endif
+#ifndef RTB_TRACE_TOP
+#define RTB_TRACE_TOP 1 // stage the top levels of the tree in shared memory
+#endif
+constexpr int kTraceBlock = 256;
+constexpr bool kTraceTop = RTB_TRACE_TOP != 0;
+
+// Cooperative copy of the first nodes of the (breadth-first) tree; returns how many were staged.
+__device__ __forceinline__ uint32_t stage_top_nodes(const WideView &w, Vec4f *s_top) {
+    const uint32_t n_top = kTraceTop ? (w.n_nodes < uint32_t(kTopNodesMax) ? w.n_nodes : uint32_t(kTopNodesMax)) : 0u;
+    for (uint32_t i = threadIdx.x; i < n_top * 8u; i += blockDim.x)
+        s_top[i] = __ldg(w.nodes + i);
+    return n_top;
+}
+
+// hit-queue key of a traced ray: the miss queue, or the queue of the material type it hit
+__device__ __forceinline__ uint32_t hit_key(const WfParams &p, uint32_t pi) {
+    if (pi == kNoPrim)
+        return uint32_t(kMissKey);
+    const MatT<float> &hm = p.shade.mats[p.geom.prims[pi].type_mat >> PT_MAT_SHIFT];
+    uint32_t key = uint32_t(hm.type);
+    if (key == RTB_MAT_LAMBERTIAN && !(hm.flags & 2))
+        key = uint32_t(kTexturedKey);
+    return key;
+}
+
+template <bool MEDIA> struct ExtendJob {
+    const WfParams &p;
+    Counters &C;
+    const int buf;
+    const uint32_t n; // entries of this iteration's extend queue
+    uint32_t base = 0, cnt = 0, off8 = 0;
+    unsigned long long sample_base = 0;
+    uint32_t n_new = 0; // camera samples this warp started (kept by lane 0)
+    __device__ ExtendJob(const WfParams &p_, Counters &C_, int buf_, uint32_t n_) : p(p_), C(C_), buf(buf_), n(n_) {}
+
+    __device__ __forceinline__ bool next_window(TraceWarpSmem &s, uint32_t &count) {
+        const uint32_t lane = lane_id();
+        uint32_t b = 0;
+        if (lane == 0)
+            b = atomicAdd(&C.head_ext.v[0], uint32_t(kTraceWindow));
+        b = __shfl_sync(kFullMask, b, 0);
+        if (b >= n)
+            return false;
+        base = b;
+        cnt = n - b < uint32_t(kTraceWindow) ? n - b : uint32_t(kTraceWindow);
+        // sort keys: direction octant of a live path, 8 for an empty entry (a camera sample starts there)
+        uint32_t n_empty = 0;
+        for (uint32_t r = 0; r < uint32_t(kTraceRounds); ++r) {
+            const uint32_t j = r * 32u + lane;
+            uint32_t key = kSkipKey;
+            if (j < cnt) {
+                if (__float_as_uint(p.ext_c[buf][b + j].w) == kInvalidPix) {
+                    key = 8u;
+                } else {
+                    const float4 d = p.ext_b[buf][b + j];
+                    key = RTB_TRACE_SORT ? octant_of(d.x, d.y, d.z) : 0u;
+                }
+                s.key[j] = uint8_t(key);
+            }
+            n_empty += __popc(__ballot_sync(kFullMask, key == 8u));
+        }
+        // camera samples for the empty entries: ONE global atomic per window
+        unsigned long long sb = 0;
+        if (n_empty && lane == 0)
+            sb = atomicAdd(&p.glob->next_sample, (unsigned long long)n_empty);
+        sb = __shfl_sync(kFullMask, sb, 0);
+        uint32_t avail = 0;
+        if (n_empty && sb < p.total_samples)
+            avail = p.total_samples - sb < n_empty ? uint32_t(p.total_samples - sb) : n_empty;
+        sample_base = sb;
+        if (lane == 0)
+            n_new += avail;
+        __syncwarp();
+        count = window_sort(s, cnt, avail, off8);
+        return true;
+    }
+    __device__ __forceinline__ void fetch(TraceWarpSmem &s, uint32_t k, TravLane &L, uint32_t &tag) {
+        const uint32_t idx = base + s.perm[k];
+        tag = idx;
+        if (k >= off8) { // a camera sample starts in this (empty) entry: renderer.h:72-75
+            PathState st;
+            new_path(p, sample_base + (k - off8), st);
+            p.ext_a[buf][idx] = pack_a(st);
+            p.ext_b[buf][idx] = pack_b(st);
+            p.ext_c[buf][idx] = pack_c(st);
+            p.ext_d[buf][idx] = pack_d(st);
+            L.wo = st.o;
+            L.wd = st.d;
+            L.time = st.time;
+            L.origin = kNoPrim;
+            if (MEDIA)
+                L.rng = st.rng;
+        } else {
+            const float4 a = p.ext_a[buf][idx], b = p.ext_b[buf][idx];
+            L.wo = V3<float>(a.x, a.y, a.z);
+            L.wd = V3<float>(b.x, b.y, b.z);
+            L.time = a.w;
+            L.origin = __float_as_uint(b.w);
+            if (MEDIA) { // constant_medium::hit draws from the path's stream
+                const uint2 x = *reinterpret_cast<const uint2 *>(p.ext_d[buf] + idx);
+                L.rng.s = uint64_t(x.x) | (uint64_t(x.y) << 32);
+            }
+        }
+        L.t_min = 0.001f;
+        L.t_max = Consts<float>::inf();
+    }
+    __device__ __forceinline__ void commit(uint32_t tag, const TravLane &L) {
+        p.ext_e[buf][tag] = make_float2(L.t_max, __uint_as_float(L.best));
+        if (MEDIA)
+            *reinterpret_cast<uint2 *>(p.ext_d[buf] + tag) = make_uint2(uint32_t(L.rng.s), uint32_t(L.rng.s >> 32));
+    }
+    // Every ray of the window is traced: move the paths, with their hits, into the material queues.
+    __device__ __forceinline__ void finish_window(TraceWarpSmem &s) {
+        const uint32_t lane = lane_id();
+        if (lane < 16)
+            s.hist[lane] = 0;
+        __syncwarp();
+        for (uint32_t r = 0; r < uint32_t(kTraceRounds); ++r) {
+            const uint32_t j = r * 32u + lane;
+            uint32_t key = kSkipKey;
+            if (j < cnt && s.key[j] != kSkipKey) {
+                key = hit_key(p, __float_as_uint(p.ext_e[buf][base + j].y));
+                s.key[j] = uint8_t(key);
+            }
+            const uint32_t peers = __match_any_sync(kFullMask, key);
+            if (key < uint32_t(kKeys) && int(lane) == __ffs(peers) - 1)
+                s.hist[key] += __popc(peers);
+            __syncwarp();
+        }
+        // the window's hits enter the 8 queues with one atomic instruction (their counters share a
+        // 128-byte line: L2 sees one transaction)
+        if (lane < uint32_t(kKeys)) {
+            const uint32_t h = s.hist[lane];
+            s.cur[lane] = h ? atomicAdd(&C.key.v[lane], h) : 0u;
+        }
+        __syncwarp();
+        for (uint32_t r = 0; r < uint32_t(kTraceRounds); ++r) {
+            const uint32_t j = r * 32u + lane;
+            const uint32_t key = j < cnt ? uint32_t(s.key[j]) : kSkipKey;
+            const uint32_t peers = __match_any_sync(kFullMask, key);
+            const int leader = __ffs(peers) - 1;
+            uint32_t pos = 0;
+            if (key < uint32_t(kKeys) && int(lane) == leader) {
+                pos = s.cur[key];
+                s.cur[key] = pos + __popc(peers);
+            }
+            pos = __shfl_sync(kFullMask, pos, leader) + __popc(peers & ((1u << lane) - 1u));
+            if (key < uint32_t(kKeys)) {
+                if (pos >= p.cap) { // cannot happen while the capacity bound of WavefrontPool::ensure holds
+                    atomicExch(&p.glob->overflow, 1ull);
+                } else {
+                    const uint32_t idx = base + j;
+                    const size_t o = size_t(key) * p.cap + pos;
+                    __stcs(p.hit_a + o, __ldcs(p.ext_a[buf] + idx));
+                    __stcs(p.hit_b + o, __ldcs(p.ext_b[buf] + idx));
+                    __stcs(p.hit_c + o, __ldcs(p.ext_c[buf] + idx));
+                    __stcs(p.hit_d + o, __ldcs(p.ext_d[buf] + idx));
+                    __stcs(p.hit_e + o, __ldcs(p.ext_e[buf] + idx));
+                }
+            }
+            __syncwarp();
+        }
+    }
+};
+
+template <bool COUNT, bool MEDIA, bool INST>
+__global__ void __launch_bounds__(kTraceBlock, RTB_TRACE_MIN_BLOCKS) k_extend_w(WfParams p, int it) {
+    __shared__ Vec4f s_top[kTraceTop ? kTopNodesMax * 8 : 8];
+    __shared__ TraceWarpSmem s_warp[kTraceBlock / 32];
+    const uint32_t n_top = stage_top_nodes(p.wide, s_top);
+    Counters &C = p.ctr[it % 3];
+    if (blockIdx.x == 0)
+        for (uint32_t i = threadIdx.x; i < sizeof(Counters) / 4; i += blockDim.x)
+            reinterpret_cast<uint32_t *>(&p.ctr[(it + 2) % 3])[i] = 0;
+    __syncthreads();
+    ExtendJob<MEDIA> job(p, C, it & 1, C.n_ext.v[0]);
+    uint64_t counters[2] = {0, 0};
+    uint32_t overflow = 0;
+    warp_trace<ExtendJob<MEDIA>, false, MEDIA, INST, kTraceTop>(p.geom, p.wide, s_top, n_top, s_warp[threadIdx.x >> 5], job,
+                                                               counters, overflow);
+    if (overflow)
+        atomicExch(&p.glob->overflow, 16ull + overflow);
+    if (lane_id() == 0 && job.n_new)
+        atomicAdd(&p.glob->paths, (unsigned long long)job.n_new);
+    if (COUNT) {
+        const unsigned long long x = warp_sum(counters[0]), y = warp_sum(counters[1]);
+        if (lane_id() == 0) {
+            atomicAdd(&p.glob->nodes_visited, x);
+            atomicAdd(&p.glob->prim_tests, y);
+            atomicAdd(&p.glob->extend_nodes, x);
+        }
+    }
+}
+
+template <bool MEDIA> struct ConnectJob {
+    const WfParams &p;
+    Counters &C;
+    const uint32_t n;
+    uint32_t base = 0;
+    uint32_t pix = 0; // per lane: the pixel of the ray it walks
+    __device__ ConnectJob(const WfParams &p_, Counters &C_, uint32_t n_) : p(p_), C(C_), n(n_) {}
+    __device__ __forceinline__ bool next_window(TraceWarpSmem &s, uint32_t &count) {
+        const uint32_t lane = lane_id();
+        uint32_t b = 0;
+        if (lane == 0)
+            b = atomicAdd(&C.head_shadow.v[0], uint32_t(kTraceWindow));
+        b = __shfl_sync(kFullMask, b, 0);
+        if (b >= n)
+            return false;
+        base = b;
+        const uint32_t cnt = n - b < uint32_t(kTraceWindow) ? n - b : uint32_t(kTraceWindow);
+        for (uint32_t r = 0; r < uint32_t(kTraceRounds); ++r) {
+            const uint32_t j = r * 32u + lane;
+            if (j < cnt) {
+                const float4 d = p.sh_b[b + j];
+                s.key[j] = uint8_t(RTB_TRACE_SORT ? octant_of(d.x, d.y, d.z) : 0u);
+            }
+        }
+        __syncwarp();
+        uint32_t off8;
+        count = window_sort(s, cnt, 0u, off8);
+        return true;
+    }
+    __device__ __forceinline__ void fetch(TraceWarpSmem &s, uint32_t k, TravLane &L, uint32_t &tag) {
+        const uint32_t idx = base + s.perm[k];
+        tag = idx;
+        const float4 a = __ldcs(p.sh_a + idx), b = __ldcs(p.sh_b + idx);
+        L.wo = V3<float>(a.x, a.y, a.z);
+        L.wd = V3<float>(b.x, b.y, b.z);
+        pix = __float_as_uint(b.w);
+        L.time = 0.0f; // shadow rays carry time 0 (direct_light_integrator.h:115)
+        L.origin = __float_as_uint(p.sh_c[idx].w);
+        // t_min is 0.001 along the UNIT direction; the stored direction may be the unnormalised segment
+        const float len = isfinite(a.w) ? length(L.wd) : 1.0f;
+        L.t_min = 0.001f / len;
+        L.t_max = a.w;
+        if (MEDIA) // media on a shadow ray draw from a stream keyed by the queue entry
+            L.rng = pcg_seed((uint64_t(__float_as_uint(a.x)) << 32) ^ __float_as_uint(b.y), p.seed ^ idx);
+    }
+    __device__ __forceinline__ void commit(uint32_t tag, const TravLane &L) {
+        if (L.best == kNoPrim) { // unoccluded: the (already weighted) contribution counts
+            const float4 c = __ldcs(p.sh_c + tag);
+            accum_add(p.accum, pix, V3<float>(c.x, c.y, c.z));
+        }
+    }
+    __device__ __forceinline__ void finish_window(TraceWarpSmem &) {}
+};
+
+template <bool COUNT, bool MEDIA, bool INST>
+__global__ void __launch_bounds__(kTraceBlock, RTB_TRACE_MIN_BLOCKS) k_connect_w(WfParams p, int it) {
+    __shared__ Vec4f s_top[kTraceTop ? kTopNodesMax * 8 : 8];
+    __shared__ TraceWarpSmem s_warp[kTraceBlock / 32];
+    const uint32_t n_top = stage_top_nodes(p.wide, s_top);
+    Counters &C = p.ctr[it % 3];
+    const uint32_t n = C.n_shadow.v[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(&p.glob->rays_shadow, (unsigned long long)n);
+    __syncthreads();
+    ConnectJob<MEDIA> job(p, C, n);
+    uint64_t counters[2] = {0, 0};
+    uint32_t overflow = 0;
+    warp_trace<ConnectJob<MEDIA>, true, MEDIA, INST, kTraceTop>(p.geom, p.wide, s_top, n_top, s_warp[threadIdx.x >> 5], job,
+                                                               counters, overflow);
+    if (overflow)
+        atomicExch(&p.glob->overflow, 32ull + overflow);
+    if (COUNT) {
+        const unsigned long long x = warp_sum(counters[0]), y = warp_sum(counters[1]);
+        if (lane_id() == 0) {
+            atomicAdd(&p.glob->nodes_visited, x);
+            atomicAdd(&p.glob->prim_tests, y);
+        }
+    }
+}
+
+// ---- rtb_trace_batch precision 34 / 36: caller rays through the same scheduler ----------------------
+__global__ void k_batch_rays_in(const rtb_ray *__restrict__ rays, uint32_t n, const int32_t *__restrict__ orig_to_sorted,
+                                int n_orig, float4 *a, float4 *b, float2 *t) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const rtb_ray q = rays[i];
+        uint32_t origin = kNoPrim;
+        if (q.origin_prim >= 0 && q.origin_prim < n_orig)
+            origin = uint32_t(orig_to_sorted[q.origin_prim]);
+        a[i] = make_float4(float(q.o[0]), float(q.o[1]), float(q.o[2]), float(q.time));
+        b[i] = make_float4(float(q.d[0]), float(q.d[1]), float(q.d[2]), __uint_as_float(origin));
+        t[i] = make_float2(float(q.t_min), float(q.t_max));
+    }
+}
+template <bool ANY>
+__global__ void __launch_bounds__(kTraceBlock, RTB_TRACE_MIN_BLOCKS)
+    k_trace_batch_w(GeomView<float> g, WideView w, BatchTraceJob job, unsigned long long *visits, uint32_t *flag) {
+    __shared__ Vec4f s_top[kTraceTop ? kTopNodesMax * 8 : 8];
+    __shared__ TraceWarpSmem s_warp[kTraceBlock / 32];
+    const uint32_t n_top = stage_top_nodes(w, s_top);
+    __syncthreads();
+    uint64_t counters[2] = {0, 0};
+    uint32_t overflow = 0;
+    warp_trace<BatchTraceJob, ANY, true, true, kTraceTop>(g, w, s_top, n_top, s_warp[threadIdx.x >> 5], job, counters, overflow);
+    if (overflow)
+        atomicExch(flag, overflow);
+    if (visits) {
+        const unsigned long long x = warp_sum(counters[0]), y = warp_sum(counters[1]);
+        if (lane_id() == 0) {
+            atomicAdd(&visits[0], x);
+            atomicAdd(&visits[1], y);
+        }
+    }
+}
+__global__ void k_batch_hits_out(GeomView<float> g, const rtb_ray *__restrict__ rays, const float2 *__restrict__ res, uint32_t n,
+                                 rtb_hit *__restrict__ hits) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const rtb_ray q = rays[i];
+        const uint32_t pi = __float_as_uint(res[i].y);
+        rtb_hit h;
+        std::memset(&h, 0, sizeof(h));
+        h.prim = -1;
+        h.material = -1;
+        if (pi != kNoPrim) {
+            const V3<float> o{float(q.o[0]), float(q.o[1]), float(q.o[2])}, d{float(q.d[0]), float(q.d[1]), float(q.d[2])};
+            const RecT<float> rec = make_record<float, true, true>(g, pi, o, d, float(q.time), res[i].x);
+            h.t = rec.t;
+            h.p[0] = rec.p.x;
+            h.p[1] = rec.p.y;
+            h.p[2] = rec.p.z;
+            h.normal[0] = rec.normal.x;
+            h.normal[1] = rec.normal.y;
+            h.normal[2] = rec.normal.z;
+            h.u = rec.u;
+            h.v = rec.v;
+            h.prim = g.prim_orig[pi];
+            h.front_face = rec.front_face ? 1 : 0;
+            h.material = int32_t(g.prims[pi].type_mat >> PT_MAT_SHIFT);
+        }
+        hits[i] = h;
+    }
+}
+
 // ---- (B) fused kernel for shared-memory-resident scenes ----------------------------------------
 
 constexpr uint32_t kSampleChunk = 256; // samples a warp reserves per atomic
@@ -1541,7 +1888,7 @@ template <class K> int blocks_per_sm(K kernel, int threads) {
 struct WavefrontPool {
     uint32_t P = 0;
     uint32_t cap = 0, n_cursor = 0;
-    DeviceBuffer ext[2][4], hit[5], sh_a, sh_b, sh_c, cursor, ctr, glob;
+    DeviceBuffer ext[2][4], ext_e[2], hit[5], sh_a, sh_b, sh_c, cursor, ctr, glob;
     uint32_t *h_live = nullptr; // pinned: extend-queue length probes
     Globals *h_glob = nullptr;  // pinned
     cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -1578,6 +1925,8 @@ struct WavefrontPool {
         for (auto &q : ext)
             for (auto &arr : q)
                 arr.alloc(n * 16);
+        for (auto &arr : ext_e)
+            arr.alloc(n * 8);
         for (int k = 0; k < 4; ++k)
             hit[k].alloc(n * 16 * kKeys);
         hit[4].alloc(n * 8 * kKeys);
@@ -1637,6 +1986,7 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
     WfParams W;
     std::memset(&W, 0, sizeof(W));
     W.geom = geom;
+    W.wide = sc.wide();
     W.shade = sc.shade<float>();
     W.cam = sc.host.f32.camera;
     pool.ensure_common();
@@ -1745,6 +2095,7 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
             W.ext_b[b] = pool.ext[b][1].as<float4>();
             W.ext_c[b] = pool.ext[b][2].as<float4>();
             W.ext_d[b] = pool.ext[b][3].as<uint4>();
+            W.ext_e[b] = pool.ext_e[b].as<float2>();
         }
         W.hit_a = pool.hit[0].as<float4>();
         W.hit_b = pool.hit[1].as<float4>();
@@ -1775,6 +2126,10 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
         const bool inst = sc.host.n_instances > 0; // instance code is compiled out of the kernels otherwise
         const uint32_t minor_mask = (1u << RTB_MAT_METAL) | (1u << RTB_MAT_DIELECTRIC) | (1u << RTB_MAT_DIFFUSE_LIGHT) |
                                     (1u << RTB_MAT_ISOTROPIC);
+        // the warp-scheduled 4-wide traversal, unless round 1's kernels are asked for (or the scene is
+        // small enough for the lockstep walk of the shared-memory copy, which those kernels hold)
+        const bool wide = ctx->opt_binary_traversal == 0 && !geom.flat;
+        int trace_grid = 0, connect_grid = 0;
         constexpr int kBatch = 4; // iterations between two host-side liveness probes
         int probe = 0, zero_probes = 0;
         const int it0 = it;
@@ -1788,7 +2143,18 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
                         RTB_CUDA(cudaEventRecord(pool.ext_event(n_ext_events++), st));
                 };
                 mark();
-                {
+                if (wide) {
+                    typedef void (*ExtendKernel)(WfParams, int);
+                    static const ExtendKernel table[2][2][2] = {
+                        {{k_extend_w<false, false, false>, k_extend_w<false, false, true>},
+                         {k_extend_w<false, true, false>, k_extend_w<false, true, true>}},
+                        {{k_extend_w<true, false, false>, k_extend_w<true, false, true>},
+                         {k_extend_w<true, true, false>, k_extend_w<true, true, true>}}};
+                    const ExtendKernel k = table[count ? 1 : 0][media ? 1 : 0][inst ? 1 : 0];
+                    if (!trace_grid)
+                        trace_grid = sms * blocks_per_sm(k, kTraceBlock);
+                    k<<<trace_grid, kTraceBlock, 0, st>>>(W, it);
+                } else {
                     typedef void (*ExtendKernel)(WfParams, int);
                     static const ExtendKernel table[2][2][2] = {
                         {{k_extend<false, false, false>, k_extend<false, false, true>},
@@ -1825,7 +2191,19 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
                     k_miss<false><<<grid, 128, 0, st>>>(W, it);
                 ++launches;
                 mark();
-                if (nee) {
+                if (nee && wide) {
+                    typedef void (*ConnectKernel)(WfParams, int);
+                    static const ConnectKernel table[2][2][2] = {
+                        {{k_connect_w<false, false, false>, k_connect_w<false, false, true>},
+                         {k_connect_w<false, true, false>, k_connect_w<false, true, true>}},
+                        {{k_connect_w<true, false, false>, k_connect_w<true, false, true>},
+                         {k_connect_w<true, true, false>, k_connect_w<true, true, true>}}};
+                    const ConnectKernel k = table[count ? 1 : 0][media ? 1 : 0][inst ? 1 : 0];
+                    if (!connect_grid)
+                        connect_grid = sms * blocks_per_sm(k, kTraceBlock);
+                    k<<<connect_grid, kTraceBlock, 0, st>>>(W, it);
+                    ++launches;
+                } else if (nee) {
                     typedef void (*ConnectKernel)(WfParams, int);
                     static const ConnectKernel table[2][2][2] = {
                         {{k_connect<false, false, false>, k_connect<false, false, true>},
@@ -1945,6 +2323,47 @@ void launch_trace_fast_batch(rtb_context *ctx, const rtb_ray *d_rays, uint64_t n
                                                          int(sc.host.orig_to_sorted.size()), d_rays, n, d_hits, d_visits,
                                                          plane_records);
     RTB_CUDA(cudaGetLastError());
+}
+
+void launch_trace_wide_batch(rtb_context *ctx, const rtb_ray *d_rays, uint64_t n, rtb_hit *d_hits,
+                             unsigned long long *d_visits, bool any_hit) {
+    const DeviceScene &sc = *ctx->scene;
+    if (n >= (1ull << 31))
+        throw std::runtime_error("precision 34 / 36: at most 2^31 - 1 rays per call");
+    const GeomView<float> g = sc.geom<float>();
+    const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
+    cudaStream_t st = ctx->stream;
+    DeviceBuffer a, b, t, res, misc;
+    a.alloc(n * 16);
+    b.alloc(n * 16);
+    t.alloc(n * 8);
+    res.alloc(n * 8);
+    misc.alloc(2 * sizeof(uint32_t)); // [0] work cursor, [1] overflow flag
+    RTB_CUDA(cudaMemsetAsync(misc.as<void>(), 0, 2 * sizeof(uint32_t), st));
+    k_batch_rays_in<<<sms * 4, 256, 0, st>>>(d_rays, uint32_t(n), sc.orig_to_sorted.as<int32_t>(),
+                                             int(sc.host.orig_to_sorted.size()), a.as<float4>(), b.as<float4>(), t.as<float2>());
+    BatchTraceJob job;
+    job.ray_a = a.as<Vec4f>();
+    job.ray_b = b.as<Vec4f>();
+    job.ray_t = t.as<Vec2f>();
+    job.out = res.as<Vec2f>();
+    job.n = uint32_t(n);
+    job.head = misc.as<uint32_t>();
+    job.base = 0;
+    job.seed = 0x51ed270b;
+    if (any_hit)
+        k_trace_batch_w<true><<<sms * blocks_per_sm(k_trace_batch_w<true>, kTraceBlock), kTraceBlock, 0, st>>>(
+            g, sc.wide(), job, d_visits, misc.as<uint32_t>() + 1);
+    else
+        k_trace_batch_w<false><<<sms * blocks_per_sm(k_trace_batch_w<false>, kTraceBlock), kTraceBlock, 0, st>>>(
+            g, sc.wide(), job, d_visits, misc.as<uint32_t>() + 1);
+    k_batch_hits_out<<<sms * 4, 256, 0, st>>>(g, d_rays, res.as<float2>(), uint32_t(n), d_hits);
+    RTB_CUDA(cudaGetLastError());
+    uint32_t flag = 0;
+    RTB_CUDA(cudaMemcpyAsync(&flag, misc.as<uint32_t>() + 1, sizeof(flag), cudaMemcpyDeviceToHost, st));
+    RTB_CUDA(cudaStreamSynchronize(st));
+    if (flag)
+        throw std::runtime_error("wide traversal: internal error " + std::to_string(flag) + " (stack / scheduler guard)");
 }
 
 void launch_resolve_rgb8(rtb_context *ctx, const float4 *d_accum, int w, int h, int spp, uint8_t *d_rgb8,

@@ -1,12 +1,15 @@
-// rtb_wide.cuh — 4-wide BVH: the binary tree of rtb_bvh.hpp collapsed level pairs at a time, and a
-// traversal over it.  GROUNDWORK for the next round: the binary
-// while-while traversal of k_extend runs a lean loop at 9-18 of 32 lanes, i.e. what it loses is
-// lane utilisation, and a wider node halves the number of dependent steps per ray (one 128-byte
-// fetch and four slab tests per step instead of 64 bytes and two).  Nothing in librtb200.so includes
-// this header yet: it is instantiated by tests/hostcheck only, where the 4-wide traversal is held
-// to the same answers as the binary one (fp64: the reference's t and primitive bit for bit).
+// rtb_wide.cuh — the 4-wide BVH the production traversal kernels walk (rtb_trace.cuh): the binary
+// SAH tree of rtb_bvh.hpp collapsed two levels at a time into 128-byte nodes, laid out breadth
+// first, and a scalar reference traversal over it.
 //
-// Reference counterpart: bvh_node::hit (src/geometry/bvh.h:40-50).
+// Why wide: the binary while-while traversal of round 1 spent one dependent 64-byte fetch per two
+// boxes and ran at 12-18 of 32 lanes (ncu).  A 128-byte node brings four
+// boxes per dependent fetch (half the steps per ray: 7.1 instead of 15.2 on the scene09 rays,
+// 10.4 instead of 21.7 on the 1 M-sphere field), its structure-of-arrays rows feed the packed
+// FFMA2 slab test of sm_100a two children at a time, and the breadth-first order makes the top
+// levels of the tree a contiguous prefix that the kernels stage in shared memory.
+//
+// Reference counterpart: bvh_node::hit (src/geometry/bvh.h:40-50), aabb::hit (aabb.h:31-48).
 #ifndef RTB_WIDE_CUH
 #define RTB_WIDE_CUH
 
@@ -17,11 +20,13 @@
 
 namespace rtb {
 
-// 128 bytes: up to four children, boxes as structure of arrays (one float4 per plane), and their
-// refs in the encoding of Node32::ref — an interior child is an index into the Node128 array, a
+// 128 bytes = eight 16-byte rows: lo.x[4] lo.y[4] lo.z[4] hi.x[4] hi.y[4] hi.z[4] ref[4] pad[4].
+// A ray reads the "near" row of an axis at byte offset axis*16 + (dir < 0 ? 48 : 0) and the "far"
+// row at the other one, so no min/max is needed to order the two planes of a slab.
+// ref[i] in the encoding of Node32::ref: an interior child is an index into the Node128 array, a
 // leaf child is the binary tree's own leaf ref (kLeafFlag | count | [kLeafInstanceFlag] | first).
-// Unused slots hold an inverted box, which no ray enters.
-struct alignas(16) Node128 {
+// Unused slots hold an inverted box (lo = +inf, hi = -inf), which no ray enters, and kEmptyRef.
+struct alignas(128) Node128 {
     float lo[3][4];
     float hi[3][4];
     uint32_t ref[4];
@@ -29,17 +34,26 @@ struct alignas(16) Node128 {
 };
 static_assert(sizeof(Node128) == 128, "wide BVH node must be 128 bytes");
 
+// Traversal stack of the kernels in rtb_trace.cuh: entries (ref, entry distance) per lane.  A
+// descent pushes at most three siblings per level and one marker per instance entered; the scene
+// upload refuses a tree that could need more (wide_stack_need).
+constexpr int kWideStack = 64;
+
 struct WideTree {
-    std::vector<Node128> nodes;
+    std::vector<Node128> nodes;       // [top-level tree, breadth first][bottom-level tree of chain 0]...
     uint32_t root_ref = kEmptyRef;    // of the top-level tree
-    std::vector<uint32_t> prim_root;  // per sorted primitive: root ref of an instance's bottom-level tree
+    std::vector<uint32_t> chain_root; // per wrapper chain: root ref of that instance's bottom-level tree (kEmptyRef: none)
     uint64_t n_children = 0;          // occupied child slots (n_children / nodes.size() = mean arity)
+    uint32_t n_top_nodes = 0;         // nodes of the top-level tree = nodes[0 .. n_top_nodes)
+    int max_depth = 0;                // deepest wide node (root = 1), top level + bottom level
 };
 
-// Collapses the binary tree rooted at the child pair `ref2` (Node32 refs are global indices into
-// `nodes2`, top level and bottom levels alike).  A node keeps absorbing the children of its
+// Collapses the binary tree under `ref2` (Node32 refs are global indices into `nodes2`) and
+// appends its nodes to `out` in breadth-first order.  A node keeps absorbing the children of its
 // largest interior child (by surface area) until it has four children or only leaves.
-inline uint32_t collapse_wide(const std::vector<Node32> &nodes2, uint32_t ref2, WideTree &out) {
+inline uint32_t collapse_wide(const std::vector<Node32> &nodes2, uint32_t ref2, WideTree &out, int *depth_out = nullptr) {
+    if (depth_out)
+        *depth_out = 0;
     if (ref2 & kLeafFlag) // leaves (and kEmptyRef) keep their ref
         return ref2;
     struct Child {
@@ -59,56 +73,86 @@ inline uint32_t collapse_wide(const std::vector<Node32> &nodes2, uint32_t ref2, 
         const double x = double(c.hi[0]) - c.lo[0], y = double(c.hi[1]) - c.lo[1], z = double(c.hi[2]) - c.lo[2];
         return x * y + y * z + z * x;
     };
-    Child ch[4] = {child_of(ref2), child_of(ref2 + 1)};
-    int n = 2;
-    while (n < 4) {
-        int pick = -1;
-        for (int i = 0; i < n; ++i)
-            if (!(ch[i].ref & kLeafFlag) && (pick < 0 || area(ch[i]) > area(ch[pick])))
-                pick = i;
-        if (pick < 0)
-            break;
-        const uint32_t r = ch[pick].ref;
-        ch[pick] = child_of(r);
-        ch[n++] = child_of(r + 1);
-    }
-    const uint32_t self = uint32_t(out.nodes.size());
+    struct Pending {
+        uint32_t ref2, self;
+        int depth;
+    };
+    const uint32_t root = uint32_t(out.nodes.size());
     out.nodes.emplace_back();
-    Node128 node;
+    std::vector<Pending> queue{{ref2, root, 1}};
     const float inf = std::numeric_limits<float>::infinity();
-    for (int i = 0; i < 4; ++i) {
-        for (int k = 0; k < 3; ++k) {
-            node.lo[k][i] = i < n ? ch[i].lo[k] : inf;
-            node.hi[k][i] = i < n ? ch[i].hi[k] : -inf;
+    int deepest = 0;
+    for (size_t head = 0; head < queue.size(); ++head) {
+        const Pending cur = queue[head];
+        deepest = cur.depth > deepest ? cur.depth : deepest;
+        Child ch[4] = {child_of(cur.ref2), child_of(cur.ref2 + 1)};
+        int n = 2;
+        while (n < 4) {
+            int pick = -1;
+            for (int i = 0; i < n; ++i)
+                if (!(ch[i].ref & kLeafFlag) && (pick < 0 || area(ch[i]) > area(ch[pick])))
+                    pick = i;
+            if (pick < 0)
+                break;
+            const uint32_t r = ch[pick].ref;
+            ch[pick] = child_of(r);
+            ch[n++] = child_of(r + 1);
         }
-        node.ref[i] = kEmptyRef;
-        node.pad[i] = 0;
+        Node128 node;
+        for (int i = 0; i < 4; ++i) {
+            for (int k = 0; k < 3; ++k) {
+                node.lo[k][i] = i < n ? ch[i].lo[k] : inf;
+                node.hi[k][i] = i < n ? ch[i].hi[k] : -inf;
+            }
+            node.ref[i] = kEmptyRef;
+            node.pad[i] = 0;
+        }
+        for (int i = 0; i < n; ++i) {
+            if (ch[i].ref & kLeafFlag) {
+                node.ref[i] = ch[i].ref;
+            } else { // interior: its node is appended now, i.e. level by level
+                node.ref[i] = uint32_t(out.nodes.size());
+                out.nodes.emplace_back();
+                queue.push_back({ch[i].ref, node.ref[i], cur.depth + 1});
+            }
+        }
+        out.nodes[cur.self] = node;
+        out.n_children += uint64_t(n);
     }
-    for (int i = 0; i < n; ++i)
-        node.ref[i] = collapse_wide(nodes2, ch[i].ref, out); // may grow out.nodes: `node` is a local copy
-    out.nodes[self] = node;
-    out.n_children += uint64_t(n);
-    return self;
+    if (depth_out)
+        *depth_out = deepest;
+    return root;
 }
 
-// The whole scene: the top-level tree and the bottom-level tree of every instance record.
-template <class R> inline WideTree build_wide(const std::vector<Node32> &nodes2, uint32_t root_ref2, const PrimT<R> *prims, size_t n_prims) {
+// The whole scene: the top-level tree first, then the bottom-level tree of every instance record.
+template <class R>
+inline WideTree build_wide(const std::vector<Node32> &nodes2, uint32_t root_ref2, const PrimT<R> *prims, size_t n_prims,
+                           size_t n_chains) {
     WideTree w;
-    w.root_ref = collapse_wide(nodes2, root_ref2, w);
-    w.prim_root.assign(n_prims, kEmptyRef);
+    int top_depth = 0, deepest_bottom = 0;
+    w.root_ref = collapse_wide(nodes2, root_ref2, w, &top_depth);
+    w.n_top_nodes = uint32_t(w.nodes.size());
+    w.chain_root.assign(n_chains, kEmptyRef);
     for (size_t i = 0; i < n_prims; ++i)
-        if ((prims[i].type_mat & PT_TYPE_MASK) == PT_INSTANCE)
-            w.prim_root[i] = collapse_wide(nodes2, prims[i].aux, w);
+        if ((prims[i].type_mat & PT_TYPE_MASK) == PT_INSTANCE && prims[i].aux2 < n_chains) {
+            int d = 0;
+            w.chain_root[prims[i].aux2] = collapse_wide(nodes2, prims[i].aux, w, &d);
+            deepest_bottom = d > deepest_bottom ? d : deepest_bottom;
+        }
+    w.max_depth = top_depth + deepest_bottom;
     return w;
 }
 
-// traverse() of rtb_geom.cuh over the 4-wide tree (instance entry / exit in the leaf phase).  The
-// descent step tests four boxes, continues with the nearest child hit and pushes the others far
-// to near; leaves are processed exactly as in the binary traversal, so the set of primitives
-// tested against a ray's shrinking [t_min, t_max] gives the same closest hit (ties between
-// coincident surfaces aside, as between any two traversal orders).
+inline int wide_stack_need(const WideTree &w) { return 3 * w.max_depth + 2; }
+
+// Scalar traversal over the 4-wide tree: what the warp-scheduled kernels of rtb_trace.cuh compute
+// per ray, written as one loop (the CPU suite holds it to the reference's hits bit for bit in fp64
+// and holds the kernels' scheduler to it).  The descent step tests four boxes, continues with the
+// nearest child hit and pushes the others far to near; leaves are processed exactly as in the
+// binary traversal, so the set of primitives tested against a ray's shrinking [t_min, t_max]
+// gives the same closest hit (ties between coincident surfaces aside, as between any two orders).
 template <class R, bool ANY, bool ROBUST, class Rng, class Stack, bool MEDIA = true>
-RTB_HD uint32_t traverse_wide(const GeomView<R> &g, const Node128 *nodes4, uint32_t root_ref, const uint32_t *prim_root, V3<R> o,
+RTB_HD uint32_t traverse_wide(const GeomView<R> &g, const Node128 *nodes4, uint32_t root_ref, const uint32_t *chain_root, V3<R> o,
                               V3<R> d, R time, R t_min, R t_max, uint32_t origin_prim, Rng &rng, R &t_hit,
                               uint64_t *n_nodes, uint64_t *n_tests, Stack &stack) {
     uint32_t best = kNoPrim;
@@ -167,7 +211,7 @@ RTB_HD uint32_t traverse_wide(const GeomView<R> &g, const Node128 *nodes4, uint3
                     stack.push(kSentinelRef);
                     enter_instance<R, ROBUST>(g, int(p.aux2), co, cd);
                     sr.set(co, cd);
-                    cur = prim_root[i];
+                    cur = chain_root[p.aux2];
                     entered = true;
                     break;
                 }

@@ -90,4 +90,5 @@ def hostcheck():
     L.hc_light_eval.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_void_p]
     L.hc_camera_derived.argtypes = [C.c_void_p, C.c_void_p]
     L.hc_wide_info.argtypes = [C.c_void_p, C.c_void_p]
+    L.hc_sched_stats.argtypes = [C.c_void_p]
     return L

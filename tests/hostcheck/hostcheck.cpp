@@ -9,9 +9,12 @@
 // (librtb200.so) contains no host execution path and fails loudly without a GPU.
 #include "rtb200_types.h"
 #include "rtb_scene_host.hpp"
+#include "rtb_trace.cuh"
 #include "rtb_wide.cuh"
 
+#include <algorithm>
 #include <map>
+#include <string>
 
 #include <cstdio>
 #include <cstring>
@@ -59,14 +62,8 @@ template <class R> ShadeView<R> shade_view(HostScene &H) {
     return s;
 }
 
-// the 4-wide tree of a scene (rtb_wide.cuh), built on first use
-std::map<const HostScene *, WideTree> g_wide;
-const WideTree &wide_of(HostScene &H) {
-    auto it = g_wide.find(&H);
-    if (it == g_wide.end())
-        it = g_wide.emplace(&H, build_wide(H.nodes, H.root_ref, H.f32.prims.data(), H.f32.prims.size())).first;
-    return it->second;
-}
+// the 4-wide tree of a scene (rtb_wide.cuh), built by build_host_scene
+const WideTree &wide_of(HostScene &H) { return H.wide; }
 
 template <class R, bool ROBUST>
 void trace_batch(HostScene &H, const rtb_ray *rays, uint64_t n, rtb_hit *hits, uint64_t stats[2], bool use_flat,
@@ -86,7 +83,7 @@ void trace_batch(HostScene &H, const rtb_ray *rays, uint64_t n, rtb_hit *hits, u
         uint32_t storage[kStackDepth];
         LocalStack stack(storage);
         const uint32_t pi =
-            wide ? traverse_wide<R, false, ROBUST>(g, W->nodes.data(), W->root_ref, W->prim_root.data(), o, d, R(q.time),
+            wide ? traverse_wide<R, false, ROBUST>(g, W->nodes.data(), W->root_ref, W->chain_root.data(), o, d, R(q.time),
                                                    R(q.t_min), R(q.t_max), origin, draw, t, &stats[0], &stats[1], stack)
             : use_flat && g.flat
                 ? traverse_flat<R, false, ROBUST>(g, o, d, R(q.time), R(q.t_min), R(q.t_max), origin, draw, t,
@@ -119,6 +116,74 @@ void trace_batch(HostScene &H, const rtb_ray *rays, uint64_t n, rtb_hit *hits, u
         h.prim = g.prim_orig[pi];
         h.front_face = rec.front_face;
         h.material = int(g.prims[pi].type_mat >> PT_MAT_SHIFT);
+    }
+}
+
+// The production scheduler of rtb_trace.cuh (votes, window sort, refill) on emulated warps
+// (rtb_warp.cuh): `warps` warps of 32 fibers pull windows off one cursor, as the persistent
+// kernel's warps do.  Fills t / primitive only (records are tested through the scalar paths).
+void trace_batch_warp(HostScene &H, const rtb_ray *rays, uint64_t n, rtb_hit *hits, uint64_t stats[2], bool any_hit,
+                      int warps) {
+    const GeomView<float> g = geom_view<float>(H);
+    const WideTree &W = wide_of(H);
+    WideView wv;
+    wv.nodes = reinterpret_cast<const Vec4f *>(W.nodes.data());
+    wv.chain_root = W.chain_root.data();
+    wv.root_ref = W.root_ref;
+    wv.n_nodes = uint32_t(W.nodes.size());
+    std::vector<Vec4f> a(n), b(n);
+    std::vector<Vec2f> tt(n), out(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        const rtb_ray &q = rays[i];
+        uint32_t origin = kNoPrim;
+        if (q.origin_prim >= 0 && q.origin_prim < int(H.orig_to_sorted.size()))
+            origin = uint32_t(H.orig_to_sorted[q.origin_prim]);
+        a[i] = Vec4f{float(q.o[0]), float(q.o[1]), float(q.o[2]), float(q.time)};
+        b[i] = Vec4f{float(q.d[0]), float(q.d[1]), float(q.d[2]), u2f(origin)};
+        tt[i] = Vec2f{float(q.t_min), float(q.t_max)};
+        out[i] = Vec2f{-1.f, u2f(0x12345678u)};
+    }
+    uint32_t head = 0, overflow = 0;
+    // the top of the tree from a separate copy, as the kernels read it from shared memory
+    const uint32_t n_top = std::min<uint32_t>(wv.n_nodes, kTopNodesMax);
+    std::vector<Vec4f> top(wv.nodes, wv.nodes + size_t(n_top) * 8);
+    const bool media = H.has_media, inst = H.n_instances > 0;
+    for (int wi = 0; wi < warps; ++wi) {
+        TraceWarpSmem smem;
+        HostWarp hw;
+        head = uint32_t(n * uint64_t(wi) / uint64_t(warps));
+        hw.run([&]() {
+            BatchTraceJob job;
+            job.ray_a = a.data();
+            job.ray_b = b.data();
+            job.ray_t = tt.data();
+            job.out = out.data();
+            job.n = uint32_t(n * uint64_t(wi + 1) / uint64_t(warps)); // this warp's share of the batch
+            job.head = &head;
+            job.base = 0;
+            job.seed = 0x51ed270b;
+            uint64_t c[2] = {0, 0};
+            uint32_t ov = 0;
+            if (any_hit)
+                warp_trace<BatchTraceJob, true, true, true, true>(g, wv, top.data(), n_top, smem, job, c, ov);
+            else if (media || inst)
+                warp_trace<BatchTraceJob, false, true, true, true>(g, wv, top.data(), n_top, smem, job, c, ov);
+            else
+                warp_trace<BatchTraceJob, false, false, false, false>(g, wv, nullptr, 0, smem, job, c, ov);
+            stats[0] += c[0];
+            stats[1] += c[1];
+            overflow |= ov;
+        });
+    }
+    if (overflow)
+        throw std::runtime_error("warp_trace: overflow flag " + std::to_string(overflow));
+    for (uint64_t i = 0; i < n; ++i) {
+        rtb_hit &h = hits[i];
+        std::memset(&h, 0, sizeof(h));
+        const uint32_t pi = f2u(out[i].y);
+        h.prim = pi == kNoPrim ? -1 : g.prim_orig[pi];
+        h.material = pi == kNoPrim ? -1 : int(g.prims[pi].type_mat >> PT_MAT_SHIFT);
+        h.t = pi == kNoPrim ? 0.0 : double(out[i].x);
     }
 }
 
@@ -218,7 +283,6 @@ void *hc_scene_create(const void *blob, uint64_t nbytes, int max_leaf) {
     }
 }
 void hc_scene_destroy(void *h) {
-    g_wide.erase(static_cast<HostScene *>(h));
     delete static_cast<HostScene *>(h);
 }
 
@@ -227,6 +291,24 @@ void hc_wide_info(void *h, uint64_t out[2]) {
     const WideTree &w = wide_of(*static_cast<HostScene *>(h));
     out[0] = w.nodes.size();
     out[1] = w.n_children;
+}
+
+// votes of the emulated scheduler since the last call: {node steps, lanes in them, leaf steps, lanes,
+// refills, lanes refilled}; resets the counters
+void hc_sched_stats(uint64_t out[6]) {
+    TraceSchedStats &s = trace_sched_stats();
+    out[0] = s.node_steps;
+    out[1] = s.node_lanes;
+    out[2] = s.leaf_steps;
+    out[3] = s.leaf_lanes;
+    out[4] = s.switches;
+    out[5] = s.switch_lanes;
+    s = TraceSchedStats();
+}
+
+void hc_sched_tuning(int node_min, int switch_min) {
+    trace_tuning().node_min = uint32_t(node_min);
+    trace_tuning().switch_min = uint32_t(switch_min);
 }
 
 // sizes = {nodes, sorted prims, instances}
@@ -263,7 +345,17 @@ void hc_trace_batch(void *h, const rtb_ray *rays, uint64_t n, int precision, rtb
     // through the BVH; 34: the same with instance entry / exit inside the descent; 35: as 32 with
     // the records of planar primitives from plane_record() (the fused kernel's shading input)
     // 67 / 37: fp64 / fp32 through the 4-wide tree of rtb_wide.cuh (stats[0] counts 128-byte nodes)
-    if (precision == 67)
+    // 38 / 39: fp32 through the production warp scheduler of rtb_trace.cuh on emulated warps
+    // (closest hit / any hit)
+    if (precision == 38 || precision == 39) {
+        try {
+            trace_batch_warp(*H, rays, n, hits, local, precision == 39, 3);
+        } catch (const std::exception &e) {
+            std::fprintf(stderr, "hc_trace_batch(%d): %s\n", precision, e.what());
+            for (uint64_t i = 0; i < n; ++i)
+                hits[i].prim = -2;
+        }
+    } else if (precision == 67)
         trace_batch<double, false>(*H, rays, n, hits, local, false, false, false, true);
     else if (precision == 37)
         trace_batch<float, true>(*H, rays, n, hits, local, false, false, false, true);

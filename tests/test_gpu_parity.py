@@ -42,6 +42,9 @@ def test_fp32_hits_agree_vs_golden(up, golden, abi, sid):
     got = up(sid).trace(parity.to_segment_form(g["rays"]), 32)
     mask = parity.deterministic_mask(T, g["hits"], got)
     assert ((got["prim"] != g["hits"]["prim"]) & mask).sum() <= 1
+    got = up(sid).trace(parity.to_segment_form(g["rays"]), 34)   # the renderer's warp-scheduled 4-wide traversal
+    mask = parity.deterministic_mask(T, g["hits"], got)
+    assert ((got["prim"] != g["hits"]["prim"]) & mask).sum() <= 1
 
 
 @pytest.mark.parametrize("sid,integrator", [(7, 1), (21, 3), (21, 4), (23, 4), (9, 1), (1, 1)])
@@ -83,6 +86,22 @@ def test_million_ray_batches_vs_live_reference(up, golden, abi, sid, integrator)
     mask = parity.deterministic_mask(T, hits, got32)
     agree = (got32["prim"] == hits["prim"])[mask].mean()
     assert agree >= parity.FP32_MIN_AGREEMENT, agree
+    # the kernel the renderer's extend stage runs on BVH scenes (warp-scheduled 4-wide traversal,
+    # csrc/rtb_trace.cuh), fed with the same rays: same gate, and its any-hit form (the connect
+    # stage) must report a blocker exactly where the reference finds a hit
+    seg = parity.to_segment_form(rays)
+    got34 = ctx.trace(seg, 34)
+    mask = parity.deterministic_mask(T, hits, got34)
+    agree = (got34["prim"] == hits["prim"])[mask].mean()
+    assert agree >= parity.FP32_MIN_AGREEMENT, agree
+    same_t = np.isclose(got34["t"], hits["t"], rtol=1e-4, atol=1e-6)[mask & (hits["prim"] >= 0) & (got34["prim"] == hits["prim"])]
+    assert same_t.mean() >= 0.9999
+    got36 = ctx.trace(seg, 36)
+    blocked = got36["prim"] >= 0
+    ref_hit = hits["prim"] >= 0
+    assert blocked[mask & ref_hit].mean() >= parity.FP32_MIN_AGREEMENT
+    if not (T["prims"]["type"] == parity.PRIM_MEDIUM).any():   # media block shadow rays at random (constant_medium.h:85)
+        assert (~blocked[mask & ~ref_hit]).mean() >= parity.FP32_MIN_AGREEMENT
 
 
 @pytest.mark.parametrize("sid", GOLDEN_SCENES)

@@ -271,3 +271,56 @@ def test_wide_bvh_on_a_deep_tree(hostcheck, abi):
     assert np.array_equal(b64["prim"], w64["prim"]) and np.array_equal(b64["t"], w64["t"])
     assert np.array_equal(b32["prim"], w32["prim"]) and np.array_equal(b32["t"], w32["t"])
     assert info[1] / info[0] > 3.0 and sw[0] < 0.65 * (sb[0] / 2)      # near-full nodes, far fewer dependent steps
+
+
+@pytest.mark.parametrize("sid", GOLDEN_SCENES)
+def test_warp_scheduler_matches_the_scalar_wide_traversal(hostcheck, scenes, golden, abi, sid):
+    """The production traversal (csrc/rtb_trace.cuh: windows sorted by octant, lanes refilled as they
+    finish, node / leaf steps chosen by a warp vote, children pushed with their entry distance) run
+    on emulated warps (csrc/rtb_warp.cuh) must give, ray by ray, the t and the primitive of the plain
+    one-ray loop over the same 4-wide tree, and through it the reference's primitive."""
+    g = golden(sid)
+    T = abi.parse_blob(g.blob)
+    ref = g["hits"]
+    seg = parity.to_segment_form(g["rays"])
+    w32, _ = trace(hostcheck, scenes(sid), seg, 37, abi)
+    k32, sk = trace(hostcheck, scenes(sid), seg, 38, abi)
+    assert (k32["prim"] != -2).all()
+    mask = parity.deterministic_mask(T, ref, w32) & parity.deterministic_mask(T, ref, k32)
+    assert mask.mean() > 0.3
+    same = (w32["prim"][mask] == k32["prim"][mask]) & (w32["t"][mask] == k32["t"][mask])
+    # a different visiting order may only change the answer between surfaces hit at the same t
+    diff = np.flatnonzero(~same)
+    assert np.all(np.abs(w32["t"][mask][diff] - k32["t"][mask][diff]) <= 1e-6 * np.abs(w32["t"][mask][diff])), \
+        f"{len(diff)} rays differ beyond ties"
+    assert len(diff) <= max(1, len(same) // 1000)
+    assert sk[0] > 0 or T["prims"].shape[0] <= 4
+
+
+def test_warp_scheduler_on_a_deep_tree(hostcheck, abi):
+    """40 x 40 sphere field (1,600 spheres + ground), 20,000 random rays: closest hits of the
+    emulated warp scheduler equal the scalar 4-wide traversal bit for bit, and the any-hit variant
+    (shadow rays) reports a blocker exactly where the closest-hit query finds one."""
+    import importlib
+    scn = importlib.import_module("ray_tracing-rendering_b200.scenes")
+    blob = scn.sphere_field(half_extent=20, width=64, height=36, spp=1)
+    h = hostcheck.hc_scene_create(blob, len(blob), 4)
+    assert h
+    try:
+        rng = np.random.default_rng(5)
+        n = 20_000
+        rays = np.zeros(n, abi.RAY)
+        rays["o"] = rng.uniform(-25, 25, (n, 3)) * np.array([1, 0, 1]) + np.array([0, 1, 0]) * rng.uniform(0.05, 6, (n, 1))
+        d = rng.normal(size=(n, 3))
+        rays["d"] = d / np.linalg.norm(d, axis=1, keepdims=True)
+        rays["t_min"], rays["t_max"], rays["origin_prim"] = 0.001, np.inf, -1
+        w32, sw = trace(hostcheck, h, rays, 37, abi)
+        k32, sk = trace(hostcheck, h, rays, 38, abi)
+        a32, _ = trace(hostcheck, h, rays, 39, abi)
+    finally:
+        hostcheck.hc_scene_destroy(h)
+    assert (w32["prim"] >= 0).mean() > 0.5
+    assert np.array_equal(w32["prim"], k32["prim"]) and np.array_equal(w32["t"], k32["t"])
+    assert np.array_equal(a32["prim"] >= 0, w32["prim"] >= 0)
+    # dropping popped subtrees that lie behind the closest hit saves node fetches
+    assert sk[0] <= sw[0]

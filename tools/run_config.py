@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--count", action="store_true")
     ap.add_argument("--reps", type=int, default=1)
     ap.add_argument("--warm", type=int, default=1)
+    ap.add_argument("--binary", action="store_true", help="round 1's traversal kernels (RTB_OPT_BINARY_TRAVERSAL)")
     a = ap.parse_args()
     pkg = importlib.import_module(PKG)
     configs = importlib.import_module(PKG + ".configs")
@@ -32,6 +33,8 @@ def main():
     cfg = configs.get(a.config)
     spp = a.spp or cfg.spp
     ctx = pkg.Context(0)
+    if a.binary:
+        ctx.set_option(binding.OPT_BINARY_TRAVERSAL, 1)
     ctx.upload_scene(cfg.blob())
     flags = (binding.RENDER_FORCE_WAVEFRONT if a.wavefront else 0) | (binding.RENDER_FORCE_FUSED if a.fused else 0) | (binding.RENDER_TIME_EXTEND if a.time else 0) \
         | (binding.RENDER_COUNT_VISITS if a.count else 0)
