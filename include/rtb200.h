@@ -194,6 +194,50 @@ RTB_API int rtb_cancel(rtb_context *ctx);
  * the accumulators of the LAST rtb_render on this context.  rgb8: height*width*3. */
 RTB_API int rtb_resolve_rgb8(rtb_context *ctx, int32_t spp, uint8_t *rgb8_host);
 
+/* ---- multi-GPU (replaces the tile queue over CPU threads, renderer.h:40-94) ----------------------
+ *
+ * The scene is replicated; every GPU renders a slice of the samples of every pixel (rows too when
+ * the job has fewer samples than GPUs; the split is planned by the library) and ONE collective —
+ * ncclReduce(SUM) over NVLink of float3 means, staged by a kernel that folds in the division by
+ * spp — combines them on the first GPU.  The random stream of a sample depends only on
+ * (pixel, sample, seed), so the result equals the one-GPU image up to float summation order.
+ * NCCL (libnccl.so.2) is bound at run time, on first use. */
+
+/* (1) One process, several GPUs: a group owns one context, host thread, stream and NCCL
+ * communicator per device — what a C++ caller of Renderer::render uses (SURVEY 8b:
+ * ctx_create(device_ids, n)). */
+typedef struct rtb_group rtb_group;
+RTB_API int rtb_group_create(const int *device_ids, int n_devices, rtb_group **out);
+RTB_API void rtb_group_destroy(rtb_group *g);
+RTB_API const char *rtb_group_last_error(const rtb_group *g);
+RTB_API int rtb_group_size(const rtb_group *g);
+/* the i-th device's context (options, scene stats, batch queries); owned by the group */
+RTB_API rtb_context *rtb_group_context(rtb_group *g, int i);
+/* builds the BVH once and copies the tables to every device of the group */
+RTB_API int rtb_group_scene_upload(rtb_group *g, const void *blob, uint64_t nbytes);
+/* Renders the WHOLE job `params` describes (its sample / row split fields are ignored) on all
+ * devices.  accum_rgba_host: height*width float4 linear sums as rtb_render returns them;
+ * rgb8_host: height*width*3 bytes as rtb_resolve_rgb8 returns them; either may be NULL.
+ * stats: sums over the devices, times = the slowest device. */
+RTB_API int rtb_group_render(rtb_group *g, const rtb_render_params *params, float *accum_rgba_host,
+                             uint8_t *rgb8_host, rtb_render_stats *stats);
+RTB_API int rtb_group_cancel(rtb_group *g);
+
+/* (2) One process per GPU (e.g. under torchrun): rank 0 makes a unique id, the launcher hands its
+ * RTB_COMM_ID_BYTES bytes to every rank, every rank joins with rtb_comm_init on its own context. */
+#define RTB_COMM_ID_BYTES 128
+RTB_API int rtb_comm_unique_id(void *id_out);
+RTB_API int rtb_comm_init(rtb_context *ctx, int n_ranks, int rank, const void *id);
+RTB_API void rtb_comm_release(rtb_context *ctx);
+/* This rank's slice of the WHOLE job + the reduce onto rank 0 (collective: every rank calls it with
+ * the same params).  On rank 0 the complete image's float4 sums are left in the context's
+ * accumulators (rtb_resolve_rgb8 / rtb_accum_copy_device read them) and copied to accum_rgba_host /
+ * rgb8_host when given; other ranks pass NULL.  cuda_stream: NULL = the context's stream. */
+RTB_API int rtb_render_reduce(rtb_context *ctx, const rtb_render_params *params, float *accum_rgba_host,
+                              uint8_t *rgb8_host, void *cuda_stream, rtb_render_stats *stats);
+/* the accumulators of the last render on ctx -> a device buffer of the caller (height*width float4) */
+RTB_API int rtb_accum_copy_device(rtb_context *ctx, void *dst_device, void *cuda_stream);
+
 /* ---- parity-layer batch entry points ---------------------------------------------------- */
 
 /* hittable::hit of the world on caller rays (bvh.h:40-50 and everything below it).

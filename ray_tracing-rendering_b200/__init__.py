@@ -7,5 +7,5 @@ The directory name contains a hyphen, so import it with
 ``importlib.import_module("ray_tracing-rendering_b200")``.
 """
 from . import abi  # noqa: F401
-from .binding import Context, RenderParams, RtbError, load  # noqa: F401
+from .binding import Context, Group, RenderParams, RtbError, load  # noqa: F401
 from .renderer import Renderer, INTEGRATOR_NAMES  # noqa: F401

@@ -31,7 +31,11 @@ EXPORTS = ["rtb_version", "rtb_context_create", "rtb_context_destroy", "rtb_last
            "rtb_set_option", "rtb_scene_upload", "rtb_scene_get_stats", "rtb_camera_derived", "rtb_render",
            "rtb_render_device", "rtb_cancel", "rtb_resolve_rgb8", "rtb_trace_batch",
            "rtb_bsdf_eval_batch", "rtb_bsdf_sample_batch", "rtb_light_eval_batch",
-           "rtb_texture_eval_batch"]
+           "rtb_texture_eval_batch",
+           "rtb_group_create", "rtb_group_destroy", "rtb_group_last_error", "rtb_group_size", "rtb_group_context",
+           "rtb_group_scene_upload", "rtb_group_render", "rtb_group_cancel",
+           "rtb_comm_unique_id", "rtb_comm_init", "rtb_comm_release", "rtb_render_reduce", "rtb_accum_copy_device"]
+COMM_ID_BYTES = 128
 
 
 class RenderParams(C.Structure):
@@ -103,6 +107,23 @@ def load():
     L.rtb_bsdf_sample_batch.argtypes = [vp, i32, vp, u64, i32, u64, vp]
     L.rtb_light_eval_batch.argtypes = [vp, i32, vp, u64, i32, u64, vp]
     L.rtb_texture_eval_batch.argtypes = [vp, i32, vp, u64, i32, vp]
+    L.rtb_group_create.argtypes = [vp, i32, C.POINTER(vp)]
+    L.rtb_group_destroy.argtypes = [vp]
+    L.rtb_group_destroy.restype = None
+    L.rtb_group_last_error.argtypes = [vp]
+    L.rtb_group_last_error.restype = C.c_char_p
+    L.rtb_group_size.argtypes = [vp]
+    L.rtb_group_context.argtypes = [vp, i32]
+    L.rtb_group_context.restype = vp
+    L.rtb_group_scene_upload.argtypes = [vp, vp, u64]
+    L.rtb_group_render.argtypes = [vp, C.POINTER(RenderParams), vp, vp, C.POINTER(RenderStats)]
+    L.rtb_group_cancel.argtypes = [vp]
+    L.rtb_comm_unique_id.argtypes = [vp]
+    L.rtb_comm_init.argtypes = [vp, i32, i32, vp]
+    L.rtb_comm_release.argtypes = [vp]
+    L.rtb_comm_release.restype = None
+    L.rtb_render_reduce.argtypes = [vp, C.POINTER(RenderParams), vp, vp, vp, C.POINTER(RenderStats)]
+    L.rtb_accum_copy_device.argtypes = [vp, vp, vp]
     _lib = L
     return L
 
@@ -187,6 +208,31 @@ class Context:
     def cancel(self):
         self._check(self._lib.rtb_cancel(self._h))
 
+    # ---- multi-GPU, one process per GPU: the library's own NCCL communicator
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """On rank 0; hand the bytes to every rank (e.g. torch.distributed.broadcast_object_list)."""
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        rc = load().rtb_comm_unique_id(C.cast(buf, C.c_void_p))
+        if rc != RTB_OK:
+            raise RtbError(rc, "rtb_comm_unique_id failed (libnccl.so.2 missing?)")
+        return buf.raw
+
+    def comm_init(self, n_ranks: int, rank: int, unique_id: bytes = None):
+        buf = C.create_string_buffer(unique_id, COMM_ID_BYTES) if unique_id is not None else None
+        self._check(self._lib.rtb_comm_init(self._h, n_ranks, rank, C.cast(buf, C.c_void_p) if buf is not None else None))
+
+    def render_reduce(self, params: RenderParams, out=None, rgb8=None, stream: int = 0):
+        """Collective: this rank's slice of the WHOLE job + ncclReduce onto rank 0 (inside the library).
+        out / rgb8: optional host arrays (rank 0).  Returns the stats dict."""
+        st = RenderStats()
+        self._check(self._lib.rtb_render_reduce(self._h, C.byref(params), _ptr(out) if out is not None else None,
+                                                _ptr(rgb8) if rgb8 is not None else None, C.c_void_p(stream), C.byref(st)))
+        return st.as_dict()
+
+    def accum_copy_device(self, device_ptr: int, stream: int = 0):
+        self._check(self._lib.rtb_accum_copy_device(self._h, C.c_void_p(device_ptr), C.c_void_p(stream)))
+
     def resolve_rgb8(self, width, height, spp):
         out = np.empty((height, width, 3), np.uint8)
         self._check(self._lib.rtb_resolve_rgb8(self._h, spp, _ptr(out)))
@@ -227,3 +273,64 @@ class Context:
         self._check(self._lib.rtb_texture_eval_batch(self._h, texture, _ptr(uvp), uvp.shape[0], precision,
                                                      _ptr(out)))
         return out
+
+
+class Group:
+    """One rtb_group: several GPUs driven from this process (one host thread, stream and NCCL
+    communicator per device inside the library)."""
+
+    def __init__(self, devices):
+        self._lib = load()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        rc = self._lib.rtb_group_create(C.cast(devs, C.c_void_p), len(devices), C.byref(h))
+        if rc != RTB_OK:
+            raise RtbError(rc, self._lib.rtb_last_error(None).decode())
+        self._h = h
+        self.devices = list(devices)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rtb_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != RTB_OK:
+            raise RtbError(rc, self._lib.rtb_group_last_error(self._h).decode())
+
+    def size(self) -> int:
+        return self._lib.rtb_group_size(self._h)
+
+    def set_option(self, option: int, value: int):
+        for i in range(self.size()):
+            rc = self._lib.rtb_set_option(self._lib.rtb_group_context(self._h, i), option, value)
+            if rc != RTB_OK:
+                raise RtbError(rc, "rtb_set_option")
+
+    def upload_scene(self, blob: bytes):
+        buf = C.create_string_buffer(blob, len(blob))
+        self._check(self._lib.rtb_group_scene_upload(self._h, C.cast(buf, C.c_void_p), len(blob)))
+
+    def render(self, params: RenderParams, out=None, rgb8=None, want_accum=True):
+        """The whole job on all GPUs.  Returns (accum[h, w, 4] float32 linear SUMS or None, stats)."""
+        if out is None and want_accum:
+            out = np.empty((params.height, params.width, 4), np.float32)
+        st = RenderStats()
+        self._check(self._lib.rtb_group_render(self._h, C.byref(params), _ptr(out) if out is not None else None,
+                                               _ptr(rgb8) if rgb8 is not None else None, C.byref(st)))
+        return out, st.as_dict()
+
+    def cancel(self):
+        self._check(self._lib.rtb_group_cancel(self._h))

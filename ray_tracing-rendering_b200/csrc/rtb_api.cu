@@ -107,6 +107,54 @@ int check_batch(rtb_context *ctx, const void *in, const void *out, uint64_t n, i
 
 } // namespace
 
+namespace rtb {
+
+int check_render_params(rtb_context *ctx, const rtb_render_params *p) { return check_params(ctx, p); }
+
+// blob -> host tables (BVH build included); throws std::runtime_error("scene: ...") on a bad blob
+std::shared_ptr<const HostScene> build_scene_for(rtb_context *ctx, const void *blob, uint64_t nbytes) {
+    try {
+        SceneView view(blob, nbytes);
+        return std::make_shared<const HostScene>(
+            build_host_scene(view, ctx->opt_max_leaf, 0.01 * ctx->opt_trav_cost_pct, ctx->opt_layout_dfs != 0));
+    } catch (const CudaError &) {
+        throw;
+    } catch (const std::exception &e) {
+        throw std::runtime_error(std::string("scene: ") + e.what());
+    }
+}
+
+void upload_scene(rtb_context *ctx, std::shared_ptr<const HostScene> host) {
+    std::unique_ptr<DeviceScene> sc(new DeviceScene(std::move(host)));
+    const HostScene &H = sc->host;
+    cudaStream_t s = ctx->stream;
+    size_t bytes = 0;
+    upload_typed(sc->f32, H.f32, s, bytes);
+    upload_typed(sc->f64, H.f64, s, bytes);
+    sc->nodes.upload(H.nodes, s);
+    sc->chains.upload(H.chains, s);
+    sc->affine.upload(H.affine, s);
+    sc->prim_chain.upload(H.prim_chain, s);
+    sc->prim_orig.upload(H.prim_orig, s);
+    sc->orig_to_sorted.upload(H.orig_to_sorted, s);
+    sc->images.upload(H.images, s);
+    sc->image_bytes.upload(H.image_bytes, s);
+    sc->env_texels.upload(H.env_texels, s);
+    sc->env_tables.upload(H.env_tables, s);
+    sc->wide_nodes.upload(H.wide.qnodes, s);
+    sc->wide_chain_root.upload(H.wide.chain_root, s);
+    bytes += sc->wide_nodes.bytes() + sc->wide_chain_root.bytes();
+    bytes += sc->nodes.bytes() + sc->chains.bytes() + sc->prim_chain.bytes() + sc->prim_orig.bytes() +
+             sc->orig_to_sorted.bytes() + sc->images.bytes() + sc->image_bytes.bytes() +
+             sc->env_texels.bytes() + sc->env_tables.bytes();
+    sc->device_bytes = bytes;
+    RTB_CUDA(cudaStreamSynchronize(s));
+    ctx->scene = std::move(sc);
+    ++ctx->scene_serial;
+}
+
+} // namespace rtb
+
 extern "C" {
 
 const char *rtb_version(void) { return "rtb200 0.1.0 sm_100a"; }
@@ -154,6 +202,7 @@ void rtb_context_destroy(rtb_context *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream)
         cudaStreamSynchronize(ctx->stream);
+    rtb_comm_release(ctx);
     wavefront_release(ctx);
     ctx->scene.reset();
     ctx->accum.release();
@@ -191,42 +240,7 @@ int rtb_scene_upload(rtb_context *ctx, const void *blob, uint64_t nbytes) {
         return RTB_ERR_INVALID_ARGUMENT;
     if (!blob)
         return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_scene_upload: blob is NULL");
-    return guarded(ctx, [&] {
-        std::unique_ptr<DeviceScene> sc(new DeviceScene());
-        try {
-            SceneView view(blob, nbytes);
-            sc->host = build_host_scene(view, ctx->opt_max_leaf, 0.01 * ctx->opt_trav_cost_pct, ctx->opt_layout_dfs != 0);
-        } catch (const CudaError &) {
-            throw;
-        } catch (const std::exception &e) {
-            throw std::runtime_error(std::string("scene: ") + e.what());
-        }
-        const HostScene &H = sc->host;
-        cudaStream_t s = ctx->stream;
-        size_t bytes = 0;
-        upload_typed(sc->f32, H.f32, s, bytes);
-        upload_typed(sc->f64, H.f64, s, bytes);
-        sc->nodes.upload(H.nodes, s);
-        sc->chains.upload(H.chains, s);
-        sc->affine.upload(H.affine, s);
-        sc->prim_chain.upload(H.prim_chain, s);
-        sc->prim_orig.upload(H.prim_orig, s);
-        sc->orig_to_sorted.upload(H.orig_to_sorted, s);
-        sc->images.upload(H.images, s);
-        sc->image_bytes.upload(H.image_bytes, s);
-        sc->env_texels.upload(H.env_texels, s);
-        sc->env_tables.upload(H.env_tables, s);
-        sc->wide_nodes.upload(H.wide.nodes, s);
-        sc->wide_chain_root.upload(H.wide.chain_root, s);
-        bytes += sc->wide_nodes.bytes() + sc->wide_chain_root.bytes();
-        bytes += sc->nodes.bytes() + sc->chains.bytes() + sc->prim_chain.bytes() + sc->prim_orig.bytes() +
-                 sc->orig_to_sorted.bytes() + sc->images.bytes() + sc->image_bytes.bytes() +
-                 sc->env_texels.bytes() + sc->env_tables.bytes();
-        sc->device_bytes = bytes;
-        RTB_CUDA(cudaStreamSynchronize(s));
-        ctx->scene = std::move(sc);
-        ++ctx->scene_serial;
-    });
+    return guarded(ctx, [&] { upload_scene(ctx, build_scene_for(ctx, blob, nbytes)); });
 }
 
 int rtb_scene_get_stats(rtb_context *ctx, rtb_scene_stats *out) {

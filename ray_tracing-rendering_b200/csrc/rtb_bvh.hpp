@@ -58,7 +58,8 @@ struct Box {
 struct BuildItem {
     Box box;
     uint32_t id;
-    bool solitary; // must be alone in its leaf (instances)
+    bool solitary;         // must be alone in its leaf (instances, primitives kept out of the wide tree)
+    bool instance = false; // the item is an instance record: its leaf ref carries kLeafInstanceFlag
 };
 
 struct BuildResult {
@@ -183,7 +184,7 @@ inline BuildResult build_bvh(const std::vector<BuildItem> &items, int max_leaf, 
         if (count < 1 || count > uint32_t(kMaxLeafPrims) || first > kLeafFirstMask - 2)
             throw std::runtime_error("bvh: leaf does not fit the node reference encoding");
         nd.ref = kLeafFlag | ((count - 1) << 27) | first;
-        if (count == 1 && items[idx[t.begin]].solitary)
+        if (count == 1 && items[idx[t.begin]].instance)
             nd.ref |= kLeafInstanceFlag;
         nd.count = count;
     };

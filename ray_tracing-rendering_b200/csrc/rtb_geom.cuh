@@ -33,6 +33,11 @@ enum : uint32_t {
     PT_INSTANCE = 6,
     PT_TYPE_MASK = 7,
     PT_DUP_LEAF = 8, // reference tests this object twice per ray (bvh.h:68-69)
+    // bits 4-6: the hit queue a path that hits this primitive goes to (its material's type, or 6 for
+    // a lambertian with a procedural / image albedo) — baked in at upload so that sorting hits by
+    // material costs no look-up: the traversal already holds the record of the primitive it hit
+    PT_KEY_SHIFT = 4,
+    PT_KEY_MASK = 7,
     PT_MAT_SHIFT = 8
 };
 

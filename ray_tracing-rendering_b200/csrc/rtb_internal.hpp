@@ -68,7 +68,11 @@ template <class R> struct DeviceTyped {
 };
 
 struct DeviceScene {
-    HostScene host; // kept for ids, counts and the host-side maps
+    // kept for ids, counts and the host-side maps; shared between the contexts of a multi-GPU group
+    // (the BVH is built once, the tables are uploaded to every device)
+    std::shared_ptr<const HostScene> host_ptr;
+    const HostScene &host;
+    explicit DeviceScene(std::shared_ptr<const HostScene> h) : host_ptr(std::move(h)), host(*host_ptr) {}
     DeviceTyped<float> f32;
     DeviceTyped<double> f64;
     DeviceBuffer nodes, chains, affine, prim_chain, prim_orig, orig_to_sorted, images, image_bytes, env_texels,
@@ -101,7 +105,10 @@ struct DeviceScene {
         w.nodes = wide_nodes.as<Vec4f>();
         w.chain_root = wide_chain_root.as<uint32_t>();
         w.root_ref = host.wide.root_ref;
-        w.n_nodes = uint32_t(host.wide.nodes.size());
+        w.n_nodes = uint32_t(host.wide.qnodes.size());
+        w.n_global = uint32_t(host.wide.global_prims.size());
+        for (int i = 0; i < kMaxGlobalPrims; ++i)
+            w.global_prim[i] = size_t(i) < host.wide.global_prims.size() ? host.wide.global_prims[size_t(i)] : 0u;
         return w;
     }
     template <class R> ShadeView<R> shade() const {
@@ -144,6 +151,11 @@ struct rtb_context {
     int opt_trav_cost_pct = 100; // RTB_OPT_BVH_TRAVERSAL_COST_PCT
     int opt_layout_dfs = 0;      // RTB_OPT_BVH_LAYOUT_DFS
     int opt_binary_traversal = 0; // RTB_OPT_BINARY_TRAVERSAL: round 1's per-chunk while-while kernels (A/B measurements)
+    // multi-GPU (rtb_multi.cu): this context's rank in an NCCL communicator and its staging buffers
+    void *comm = nullptr; // ncclComm_t
+    int comm_rank = 0, comm_size = 1;
+    bool comm_owned = false;           // created by rtb_comm_init (a group owns its communicators itself)
+    rtb::DeviceBuffer stage_send, stage_recv, stage_out, stage_rgb8;
 };
 
 namespace rtb {
@@ -163,6 +175,11 @@ void launch_light_eval(rtb_context *ctx, int light, const rtb_light_query *d_q, 
                        rtb_light_value *d_out);
 template <class R>
 void launch_texture_eval(rtb_context *ctx, int texture, const double *d_uvp, uint64_t n, double *d_rgb);
+
+// rtb_api.cu
+std::shared_ptr<const HostScene> build_scene_for(rtb_context *ctx, const void *blob, uint64_t nbytes);
+void upload_scene(rtb_context *ctx, std::shared_ptr<const HostScene> host); // copies the tables to ctx's device
+int check_render_params(rtb_context *ctx, const rtb_render_params *p);
 
 // rtb_wavefront.cu
 void wavefront_render(rtb_context *ctx, const rtb_render_params &p, float4 *d_accum, cudaStream_t stream,

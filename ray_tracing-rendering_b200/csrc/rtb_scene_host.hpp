@@ -10,6 +10,7 @@
 #include "rtb_shading.cuh"
 #include "rtb_wide.cuh"
 
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <stdexcept>
@@ -354,6 +355,31 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double t
         else
             top.push_back(it);
     }
+    // "Global" primitives: at most kMaxGlobalPrims top-level primitives whose boxes dwarf what is left
+    // of the scene without them (a ground sphere, the boundary of a world-filling fog).  They stay in
+    // the binary tree (alone in their leaves) but are left out of the 4-wide tree the production
+    // kernels walk, which test them up front for every ray (rtb_wide.cuh build_wide).
+    std::vector<uint32_t> global_ids;
+    if (top.size() > 8) {
+        Box all;
+        for (const BuildItem &it : top)
+            all.grow(it.box);
+        std::vector<size_t> cand;
+        for (size_t i = 0; i < top.size(); ++i)
+            if (top[i].box.area() >= 0.25 * all.area())
+                cand.push_back(i);
+        if (!cand.empty() && cand.size() <= size_t(kMaxGlobalPrims)) {
+            Box rest;
+            for (size_t i = 0; i < top.size(); ++i)
+                if (std::find(cand.begin(), cand.end(), i) == cand.end())
+                    rest.grow(top[i].box);
+            if (rest.valid() && rest.area() <= 0.5 * all.area())
+                for (size_t i : cand) {
+                    top[i].solitary = true;
+                    global_ids.push_back(top[i].id);
+                }
+        }
+    }
     // instances join the top level with their world-space bounds
     struct Inst {
         int chain;
@@ -369,6 +395,7 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double t
         ti.box = box_to_world(in.obj_box, X, C[in.chain].first, C[in.chain].count);
         ti.id = uint32_t(np + insts.size()); // ids >= np denote instances
         ti.solitary = true;
+        ti.instance = true;
         top.push_back(ti);
         insts.push_back(in);
     }
@@ -494,6 +521,17 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double t
         H.f64.mats.push_back(d);
         H.f32.mats.push_back(f);
     }
+    // hit-queue key of every primitive (PT_KEY_SHIFT): material type, or 6 for textured lambertians
+    for (size_t i = 0; i < H.f32.prims.size(); ++i) {
+        if ((H.f32.prims[i].type_mat & PT_TYPE_MASK) == PT_INSTANCE)
+            continue;
+        const MatT<float> &m = H.f32.mats[H.f32.prims[i].type_mat >> PT_MAT_SHIFT];
+        uint32_t key = uint32_t(m.type);
+        if (m.type == RTB_MAT_LAMBERTIAN && !(m.flags & 2))
+            key = uint32_t(RTB_MAT_TYPE_COUNT);
+        H.f32.prims[i].type_mat |= key << PT_KEY_SHIFT;
+        H.f64.prims[i].type_mat |= key << PT_KEY_SHIFT;
+    }
     for (uint64_t i = 0; i < S.n_textures(); ++i) {
         const rtb_texture &t = S.textures()[i];
         TexT<double> d;
@@ -583,7 +621,10 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double t
     }
 
     // the production traversal's tree (rtb_trace.cuh)
-    H.wide = build_wide(H.nodes, H.root_ref, H.f32.prims.data(), H.f32.prims.size(), H.chains.size());
+    std::vector<uint32_t> globals;
+    for (uint32_t id : global_ids)
+        globals.push_back(uint32_t(H.orig_to_sorted[id]));
+    H.wide = build_wide(H.nodes, H.root_ref, H.f32.prims.data(), H.f32.prims.size(), H.chains.size(), globals);
     if (wide_stack_need(H.wide) > kWideStack)
         throw std::runtime_error("scene: BVH of depth " + std::to_string(H.wide.max_depth) +
                                  " exceeds the traversal stack (kWideStack)");

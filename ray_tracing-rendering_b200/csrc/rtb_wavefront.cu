@@ -1327,7 +1327,7 @@ __global__ void __launch_bounds__(kWfBlock, RTB_EXTEND_MIN_BLOCKS) k_connect(WfP
 #define RTB_TRACE_MIN_BLOCKS 3 // resident CTAs of 256 threads per SM the traversal kernels are compiled for
 #endif
 #ifndef RTB_TRACE_TOP
-#define RTB_TRACE_TOP 1 // stage the top levels of the tree in shared memory
+#define RTB_TRACE_TOP 0 // stage the top levels of the tree in shared memory (measured: no gain)
 #endif
 constexpr int kTraceBlock = 256;
 constexpr bool kTraceTop = RTB_TRACE_TOP != 0;
@@ -1335,59 +1335,50 @@ constexpr bool kTraceTop = RTB_TRACE_TOP != 0;
 // Cooperative copy of the first nodes of the (breadth-first) tree; returns how many were staged.
 __device__ __forceinline__ uint32_t stage_top_nodes(const WideView &w, Vec4f *s_top) {
     const uint32_t n_top = kTraceTop ? (w.n_nodes < uint32_t(kTopNodesMax) ? w.n_nodes : uint32_t(kTopNodesMax)) : 0u;
-    for (uint32_t i = threadIdx.x; i < n_top * 8u; i += blockDim.x)
-        s_top[i] = __ldg(w.nodes + i);
+    for (uint32_t i = threadIdx.x; i < n_top * kNodeRows; i += blockDim.x)
+        s_top[(i / kNodeRows) * kTopStride + (i % kNodeRows)] = __ldg(w.nodes + i);
     return n_top;
 }
 
-// hit-queue key of a traced ray: the miss queue, or the queue of the material type it hit
-__device__ __forceinline__ uint32_t hit_key(const WfParams &p, uint32_t pi) {
-    if (pi == kNoPrim)
-        return uint32_t(kMissKey);
-    const MatT<float> &hm = p.shade.mats[p.geom.prims[pi].type_mat >> PT_MAT_SHIFT];
-    uint32_t key = uint32_t(hm.type);
-    if (key == RTB_MAT_LAMBERTIAN && !(hm.flags & 2))
-        key = uint32_t(kTexturedKey);
-    return key;
-}
+__device__ __forceinline__ uint32_t total_warps() { return gridDim.x * (blockDim.x >> 5); }
 
 template <bool MEDIA> struct ExtendJob {
     const WfParams &p;
     Counters &C;
     const int buf;
-    const uint32_t n; // entries of this iteration's extend queue
+    const uint32_t n;   // entries of this iteration's extend queue
+    const uint32_t warps;
+    uint32_t win = 0;   // size of the window being walked
     uint32_t base = 0, cnt = 0, off8 = 0;
     unsigned long long sample_base = 0;
     uint32_t n_new = 0; // camera samples this warp started (kept by lane 0)
-    __device__ ExtendJob(const WfParams &p_, Counters &C_, int buf_, uint32_t n_) : p(p_), C(C_), buf(buf_), n(n_) {}
+    __device__ ExtendJob(const WfParams &p_, Counters &C_, int buf_, uint32_t n_)
+        : p(p_), C(C_), buf(buf_), n(n_), warps(total_warps()) {}
 
     __device__ __forceinline__ bool next_window(TraceWarpSmem &s, uint32_t &count) {
         const uint32_t lane = lane_id();
+        win = guided_window(n, warps, base, win);
         uint32_t b = 0;
         if (lane == 0)
-            b = atomicAdd(&C.head_ext.v[0], uint32_t(kTraceWindow));
+            b = atomicAdd(&C.head_ext.v[0], win);
         b = __shfl_sync(kFullMask, b, 0);
         if (b >= n)
             return false;
         base = b;
-        cnt = n - b < uint32_t(kTraceWindow) ? n - b : uint32_t(kTraceWindow);
-        // sort keys: direction octant of a live path, 8 for an empty entry (a camera sample starts there)
-        uint32_t n_empty = 0;
-        for (uint32_t r = 0; r < uint32_t(kTraceRounds); ++r) {
-            const uint32_t j = r * 32u + lane;
-            uint32_t key = kSkipKey;
-            if (j < cnt) {
-                if (__float_as_uint(p.ext_c[buf][b + j].w) == kInvalidPix) {
-                    key = 8u;
-                } else {
-                    const float4 d = p.ext_b[buf][b + j];
-                    key = RTB_TRACE_SORT ? octant_of(d.x, d.y, d.z) : 0u;
-                }
-                s.key[j] = uint8_t(key);
-            }
-            n_empty += __popc(__ballot_sync(kFullMask, key == 8u));
+        cnt = n - b < win ? n - b : win;
+        // sort keys: direction octant of a live path, 8 for an empty entry (a camera sample starts there).
+        // Loads only in this loop: they overlap.
+        const float4 *qc = p.ext_c[buf] + b, *qb = p.ext_b[buf] + b;
+#pragma unroll 4
+        for (uint32_t j = lane; j < cnt; j += 32u) {
+            const uint32_t pix = __float_as_uint(reinterpret_cast<const float *>(qc + j)[3]);
+            const float4 d = qb[j];
+            s.key[j] = uint8_t(pix == kInvalidPix ? kFreshKey : (RTB_TRACE_SORT ? octant_of(d.x, d.y, d.z) : 0u));
         }
+        __syncwarp();
+        window_hist(s, cnt, 9u);
         // camera samples for the empty entries: ONE global atomic per window
+        const uint32_t n_empty = s.hist[kFreshKey];
         unsigned long long sb = 0;
         if (n_empty && lane == 0)
             sb = atomicAdd(&p.glob->next_sample, (unsigned long long)n_empty);
@@ -1398,102 +1389,107 @@ template <bool MEDIA> struct ExtendJob {
         sample_base = sb;
         if (lane == 0)
             n_new += avail;
-        __syncwarp();
-        count = window_sort(s, cnt, avail, off8);
+        count = window_place(s, cnt, 9u, kFreshKey, avail);
+        off8 = s.hist[kFreshKey]; // window positions [off8, count) are the camera samples
         return true;
     }
-    __device__ __forceinline__ void fetch(TraceWarpSmem &s, uint32_t k, TravLane &L, uint32_t &tag) {
-        const uint32_t idx = base + s.perm[k];
-        tag = idx;
+    __device__ __forceinline__ void prefetch(TraceWarpSmem &s, uint32_t from, uint32_t to) {
+        const uint32_t k = from + lane_id();
+        if (k < to && k < off8) {
+            const uint32_t idx = base + s.perm[k], slot = k % kDeck;
+            async_copy<16>(&s.deck_a[slot], p.ext_a[buf] + idx);
+            async_copy<16>(&s.deck_b[slot], p.ext_b[buf] + idx);
+            if (MEDIA)
+                async_copy<8>(&s.deck_c[slot], p.ext_d[buf] + idx);
+        }
+    }
+    __device__ __forceinline__ void fetch(TraceWarpSmem &s, uint32_t k, TravLane &L, V3<float> &o, V3<float> &d,
+                                          uint32_t &tag) {
+        tag = s.perm[k];
         if (k >= off8) { // a camera sample starts in this (empty) entry: renderer.h:72-75
+            const uint32_t idx = base + tag;
             PathState st;
             new_path(p, sample_base + (k - off8), st);
             p.ext_a[buf][idx] = pack_a(st);
             p.ext_b[buf][idx] = pack_b(st);
             p.ext_c[buf][idx] = pack_c(st);
             p.ext_d[buf][idx] = pack_d(st);
-            L.wo = st.o;
-            L.wd = st.d;
+            o = st.o;
+            d = st.d;
             L.time = st.time;
             L.origin = kNoPrim;
             if (MEDIA)
                 L.rng = st.rng;
         } else {
-            const float4 a = p.ext_a[buf][idx], b = p.ext_b[buf][idx];
-            L.wo = V3<float>(a.x, a.y, a.z);
-            L.wd = V3<float>(b.x, b.y, b.z);
+            const uint32_t slot = k % kDeck;
+            const float4 a = s.deck_a[slot], b = s.deck_b[slot];
+            o = V3<float>(a.x, a.y, a.z);
+            d = V3<float>(b.x, b.y, b.z);
             L.time = a.w;
             L.origin = __float_as_uint(b.w);
             if (MEDIA) { // constant_medium::hit draws from the path's stream
-                const uint2 x = *reinterpret_cast<const uint2 *>(p.ext_d[buf] + idx);
+                const uint2 x = s.deck_c[slot];
                 L.rng.s = uint64_t(x.x) | (uint64_t(x.y) << 32);
             }
         }
         L.t_min = 0.001f;
         L.t_max = Consts<float>::inf();
     }
-    __device__ __forceinline__ void commit(uint32_t tag, const TravLane &L) {
-        p.ext_e[buf][tag] = make_float2(L.t_max, __uint_as_float(L.best));
+    __device__ __forceinline__ void world_ray(uint32_t tag, V3<float> &o, V3<float> &d) {
+        const float4 a = p.ext_a[buf][base + tag], b = p.ext_b[buf][base + tag];
+        o = V3<float>(a.x, a.y, a.z);
+        d = V3<float>(b.x, b.y, b.z);
+    }
+    __device__ __forceinline__ void commit(TraceWarpSmem &s, uint32_t tag, const TravLane &L) {
+        const uint32_t idx = base + tag;
+        p.ext_e[buf][idx] = make_float2(L.t_max, __uint_as_float(L.best));
+        s.key[tag] = uint8_t(L.best == kNoPrim ? uint32_t(kMissKey) : L.best_key);
         if (MEDIA)
-            *reinterpret_cast<uint2 *>(p.ext_d[buf] + tag) = make_uint2(uint32_t(L.rng.s), uint32_t(L.rng.s >> 32));
+            *reinterpret_cast<uint2 *>(p.ext_d[buf] + idx) = make_uint2(uint32_t(L.rng.s), uint32_t(L.rng.s >> 32));
     }
     // Every ray of the window is traced: move the paths, with their hits, into the material queues.
     __device__ __forceinline__ void finish_window(TraceWarpSmem &s) {
         const uint32_t lane = lane_id();
-        if (lane < 16)
-            s.hist[lane] = 0;
         __syncwarp();
-        for (uint32_t r = 0; r < uint32_t(kTraceRounds); ++r) {
-            const uint32_t j = r * 32u + lane;
-            uint32_t key = kSkipKey;
-            if (j < cnt && s.key[j] != kSkipKey) {
-                key = hit_key(p, __float_as_uint(p.ext_e[buf][base + j].y));
-                s.key[j] = uint8_t(key);
-            }
-            const uint32_t peers = __match_any_sync(kFullMask, key);
-            if (key < uint32_t(kKeys) && int(lane) == __ffs(peers) - 1)
-                s.hist[key] += __popc(peers);
-            __syncwarp();
-        }
-        // the window's hits enter the 8 queues with one atomic instruction (their counters share a
+        window_hist(s, cnt, uint32_t(kKeys));
+        // the window's hits enter the 8 queues with ONE atomic instruction (their counters share a
         // 128-byte line: L2 sees one transaction)
+        uint32_t gbase = 0;
         if (lane < uint32_t(kKeys)) {
             const uint32_t h = s.hist[lane];
-            s.cur[lane] = h ? atomicAdd(&C.key.v[lane], h) : 0u;
+            gbase = h ? atomicAdd(&C.key.v[lane], h) : 0u;
+        }
+        const uint32_t total = window_place(s, cnt, uint32_t(kKeys), kSkipKey, 0u); // perm: entries by hit key
+        if (lane < uint32_t(kKeys))
+            s.cur[lane] = gbase - s.hist[lane]; // queue position of window position q with key k: cur[k] + q
+        __syncwarp();
+        // copies only in this loop (no collective): the loads of consecutive trips overlap
+#pragma unroll 2
+        for (uint32_t q = lane; q < total; q += 32u) {
+            const uint32_t j = s.perm[q], key = s.key[j];
+            const uint32_t pos = s.cur[key] + q;
+            if (pos >= p.cap) { // cannot happen while the capacity bound of WavefrontPool::ensure holds
+                atomicExch(&p.glob->overflow, 1ull);
+                continue;
+            }
+            const uint32_t idx = base + j;
+            const size_t o = size_t(key) * p.cap + pos;
+            const float4 a = __ldcs(p.ext_a[buf] + idx), b = __ldcs(p.ext_b[buf] + idx), c = __ldcs(p.ext_c[buf] + idx);
+            const uint4 d = __ldcs(p.ext_d[buf] + idx);
+            const float2 e = __ldcs(p.ext_e[buf] + idx);
+            __stcs(p.hit_a + o, a);
+            __stcs(p.hit_b + o, b);
+            __stcs(p.hit_c + o, c);
+            __stcs(p.hit_d + o, d);
+            __stcs(p.hit_e + o, e);
         }
         __syncwarp();
-        for (uint32_t r = 0; r < uint32_t(kTraceRounds); ++r) {
-            const uint32_t j = r * 32u + lane;
-            const uint32_t key = j < cnt ? uint32_t(s.key[j]) : kSkipKey;
-            const uint32_t peers = __match_any_sync(kFullMask, key);
-            const int leader = __ffs(peers) - 1;
-            uint32_t pos = 0;
-            if (key < uint32_t(kKeys) && int(lane) == leader) {
-                pos = s.cur[key];
-                s.cur[key] = pos + __popc(peers);
-            }
-            pos = __shfl_sync(kFullMask, pos, leader) + __popc(peers & ((1u << lane) - 1u));
-            if (key < uint32_t(kKeys)) {
-                if (pos >= p.cap) { // cannot happen while the capacity bound of WavefrontPool::ensure holds
-                    atomicExch(&p.glob->overflow, 1ull);
-                } else {
-                    const uint32_t idx = base + j;
-                    const size_t o = size_t(key) * p.cap + pos;
-                    __stcs(p.hit_a + o, __ldcs(p.ext_a[buf] + idx));
-                    __stcs(p.hit_b + o, __ldcs(p.ext_b[buf] + idx));
-                    __stcs(p.hit_c + o, __ldcs(p.ext_c[buf] + idx));
-                    __stcs(p.hit_d + o, __ldcs(p.ext_d[buf] + idx));
-                    __stcs(p.hit_e + o, __ldcs(p.ext_e[buf] + idx));
-                }
-            }
-            __syncwarp();
-        }
     }
 };
 
 template <bool COUNT, bool MEDIA, bool INST>
 __global__ void __launch_bounds__(kTraceBlock, RTB_TRACE_MIN_BLOCKS) k_extend_w(WfParams p, int it) {
-    __shared__ Vec4f s_top[kTraceTop ? kTopNodesMax * 8 : 8];
+    __shared__ Vec4f s_top[kTraceTop ? kTopNodesMax * kTopStride : 1];
     __shared__ TraceWarpSmem s_warp[kTraceBlock / 32];
     const uint32_t n_top = stage_top_nodes(p.wide, s_top);
     Counters &C = p.ctr[it % 3];
@@ -1502,7 +1498,7 @@ __global__ void __launch_bounds__(kTraceBlock, RTB_TRACE_MIN_BLOCKS) k_extend_w(
             reinterpret_cast<uint32_t *>(&p.ctr[(it + 2) % 3])[i] = 0;
     __syncthreads();
     ExtendJob<MEDIA> job(p, C, it & 1, C.n_ext.v[0]);
-    uint64_t counters[2] = {0, 0};
+    uint64_t counters[3] = {0, 0, 0};
     uint32_t overflow = 0;
     warp_trace<ExtendJob<MEDIA>, false, MEDIA, INST, kTraceTop>(p.geom, p.wide, s_top, n_top, s_warp[threadIdx.x >> 5], job,
                                                                counters, overflow);
@@ -1517,6 +1513,7 @@ __global__ void __launch_bounds__(kTraceBlock, RTB_TRACE_MIN_BLOCKS) k_extend_w(
             atomicAdd(&p.glob->prim_tests, y);
             atomicAdd(&p.glob->extend_nodes, x);
         }
+        atomicMax(&p.glob->max_nodes_per_ray, (unsigned long long)counters[2]);
     }
 }
 
@@ -1524,48 +1521,65 @@ template <bool MEDIA> struct ConnectJob {
     const WfParams &p;
     Counters &C;
     const uint32_t n;
+    const uint32_t warps;
+    uint32_t win = 0;
     uint32_t base = 0;
     uint32_t pix = 0; // per lane: the pixel of the ray it walks
-    __device__ ConnectJob(const WfParams &p_, Counters &C_, uint32_t n_) : p(p_), C(C_), n(n_) {}
+    __device__ ConnectJob(const WfParams &p_, Counters &C_, uint32_t n_)
+        : p(p_), C(C_), n(n_), warps(total_warps()) {}
     __device__ __forceinline__ bool next_window(TraceWarpSmem &s, uint32_t &count) {
         const uint32_t lane = lane_id();
+        win = guided_window(n, warps, base, win);
         uint32_t b = 0;
         if (lane == 0)
-            b = atomicAdd(&C.head_shadow.v[0], uint32_t(kTraceWindow));
+            b = atomicAdd(&C.head_shadow.v[0], win);
         b = __shfl_sync(kFullMask, b, 0);
         if (b >= n)
             return false;
         base = b;
-        const uint32_t cnt = n - b < uint32_t(kTraceWindow) ? n - b : uint32_t(kTraceWindow);
-        for (uint32_t r = 0; r < uint32_t(kTraceRounds); ++r) {
-            const uint32_t j = r * 32u + lane;
-            if (j < cnt) {
-                const float4 d = p.sh_b[b + j];
-                s.key[j] = uint8_t(RTB_TRACE_SORT ? octant_of(d.x, d.y, d.z) : 0u);
-            }
+        const uint32_t cnt = n - b < win ? n - b : win;
+#pragma unroll 4
+        for (uint32_t j = lane; j < cnt; j += 32u) {
+            const float4 d = p.sh_b[b + j];
+            s.key[j] = uint8_t(RTB_TRACE_SORT ? octant_of(d.x, d.y, d.z) : 0u);
         }
         __syncwarp();
-        uint32_t off8;
-        count = window_sort(s, cnt, 0u, off8);
+        window_hist(s, cnt, 8u);
+        count = window_place(s, cnt, 8u, kSkipKey, 0u);
         return true;
     }
-    __device__ __forceinline__ void fetch(TraceWarpSmem &s, uint32_t k, TravLane &L, uint32_t &tag) {
-        const uint32_t idx = base + s.perm[k];
+    __device__ __forceinline__ void prefetch(TraceWarpSmem &s, uint32_t from, uint32_t to) {
+        const uint32_t k = from + lane_id();
+        if (k < to) {
+            const uint32_t idx = base + s.perm[k], slot = k % kDeck;
+            async_copy<16>(&s.deck_a[slot], p.sh_a + idx);
+            async_copy<16>(&s.deck_b[slot], p.sh_b + idx);
+            async_copy<4>(&s.deck_c[slot], reinterpret_cast<const float *>(p.sh_c + idx) + 3);
+        }
+    }
+    __device__ __forceinline__ void fetch(TraceWarpSmem &s, uint32_t k, TravLane &L, V3<float> &o, V3<float> &d,
+                                          uint32_t &tag) {
+        const uint32_t idx = base + s.perm[k], slot = k % kDeck;
         tag = idx;
-        const float4 a = __ldcs(p.sh_a + idx), b = __ldcs(p.sh_b + idx);
-        L.wo = V3<float>(a.x, a.y, a.z);
-        L.wd = V3<float>(b.x, b.y, b.z);
+        const float4 a = s.deck_a[slot], b = s.deck_b[slot];
+        o = V3<float>(a.x, a.y, a.z);
+        d = V3<float>(b.x, b.y, b.z);
         pix = __float_as_uint(b.w);
         L.time = 0.0f; // shadow rays carry time 0 (direct_light_integrator.h:115)
-        L.origin = __float_as_uint(p.sh_c[idx].w);
+        L.origin = s.deck_c[slot].x;
         // t_min is 0.001 along the UNIT direction; the stored direction may be the unnormalised segment
-        const float len = isfinite(a.w) ? length(L.wd) : 1.0f;
+        const float len = isfinite(a.w) ? length(d) : 1.0f;
         L.t_min = 0.001f / len;
         L.t_max = a.w;
         if (MEDIA) // media on a shadow ray draw from a stream keyed by the queue entry
             L.rng = pcg_seed((uint64_t(__float_as_uint(a.x)) << 32) ^ __float_as_uint(b.y), p.seed ^ idx);
     }
-    __device__ __forceinline__ void commit(uint32_t tag, const TravLane &L) {
+    __device__ __forceinline__ void world_ray(uint32_t tag, V3<float> &o, V3<float> &d) {
+        const float4 a = p.sh_a[tag], b = p.sh_b[tag];
+        o = V3<float>(a.x, a.y, a.z);
+        d = V3<float>(b.x, b.y, b.z);
+    }
+    __device__ __forceinline__ void commit(TraceWarpSmem &, uint32_t tag, const TravLane &L) {
         if (L.best == kNoPrim) { // unoccluded: the (already weighted) contribution counts
             const float4 c = __ldcs(p.sh_c + tag);
             accum_add(p.accum, pix, V3<float>(c.x, c.y, c.z));
@@ -1576,7 +1590,7 @@ template <bool MEDIA> struct ConnectJob {
 
 template <bool COUNT, bool MEDIA, bool INST>
 __global__ void __launch_bounds__(kTraceBlock, RTB_TRACE_MIN_BLOCKS) k_connect_w(WfParams p, int it) {
-    __shared__ Vec4f s_top[kTraceTop ? kTopNodesMax * 8 : 8];
+    __shared__ Vec4f s_top[kTraceTop ? kTopNodesMax * kTopStride : 1];
     __shared__ TraceWarpSmem s_warp[kTraceBlock / 32];
     const uint32_t n_top = stage_top_nodes(p.wide, s_top);
     Counters &C = p.ctr[it % 3];
@@ -1585,7 +1599,7 @@ __global__ void __launch_bounds__(kTraceBlock, RTB_TRACE_MIN_BLOCKS) k_connect_w
         atomicAdd(&p.glob->rays_shadow, (unsigned long long)n);
     __syncthreads();
     ConnectJob<MEDIA> job(p, C, n);
-    uint64_t counters[2] = {0, 0};
+    uint64_t counters[3] = {0, 0, 0};
     uint32_t overflow = 0;
     warp_trace<ConnectJob<MEDIA>, true, MEDIA, INST, kTraceTop>(p.geom, p.wide, s_top, n_top, s_warp[threadIdx.x >> 5], job,
                                                                counters, overflow);
@@ -1616,11 +1630,11 @@ __global__ void k_batch_rays_in(const rtb_ray *__restrict__ rays, uint32_t n, co
 template <bool ANY>
 __global__ void __launch_bounds__(kTraceBlock, RTB_TRACE_MIN_BLOCKS)
     k_trace_batch_w(GeomView<float> g, WideView w, BatchTraceJob job, unsigned long long *visits, uint32_t *flag) {
-    __shared__ Vec4f s_top[kTraceTop ? kTopNodesMax * 8 : 8];
+    __shared__ Vec4f s_top[kTraceTop ? kTopNodesMax * kTopStride : 1];
     __shared__ TraceWarpSmem s_warp[kTraceBlock / 32];
     const uint32_t n_top = stage_top_nodes(w, s_top);
     __syncthreads();
-    uint64_t counters[2] = {0, 0};
+    uint64_t counters[3] = {0, 0, 0};
     uint32_t overflow = 0;
     warp_trace<BatchTraceJob, ANY, true, true, kTraceTop>(g, w, s_top, n_top, s_warp[threadIdx.x >> 5], job, counters, overflow);
     if (overflow)
@@ -2351,12 +2365,13 @@ void launch_trace_wide_batch(rtb_context *ctx, const rtb_ray *d_rays, uint64_t n
     job.head = misc.as<uint32_t>();
     job.base = 0;
     job.seed = 0x51ed270b;
+    const int grid = sms * (any_hit ? blocks_per_sm(k_trace_batch_w<true>, kTraceBlock) : blocks_per_sm(k_trace_batch_w<false>, kTraceBlock));
+    job.win = 0;
+    job.warps = uint32_t(grid) * (kTraceBlock / 32);
     if (any_hit)
-        k_trace_batch_w<true><<<sms * blocks_per_sm(k_trace_batch_w<true>, kTraceBlock), kTraceBlock, 0, st>>>(
-            g, sc.wide(), job, d_visits, misc.as<uint32_t>() + 1);
+        k_trace_batch_w<true><<<grid, kTraceBlock, 0, st>>>(g, sc.wide(), job, d_visits, misc.as<uint32_t>() + 1);
     else
-        k_trace_batch_w<false><<<sms * blocks_per_sm(k_trace_batch_w<false>, kTraceBlock), kTraceBlock, 0, st>>>(
-            g, sc.wide(), job, d_visits, misc.as<uint32_t>() + 1);
+        k_trace_batch_w<false><<<grid, kTraceBlock, 0, st>>>(g, sc.wide(), job, d_visits, misc.as<uint32_t>() + 1);
     k_batch_hits_out<<<sms * 4, 256, 0, st>>>(g, d_rays, res.as<float2>(), uint32_t(n), d_hits);
     RTB_CUDA(cudaGetLastError());
     uint32_t flag = 0;

@@ -15,6 +15,7 @@
 
 #include "rtb_geom.cuh"
 
+#include <cmath>
 #include <limits>
 #include <vector>
 
@@ -38,12 +39,34 @@ static_assert(sizeof(Node128) == 128, "wide BVH node must be 128 bytes");
 // descent pushes at most three siblings per level and one marker per instance entered; the scene
 // upload refuses a tree that could need more (wide_stack_need).
 constexpr int kWideStack = 64;
+constexpr int kMaxGlobalPrims = 4; // primitives left out of the wide tree and tested for every ray
+
+// The node the kernels fetch: the same four children in 64 bytes.  Child boxes are quantised to 8 bits
+// per plane on a grid laid over the node's own box (origin o, cell size s per axis, plane = o + q s),
+// rounded outwards, so a ray that enters a child's exact box always enters its quantised one; the
+// primitive tests are unchanged, hence so is every hit.  Why: ncu showed the fp32 128-byte node
+// binding on the L1 data pipe (seven 16-byte rows = seven wavefronts per lane and step, 78 % of
+// the L1 cycles on the 1 M-sphere field); four rows cut the wavefronts, the tree's cache footprint
+// and the registers a step holds in flight by 40-50 %.
+//   row 0: o.x o.y o.z s.x          row 1: lo.x[4] lo.y[4] lo.z[4] hi.x[4]   (bytes, child 0..3)
+//   row 2: hi.y[4] hi.z[4] s.y s.z  row 3: ref[4]
+// Unused slots: lo = 255, hi = 0 (inverted: no ray enters) and kEmptyRef.
+struct alignas(64) QNode64 {
+    float ox, oy, oz, sx;
+    uint32_t lox, loy, loz, hix;
+    uint32_t hiy, hiz;
+    float sy, sz;
+    uint32_t ref[4];
+};
+static_assert(sizeof(QNode64) == 64, "quantised wide BVH node must be 64 bytes");
 
 struct WideTree {
+    std::vector<QNode64> qnodes;      // nodes[] quantised: what the device holds
     std::vector<Node128> nodes;       // [top-level tree, breadth first][bottom-level tree of chain 0]...
     uint32_t root_ref = kEmptyRef;    // of the top-level tree
     std::vector<uint32_t> chain_root; // per wrapper chain: root ref of that instance's bottom-level tree (kEmptyRef: none)
     uint64_t n_children = 0;          // occupied child slots (n_children / nodes.size() = mean arity)
+    std::vector<uint32_t> global_prims; // sorted primitive indices left OUT of the tree (see build_wide): tested for every ray
     uint32_t n_top_nodes = 0;         // nodes of the top-level tree = nodes[0 .. n_top_nodes)
     int max_depth = 0;                // deepest wide node (root = 1), top level + bottom level
 };
@@ -51,11 +74,22 @@ struct WideTree {
 // Collapses the binary tree under `ref2` (Node32 refs are global indices into `nodes2`) and
 // appends its nodes to `out` in breadth-first order.  A node keeps absorbing the children of its
 // largest interior child (by surface area) until it has four children or only leaves.
-inline uint32_t collapse_wide(const std::vector<Node32> &nodes2, uint32_t ref2, WideTree &out, int *depth_out = nullptr) {
+// `skip`: sorted primitive indices whose (single-primitive) leaves are left out of the wide tree.
+inline uint32_t collapse_wide(const std::vector<Node32> &nodes2, uint32_t ref2, WideTree &out, int *depth_out = nullptr,
+                              const std::vector<uint32_t> *skip = nullptr) {
     if (depth_out)
         *depth_out = 0;
+    auto skipped = [&](uint32_t ref) {
+        if (!skip || !(ref & kLeafFlag) || ref == kEmptyRef || ((ref >> 27) & 15u) != 0)
+            return false;
+        const uint32_t first = ref & kLeafFirstMask;
+        for (uint32_t g : *skip)
+            if (g == first)
+                return true;
+        return false;
+    };
     if (ref2 & kLeafFlag) // leaves (and kEmptyRef) keep their ref
-        return ref2;
+        return skipped(ref2) ? kEmptyRef : ref2;
     struct Child {
         float lo[3], hi[3];
         uint32_t ref;
@@ -85,9 +119,16 @@ inline uint32_t collapse_wide(const std::vector<Node32> &nodes2, uint32_t ref2, 
     for (size_t head = 0; head < queue.size(); ++head) {
         const Pending cur = queue[head];
         deepest = cur.depth > deepest ? cur.depth : deepest;
-        Child ch[4] = {child_of(cur.ref2), child_of(cur.ref2 + 1)};
+        Child ch[5] = {child_of(cur.ref2), child_of(cur.ref2 + 1)};
         int n = 2;
-        while (n < 4) {
+        for (;;) {
+            for (int i = 0; i < n;) // drop the leaves of left-out primitives
+                if (skipped(ch[i].ref))
+                    ch[i] = ch[--n];
+                else
+                    ++i;
+            if (n >= 4)
+                break;
             int pick = -1;
             for (int i = 0; i < n; ++i)
                 if (!(ch[i].ref & kLeafFlag) && (pick < 0 || area(ch[i]) > area(ch[pick])))
@@ -124,13 +165,21 @@ inline uint32_t collapse_wide(const std::vector<Node32> &nodes2, uint32_t ref2, 
     return root;
 }
 
+inline void quantize_wide(WideTree &w);
+
 // The whole scene: the top-level tree first, then the bottom-level tree of every instance record.
+// `globals`: top-level primitives (sorted indices, each alone in its leaf) whose boxes dwarf the rest of
+// the scene — a ground sphere of radius 1000 under a field of spheres of radius 0.2, the boundary of
+// a fog that fills the world.  Every ray meets their box anyway, so the kernels test them once, up
+// front, with all refilled lanes in step, and the tree (and its quantisation grids, which span a
+// node's children) is built over the remaining primitives only.
 template <class R>
 inline WideTree build_wide(const std::vector<Node32> &nodes2, uint32_t root_ref2, const PrimT<R> *prims, size_t n_prims,
-                           size_t n_chains) {
+                           size_t n_chains, const std::vector<uint32_t> &globals = std::vector<uint32_t>()) {
     WideTree w;
+    w.global_prims = globals;
     int top_depth = 0, deepest_bottom = 0;
-    w.root_ref = collapse_wide(nodes2, root_ref2, w, &top_depth);
+    w.root_ref = collapse_wide(nodes2, root_ref2, w, &top_depth, globals.empty() ? nullptr : &globals);
     w.n_top_nodes = uint32_t(w.nodes.size());
     w.chain_root.assign(n_chains, kEmptyRef);
     for (size_t i = 0; i < n_prims; ++i)
@@ -140,10 +189,70 @@ inline WideTree build_wide(const std::vector<Node32> &nodes2, uint32_t root_ref2
             deepest_bottom = d > deepest_bottom ? d : deepest_bottom;
         }
     w.max_depth = top_depth + deepest_bottom;
+    quantize_wide(w);
     return w;
 }
 
 inline int wide_stack_need(const WideTree &w) { return 3 * w.max_depth + 2; }
+
+// nodes[] -> qnodes[].  The grid of a node spans the union of its children's (already padded) boxes;
+// a quarter cell of slack on top of the outward rounding covers the rounding of the kernel's decode
+// (qnode_slabs: four fp32 roundings on values of the size of t).
+inline void quantize_wide(WideTree &w) {
+    w.qnodes.resize(w.nodes.size());
+    for (size_t n = 0; n < w.nodes.size(); ++n) {
+        const Node128 &src = w.nodes[n];
+        QNode64 q;
+        float o[3], s[3];
+        for (int k = 0; k < 3; ++k) {
+            float lo = std::numeric_limits<float>::infinity(), hi = -lo;
+            for (int i = 0; i < 4; ++i)
+                if (src.ref[i] != kEmptyRef) {
+                    lo = src.lo[k][i] < lo ? src.lo[k][i] : lo;
+                    hi = src.hi[k][i] > hi ? src.hi[k][i] : hi;
+                }
+            if (!(lo <= hi))
+                lo = hi = 0.f;
+            o[k] = lo;
+            const double cell = (double(hi) - double(lo)) / 254.0; // one cell of head room at the top
+            float sf = float(cell);
+            if (double(sf) < cell)
+                sf = std::nextafterf(sf, std::numeric_limits<float>::infinity());
+            if (!(sf > 0.f))
+                sf = 1e-30f;
+            s[k] = sf;
+        }
+        uint32_t lo_w[3] = {0, 0, 0}, hi_w[3] = {0, 0, 0};
+        for (int i = 0; i < 4; ++i)
+            for (int k = 0; k < 3; ++k) {
+                uint32_t ql = 255, qh = 0;
+                if (src.ref[i] != kEmptyRef) {
+                    const double a = (double(src.lo[k][i]) - double(o[k])) / double(s[k]) - 0.25;
+                    const double b = (double(src.hi[k][i]) - double(o[k])) / double(s[k]) + 0.25;
+                    const double fl = std::floor(a), ce = std::ceil(b);
+                    ql = uint32_t(fl < 0 ? 0 : (fl > 255 ? 255 : fl));
+                    qh = uint32_t(ce < 0 ? 0 : (ce > 255 ? 255 : ce));
+                }
+                lo_w[k] |= ql << (8 * i);
+                hi_w[k] |= qh << (8 * i);
+            }
+        q.ox = o[0];
+        q.oy = o[1];
+        q.oz = o[2];
+        q.sx = s[0];
+        q.sy = s[1];
+        q.sz = s[2];
+        q.lox = lo_w[0];
+        q.loy = lo_w[1];
+        q.loz = lo_w[2];
+        q.hix = hi_w[0];
+        q.hiy = hi_w[1];
+        q.hiz = hi_w[2];
+        for (int i = 0; i < 4; ++i)
+            q.ref[i] = src.ref[i];
+        w.qnodes[n] = q;
+    }
+}
 
 // Scalar traversal over the 4-wide tree: what the warp-scheduled kernels of rtb_trace.cuh compute
 // per ray, written as one loop (the CPU suite holds it to the reference's hits bit for bit in fp64
@@ -154,12 +263,47 @@ inline int wide_stack_need(const WideTree &w) { return 3 * w.max_depth + 2; }
 template <class R, bool ANY, bool ROBUST, class Rng, class Stack, bool MEDIA = true>
 RTB_HD uint32_t traverse_wide(const GeomView<R> &g, const Node128 *nodes4, uint32_t root_ref, const uint32_t *chain_root, V3<R> o,
                               V3<R> d, R time, R t_min, R t_max, uint32_t origin_prim, Rng &rng, R &t_hit,
-                              uint64_t *n_nodes, uint64_t *n_tests, Stack &stack) {
+                              uint64_t *n_nodes, uint64_t *n_tests, Stack &stack, const uint32_t *globals = nullptr,
+                              uint32_t n_globals = 0) {
     uint32_t best = kNoPrim;
     V3<R> co = o, cd = d; // current-level ray
     SlabRay<R, ROBUST> sr;
     sr.set(o, d);
+    // the primitives kept out of the tree (build_wide): tested first, for every ray
+    for (uint32_t gi = 0; gi < n_globals; ++gi) {
+        const uint32_t i = globals[gi];
+        const PrimT<R> p = g.prims[i];
+        const uint32_t type = p.type_mat & PT_TYPE_MASK;
+        if (n_tests)
+            ++*n_tests;
+        R t;
+        bool h;
+        if (MEDIA && type == PT_MEDIUM) {
+            h = hit_medium<R, ROBUST>(g, p, o, d, time, t_min, t_max, rng(), t);
+            if (p.type_mat & PT_DUP_LEAF) {
+                R t2;
+                if (hit_medium<R, ROBUST>(g, p, o, d, time, t_min, h ? t : t_max, rng(), t2)) {
+                    h = true;
+                    t = t2;
+                }
+            }
+        } else {
+            h = hit_simple<R, ROBUST>(g, p, type, o, d, safe_inv(d), time, t_min, t_max, ROBUST && i == origin_prim, t);
+        }
+        if (h) {
+            best = i;
+            t_max = t;
+            if (ANY) {
+                t_hit = t;
+                return best;
+            }
+        }
+    }
     uint32_t cur = root_ref;
+    if (cur == kEmptyRef) {
+        t_hit = t_max;
+        return best;
+    }
     while (true) {
         while (!(cur & kLeafFlag)) { // descend
             const Node128 &n = nodes4[cur];

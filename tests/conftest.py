@@ -91,4 +91,5 @@ def hostcheck():
     L.hc_camera_derived.argtypes = [C.c_void_p, C.c_void_p]
     L.hc_wide_info.argtypes = [C.c_void_p, C.c_void_p]
     L.hc_sched_stats.argtypes = [C.c_void_p]
+    L.hc_qnode_check.argtypes = [C.c_void_p, C.c_void_p]
     return L

@@ -84,7 +84,8 @@ void trace_batch(HostScene &H, const rtb_ray *rays, uint64_t n, rtb_hit *hits, u
         LocalStack stack(storage);
         const uint32_t pi =
             wide ? traverse_wide<R, false, ROBUST>(g, W->nodes.data(), W->root_ref, W->chain_root.data(), o, d, R(q.time),
-                                                   R(q.t_min), R(q.t_max), origin, draw, t, &stats[0], &stats[1], stack)
+                                                   R(q.t_min), R(q.t_max), origin, draw, t, &stats[0], &stats[1], stack,
+                                                   W->global_prims.data(), uint32_t(W->global_prims.size()))
             : use_flat && g.flat
                 ? traverse_flat<R, false, ROBUST>(g, o, d, R(q.time), R(q.t_min), R(q.t_max), origin, draw, t,
                                                   &stats[0], &stats[1])
@@ -127,10 +128,13 @@ void trace_batch_warp(HostScene &H, const rtb_ray *rays, uint64_t n, rtb_hit *hi
     const GeomView<float> g = geom_view<float>(H);
     const WideTree &W = wide_of(H);
     WideView wv;
-    wv.nodes = reinterpret_cast<const Vec4f *>(W.nodes.data());
+    wv.nodes = reinterpret_cast<const Vec4f *>(W.qnodes.data());
     wv.chain_root = W.chain_root.data();
     wv.root_ref = W.root_ref;
-    wv.n_nodes = uint32_t(W.nodes.size());
+    wv.n_nodes = uint32_t(W.qnodes.size());
+    wv.n_global = uint32_t(W.global_prims.size());
+    for (int i = 0; i < kMaxGlobalPrims; ++i)
+        wv.global_prim[i] = size_t(i) < W.global_prims.size() ? W.global_prims[size_t(i)] : 0u;
     std::vector<Vec4f> a(n), b(n);
     std::vector<Vec2f> tt(n), out(n);
     for (uint64_t i = 0; i < n; ++i) {
@@ -146,7 +150,9 @@ void trace_batch_warp(HostScene &H, const rtb_ray *rays, uint64_t n, rtb_hit *hi
     uint32_t head = 0, overflow = 0;
     // the top of the tree from a separate copy, as the kernels read it from shared memory
     const uint32_t n_top = std::min<uint32_t>(wv.n_nodes, kTopNodesMax);
-    std::vector<Vec4f> top(wv.nodes, wv.nodes + size_t(n_top) * 8);
+    std::vector<Vec4f> top(size_t(n_top) * kTopStride);
+    for (uint32_t i = 0; i < n_top * kNodeRows; ++i)
+        top[(i / kNodeRows) * kTopStride + (i % kNodeRows)] = wv.nodes[i];
     const bool media = H.has_media, inst = H.n_instances > 0;
     for (int wi = 0; wi < warps; ++wi) {
         TraceWarpSmem smem;
@@ -161,8 +167,10 @@ void trace_batch_warp(HostScene &H, const rtb_ray *rays, uint64_t n, rtb_hit *hi
             job.n = uint32_t(n * uint64_t(wi + 1) / uint64_t(warps)); // this warp's share of the batch
             job.head = &head;
             job.base = 0;
+            job.win = 0;
+            job.warps = 24u;
             job.seed = 0x51ed270b;
-            uint64_t c[2] = {0, 0};
+            uint64_t c[3] = {0, 0, 0};
             uint32_t ov = 0;
             if (any_hit)
                 warp_trace<BatchTraceJob, true, true, true, true>(g, wv, top.data(), n_top, smem, job, c, ov);
@@ -304,6 +312,35 @@ void hc_sched_stats(uint64_t out[6]) {
     out[4] = s.switches;
     out[5] = s.switch_lanes;
     s = TraceSchedStats();
+}
+
+// Quantised nodes (QNode64) against the fp32 nodes they were made from: out = {children whose
+// quantised box does NOT contain the original one (must be 0), children, sum over children and axes
+// of the relative growth of the box extent in 1e-6 units}
+void hc_qnode_check(void *h, uint64_t out[3]) {
+    const WideTree &w = wide_of(*static_cast<HostScene *>(h));
+    out[0] = out[1] = out[2] = 0;
+    for (size_t n = 0; n < w.nodes.size(); ++n) {
+        const Node128 &a = w.nodes[n];
+        const QNode64 &q = w.qnodes[n];
+        const double o[3] = {q.ox, q.oy, q.oz}, s[3] = {q.sx, q.sy, q.sz};
+        const uint32_t lo[3] = {q.lox, q.loy, q.loz}, hi[3] = {q.hix, q.hiy, q.hiz};
+        for (int i = 0; i < 4; ++i) {
+            if (a.ref[i] == kEmptyRef)
+                continue;
+            ++out[1];
+            bool ok = q.ref[i] == a.ref[i];
+            for (int k = 0; k < 3; ++k) {
+                const double ql = o[k] + double((lo[k] >> (8 * i)) & 255u) * s[k], qh = o[k] + double((hi[k] >> (8 * i)) & 255u) * s[k];
+                ok = ok && ql <= double(a.lo[k][i]) && qh >= double(a.hi[k][i]);
+                const double ext = double(a.hi[k][i]) - double(a.lo[k][i]);
+                if (ext > 0)
+                    out[2] += uint64_t(1e6 * std::min(10.0, ((qh - ql) - ext) / ext));
+            }
+            if (!ok)
+                ++out[0];
+        }
+    }
 }
 
 void hc_sched_tuning(int node_min, int switch_min) {

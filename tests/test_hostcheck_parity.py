@@ -322,5 +322,16 @@ def test_warp_scheduler_on_a_deep_tree(hostcheck, abi):
     assert (w32["prim"] >= 0).mean() > 0.5
     assert np.array_equal(w32["prim"], k32["prim"]) and np.array_equal(w32["t"], k32["t"])
     assert np.array_equal(a32["prim"] >= 0, w32["prim"] >= 0)
-    # dropping popped subtrees that lie behind the closest hit saves node fetches
-    assert sk[0] <= sw[0]
+    # the kernels' 8-bit child boxes are a little wider than the fp32 ones (more nodes entered), popped
+    # subtrees behind the closest hit are dropped (fewer): within a few per cent of the exact walk
+    assert sk[0] <= 1.08 * sw[0]
+
+
+@pytest.mark.parametrize("sid", GOLDEN_SCENES)
+def test_quantised_nodes_contain_their_children(hostcheck, scenes, sid):
+    """The 64-byte node the kernels fetch (8-bit child planes on the node's own grid) must bound every
+    child at least as widely as the fp32 node it was made from — that is what keeps the hits of the
+    quantised traversal equal to the exact one."""
+    out = np.zeros(3, np.uint64)
+    hostcheck.hc_qnode_check(scenes(sid), _ptr(out))
+    assert out[0] == 0, f"{out[0]} of {out[1]} children escape their quantised box"

@@ -16,7 +16,7 @@ while [ $# -ge 2 ]; do
         -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr -Xptxas -v --use_fast_math $flags \
         -c "$CSRC/rtb_wavefront.cu" -o "$OUT/wf_$name.o" 2> "$OUT/wf_$name.ptxas.log"
     nvcc -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT/librtb200_$name.so" "$CSRC/build/rtb_api.o" \
-        "$OUT/wf_$name.o" "$CSRC/build/rtb_batch_f32.o" "$CSRC/build/rtb_batch_f64.o" -lcudart_static \
+        "$OUT/wf_$name.o" "$CSRC/build/rtb_batch_f32.o" "$CSRC/build/rtb_batch_f64.o" "$CSRC/build/rtb_multi.o" -lcudart_static -ldl \
         -Xlinker --exclude-libs=ALL
     rm -f "$OUT/wf_$name.o"
     echo "built $name ($flags)"
