@@ -2,23 +2,32 @@
 """bench.py — headline benchmark of the path-integration hot path.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--config C1..C5] [--spp S]
+                  [--scaling weak|strong] [--no-extras]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Default workload (BASELINE.json configs[0], the configuration the metric is quoted on): C1 =
+Headline workload (BASELINE.json configs[0], the configuration the metric is quoted on): C1 =
 scene07 Cornell box, 600x600, 400 spp, depth 50, integrator 1 (Russian roulette).  One STEP is
 one full render of that configuration per GPU (144 M camera paths, ~470 M rays).  --config
-selects another BASELINE configuration (ray_tracing-rendering_b200/configs.py); --spp reduces
-the samples per pixel of a step (stated in config.workload; cost is linear in spp).
+selects another BASELINE configuration (ray_tracing-rendering_b200/configs.py) as the headline;
+--spp reduces the samples per pixel of a step (stated in config.workload and config.spp_run).
 
 native arm      value   Mpaths/s with the scene resident in HBM: K steps bracketed by CUDA events
                         (barrier + synchronize on both sides, max over ranks); with N > 1 ranks
                         every rank renders 400 spp of its own sample slice (weak scaling) and the
-                        float4 accumulators are SUM-reduced over NCCL inside the timed region.
+                        images are reduced INSIDE the library: a kernel stages float3 means (the
+                        division by spp fused in), ncclReduce on the library's own communicator
+                        (rtb_comm_init / rtb_render_reduce), inside the timed region.
                 e2e     the same metric through the host-buffer C-ABI: rtb_scene_upload (H2D of
-                        the scene blob) + rtb_render / rtb_render_device + D2H of the accumulators
-                        into pinned host memory, every step.
-                roofline for the dominant kernel (extend = BVH traversal), cpu_baseline = the
-                        unmodified reference's Renderer::render on this box's host cores.
+                        the scene blob) + the render + D2H of the accumulators into pinned host
+                        memory, every step.
+                roofline for the dominant kernel against the roof that binds it (FP32 issue for
+                        the shared-memory scenes, L2 for BVH scenes; the SURVEY 8(d) HBM figure is
+                        kept as a secondary key), cpu_baseline = the unmodified reference's
+                        Renderer::render on this box's host cores.
+                configs every other BASELINE configuration (C2, C3, C4, C4env, C5), measured in the
+                        same run on rank 0's GPU (N = 1 only; spp of a step stated per entry).
+                strong  strong scaling inside the same run: C1 (400 spp in total) and C5 (4K,
+                        1 M spheres, 256 spp in total per step) with the work split over all N GPUs.
 reference arm   --impl reference: the unmodified reference (oracle/_ref, compiled from
                 /root/reference in the build container) on all host threads; rank 0 only.
 Prints ONE JSON line.
@@ -117,7 +126,7 @@ class ClockSampler(threading.Thread):
 
 def cpu_reference(steps, warmup, budget_s):
     """The reference's CPU implementation of the path on all host threads:
-    (Mpaths/s, cores, kind, sample text, secs per step).  kind "reference" = the unmodified
+    (Mpaths/s, cores, kind, sample text, secs per step, spp of a step).  kind "reference" = the unmodified
     reference compiled from /root/reference (oracle/_ref, Renderer::render untouched); where that
     library did not travel, kind "port" = the CPU restatement oracle/port on the same scene."""
     from oracle import refbind
@@ -153,213 +162,275 @@ def cpu_reference(steps, warmup, budget_s):
         what = "CPU restatement oracle/port (brute-force closest hit, no BVH)"
     paths = W * H * spp * steps
     sample = f"{W}x{H} at {spp} of {SPP} spp per step, {steps} steps (cost is linear in spp); {what}, all hardware threads"
-    return paths / secs / 1e6, cores, kind, sample, secs / steps
+    return paths / secs / 1e6, cores, kind, sample, secs / steps, spp
+
+
+def config_dict(world=1, spp_run=None, schedule=None, extra=None):
+    """The same keys in both arms (the driver compares them)."""
+    d = {"workload": WORKLOAD, "name": CONFIG, "integrator": INTEGRATOR, "width": W, "height": H, "spp": SPP,
+         "spp_run": SPP if spp_run is None else spp_run, "max_depth": DEPTH}
+    if extra:
+        d.update(extra)
+    return d
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    value, cores, kind, sample, ms = cpu_reference(args.steps, args.warmup, 120.0)
+    value, cores, kind, sample, ms, spp_run = cpu_reference(args.steps, args.warmup, 120.0)
     out = {"metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-           "config": {"workload": WORKLOAD, "name": CONFIG, "integrator": INTEGRATOR, "width": W, "height": H, "spp": SPP},
+           "config": config_dict(spp_run=spp_run),
            "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
 
 
-def run_native(args, rank, local_rank, world):
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-    pkg = importlib.import_module(PKG)
-    scenes = importlib.import_module(PKG + ".scenes")
-    binding = importlib.import_module(PKG + ".binding")
-    dmod = importlib.import_module(PKG + ".distributed")
+def load_json(*parts):
+    try:
+        with open(os.path.join(ROOT, *parts)) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        # keep stdout to the ONE JSON line: NCCL prints its version banner to fd 1 when the
-        # communicator comes up, so fd 1 points at stderr until the first collective is through
-        sys.stdout.flush()
-        saved_stdout = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=dev)
-            warm = torch.zeros(1, device=dev)
-            dist.all_reduce(warm)
-            torch.cuda.synchronize(dev)
-        finally:
+
+class Bench:
+    """One rank of the native arm: context, stream, library communicator, measurement helpers."""
+
+    def __init__(self, args, rank, local_rank, world):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.args, self.rank, self.local_rank, self.world = args, rank, local_rank, world
+        self.pkg = importlib.import_module(PKG)
+        self.binding = importlib.import_module(PKG + ".binding")
+        self.configs = importlib.import_module(PKG + ".configs")
+        self.abi = importlib.import_module(PKG + ".abi")
+        torch.cuda.set_device(local_rank)
+        self.dev = torch.device("cuda", local_rank)
+        if world > 1:
+            # keep stdout to the ONE JSON line: NCCL prints its version banner to fd 1 when a
+            # communicator comes up, so fd 1 points at stderr until both communicators are through
             sys.stdout.flush()
-            os.dup2(saved_stdout, 1)
-            os.close(saved_stdout)
-    ctx = pkg.Context(local_rank)
-    blob = importlib.import_module(PKG + ".configs").get(CONFIG).blob()   # the product's own builder; no reference code
-    ctx.upload_scene(blob)
-    stream = torch.cuda.Stream(dev)          # kernels, events and the NCCL reduce all run on this stream
-    accum = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
-    host = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
-    # weak scaling (default): every rank renders SPP samples per pixel; strong: SPP in total
-    strong = args.scaling == "strong"
-    total_spp = SPP if strong else SPP * world
+            saved_stdout = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group("nccl", device_id=self.dev)
+                warm = torch.zeros(1, device=self.dev)
+                dist.all_reduce(warm)
+                torch.cuda.synchronize(self.dev)
+                self.ctx = self.pkg.Context(local_rank)
+                ids = [self.binding.Context.comm_unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(ids, src=0)
+                self.ctx.comm_init(world, rank, ids[0])      # the library's own NCCL communicator
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved_stdout, 1)
+                os.close(saved_stdout)
+        else:
+            self.ctx = self.pkg.Context(local_rank)
+        self.stream = torch.cuda.Stream(self.dev)   # kernels, events and the library's ncclReduce all run on this stream
+        torch.cuda.synchronize(self.dev)
+        torch.cuda.set_stream(self.stream)
+        self.micro = load_json("profiles", "microbench.json")
+        self.captured = load_json("profiles", "extend_traffic.json")
+        self.hbm_peak, self.hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+        peaks = load_json("MEASURED_PEAKS.json")
+        if "hbm_gbs" in peaks:
+            self.hbm_peak, self.hbm_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
 
-    def params(flags=0, seed=1):
-        # samples of every pixel are split across the ranks; rows too when spp < ranks (plan_split)
-        pl = dmod.plan_split(total_spp, H, rank, world)
-        return ctx.params(W, H, total_spp, INTEGRATOR, DEPTH, 3, seed, pl["sample_offset"], pl["sample_stride"], 0,
-                          flags, pl["row_offset"], pl["row_stride"])
+    def sync(self):
+        self.torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize(self.dev)
 
-    def sync():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize(dev)
-
-    def step(seed):
-        st = ctx.render_device(params(seed=seed), accum.data_ptr(), stream.cuda_stream)
-        dmod.reduce_sum(accum)
-        return st
-
-    def step_e2e(seed):
-        if world == 1:
-            ctx.upload_scene(blob)                                   # H2D: the scene tables
-            _, st = ctx.render(params(seed=seed), out=host.numpy())  # render + D2H of the accumulators
-            return st
+    def measure(self, name, spp_step, steps, warmup, strong, with_e2e=True, clocks=False):
+        """K steps of configuration `name` at spp_step samples per pixel per step — per GPU (weak) or
+        in total (strong).  Returns device-timed and end-to-end figures (max over ranks)."""
+        torch, dist, ctx = self.torch, self.dist, self.ctx
+        cfg = self.configs.get(name)
+        w, h = cfg.width, cfg.height
+        total_spp = spp_step if strong else spp_step * self.world
+        blob = cfg.blob()                       # the product's own builder; no reference code
         ctx.upload_scene(blob)
-        st = ctx.render_device(params(seed=seed), accum.data_ptr(), stream.cuda_stream)
-        dmod.reduce_sum(accum)
-        if rank == 0:
-            host.copy_(accum, non_blocking=False)
-        return st
+        accum = torch.zeros((h, w, 4), dtype=torch.float32, device=self.dev) if self.world == 1 else None
+        host = torch.empty((h, w, 4), dtype=torch.float32).pin_memory() if (self.rank == 0 and with_e2e) else None
 
-    def timed(fn):
-        sampler = ClockSampler(local_rank)   # started before the warm-up: nvidia-smi takes a while to come up
-        sampler.start()
-        for i in range(args.warmup):
-            fn(1000 + i)
-        sync()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        agg = {"paths": 0, "rays": 0, "launches": 0}
-        sampler.t0 = time.time()
-        e0.record(stream)
-        for i in range(args.steps):
-            st = fn(i + 1)
-            agg["paths"] += st["paths"]
-            agg["rays"] += st["rays_closest"] + st["rays_shadow"]
-            agg["launches"] += st["kernel_launches"]
-        e1.record(stream)
-        sync()
-        sampler.t1 = time.time()
-        clocks = sampler.stop()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        tot = torch.tensor([agg["paths"], agg["rays"], agg["launches"]], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        return float(ms.item()), [float(x) for x in tot.tolist()], clocks
+        def params(flags=0, seed=1, spp=None):
+            # N > 1: the library plans the split of the WHOLE job over the ranks (rtb_render_reduce)
+            return ctx.params(w, h, total_spp if spp is None else spp, cfg.integrator, cfg.depth, 3, seed, 0, 1, 0, flags, 0, 1)
 
-    torch.cuda.synchronize(dev)
-    torch.cuda.set_stream(stream)
-    ms, tot, clocks = timed(step)
-    ms_e2e, tot_e2e, _ = timed(step_e2e)
+        def step(seed):
+            if self.world == 1:
+                return ctx.render_device(params(seed=seed), accum.data_ptr(), self.stream.cuda_stream)
+            return ctx.render_reduce(params(seed=seed), stream=self.stream.cuda_stream)
 
-    # roofline of the dominant kernel: per-launch CUDA-event durations measured live (on the
-    # stream the kernels run on), algorithmic bytes from the same kernel's counting variant
-    st_t = ctx.render_device(params(binding.RENDER_TIME_EXTEND, seed=77), accum.data_ptr(), stream.cuda_stream)
-    cp = ctx.params(W, H, min(SPP, 16), INTEGRATOR, DEPTH, 3, 77, 0, 1, 0, binding.RENDER_COUNT_VISITS)
-    st_c = ctx.render_device(cp, accum.data_ptr(), stream.cuda_stream)
-    fused = st_t.get("schedule") == 1
-    rays_c = st_c["rays_closest"] + st_c["rays_shadow"]
-    n_node = st_c["nodes_visited"] / rays_c
-    n_prim = st_c["prim_tests"] / rays_c
-    b_ray = 32.0 * n_node + 32.0 * n_prim + 48.0
-    # fused: the one kernel traces closest-hit AND shadow rays; wavefront: k_extend traces the closest-hit rays
-    rays_dom = st_t["rays_closest"] + (st_t["rays_shadow"] if fused else 0)
-    rays_per_launch = rays_dom / max(st_t["extend_launches"], 1)
-    us_per_launch = 1e3 * st_t["extend_ms"] / max(st_t["extend_launches"], 1)
-    achieved = b_ray * rays_dom / (st_t["extend_ms"] * 1e-3) / 1e9
-    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    except Exception:
-        pass
-    traffic, micro, ncu_counters = None, {}, None
-    try:
-        with open(os.path.join(ROOT, "profiles", "extend_traffic.json")) as f:
-            captured = json.load(f).get(CONFIG, {})
-        traffic = captured.get("dram_bytes_per_launch")
-        ncu_counters = captured.get("ncu")   # which limit binds, from the committed ncu capture of this kernel
-    except Exception:
-        pass
-    try:
-        with open(os.path.join(ROOT, "profiles", "microbench.json")) as f:
-            micro = json.load(f)
-    except Exception:
-        pass
-    # secondary figure for the cache-resident scenes: algorithmic flops per ray
-    # F_ray = 24 n_node + 30 n_sphere + 10 n_rect + F_shade against the measured FP32 FMA rate
-    ptypes = importlib.import_module(PKG + ".abi").parse_blob(blob)["prims"]["type"]
-    frac_sphere = float((ptypes <= 1).mean()) if len(ptypes) else 0.0
-    f_prim = 30.0 * frac_sphere + 10.0 * (1.0 - frac_sphere)
-    f_ray = 24.0 * n_node + f_prim * n_prim + 60.0
-    grays = rays_dom / (st_t["extend_ms"] * 1e-3) / 1e9
-    fp32_peak = micro.get("fp32_fma_tflops")
-    dominant = "k_fused (trace + shade + regenerate, scene in shared memory)" if fused else "k_extend (closest hit + refill + material sort)"
-    note = ("the scene is shared-memory resident: the dominant kernel keeps path state in registers and is "
-            "instruction-issue bound, not HBM bound; the algorithmic bytes of SURVEY 8(d) over the kernel time are "
-            "reported against the HBM peak as the contract asks and can exceed it because those bytes never leave the SM"
-            if fused else
-            "BVH traversal is divergence / issue bound (ncu: ~16 of 32 lanes active, 55 % issue slots, L2 hit 50-67 %); "
-            "algorithmic bytes per SURVEY 8(d): 32 B per node visited + 32 B per primitive tested + 48 B per ray")
-    roofline = {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "bytes_per_ray": b_ray, "nodes_per_ray": n_node, "prims_per_ray": n_prim,
-                "rays_per_launch": rays_per_launch, "us_per_launch": us_per_launch,
-                "extend_share_of_step": st_t["extend_ms"] / st_t["device_ms"],
-                "grays_per_s_in_kernel": grays,
-                "stage_ms": st_t.get("stage_ms"), "ncu": ncu_counters,
-                "fp32": {"flops_per_ray": f_ray, "achieved_tflops": grays * f_ray / 1e3, "peak_tflops": fp32_peak,
-                         "frac": (grays * f_ray / 1e3 / fp32_peak) if fp32_peak else None,
-                         "peak_source": "tools/microbench (profiles/microbench.json), FMA = 2 flops"},
-                "note": note}
+        def step_e2e(seed):
+            ctx.upload_scene(blob)                                       # H2D: the scene tables
+            if self.world == 1:
+                _, st = ctx.render(params(seed=seed), out=host.numpy())  # render + D2H of the accumulators
+                return st
+            return ctx.render_reduce(params(seed=seed), out=host.numpy() if self.rank == 0 else None,
+                                     stream=self.stream.cuda_stream)
 
+        def timed(fn):
+            sampler = None
+            if clocks:
+                sampler = ClockSampler(self.local_rank)   # started before the warm-up: nvidia-smi takes a while to come up
+                sampler.start()
+            for i in range(warmup):
+                fn(1000 + i)
+            self.sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            agg = {"paths": 0, "rays": 0, "launches": 0}
+            if sampler:
+                sampler.t0 = time.time()
+            e0.record(self.stream)
+            st = None
+            for i in range(steps):
+                st = fn(i + 1)
+                agg["paths"] += st["paths"]
+                agg["rays"] += st["rays_closest"] + st["rays_shadow"]
+                agg["launches"] += st["kernel_launches"]
+            e1.record(self.stream)
+            self.sync()
+            clk = None
+            if sampler:
+                sampler.t1 = time.time()
+                clk = sampler.stop()
+            ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=self.dev)
+            tot = torch.tensor([agg["paths"], agg["rays"], agg["launches"]], dtype=torch.float64, device=self.dev)
+            if self.world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+                dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+            return float(ms.item()), [float(x) for x in tot.tolist()], clk, st
+
+        ms, tot, clk, last = timed(step)
+        out = {"name": name, "workload": cfg.workload, "width": w, "height": h, "integrator": cfg.integrator,
+               "spp": cfg.spp, "spp_run": total_spp if strong else spp_step, "spp_total_per_step": total_spp,
+               "mpaths_per_s": tot[0] / (ms * 1e-3) / 1e6, "mrays_per_s": tot[1] / (ms * 1e-3) / 1e6,
+               "ms_per_step": ms / steps, "gpu_launches": int(tot[2]), "schedule": "fused" if last["schedule"] == 1 else "wavefront",
+               "clocks": clk, "blob_bytes": len(blob)}
+        if with_e2e:
+            ms2, tot2, _, _ = timed(step_e2e)
+            out["e2e"] = {"value": tot2[0] / (ms2 * 1e-3) / 1e6, "unit": "Mpaths/s", "h2d_bytes_per_step": len(blob),
+                          "d2h_bytes_per_step": w * h * 16, "ms_per_step": ms2 / steps}
+        self._last = (cfg, blob, accum, params)
+        return out
+
+    def roofline(self, name):
+        """Dominant kernel of the configuration measured last (N = 1): per-launch CUDA-event durations
+        measured live on the kernels' stream, algorithmic work from the same kernel's counting variant."""
+        cfg, blob, accum, params = self._last
+        ctx, binding = self.ctx, self.binding
+        st_t = ctx.render_device(params(binding.RENDER_TIME_EXTEND, seed=77), accum.data_ptr(), self.stream.cuda_stream)
+        st_c = ctx.render_device(params(binding.RENDER_COUNT_VISITS, seed=77, spp=min(cfg.spp, 16)), accum.data_ptr(),
+                                 self.stream.cuda_stream)
+        fused = st_t.get("schedule") == 1
+        rays_c = max(st_c["rays_closest"] + st_c["rays_shadow"], 1)
+        n_node, n_prim = st_c["nodes_visited"] / rays_c, st_c["prim_tests"] / rays_c
+        prims = self.abi.parse_blob(blob)["prims"]["type"]
+        frac_sphere = float((prims <= 1).mean()) if len(prims) else 0.0
+        # fused: the one kernel traces closest-hit AND shadow rays; wavefront: k_extend traces the closest-hit rays
+        rays_dom = st_t["rays_closest"] + (st_t["rays_shadow"] if fused else 0)
+        secs = max(st_t["extend_ms"], 1e-9) * 1e-3
+        grays = rays_dom / secs / 1e9
+        launches = max(st_t["extend_launches"], 1)
+        cap = self.captured.get(name, {})
+        common = {"rays_per_launch": rays_dom / launches, "us_per_launch": 1e6 * secs / launches,
+                  "share_of_step": st_t["extend_ms"] / st_t["device_ms"], "grays_per_s_in_kernel": grays,
+                  "stage_ms": st_t.get("stage_ms"), "traffic": cap.get("dram_bytes_per_launch"), "ncu": cap.get("ncu")}
+        if fused:
+            # The scene (<= 64 records) lives in shared memory, path state in registers: nothing streams
+            # from HBM (ncu: 5 MB of DRAM traffic per launch).  The kernel is bound by instruction issue;
+            # its roof is the FP32 rate: algorithmic flops of SURVEY 8(d) — a box instance counted as ONE
+            # slab test (24 flops), not as six rectangles — against the measured FP32 FMA peak.
+            n_box = int(cap.get("box_instances", 2 if name in ("C1", "C3") else 0))
+            n_rec = max(n_prim - 5.0 * n_box, 0.0)           # records tested per ray: 6 rects of a box = 1 record
+            f_ray = 24.0 * n_box + (30.0 * frac_sphere + 10.0 * (1.0 - frac_sphere)) * (n_rec - n_box) + 60.0
+            peak = float(self.micro.get("fp32_fma_tflops", 74.5))
+            ach = grays * f_ray / 1e3
+            rl = {"kernel": "k_fused (trace + shade + regenerate, scene in shared memory)", "bound": "fp32",
+                  "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                  "peak_source": "tools/microbench FP32 FMA rate (profiles/microbench.json); nominal 74.5",
+                  "flops_per_ray": f_ray, "records_per_ray": n_rec,
+                  "note": "issue bound (ncu, profiles/: 82 % of the issue slots, 24.4 of 32 lanes): the algorithmic "
+                          "flops are ~1/4 of the instructions a ray needs (compares, selects, RNG, control)"}
+            b_ray = 32.0 * n_node + 32.0 * n_rec + 48.0
+        else:
+            # BVH scenes: the tree and the primitive records are served by L1 / L2 (they fit the 126 MB L2);
+            # DRAM carries the streaming queues.  Algorithmic bytes per ray as SURVEY 8(d) defines them, with
+            # this round's 64-byte nodes: 64 n_node + 32 n_prim + 48, against the measured L2 stream rate.
+            node_bytes = 32.0 if st_t.get("binary_traversal") else 64.0
+            b_ray = node_bytes * n_node + 32.0 * n_prim + 48.0
+            peak = float(self.micro.get("l2_stream_read_gbs", 21000.0))
+            ach = grays * b_ray
+            rl = {"kernel": "k_extend_w (warp-scheduled 4-wide traversal: closest hit, refill, material sort)", "bound": "l2",
+                  "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                  "peak_source": "tools/microbench L2 stream read (profiles/microbench.json)",
+                  "note": "latency / issue bound (ncu, profiles/r02_*): ~23 of 32 lanes, ~50 % of the issue slots, "
+                          "L1 data pipe 60-80 %; DRAM traffic per launch (`traffic`) is the queue streaming, not the tree"}
+        rl.update(common)
+        rl.update({"bytes_per_ray": b_ray, "nodes_per_ray": n_node, "prims_per_ray": n_prim,
+                   "hbm_8d": {"achieved": grays * b_ray, "peak": self.hbm_peak, "unit": "GB/s", "frac": grays * b_ray / self.hbm_peak,
+                              "peak_source": self.hbm_src,
+                              "note": "SURVEY 8(d) figure against the HBM copy rate; the bytes are served on chip, so this is not the binding roof"}})
+        return rl
+
+
+def run_native(args, rank, local_rank, world):
+    B = Bench(args, rank, local_rank, world)
+    strong = args.scaling == "strong"
+    head = B.measure(CONFIG, SPP, args.steps, args.warmup, strong, with_e2e=True, clocks=True)
+    roofline = B.roofline(CONFIG) if world == 1 else None
     cpu = None
     if rank == 0 and world == 1:
         try:
-            v, cores, kind, sample, _ = cpu_reference(1, 0, 20.0)
+            v, cores, kind, sample, _, _ = cpu_reference(1, 0, 20.0)
             cpu = {"value": v, "unit": "Mpaths/s", "cores": cores, "kind": kind, "sample": sample}
         except Exception as e:  # the baseline is reported, never required for the product arm
             cpu = {"value": None, "unit": "Mpaths/s", "cores": os.cpu_count(), "kind": "reference",
                    "sample": f"unavailable: {e}"}
+    extras, strong_runs = {}, {}
+    if not args.no_extras:
+        if world == 1:
+            # the other BASELINE configurations, same run, same GPU (spp of a step stated per entry)
+            for name, spp in (("C2", 0), ("C3", 0), ("C4", 0), ("C4env", 0), ("C5", 64)):
+                if name == CONFIG:
+                    continue
+                cfg = B.configs.get(name)
+                m = B.measure(name, spp or cfg.spp, 3, 1, False, with_e2e=True)
+                m["roofline"] = B.roofline(name)
+                extras[name] = m
+        # strong scaling: the total work of a step is fixed, the library splits it over the N GPUs
+        for name, spp in (("C1", 400), ("C5", 256)):
+            strong_runs[name] = B.measure(name, spp, 2 if name == "C5" else 5, 1, True, with_e2e=False)
     if rank == 0:
-        secs = ms * 1e-3
-        out = {"metric": "Mpaths/s", "value": tot[0] / secs / 1e6, "unit": "Mpaths/s", "n_gpus": world,
-               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        out = {"metric": "Mpaths/s", "value": head["mpaths_per_s"], "unit": "Mpaths/s", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"],
                "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
-               "data": "synthetic", "impl": "native",
-               "mrays_per_s": tot[1] / secs / 1e6,
-               "config": {"workload": WORKLOAD, "name": CONFIG, "integrator": INTEGRATOR, "width": W, "height": H,
-                          "spp_per_gpu": total_spp / world, "paths_per_step_per_gpu": W * H * total_spp // world,
-                          "parallelism": f"spp-split x{world}",
-                          "collective": "one NCCL SUM-reduce of the float4 accumulators per step" if world > 1 else "none",
-                          "schedule": "fused" if fused else "wavefront",
-                          "l2": ("no L2 flush needed: the fused schedule keeps the scene in shared memory and path "
-                                 "state in registers; every step rewrites all accumulators with atomics after a memset"
-                                 if fused else
-                                 "no extra flush: every wavefront iteration streams the 8 Mi-entry queues (>= 1 GB "
-                                 "read + written, evict-first) through the 126 MB L2")},
-               "e2e": {"value": tot_e2e[0] / (ms_e2e * 1e-3) / 1e6, "unit": "Mpaths/s",
-                       "h2d_bytes_per_step": len(blob), "d2h_bytes_per_step": W * H * 16,
-                       "ms_per_step": ms_e2e / args.steps},
-               "gpu_launches": int(tot[2]), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+               "data": "synthetic", "impl": "native", "mrays_per_s": head["mrays_per_s"],
+               "config": config_dict(world, head["spp_run"], extra={
+                   "spp_per_gpu": head["spp_total_per_step"] / world,
+                   "paths_per_step_per_gpu": W * H * head["spp_total_per_step"] // world,
+                   "parallelism": f"spp-split x{world}",
+                   "collective": ("one ncclReduce(SUM) of float3 means per step, issued by the library "
+                                  "(rtb_render_reduce), staging kernel fused with the division by spp") if world > 1 else "none",
+                   "schedule": head["schedule"],
+                   "l2": ("no L2 flush needed: the fused schedule keeps the scene in shared memory and path "
+                          "state in registers; every step rewrites all accumulators with atomics after a memset"
+                          if head["schedule"] == "fused" else
+                          "no extra flush: every wavefront iteration streams the 8 Mi-entry queues (>= 1 GB "
+                          "read + written, evict-first) through the 126 MB L2")}),
+               "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": head["clocks"],
+               "roofline": roofline, "cpu_baseline": cpu, "configs": extras, "strong": strong_runs}
         print(json.dumps(out), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        B.dist.barrier()
+        B.dist.destroy_process_group()
 
 
 def main():
@@ -371,6 +442,7 @@ def main():
     ap.add_argument("--config", default="C1")
     ap.add_argument("--spp", type=int, default=0)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-extras", action="store_true", help="headline only (skip the other configurations and the strong-scaling runs)")
     args = ap.parse_args()
     select_config(args.config, args.spp)
     rank = int(os.environ.get("RANK", "0"))

@@ -153,8 +153,10 @@ enum rtb_option {
     RTB_OPT_BVH_TRAVERSAL_COST_PCT = 4,
     /* node order: 0 = level order, 1 = sibling pairs depth-first (left subtree right after its pair) */
     RTB_OPT_BVH_LAYOUT_DFS = 5,
-    /* 1: trace BVH scenes with round 1's kernels (binary tree, one 32-ray chunk per warp at a time)
-     * instead of the warp-scheduled 4-wide traversal; kept for A/B measurements (default 0) */
+    /* which traversal kernels the wavefront schedule uses on BVH scenes: 0 (default) = by scene — the
+     * warp-scheduled 4-wide traversal (csrc/rtb_trace.cuh) unless the tree mixes media or instances
+     * with its primitives, where round 1's binary while-while kernels measure faster; 1 = always the
+     * binary kernels; 2 = always the 4-wide kernels (A/B measurements, tests) */
     RTB_OPT_BINARY_TRAVERSAL = 6
 };
 RTB_API int rtb_set_option(rtb_context *ctx, int option, int64_t value);

@@ -229,7 +229,7 @@ int rtb_set_option(rtb_context *ctx, int option, int64_t value) {
     else if (option == RTB_OPT_BVH_LAYOUT_DFS)
         ctx->opt_layout_dfs = value != 0;
     else if (option == RTB_OPT_BINARY_TRAVERSAL)
-        ctx->opt_binary_traversal = value != 0;
+        ctx->opt_binary_traversal = int(value);
     else
         return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_set_option: unknown option");
     return RTB_OK;

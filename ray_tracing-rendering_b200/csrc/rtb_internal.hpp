@@ -150,7 +150,7 @@ struct rtb_context {
     int opt_max_leaf = 4;        // RTB_OPT_BVH_MAX_LEAF
     int opt_trav_cost_pct = 100; // RTB_OPT_BVH_TRAVERSAL_COST_PCT
     int opt_layout_dfs = 0;      // RTB_OPT_BVH_LAYOUT_DFS
-    int opt_binary_traversal = 0; // RTB_OPT_BINARY_TRAVERSAL: round 1's per-chunk while-while kernels (A/B measurements)
+    int opt_binary_traversal = 0; // RTB_OPT_BINARY_TRAVERSAL: 0 by scene, 1 binary, 2 wide
     // multi-GPU (rtb_multi.cu): this context's rank in an NCCL communicator and its staging buffers
     void *comm = nullptr; // ncclComm_t
     int comm_rank = 0, comm_size = 1;

@@ -47,13 +47,13 @@
 namespace rtb {
 
 #ifndef RTB_TRACE_NODE_MIN
-#define RTB_TRACE_NODE_MIN 20 // a node step runs when at least this many lanes want one (or no lane waits at a leaf)
+#define RTB_TRACE_NODE_MIN 16 // a node step runs when at least this many lanes want one (or no lane waits at a leaf)
 #endif
 #ifndef RTB_TRACE_SWITCH_MIN
 #define RTB_TRACE_SWITCH_MIN 8 // lanes without a ray that trigger a refill from the window
 #endif
 #ifndef RTB_TRACE_SORT
-#define RTB_TRACE_SORT 1 // counting-sort each window by direction octant
+#define RTB_TRACE_SORT 0 // counting-sort each window by direction octant (measured on B200: no gain)
 #endif
 #ifndef RTB_TRACE_GUARD
 #define RTB_TRACE_GUARD 1 // bound the scheduler loop (an internal error becomes a flag, not a hung GPU)
@@ -268,7 +268,7 @@ template <bool INST, class Job> RTB_WD void trav_pop(TravLane &L, Vec2u *stack, 
 }
 
 // One 4-wide node: L.cur is an interior node on entry, the next thing to do on exit.
-template <bool TOP, bool INST, class Job>
+template <bool ANY, bool TOP, bool INST, class Job>
 RTB_WD void trav_node_step(const WideView &w, const Vec4f *s_top, uint32_t n_top, TravLane &L, Vec2u *stack,
                            uint32_t &overflow, Job &job, uint32_t tag) {
     const Vec4f *nb = node_address<TOP>(w, s_top, n_top, L.cur);
@@ -572,7 +572,7 @@ RTB_WD void warp_trace(const GeomView<float> &g, const WideView &w, const Vec4f 
             if (node_step) {
                 if (ref_is_node(L.cur)) {
                     ++nodes;
-                    trav_node_step<TOP, INST>(w, s_top, n_top, L, stack, overflow, job, tag);
+                    trav_node_step<ANY, TOP, INST>(w, s_top, n_top, L, stack, overflow, job, tag);
                 }
             } else {
                 if (ref_is_leaf(L.cur))

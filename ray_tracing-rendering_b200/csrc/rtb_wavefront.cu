@@ -1326,10 +1326,16 @@ __global__ void __launch_bounds__(kWfBlock, RTB_EXTEND_MIN_BLOCKS) k_connect(WfP
 #ifndef RTB_TRACE_MIN_BLOCKS
 #define RTB_TRACE_MIN_BLOCKS 3 // resident CTAs of 256 threads per SM the traversal kernels are compiled for
 #endif
+#ifndef RTB_TRACE_MIN_BLOCKS_LEAN
+#define RTB_TRACE_MIN_BLOCKS_LEAN 4 // ... for scenes without media and instances (64 registers, no spills; C5 69.1 -> 67.0 ms)
+#endif
 #ifndef RTB_TRACE_TOP
 #define RTB_TRACE_TOP 0 // stage the top levels of the tree in shared memory (measured: no gain)
 #endif
-constexpr int kTraceBlock = 256;
+#ifndef RTB_TRACE_BLOCK
+#define RTB_TRACE_BLOCK 256
+#endif
+constexpr int kTraceBlock = RTB_TRACE_BLOCK;
 constexpr bool kTraceTop = RTB_TRACE_TOP != 0;
 
 // Cooperative copy of the first nodes of the (breadth-first) tree; returns how many were staged.
@@ -1488,7 +1494,7 @@ template <bool MEDIA> struct ExtendJob {
 };
 
 template <bool COUNT, bool MEDIA, bool INST>
-__global__ void __launch_bounds__(kTraceBlock, RTB_TRACE_MIN_BLOCKS) k_extend_w(WfParams p, int it) {
+__global__ void __launch_bounds__(kTraceBlock, (MEDIA || INST) ? RTB_TRACE_MIN_BLOCKS : RTB_TRACE_MIN_BLOCKS_LEAN) k_extend_w(WfParams p, int it) {
     __shared__ Vec4f s_top[kTraceTop ? kTopNodesMax * kTopStride : 1];
     __shared__ TraceWarpSmem s_warp[kTraceBlock / 32];
     const uint32_t n_top = stage_top_nodes(p.wide, s_top);
@@ -1589,7 +1595,7 @@ template <bool MEDIA> struct ConnectJob {
 };
 
 template <bool COUNT, bool MEDIA, bool INST>
-__global__ void __launch_bounds__(kTraceBlock, RTB_TRACE_MIN_BLOCKS) k_connect_w(WfParams p, int it) {
+__global__ void __launch_bounds__(kTraceBlock, (MEDIA || INST) ? RTB_TRACE_MIN_BLOCKS : RTB_TRACE_MIN_BLOCKS_LEAN) k_connect_w(WfParams p, int it) {
     __shared__ Vec4f s_top[kTraceTop ? kTopNodesMax * kTopStride : 1];
     __shared__ TraceWarpSmem s_warp[kTraceBlock / 32];
     const uint32_t n_top = stage_top_nodes(p.wide, s_top);
@@ -2142,7 +2148,12 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
                                     (1u << RTB_MAT_ISOTROPIC);
         // the warp-scheduled 4-wide traversal, unless round 1's kernels are asked for (or the scene is
         // small enough for the lockstep walk of the shared-memory copy, which those kernels hold)
-        const bool wide = ctx->opt_binary_traversal == 0 && !geom.flat;
+        // Measured on B200 (profiles/r02_traversal.txt): on the 1 M-sphere field (one primitive type, no
+        // wrappers) the 4-wide kernels are 16 % faster in extend; on scene09 (rects, spheres, an instance
+        // and two media in one tree) the heterogeneous leaf steps run at 5-10 lanes and round 1's plain
+        // kernels are 12 % faster.  opt_binary_traversal: 0 = by that rule, 1 = always binary, 2 = always wide.
+        const bool mixed = media || inst;
+        const bool wide = !geom.flat && (ctx->opt_binary_traversal == 2 || (ctx->opt_binary_traversal == 0 && !mixed));
         int trace_grid = 0, connect_grid = 0;
         constexpr int kBatch = 4; // iterations between two host-side liveness probes
         int probe = 0, zero_probes = 0;

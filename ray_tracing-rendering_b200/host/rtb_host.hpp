@@ -1227,13 +1227,23 @@ class Renderer {
     };
     Renderer() : m_is_rendering(false) {}
     ~Renderer() {
-        if (m_ctx)
+        if (m_group)
+            rtb_group_destroy(m_group);
+        else if (m_ctx)
             rtb_context_destroy(m_ctx);
     }
     Renderer(const Renderer &) = delete;
     Renderer &operator=(const Renderer &) = delete;
 
-    void set_device(int device) { m_device = device; }
+    void set_device(int device) { m_devices.assign(1, device); }
+    // Several GPUs of this box: the samples of every pixel (rows too when there are fewer samples
+    // than GPUs) are split over them and reduced over NCCL inside the library (rtb_group_*) — the
+    // GPU counterpart of the reference's tile queue over CPU threads (renderer.h:40-94).
+    void set_devices(const std::vector<int> &devices) {
+        if (!devices.empty())
+            m_devices = devices;
+    }
+    int device_count() const { return int(m_devices.size()); }
     void set_integrator(std::shared_ptr<Integrator> integrator) { m_integrator = integrator; }
     void set_samples(int samples) { m_settings.samples_per_pixel = samples; }
     void set_max_depth(int depth) {
@@ -1247,7 +1257,9 @@ class Renderer {
     int passes_done() const { return m_passes_done; }
     void cancel() { // renderer.h:113 — safe from another thread
         m_is_rendering = false;
-        if (m_ctx)
+        if (m_group)
+            rtb_group_cancel(m_group);
+        else if (m_ctx)
             rtb_cancel(m_ctx);
     }
     bool is_rendering() const { return m_is_rendering; }
@@ -1258,11 +1270,22 @@ class Renderer {
                 RenderBuffer &target_buffer, const std::vector<shared_ptr<Light>> &lights = {}) {
         m_is_rendering = true;
         const auto start = std::chrono::high_resolution_clock::now();
+        const bool multi = m_devices.size() > 1;
+        if (multi && !m_group) {
+            if (rtb_group_create(m_devices.data(), int(m_devices.size()), &m_group) != RTB_OK)
+                throw std::runtime_error(std::string("rtb_group_create: ") + rtb_last_error(nullptr));
+            m_ctx = rtb_group_context(m_group, 0);
+        }
         if (!m_ctx)
-            rtb::check(rtb_context_create(m_device, &m_ctx), nullptr, "rtb_context_create");
+            rtb::check(rtb_context_create(m_devices[0], &m_ctx), nullptr, "rtb_context_create");
         const int w = target_buffer.width(), h = target_buffer.height();
         const auto blob = rtb::flatten(*world, *cam, background, lights, w, h, m_settings.samples_per_pixel);
-        rtb::check(rtb_scene_upload(m_ctx, blob.data(), blob.size()), m_ctx, "rtb_scene_upload");
+        if (multi) {
+            if (rtb_group_scene_upload(m_group, blob.data(), blob.size()) != RTB_OK)
+                throw std::runtime_error(std::string("rtb_group_scene_upload: ") + rtb_group_last_error(m_group));
+        } else {
+            rtb::check(rtb_scene_upload(m_ctx, blob.data(), blob.size()), m_ctx, "rtb_scene_upload");
+        }
         if (!m_integrator) { // renderer.h:76-79: without an integrator nothing is accumulated
             m_is_rendering = false;
             return;
@@ -1293,11 +1316,23 @@ class Renderer {
         m_passes_done = 0;
         for (int pass = 0; pass < passes && m_is_rendering; ++pass) {
             p.sample_offset = pass;
-            const int rc = rtb_render(m_ctx, &p, acc.data(), &m_stats);
+            int rc;
+            if (multi) { // the group plans its own split: a pass is a job of its own (spp / passes samples, its own seed)
+                rtb_render_params q = p;
+                q.sample_offset = 0;
+                q.sample_stride = 1;
+                q.spp = (p.spp - pass + passes - 1) / passes;
+                q.seed = m_seed + 0x9e3779b97f4a7c15ull * uint64_t(pass);
+                rc = rtb_group_render(m_group, &q, acc.data(), nullptr, &m_stats);
+            } else {
+                rc = rtb_render(m_ctx, &p, acc.data(), &m_stats);
+            }
             if (rc == RTB_ERR_CANCELLED)
                 break;
             if (rc != RTB_OK) {
                 m_is_rendering = false;
+                if (multi)
+                    throw std::runtime_error(std::string("rtb_group_render: ") + rtb_group_last_error(m_group));
                 rtb::check(rc, m_ctx, "rtb_render");
             }
             samples_done += (p.spp - pass + passes - 1) / passes;
@@ -1335,9 +1370,10 @@ class Renderer {
     Settings m_settings;
     std::atomic<bool> m_is_rendering;
     std::shared_ptr<Integrator> m_integrator;
-    rtb_context *m_ctx = nullptr;
+    rtb_context *m_ctx = nullptr; // the single device's context, or the group's first
+    rtb_group *m_group = nullptr; // several devices
     rtb_render_stats m_stats{};
-    int m_device = 0;
+    std::vector<int> m_devices = std::vector<int>(1, 0);
     uint64_t m_seed = 1;
     int m_preview_passes = 0;
     std::atomic<int> m_passes_done{0};

@@ -29,6 +29,34 @@ def test_image_statistics_match_reference(gpu_ctx, golden, sid, integrator):
     assert parity.image_gates(rep) == [], rep
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+def test_both_traversal_kernels_render_scene09(gpu_ctx, golden, binding, mode):
+    """BVH scenes are traced by the warp-scheduled 4-wide kernels (csrc/rtb_trace.cuh) or by round 1's
+    binary while-while kernels; the default picks by scene (scene09, with media and an instance in
+    its tree, gets the binary ones).  Both, forced, must pass the image gates and the path-length
+    check on the scene that uses every primitive type."""
+    g = golden(9)
+    gpu_ctx.set_option(binding.OPT_BINARY_TRAVERSAL, mode)
+    try:
+        gpu_ctx.upload_scene(g.blob)
+        ref_sum, ref_sumsq, ref_spp = g["img_1_sum"], g["img_1_sumsq"], int(g["img_1_spp"][0])
+        h, w, _ = ref_sum.shape
+        spp = max(ref_spp // 2, 64)
+        means, rays, paths = [], 0, 0
+        for i in range(8):
+            acc, st = gpu_ctx.render(gpu_ctx.params(w, h, spp, 1, seed=200 + i))
+            assert st["paths"] == w * h * spp and np.isfinite(acc).all()
+            means.append(acc[..., :3] / spp)
+            rays += st["rays_closest"]
+            paths += st["paths"]
+        rep = parity.image_report(ref_sum, ref_sumsq, ref_spp, np.stack(means))
+        assert parity.image_gates(rep) == [], rep
+        ref_rpp = float(g["img_1_rays"][0]) / (w * h * ref_spp)
+        assert abs(rays / paths - ref_rpp) <= 0.01 * ref_rpp
+    finally:
+        gpu_ctx.set_option(binding.OPT_BINARY_TRAVERSAL, 0)
+
+
 def test_rays_per_path_match_reference(gpu_ctx, golden):
     """Path lengths are a sensitive whole-pipeline statistic (3.25 closest-hit
     rays per path on scene07/int1)."""
