@@ -157,7 +157,11 @@ enum rtb_option {
      * warp-scheduled 4-wide traversal (csrc/rtb_trace.cuh) unless the tree mixes media or instances
      * with its primitives, where round 1's binary while-while kernels measure faster; 1 = always the
      * binary kernels; 2 = always the 4-wide kernels (A/B measurements, tests) */
-    RTB_OPT_BINARY_TRAVERSAL = 6
+    RTB_OPT_BINARY_TRAVERSAL = 6,
+    /* scenes with more primitives than this (default 100000) get their fp64 validation tables on the
+     * first precision-64 call instead of at rtb_scene_upload (a third of the upload of the 1 M-sphere
+     * scene); 0 = always on first use.  Applied by the NEXT rtb_scene_upload */
+    RTB_OPT_LAZY_F64_PRIMS = 7
 };
 RTB_API int rtb_set_option(rtb_context *ctx, int option, int64_t value);
 
@@ -165,7 +169,7 @@ RTB_API int rtb_set_option(rtb_context *ctx, int option, int64_t value);
 
 /* Copies the flattened scene (rtb200_scene.h) to the device: builds the two-level
  * SAH BVH that replaces bvh_node (src/geometry/bvh.h:52-94), the fp32 production
- * tables and the fp64 validation tables.  The blob may be freed on return.
+ * tables and the fp64 validation tables (large scenes: on their first use, RTB_OPT_LAZY_F64_PRIMS).  The blob may be freed on return.
  * Replaces: the shared_ptr graph handed to Renderer::render (renderer.h:30). */
 RTB_API int rtb_scene_upload(rtb_context *ctx, const void *blob, uint64_t nbytes);
 RTB_API int rtb_scene_get_stats(rtb_context *ctx, rtb_scene_stats *out);

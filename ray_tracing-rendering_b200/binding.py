@@ -24,7 +24,7 @@ RENDER_TIME_EXTEND = 2
 RENDER_FORCE_WAVEFRONT = 4
 RENDER_FORCE_FUSED = 8
 OPT_FLAT_TRAVERSAL, OPT_FUSED_SCHEDULE = 1, 2
-OPT_BVH_MAX_LEAF, OPT_BVH_TRAVERSAL_COST_PCT, OPT_BVH_LAYOUT_DFS, OPT_BINARY_TRAVERSAL = 3, 4, 5, 6
+OPT_BVH_MAX_LEAF, OPT_BVH_TRAVERSAL_COST_PCT, OPT_BVH_LAYOUT_DFS, OPT_BINARY_TRAVERSAL, OPT_LAZY_F64_PRIMS = 3, 4, 5, 6, 7
 
 # Every symbol include/rtb200.h declares (tests check the library exports them all).
 EXPORTS = ["rtb_version", "rtb_context_create", "rtb_context_destroy", "rtb_last_error",
@@ -170,8 +170,9 @@ class Context:
 
     # ---- scene
     def upload_scene(self, blob: bytes):
-        buf = C.create_string_buffer(blob, len(blob))
-        self._check(self._lib.rtb_scene_upload(self._h, C.cast(buf, C.c_void_p), len(blob)))
+        # the library copies what it needs: hand it the bytes object's own buffer (no 200 MB staging copy)
+        blob = bytes(blob) if not isinstance(blob, bytes) else blob
+        self._check(self._lib.rtb_scene_upload(self._h, C.cast(C.c_char_p(blob), C.c_void_p), len(blob)))
 
     def scene_stats(self) -> dict:
         s = SceneStats()

@@ -115,8 +115,15 @@ int check_render_params(rtb_context *ctx, const rtb_render_params *p) { return c
 std::shared_ptr<const HostScene> build_scene_for(rtb_context *ctx, const void *blob, uint64_t nbytes) {
     try {
         SceneView view(blob, nbytes);
-        return std::make_shared<const HostScene>(
-            build_host_scene(view, ctx->opt_max_leaf, 0.01 * ctx->opt_trav_cost_pct, ctx->opt_layout_dfs != 0));
+        // Large scenes: the fp64 twin of the per-primitive / per-material tables (read by the validation
+        // entry points only) is built when a precision-64 call first asks for it (ensure_f64): it was a
+        // quarter of the host time and a third of the bytes of every upload of the 1 M-sphere scene.
+        const bool want_f64 = int64_t(view.n_prims()) <= ctx->opt_lazy_f64_prims;
+        auto host = std::make_shared<HostScene>(
+            build_host_scene(view, ctx->opt_max_leaf, 0.01 * ctx->opt_trav_cost_pct, ctx->opt_layout_dfs != 0, want_f64));
+        if (!want_f64)
+            host->blob_copy.assign(static_cast<const char *>(blob), static_cast<const char *>(blob) + nbytes);
+        return host;
     } catch (const CudaError &) {
         throw;
     } catch (const std::exception &e) {
@@ -130,7 +137,11 @@ void upload_scene(rtb_context *ctx, std::shared_ptr<const HostScene> host) {
     cudaStream_t s = ctx->stream;
     size_t bytes = 0;
     upload_typed(sc->f32, H.f32, s, bytes);
-    upload_typed(sc->f64, H.f64, s, bytes);
+    upload_typed(sc->f64, H.f64, s, bytes); // (large tables empty when H.has_f64 is false)
+    sc->f64_ready = H.has_f64;
+    sc->build_max_leaf = ctx->opt_max_leaf;
+    sc->build_trav_cost = 0.01 * ctx->opt_trav_cost_pct;
+    sc->build_layout_dfs = ctx->opt_layout_dfs != 0;
     sc->nodes.upload(H.nodes, s);
     sc->chains.upload(H.chains, s);
     sc->affine.upload(H.affine, s);
@@ -151,6 +162,23 @@ void upload_scene(rtb_context *ctx, std::shared_ptr<const HostScene> host) {
     RTB_CUDA(cudaStreamSynchronize(s));
     ctx->scene = std::move(sc);
     ++ctx->scene_serial;
+}
+
+// The fp64 validation tables of a large scene, on first use: the scene is flattened again from the
+// retained blob (same deterministic BVH, hence the same primitive order) with the fp64 tables on.
+void ensure_f64(rtb_context *ctx) {
+    DeviceScene &sc = *ctx->scene;
+    if (sc.f64_ready)
+        return;
+    SceneView view(sc.host.blob_copy.data(), sc.host.blob_copy.size());
+    const HostScene H = build_host_scene(view, sc.build_max_leaf, sc.build_trav_cost, sc.build_layout_dfs, true);
+    if (H.prim_orig != sc.host.prim_orig)
+        throw std::runtime_error("internal error: the fp64 rebuild ordered the primitives differently");
+    size_t bytes = 0;
+    upload_typed(sc.f64, H.f64, ctx->stream, bytes);
+    RTB_CUDA(cudaStreamSynchronize(ctx->stream));
+    sc.device_bytes += bytes;
+    sc.f64_ready = true;
 }
 
 } // namespace rtb
@@ -230,6 +258,8 @@ int rtb_set_option(rtb_context *ctx, int option, int64_t value) {
         ctx->opt_layout_dfs = value != 0;
     else if (option == RTB_OPT_BINARY_TRAVERSAL)
         ctx->opt_binary_traversal = int(value);
+    else if (option == RTB_OPT_LAZY_F64_PRIMS)
+        ctx->opt_lazy_f64_prims = value < 0 ? 0 : value;
     else
         return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_set_option: unknown option");
     return RTB_OK;
@@ -346,6 +376,8 @@ int rtb_trace_batch(rtb_context *ctx, const rtb_ray *rays, uint64_t n, int preci
     if (rc != RTB_OK)
         return rc;
     return guarded(ctx, [&] {
+        if (precision == 64)
+            ensure_f64(ctx);
         DeviceBuffer d_vis;
         unsigned long long *dv = nullptr;
         if (visits) {
@@ -384,6 +416,8 @@ int rtb_bsdf_eval_batch(rtb_context *ctx, int material, const rtb_bsdf_query *qu
     if (!n)
         return RTB_OK;
     return guarded(ctx, [&] {
+        if (precision == 64)
+            ensure_f64(ctx);
         run_batch(ctx, queries, n, out, [&](const rtb_bsdf_query *di, rtb_bsdf_value *dout) {
             if (precision == 64)
                 launch_bsdf_eval<double>(ctx, material, di, n, dout);
@@ -403,6 +437,8 @@ int rtb_bsdf_sample_batch(rtb_context *ctx, int material, const rtb_bsdf_query *
     if (!n)
         return RTB_OK;
     return guarded(ctx, [&] {
+        if (precision == 64)
+            ensure_f64(ctx);
         run_batch(ctx, queries, n, out, [&](const rtb_bsdf_query *di, rtb_bsdf_sample *dout) {
             if (precision == 64)
                 launch_bsdf_sample<double>(ctx, material, di, n, seed, dout);
@@ -422,6 +458,8 @@ int rtb_light_eval_batch(rtb_context *ctx, int light, const rtb_light_query *que
     if (!n)
         return RTB_OK;
     return guarded(ctx, [&] {
+        if (precision == 64)
+            ensure_f64(ctx);
         run_batch(ctx, queries, n, out, [&](const rtb_light_query *di, rtb_light_value *dout) {
             if (precision == 64)
                 launch_light_eval<double>(ctx, light, di, n, seed, dout);
@@ -441,6 +479,8 @@ int rtb_texture_eval_batch(rtb_context *ctx, int texture, const double *uvp, uin
     if (!n)
         return RTB_OK;
     return guarded(ctx, [&] {
+        if (precision == 64)
+            ensure_f64(ctx);
         DeviceBuffer d_in, d_out;
         d_in.alloc(n * 5 * sizeof(double));
         d_out.alloc(n * 3 * sizeof(double));

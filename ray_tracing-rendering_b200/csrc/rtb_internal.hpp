@@ -78,6 +78,10 @@ struct DeviceScene {
     DeviceBuffer nodes, chains, affine, prim_chain, prim_orig, orig_to_sorted, images, image_bytes, env_texels,
         env_tables, wide_nodes, wide_chain_root;
     size_t device_bytes = 0;
+    bool f64_ready = true;     // the large fp64 validation tables are resident (rtb_api.cu ensure_f64)
+    int build_max_leaf = 4;    // builder options this scene was flattened with
+    double build_trav_cost = 1.0;
+    bool build_layout_dfs = false;
 
     template <class R> const DeviceTyped<R> &typed() const;
     template <class R> GeomView<R> geom() const {
@@ -151,6 +155,7 @@ struct rtb_context {
     int opt_trav_cost_pct = 100; // RTB_OPT_BVH_TRAVERSAL_COST_PCT
     int opt_layout_dfs = 0;      // RTB_OPT_BVH_LAYOUT_DFS
     int opt_binary_traversal = 0; // RTB_OPT_BINARY_TRAVERSAL: 0 by scene, 1 binary, 2 wide
+    int64_t opt_lazy_f64_prims = 100000; // RTB_OPT_LAZY_F64_PRIMS
     // multi-GPU (rtb_multi.cu): this context's rank in an NCCL communicator and its staging buffers
     void *comm = nullptr; // ncclComm_t
     int comm_rank = 0, comm_size = 1;

@@ -11,6 +11,9 @@
 #include "rtb_wide.cuh"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <stdexcept>
@@ -53,6 +56,8 @@ struct HostScene {
     int n_top_items = 0; // primitives + instance records of the top level = prims[0 .. n_top_items)
     uint32_t root_ref = kEmptyRef; // ref of the top-level root
     bool flat_ok = false; // small enough for the lockstep / shared-memory traversal
+    bool has_f64 = true;  // f64.prims / maux / mats / texs were built (see build_host_scene)
+    std::vector<char> blob_copy; // the scene blob, kept only while has_f64 is false (to build those tables later)
 };
 
 namespace detail {
@@ -265,10 +270,27 @@ inline bool texture_reads_uv(const rtb::SceneView &S, int tex, int depth = 0) {
 }
 
 // max_leaf: primitives per BVH leaf.
+// RTB200_TIMING=1 prints the phases of build_host_scene on stderr (upload-cost work)
+struct PhaseTimer {
+    bool on = std::getenv("RTB200_TIMING") != nullptr;
+    std::chrono::high_resolution_clock::time_point t = std::chrono::high_resolution_clock::now();
+    void mark(const char *what) {
+        if (!on)
+            return;
+        const auto n = std::chrono::high_resolution_clock::now();
+        std::fprintf(stderr, "[rtb200 build] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
+
+// want_f64 = false: the large per-primitive / per-material fp64 tables (only the validation entry
+// points read them) are left empty; H.has_f64 says so and the API layer builds them on first use.
 inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double trav_cost = 1.0,
-                                  bool layout_dfs = false) {
+                                  bool layout_dfs = false, bool want_f64 = true) {
     using namespace detail;
+    PhaseTimer timer;
     S.validate();
+    timer.mark("validate");
     HostScene H;
     H.globals = S.globals();
     const rtb_prim *P = S.prims();
@@ -407,7 +429,9 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double t
         int inst; // instance index, or -1
     };
     std::vector<Slot> slots;
+    timer.mark("items + bounds");
     BuildResult tlas = build_bvh(top, max_leaf, 0, 0, trav_cost, layout_dfs);
+    timer.mark("binary SAH build (top level)");
     for (uint32_t id : tlas.order)
         slots.push_back(id < uint32_t(np) ? Slot{int(id), -1} : Slot{-1, int(id) - np});
     H.nodes = tlas.nodes;
@@ -477,15 +501,24 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double t
             T.prims.push_back(make_prim<R>(p, aux, aux2));
         }
     };
+    timer.mark("bottom levels + slots");
     emit(H.f32);
-    emit(H.f64);
+    timer.mark("emit fp32 primitives");
+    H.has_f64 = want_f64;
+    if (want_f64)
+        emit(H.f64);
+    timer.mark("emit fp64 primitives");
     for (const Slot &s : slots) {
         H.prim_orig.push_back(s.orig);
         H.prim_chain.push_back(s.inst >= 0 ? insts[s.inst].chain : P[s.orig].chain);
     }
 
     // ---- materials / textures
-    for (uint64_t i = 0; i < S.n_materials(); ++i) {
+    const unsigned host_threads = S.n_prims() >= 65536 ? builder_threads() : 1;
+    H.f32.mats.resize(S.n_materials());
+    if (want_f64)
+        H.f64.mats.resize(S.n_materials());
+    parallel_for(S.n_materials(), 4096, host_threads, [&](size_t i) {
         const rtb_material &m = S.materials()[i];
         int flags = 0;
         for (int k = 0; k < 4; ++k)
@@ -518,21 +551,27 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double t
             f.ir = float(d.ir);
             d.flags = f.flags = flags |= 4;
         }
-        H.f64.mats.push_back(d);
-        H.f32.mats.push_back(f);
-    }
+        if (want_f64)
+            H.f64.mats[i] = d;
+        H.f32.mats[i] = f;
+    });
+    timer.mark("materials");
     // hit-queue key of every primitive (PT_KEY_SHIFT): material type, or 6 for textured lambertians
-    for (size_t i = 0; i < H.f32.prims.size(); ++i) {
+    parallel_for(H.f32.prims.size(), 8192, host_threads, [&](size_t i) {
         if ((H.f32.prims[i].type_mat & PT_TYPE_MASK) == PT_INSTANCE)
-            continue;
+            return;
         const MatT<float> &m = H.f32.mats[H.f32.prims[i].type_mat >> PT_MAT_SHIFT];
         uint32_t key = uint32_t(m.type);
         if (m.type == RTB_MAT_LAMBERTIAN && !(m.flags & 2))
             key = uint32_t(RTB_MAT_TYPE_COUNT);
         H.f32.prims[i].type_mat |= key << PT_KEY_SHIFT;
-        H.f64.prims[i].type_mat |= key << PT_KEY_SHIFT;
-    }
-    for (uint64_t i = 0; i < S.n_textures(); ++i) {
+        if (want_f64)
+            H.f64.prims[i].type_mat |= key << PT_KEY_SHIFT;
+    });
+    H.f32.texs.resize(S.n_textures());
+    if (want_f64)
+        H.f64.texs.resize(S.n_textures());
+    parallel_for(S.n_textures(), 4096, host_threads, [&](size_t i) {
         const rtb_texture &t = S.textures()[i];
         TexT<double> d;
         TexT<float> f;
@@ -545,9 +584,10 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double t
         set3(f.color, t.color);
         d.scale = t.scale;
         f.scale = float(t.scale);
-        H.f64.texs.push_back(d);
-        H.f32.texs.push_back(f);
-    }
+        if (want_f64)
+            H.f64.texs[i] = d;
+        H.f32.texs[i] = f;
+    });
     for (uint64_t i = 0; i < S.n_images(); ++i)
         H.images.push_back(ImageRec{S.images()[i].width, S.images()[i].height, S.images()[i].offset});
     if (S.n_image_bytes())
@@ -621,6 +661,7 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double t
     }
 
     // the production traversal's tree (rtb_trace.cuh)
+    timer.mark("textures, lights, env tables");
     std::vector<uint32_t> globals;
     for (uint32_t id : global_ids)
         globals.push_back(uint32_t(H.orig_to_sorted[id]));
@@ -629,6 +670,7 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double t
         throw std::runtime_error("scene: BVH of depth " + std::to_string(H.wide.max_depth) +
                                  " exceeds the traversal stack (kWideStack)");
 
+    timer.mark("4-wide collapse + quantise");
     H.flat_ok = int(H.prim_orig.size()) <= kFlatMaxPrims && int(S.n_xform_ops()) <= kFlatMaxOps &&
                 int(S.n_chains()) <= kFlatMaxChains;
     H.f64.camera = derive_camera(cam);

@@ -13,6 +13,7 @@
 #ifndef RTB_WIDE_CUH
 #define RTB_WIDE_CUH
 
+#include "rtb_bvh.hpp"
 #include "rtb_geom.cuh"
 
 #include <cmath>
@@ -200,7 +201,7 @@ inline int wide_stack_need(const WideTree &w) { return 3 * w.max_depth + 2; }
 // (qnode_slabs: four fp32 roundings on values of the size of t).
 inline void quantize_wide(WideTree &w) {
     w.qnodes.resize(w.nodes.size());
-    for (size_t n = 0; n < w.nodes.size(); ++n) {
+    parallel_for(w.nodes.size(), 4096, w.nodes.size() >= 65536 ? builder_threads() : 1, [&](size_t n) {
         const Node128 &src = w.nodes[n];
         QNode64 q;
         float o[3], s[3];
@@ -251,7 +252,7 @@ inline void quantize_wide(WideTree &w) {
         for (int i = 0; i < 4; ++i)
             q.ref[i] = src.ref[i];
         w.qnodes[n] = q;
-    }
+    });
 }
 
 // Scalar traversal over the 4-wide tree: what the warp-scheduled kernels of rtb_trace.cuh compute

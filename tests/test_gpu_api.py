@@ -96,3 +96,33 @@ def test_cancel_from_another_thread(gpu_ctx, golden, binding):
     assert res.get("status") == -6
     acc, st = gpu_ctx.render(gpu_ctx.params(64, 64, 4, 1))   # usable afterwards
     assert st["paths"] == 64 * 64 * 4
+
+
+def test_fp64_tables_built_on_first_use(binding, golden):
+    """RTB_OPT_LAZY_F64_PRIMS: a scene uploaded without its fp64 validation tables (what the 1 M-sphere
+    scene gets by default) renders, and its first precision-64 call builds them: same bits as the
+    tables built at upload."""
+    import parity
+    g = golden(9)
+    ctx = binding.Context(0)
+    try:
+        ctx.set_option(binding.OPT_LAZY_F64_PRIMS, 0)
+        ctx.upload_scene(g.blob)
+        before = ctx.scene_stats()["device_bytes"]
+        acc, st = ctx.render(ctx.params(32, 32, 4, 1, seed=3))
+        assert np.isfinite(acc).all() and st["paths"] == 32 * 32 * 4
+        got = ctx.trace(g["rays"], 64)
+        assert ctx.scene_stats()["device_bytes"] > before
+        ctx.set_option(binding.OPT_LAZY_F64_PRIMS, 1 << 40)
+        ctx.upload_scene(g.blob)
+        eager = ctx.trace(g["rays"], 64)
+        assert np.array_equal(got["t"], eager["t"]) and np.array_equal(got["prim"], eager["prim"])
+        tex = np.array([[0.3, 0.6, 1.0, 2.0, 3.0]])
+        ctx.set_option(binding.OPT_LAZY_F64_PRIMS, 0)
+        ctx.upload_scene(g.blob)
+        lazy_tex = ctx.texture_eval(1, tex, 64)
+        ctx.set_option(binding.OPT_LAZY_F64_PRIMS, 1 << 40)
+        ctx.upload_scene(g.blob)
+        assert np.array_equal(lazy_tex, ctx.texture_eval(1, tex, 64))
+    finally:
+        ctx.close()
