@@ -27,6 +27,7 @@ struct SceneTables {
     std::vector<rtb_perlin> perlins;
     std::vector<rtb_light> lights;
     std::vector<float> env_texels;
+    std::vector<rtb_gate> gates;
 
     std::vector<uint8_t> serialise() const {
         struct Sec {
@@ -47,6 +48,7 @@ struct SceneTables {
             {RTB_SEC_PERLIN, sizeof(rtb_perlin), perlins.size(), perlins.data()},
             {RTB_SEC_LIGHTS, sizeof(rtb_light), lights.size(), lights.data()},
             {RTB_SEC_ENV_TEXELS, sizeof(float), env_texels.size(), env_texels.data()},
+            {RTB_SEC_GATES, sizeof(rtb_gate), gates.size(), gates.data()},
         };
         const uint32_t n = sizeof(secs) / sizeof(secs[0]);
         uint64_t off = sizeof(rtb_blob_header) + uint64_t(n) * sizeof(rtb_blob_section);
@@ -97,8 +99,9 @@ class SceneView {
         dir_.resize(hdr_.n_sections);
         std::memcpy(dir_.data(), base_ + sizeof(rtb_blob_header),
                     hdr_.n_sections * sizeof(rtb_blob_section));
-        for (const auto &s : dir_)
-            if (s.offset + s.count * s.stride > hdr_.total_bytes)
+        for (const auto &s : dir_) // (written so that no product or sum can wrap)
+            if (s.offset > hdr_.total_bytes || (s.offset & 3u) ||
+                (s.count && (s.stride == 0 || s.count > (hdr_.total_bytes - s.offset) / s.stride)))
                 throw std::runtime_error("scene blob: section out of range");
         if (count<rtb_globals>(RTB_SEC_GLOBALS) != 1 || count<rtb_camera>(RTB_SEC_CAMERA) != 1)
             throw std::runtime_error("scene blob: missing globals/camera");
@@ -140,6 +143,8 @@ class SceneView {
     uint64_t n_lights() const { return count<rtb_light>(RTB_SEC_LIGHTS); }
     const float *env_texels() const { return data<float>(RTB_SEC_ENV_TEXELS); }
     uint64_t n_env_texels() const { return count<float>(RTB_SEC_ENV_TEXELS); }
+    const rtb_gate *gates() const { return data<rtb_gate>(RTB_SEC_GATES); }
+    uint64_t n_gates() const { return count<rtb_gate>(RTB_SEC_GATES); }
 
     // Structural validation of every cross-reference; throws on the first bad one.
     void validate() const {
@@ -193,18 +198,36 @@ class SceneView {
         }
         for (int64_t i = 0; i < ni; ++i) {
             const rtb_image &im = images()[i];
-            if (im.width < 0 || im.height < 0 ||
-                im.offset + uint64_t(im.width) * im.height * 3 > n_image_bytes())
+            if (im.width < 0 || im.height < 0 || im.offset > n_image_bytes() ||
+                uint64_t(im.width) * uint64_t(im.height) > (n_image_bytes() - im.offset) / 3)
                 throw std::runtime_error("scene blob: image bytes out of range");
         }
         for (uint64_t i = 0; i < n_lights(); ++i) {
             const rtb_light &l = lights()[i];
             if (l.type < 0 || l.type > RTB_LIGHT_ENV)
                 throw std::runtime_error("scene blob: unknown light type");
-            if (l.type == RTB_LIGHT_ENV &&
-                l.env_offset + uint64_t(l.env_width) * l.env_height * 3 > n_env_texels())
-                throw std::runtime_error("scene blob: env texels out of range");
+            if (l.type == RTB_LIGHT_ENV) { // width and height both 0 (the white fallback) or both positive
+                if (l.env_width < 0 || l.env_height < 0 || (l.env_width == 0) != (l.env_height == 0))
+                    throw std::runtime_error("scene blob: env map size invalid");
+                if (l.env_offset > n_env_texels() ||
+                    uint64_t(l.env_width) * uint64_t(l.env_height) > (n_env_texels() - l.env_offset) / 3)
+                    throw std::runtime_error("scene blob: env texels out of range");
+            }
         }
+        for (uint64_t i = 0; i < n_gates(); ++i) {
+            const rtb_gate &g = gates()[i];
+            if (g.prim < 0 || g.prim >= np || prims()[g.prim].type != RTB_PRIM_SPHERE ||
+                !(prims()[g.prim].flags & RTB_PRIM_GATED))
+                throw std::runtime_error("scene blob: gate does not name a gated sphere");
+        }
+        for (int64_t i = 0; i < np; ++i)
+            if (prims()[i].flags & RTB_PRIM_GATED) {
+                int64_t n = 0;
+                for (uint64_t k = 0; k < n_gates(); ++k)
+                    n += gates()[k].prim == i;
+                if (n != 1)
+                    throw std::runtime_error("scene blob: gated primitive without exactly one gate");
+            }
     }
 
   private:

@@ -58,7 +58,8 @@ enum rtb_section_id {
     RTB_SEC_IMAGE_BYTES = 9, /* uint8_t[] pool the images index into */
     RTB_SEC_PERLIN = 10,     /* rtb_perlin[] */
     RTB_SEC_LIGHTS = 11,     /* rtb_light[] */
-    RTB_SEC_ENV_TEXELS = 12  /* float[] pool (RGB32F) the env lights index into */
+    RTB_SEC_ENV_TEXELS = 12, /* float[] pool (RGB32F) the env lights index into */
+    RTB_SEC_GATES = 13       /* rtb_gate[] (optional: absent = none) */
 };
 
 /* ---- globals & camera -------------------------------------------------- */
@@ -105,7 +106,9 @@ enum rtb_prim_flags {
     /* The reference stores the object as BOTH children of a one-object
      * bvh_node (src/geometry/bvh.h:68-69) and therefore tests it twice per
      * ray.  Only observable for stochastic primitives (media). */
-    RTB_PRIM_DUP_LEAF = 2
+    RTB_PRIM_DUP_LEAF = 2,
+    /* The primitive has an rtb_gate: it is only tested for rays that pass the gate's box. */
+    RTB_PRIM_GATED = 4
 };
 
 /* One leaf of the reference graph.  A `box` (src/geometry/box.h) contributes
@@ -132,6 +135,21 @@ typedef struct rtb_prim {
     int32_t aux1;
     double d[9];
 } rtb_prim;
+
+/* A sphere of NEGATIVE radius (the hollow-glass idiom, e.g. scenes.cpp:903) reports an inverted
+ * bounding box (sphere.h:62-66: centre -/+ radius), which surrounding_box() folds into its parent
+ * bvh_node's box as two points well inside the sphere.  The reference therefore only tests such a
+ * sphere for rays whose interval overlaps THAT node's box (bvh.h:40-50; every ancestor's box contains
+ * it) — a property of the tree the reference happened to build.  A flattener that walks a reference
+ * graph records that box here (same object space as the sphere); a sphere that is the only child of
+ * its node gets the inverted box itself, i.e. is never hit (aabb.h:31-48 fails on every ray).
+ * Scenes authored without a reference tree simply have no gates. */
+typedef struct rtb_gate {
+    int32_t prim; /* index into PRIMS: an RTB_PRIM_SPHERE carrying RTB_PRIM_GATED */
+    int32_t reserved;
+    double lo[3]; /* aabb::minimum of the bvh_node holding the sphere */
+    double hi[3]; /* aabb::maximum */
+} rtb_gate;
 
 enum rtb_xform_kind {
     RTB_XF_TRANSLATE = 0, /* a,b,c = offset              (hittable.h:34-75) */

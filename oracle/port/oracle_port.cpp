@@ -217,6 +217,21 @@ bool hit_leaf(const rtb_prim &p, V o, V d, double tm, double t_min, double t_max
     return true;
 }
 
+// aabb::hit (aabb.h:31-48) with the ray's 1/d and signs (ray.h:11-16)
+bool box_hit(const double lo[3], const double hi[3], V o, V d, double t_min, double t_max) {
+    for (int a = 0; a < 3; ++a) {
+        const double inv = 1.0 / d[a];
+        double t0 = (lo[a] - o[a]) * inv, t1 = (hi[a] - o[a]) * inv;
+        if (inv < 0)
+            std::swap(t0, t1);
+        t_min = t0 > t_min ? t0 : t_min;
+        t_max = t1 < t_max ? t1 : t_max;
+        if (t_max <= t_min)
+            return false;
+    }
+    return true;
+}
+
 // A leaf reached through its wrapper chain: translate::hit / rotate_y::hit / flip_face::hit
 // (hittable.h:51-62, 127-156, 163-170), outermost wrapper first on the way in, last on the way out.
 bool hit_wrapped(const Scene &sc, const rtb_prim &p, const Ray &r, double t_min, double t_max, Rec &rec) {
@@ -232,6 +247,12 @@ bool hit_wrapped(const Scene &sc, const rtb_prim &p, const Ray &r, double t_min,
             apply_op(sc.S->xform_ops()[first + i], o, d);
             dirs[i + 1] = d;
         }
+    }
+    if (p.flags & RTB_PRIM_GATED) { // rtb_gate: the box test of the bvh_node that holds this sphere (bvh.h:42)
+        const int64_t self = &p - sc.S->prims();
+        for (uint64_t k = 0; k < sc.S->n_gates(); ++k)
+            if (sc.S->gates()[k].prim == self && !box_hit(sc.S->gates()[k].lo, sc.S->gates()[k].hi, o, d, t_min, t_max))
+                return false;
     }
     if (!hit_leaf(p, o, d, r.tm, t_min, t_max, rec))
         return false;

@@ -348,12 +348,35 @@ struct Walker {
         if (!o)
             throw std::runtime_error("walker: null hittable");
         if (auto n = dynamic_cast<bvh_node *>(o)) {
+            // a negative-radius sphere directly below this node is only ever tested for rays that pass
+            // n->box (its own reported box is inverted, sphere.h:62-66): recorded as the sphere's gate
+            auto gated = [&](shared_ptr<hittable> &child) {
+                auto s = dynamic_cast<sphere *>(child.get());
+                return s && s->radius < 0;
+            };
+            auto add_gate = [&](int prim) {
+                rtb_gate g{};
+                g.prim = prim;
+                for (int k = 0; k < 3; ++k) {
+                    g.lo[k] = n->box.min()[k];
+                    g.hi[k] = n->box.max()[k];
+                }
+                T.prims[prim].flags |= RTB_PRIM_GATED;
+                T.gates.push_back(g);
+            };
+            const bool gl = gated(n->left), gr = gated(n->right);
             if (n->left.get() == n->right.get()) {
                 walk(n->left, boundary, flags | RTB_PRIM_DUP_LEAF);
                 n->right = n->left;
+                if (gl)
+                    add_gate(int(T.prims.size()) - 1);
             } else {
                 walk(n->left, boundary, flags);
+                if (gl)
+                    add_gate(int(T.prims.size()) - 1);
                 walk(n->right, boundary, flags);
+                if (gr)
+                    add_gate(int(T.prims.size()) - 1);
             }
         } else if (auto l = dynamic_cast<hittable_list *>(o)) {
             for (auto &c : l->objects)

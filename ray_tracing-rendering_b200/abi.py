@@ -27,6 +27,8 @@ assert LIGHT_QUERY.itemsize == 64 and LIGHT_VALUE.itemsize == 104
 # ---- scene blob sections ------------------------------------------------------------------
 SEC_GLOBALS, SEC_CAMERA, SEC_PRIMS, SEC_CHAINS, SEC_XFORM_OPS, SEC_MATERIALS = 1, 2, 3, 4, 5, 6
 SEC_TEXTURES, SEC_IMAGES, SEC_IMAGE_BYTES, SEC_PERLIN, SEC_LIGHTS, SEC_ENV_TEXELS = 7, 8, 9, 10, 11, 12
+SEC_GATES = 13
+PRIM_FLAG_BOUNDARY_ONLY, PRIM_FLAG_DUP_LEAF, PRIM_FLAG_GATED = 1, 2, 4
 
 GLOBALS = np.dtype([("background", "<f8", 3), ("image_width", "<i4"), ("image_height", "<i4"),
                     ("samples_per_pixel", "<i4"), ("scene_id", "<i4")])
@@ -47,18 +49,19 @@ PERLIN = np.dtype([("ranvec", "<f8", (256, 3)), ("perm_x", "<i4", 256), ("perm_y
 LIGHT = np.dtype([("type", "<i4"), ("env_width", "<i4"), ("env_height", "<i4"),
                   ("env_is_probe", "<i4"), ("env_offset", "<u8"), ("Q", "<f8", 3), ("u", "<f8", 3),
                   ("v", "<f8", 3), ("intensity", "<f8", 3), ("cos_cutoff", "<f8")])
+GATE = np.dtype([("prim", "<i4"), ("reserved", "<i4"), ("lo", "<f8", 3), ("hi", "<f8", 3)])
 
 SECTION_DTYPES = {
     SEC_GLOBALS: GLOBALS, SEC_CAMERA: CAMERA, SEC_PRIMS: PRIM, SEC_CHAINS: CHAIN,
     SEC_XFORM_OPS: XFORM_OP, SEC_MATERIALS: MATERIAL, SEC_TEXTURES: TEXTURE, SEC_IMAGES: IMAGE,
     SEC_IMAGE_BYTES: np.dtype("u1"), SEC_PERLIN: PERLIN, SEC_LIGHTS: LIGHT,
-    SEC_ENV_TEXELS: np.dtype("<f4"),
+    SEC_ENV_TEXELS: np.dtype("<f4"), SEC_GATES: GATE,
 }
 SECTION_NAMES = {
     SEC_GLOBALS: "globals", SEC_CAMERA: "camera", SEC_PRIMS: "prims", SEC_CHAINS: "chains",
     SEC_XFORM_OPS: "xform_ops", SEC_MATERIALS: "materials", SEC_TEXTURES: "textures",
     SEC_IMAGES: "images", SEC_IMAGE_BYTES: "image_bytes", SEC_PERLIN: "perlins",
-    SEC_LIGHTS: "lights", SEC_ENV_TEXELS: "env_texels",
+    SEC_LIGHTS: "lights", SEC_ENV_TEXELS: "env_texels", SEC_GATES: "gates",
 }
 SCENE_MAGIC = 0x31424C46
 SCENE_VERSION = 2
@@ -83,6 +86,8 @@ def parse_blob(blob: bytes) -> dict:
             raise ValueError(f"section {int(s['id'])}: stride {int(s['stride'])} != {dt.itemsize}")
         off, cnt = int(s["offset"]), int(s["count"])
         out[SECTION_NAMES[int(s["id"])]] = buf[off:off + cnt * dt.itemsize].view(dt)
+    for sid, name in SECTION_NAMES.items():     # optional sections a writer left out
+        out.setdefault(name, np.zeros(0, SECTION_DTYPES[sid]))
     return out
 
 

@@ -63,12 +63,16 @@ k_trace_batch(GeomView<Real> g, const int32_t *__restrict__ orig_to_sorted, int 
         DrawOpen draw{&rng};
         Real t;
         // the fp32 instantiation traces the way the renderer does: lockstep for small scenes
-        const uint32_t pi =
-            (kRobust && g.flat)
-                ? traverse_flat<Real, false, kRobust>(g, o, d, Real(q.time), Real(q.t_min), Real(q.t_max), origin,
-                                                      draw, t, visits ? &nodes : nullptr, visits ? &tests : nullptr)
-                : trace_bvh<INST>(g, o, d, Real(q.time), Real(q.t_min), Real(q.t_max), origin, draw, t,
-                            visits ? &nodes : nullptr, visits ? &tests : nullptr);
+        auto run = [&](const GeomView<Real> &gv, Real t_max, Real &t_out) -> uint32_t {
+            return (kRobust && gv.flat)
+                       ? traverse_flat<Real, false, kRobust>(gv, o, d, Real(q.time), Real(q.t_min), t_max, origin, draw, t_out,
+                                                             visits ? &nodes : nullptr, visits ? &tests : nullptr)
+                       : trace_bvh<INST>(gv, o, d, Real(q.time), Real(q.t_min), t_max, origin, draw, t_out,
+                                         visits ? &nodes : nullptr, visits ? &tests : nullptr);
+        };
+        // fp64: gated (negative-radius) spheres exactly as the reference reaches them (rtb_geom.cuh)
+        const uint32_t pi = (!kRobust && g.n_gated) ? trace_gated_exact<Real>(g, o, d, Real(q.t_min), Real(q.t_max), t, run)
+                                                    : run(g, Real(q.t_max), t);
         rtb_hit h;
         h.t = 0;
         h.p[0] = h.p[1] = h.p[2] = 0;

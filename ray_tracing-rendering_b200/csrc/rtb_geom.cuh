@@ -38,6 +38,9 @@ enum : uint32_t {
     // material costs no look-up: the traversal already holds the record of the primitive it hit
     PT_KEY_SHIFT = 4,
     PT_KEY_MASK = 7,
+    // a sphere of negative radius that the reference only reaches through one bvh_node's box
+    // (rtb200_scene.h rtb_gate): aux -> the box, in the MovingAux table
+    PT_GATED = 128,
     PT_MAT_SHIFT = 8
 };
 
@@ -46,7 +49,7 @@ constexpr int kMaxChainOps = 8;
 constexpr int kStackDepth = 48;
 
 // One primitive.  float: 32 bytes exactly (one sector); double: 56 bytes.
-//   SPHERE   d = cx cy cz r
+//   SPHERE   d = cx cy cz r ; PT_GATED: aux -> its gate box (a MovingAux record)
 //   MSPHERE  d = c0x c0y c0z r ; aux -> MovingAux
 //   RECT     d = a0 a1 b0 b1 k   (XY: a=x b=y | XZ: a=x b=z | YZ: a=y b=z)
 //   MEDIUM   d[0] = neg_inv_density ; aux = first boundary prim, aux2 = count
@@ -59,9 +62,12 @@ template <class R> struct PrimT {
 };
 static_assert(sizeof(PrimT<float>) == 32, "production primitive record must be one 32-byte sector");
 
+// Per-primitive auxiliary record: the second centre and the time range of a moving sphere, or the gate
+// box of a PT_GATED sphere (lo = c1, hi = time0, time1, extra).
 template <class R> struct MovingAux {
     R c1[3];
     R time0, time1;
+    R extra;
 };
 
 template <class R> struct XfOp {
@@ -116,7 +122,15 @@ template <class R> struct GeomView {
     uint32_t root_ref; // ref of the top-level root (its box is never tested)
     int32_t n_top; // prims[0 .. n_top) are the top-level items (primitives and instance records)
     int32_t flat;  // != 0: the scene is small enough for the lockstep traversal (traverse_flat)
+    // PT_GATED spheres (rtb_gate).  gate_mode 0: tested inside the traversal, the gate box against the
+    // interval of that moment (production); 1: skipped — trace_gated_exact() adds them afterwards in the
+    // reference's order.  orig_limit: primitives whose blob index is >= it are skipped (fp64 paths only).
+    int32_t gate_mode = 0;
+    int32_t orig_limit = 0x7fffffff;
+    int32_t n_gated = 0;
+    uint32_t gated[4] = {0, 0, 0, 0}; // sorted indices of the gated spheres, ascending blob index
 };
+constexpr int kMaxGated = 4;
 
 // Scenes with at most this many primitive records are traversed in lockstep from shared
 // memory instead of through the BVH.
@@ -265,12 +279,32 @@ RTB_HD bool hit_rect(const PrimT<R> &p, int AX, int A, int B, V3<R> o, V3<R> d, 
     return true;
 }
 
+// aabb::hit (aabb.h:31-48) of a gate box, with the interval the sphere itself is about to be tested with
+template <class R> RTB_HD bool gate_pass(const MovingAux<R> &b, V3<R> o, V3<R> idir, R t_min, R t_max) {
+    const R lo[3] = {b.c1[0], b.c1[1], b.c1[2]}, hi[3] = {b.time0, b.time1, b.extra};
+    for (int a = 0; a < 3; ++a) {
+        R t0 = (lo[a] - o[a]) * idir[a], t1 = (hi[a] - o[a]) * idir[a];
+        if (idir[a] < 0) {
+            const R tmp = t0;
+            t0 = t1;
+            t1 = tmp;
+        }
+        t_min = t0 > t_min ? t0 : t_min;
+        t_max = t1 < t_max ? t1 : t_max;
+        if (t_max <= t_min)
+            return false;
+    }
+    return true;
+}
+
 // One non-instance, non-medium primitive in ITS OWN object space.
 template <class R, bool ROBUST>
 RTB_HD bool hit_simple(const GeomView<R> &g, const PrimT<R> &p, uint32_t type, V3<R> o, V3<R> d,
                        V3<R> idir, R time, R t_min, R t_max, bool is_origin, R &t_out) {
     switch (type) {
     case PT_SPHERE:
+        if ((p.type_mat & PT_GATED) && (g.gate_mode != 0 || !gate_pass<R>(g.maux[p.aux], o, idir, t_min, t_max)))
+            return false;
         return hit_sphere<R, ROBUST>(V3<R>(p.d[0], p.d[1], p.d[2]), p.d[3], o, d, t_min, t_max,
                                      is_origin, t_out);
     case PT_MSPHERE:
@@ -604,6 +638,8 @@ RTB_HD uint32_t traverse(const GeomView<R> &g, V3<R> o, V3<R> d, R time, R t_min
                     entered = true;
                     break;
                 }
+                if (!ROBUST && g.prim_orig[i] >= g.orig_limit)
+                    continue;
                 if (n_tests)
                     ++*n_tests;
                 R t;
@@ -622,6 +658,9 @@ RTB_HD uint32_t traverse(const GeomView<R> &g, V3<R> o, V3<R> d, R time, R t_min
                 } else {
                     h = hit_simple<R, ROBUST>(g, p, type, co, cd, cid, time, t_min, t_max, ROBUST && i == origin_prim, t);
                 }
+                // a later primitive of the reference's walk wins a tie (its tests reject t > t_max only)
+                if (!ROBUST && h && best != kNoPrim && t == t_max && g.prim_orig[i] < g.prim_orig[best])
+                    h = false;
                 if (h) {
                     best = i;
                     t_max = t;
@@ -648,6 +687,57 @@ RTB_HD uint32_t traverse(const GeomView<R> &g, V3<R> o, V3<R> d, R time, R t_min
     uint32_t storage[kStackDepth];
     LocalStack stack(storage);
     return traverse<R, ANY, ROBUST>(g, o, d, time, t_min, t_max, origin_prim, rng, t_hit, n_nodes, n_tests, stack);
+}
+
+// Closest hit of a scene with PT_GATED spheres, exactly as the reference finds it (fp64 validation
+// paths; the production kernels test a gated sphere inside the traversal, see GeomView::gate_mode).
+// The reference tests a gated sphere S only if the box of the bvh_node holding it overlaps
+// [t_min, tA], tA = the closest hit among the primitives that PRECEDE S in its left-to-right walk
+// (bvh.h:40-50) — the blob order.  trace(view, t_max, t_out) is any closest-hit traversal of `view`.
+//   1. t* = closest hit over everything but the gated spheres (gate_mode 1);
+//   2. per gated sphere, ascending blob index: the gate cannot pass with t_max -> next; the sphere has no
+//      root below t* -> next (whatever the reference finds loses to t*); the gate passes with t* -> it
+//      passes with tA >= t*, and sphere::hit picks the same root for both bounds whenever that root is
+//      below t*; otherwise tA is measured by a second traversal restricted to the preceding primitives.
+template <class R, class Trace>
+RTB_HD uint32_t trace_gated_exact(const GeomView<R> &g, V3<R> o, V3<R> d, R t_min, R t_max, R &t_hit, Trace trace) {
+    GeomView<R> gv = g;
+    gv.gate_mode = 1;
+    R t_cur;
+    uint32_t best = trace(gv, t_max, t_cur);
+    R t_gated = t_max; // closest accepted gated sphere so far (they precede the next one)
+    for (int k = 0; k < g.n_gated; ++k) {
+        const uint32_t gi = g.gated[k];
+        const PrimT<R> p = g.prims[gi];
+        V3<R> lo = o, ld = d;
+        const int chain = g.prim_chain[gi];
+        if (chain >= 0) {
+            const ChainRec c = g.chains[chain];
+            for (int i = 0; i < c.count && i < kMaxChainOps; ++i)
+                apply_op(g.ops[c.first + i], lo, ld);
+        }
+        const V3<R> lid = safe_inv(ld);
+        const MovingAux<R> box = g.maux[p.aux];
+        if (!gate_pass<R>(box, lo, lid, t_min, t_max))
+            continue;
+        R r;
+        if (!hit_sphere<R, false>(V3<R>(p.d[0], p.d[1], p.d[2]), p.d[3], lo, ld, t_min, t_cur, false, r))
+            continue;
+        if (!gate_pass<R>(box, lo, lid, t_min, t_cur)) {
+            GeomView<R> gl = gv;
+            gl.orig_limit = g.prim_orig[gi];
+            R t_a;
+            trace(gl, t_max, t_a);
+            t_a = t_gated < t_a ? t_gated : t_a;
+            if (!gate_pass<R>(box, lo, lid, t_min, t_a))
+                continue;
+        }
+        best = gi;
+        t_cur = r;
+        t_gated = r;
+    }
+    t_hit = t_cur;
+    return best;
 }
 
 // Lockstep traversal for small scenes (the Cornell-box class: a few dozen primitives).

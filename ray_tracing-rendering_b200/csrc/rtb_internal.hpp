@@ -102,6 +102,9 @@ struct DeviceScene {
         g.root_ref = host.root_ref;
         g.n_top = host.n_top_items;
         g.flat = host.flat_ok ? 1 : 0;
+        g.n_gated = int32_t(host.gated.size());
+        for (size_t k = 0; k < host.gated.size(); ++k)
+            g.gated[k] = host.gated[k];
         return g;
     }
     WideView wide() const { // the 4-wide tree of the production traversal (rtb_trace.cuh)

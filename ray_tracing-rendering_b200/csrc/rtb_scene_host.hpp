@@ -55,6 +55,7 @@ struct HostScene {
     int n_instances = 0;
     int n_top_items = 0; // primitives + instance records of the top level = prims[0 .. n_top_items)
     uint32_t root_ref = kEmptyRef; // ref of the top-level root
+    std::vector<uint32_t> gated; // sorted indices of the PT_GATED spheres, ascending blob index (GeomView::gated)
     bool flat_ok = false; // small enough for the lockstep / shared-memory traversal
     bool has_f64 = true;  // f64.prims / maux / mats / texs were built (see build_host_scene)
     std::vector<char> blob_copy; // the scene blob, kept only while has_f64 is false (to build those tables later)
@@ -168,6 +169,7 @@ template <class R> PrimT<R> make_prim(const rtb_prim &p, uint32_t aux, uint32_t 
         break;
     }
     q.type_mat = type | ((p.flags & RTB_PRIM_DUP_LEAF) ? uint32_t(PT_DUP_LEAF) : 0u) |
+                 ((p.flags & RTB_PRIM_GATED) ? uint32_t(PT_GATED) : 0u) |
                  (uint32_t(p.material) << PT_MAT_SHIFT);
     q.aux = aux;
     q.aux2 = aux2;
@@ -483,8 +485,22 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double t
             }
             const rtb_prim &p = P[s.orig];
             uint32_t aux = 0, aux2 = 0;
-            if (p.type == RTB_PRIM_MOVING_SPHERE) {
+            if (p.flags & RTB_PRIM_GATED) { // validate(): a sphere with exactly one gate
                 MovingAux<R> m;
+                for (uint64_t k = 0; k < S.n_gates(); ++k)
+                    if (S.gates()[k].prim == s.orig) {
+                        const rtb_gate &gt = S.gates()[k];
+                        for (int a = 0; a < 3; ++a)
+                            m.c1[a] = R(gt.lo[a]);
+                        m.time0 = R(gt.hi[0]);
+                        m.time1 = R(gt.hi[1]);
+                        m.extra = R(gt.hi[2]);
+                    }
+                aux = uint32_t(T.maux.size());
+                T.maux.push_back(m);
+            } else if (p.type == RTB_PRIM_MOVING_SPHERE) {
+                MovingAux<R> m;
+                m.extra = R(0);
                 for (int k = 0; k < 3; ++k)
                     m.c1[k] = R(p.d[3 + k]);
                 m.time0 = R(p.d[6]);
@@ -512,6 +528,12 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double t
         H.prim_orig.push_back(s.orig);
         H.prim_chain.push_back(s.inst >= 0 ? insts[s.inst].chain : P[s.orig].chain);
     }
+
+    for (uint64_t i = 0; i < S.n_prims(); ++i) // (ascending blob index = the reference's traversal order)
+        if (P[i].flags & RTB_PRIM_GATED)
+            H.gated.push_back(uint32_t(H.orig_to_sorted[i]));
+    if (H.gated.size() > size_t(kMaxGated))
+        throw std::runtime_error("scene: more than " + std::to_string(kMaxGated) + " gated (negative-radius) spheres");
 
     // ---- materials / textures
     const unsigned host_threads = S.n_prims() >= 65536 ? builder_threads() : 1;
@@ -671,7 +693,8 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double t
                                  " exceeds the traversal stack (kWideStack)");
 
     timer.mark("4-wide collapse + quantise");
-    H.flat_ok = int(H.prim_orig.size()) <= kFlatMaxPrims && int(S.n_xform_ops()) <= kFlatMaxOps &&
+    // (gated spheres are only known to hit_simple(): no typed shared-memory copy for their scenes)
+    H.flat_ok = S.n_gates() == 0 && int(H.prim_orig.size()) <= kFlatMaxPrims && int(S.n_xform_ops()) <= kFlatMaxOps &&
                 int(S.n_chains()) <= kFlatMaxChains;
     H.f64.camera = derive_camera(cam);
     H.f32.camera = cast_camera<float>(H.f64.camera);

@@ -275,6 +275,8 @@ RTB_HD uint32_t traverse_wide(const GeomView<R> &g, const Node128 *nodes4, uint3
         const uint32_t i = globals[gi];
         const PrimT<R> p = g.prims[i];
         const uint32_t type = p.type_mat & PT_TYPE_MASK;
+        if (!ROBUST && g.prim_orig[i] >= g.orig_limit)
+            continue;
         if (n_tests)
             ++*n_tests;
         R t;
@@ -291,6 +293,8 @@ RTB_HD uint32_t traverse_wide(const GeomView<R> &g, const Node128 *nodes4, uint3
         } else {
             h = hit_simple<R, ROBUST>(g, p, type, o, d, safe_inv(d), time, t_min, t_max, ROBUST && i == origin_prim, t);
         }
+        if (!ROBUST && h && best != kNoPrim && t == t_max && g.prim_orig[i] < g.prim_orig[best])
+            h = false;
         if (h) {
             best = i;
             t_max = t;
@@ -360,6 +364,8 @@ RTB_HD uint32_t traverse_wide(const GeomView<R> &g, const Node128 *nodes4, uint3
                     entered = true;
                     break;
                 }
+                if (!ROBUST && g.prim_orig[i] >= g.orig_limit)
+                    continue;
                 if (n_tests)
                     ++*n_tests;
                 R t;
@@ -376,6 +382,9 @@ RTB_HD uint32_t traverse_wide(const GeomView<R> &g, const Node128 *nodes4, uint3
                 } else {
                     h = hit_simple<R, ROBUST>(g, p, type, co, cd, cid, time, t_min, t_max, ROBUST && i == origin_prim, t);
                 }
+                // a later primitive of the reference's walk wins a tie (its tests reject t > t_max only)
+                if (!ROBUST && h && best != kNoPrim && t == t_max && g.prim_orig[i] < g.prim_orig[best])
+                    h = false;
                 if (h) {
                     best = i;
                     t_max = t;

@@ -13,6 +13,13 @@ if ROOT not in sys.path:
 PKG = "ray_tracing-rendering_b200"
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 GOLDEN_SCENES = [7, 21, 23, 9, 1, 19, 26, 24, 15, 17, 18, 8]
+# the rest of the reference's catalogue (scenes.cpp:1523-2096) as smaller fixtures, generated with synthetic
+# image textures / normal maps / .hdr files in place (tests/golden/make_golden.py CATALOGUE): (scene, integrator)
+CATALOGUE_CASES = [(2, 1), (4, 1), (5, 1), (6, 0), (10, 1), (11, 2), (12, 2), (13, 2), (14, 2), (16, 4), (20, 3), (22, 4),
+                   (25, 4), (27, 4), (28, 3), (30, 4), (31, 4), (32, 4), (33, 4), (34, 4), (35, 4), (36, 4), (37, 4),
+                   (38, 3), (39, 4), (40, 4), (41, 3), (42, 1)]
+CATALOGUE_SCENES = [c[0] for c in CATALOGUE_CASES]
+ALL_SCENES = GOLDEN_SCENES + CATALOGUE_SCENES
 
 
 def pytest_configure(config):

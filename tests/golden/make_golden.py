@@ -104,8 +104,61 @@ def light_queries(n, rng, scale):
 
 only = set()
 
+# (scene id, integrator, image size, spp, light query scale): integrator 4 (MIS) or 3 (NEE) where the scene
+# has lights, 2 (PBR path) for the PBR galleries, 1 / 0 otherwise
+CATALOGUE = [(2, 1, (64, 36), 128, 10.0), (4, 1, (64, 36), 128, 10.0), (5, 1, (64, 36), 256, 10.0), (6, 0, (64, 36), 256, 10.0),
+             (10, 1, (64, 36), 128, 10.0), (11, 2, (64, 36), 256, 10.0), (12, 2, (48, 48), 256, 10.0),
+             (13, 2, (64, 36), 256, 10.0), (14, 2, (64, 36), 256, 10.0), (16, 4, (64, 36), 256, 10.0),
+             (20, 3, (64, 36), 256, 10.0), (22, 4, (48, 48), 128, 500.0), (25, 4, (64, 36), 512, 10.0),
+             (27, 4, (64, 36), 512, 10.0), (28, 3, (64, 36), 512, 10.0), (30, 4, (64, 36), 256, 10.0),
+             (31, 4, (48, 48), 256, 500.0), (32, 4, (64, 36), 256, 10.0), (33, 4, (64, 36), 256, 10.0),
+             (34, 4, (64, 36), 256, 10.0), (35, 4, (64, 36), 256, 10.0), (36, 4, (64, 36), 256, 10.0),
+             (37, 4, (48, 48), 256, 10.0), (38, 3, (64, 36), 256, 10.0), (39, 4, (64, 36), 256, 10.0),
+             (40, 4, (64, 36), 256, 10.0), (41, 3, (64, 36), 256, 10.0), (42, 1, (64, 36), 256, 10.0)]
 
-def make_scene(sid, integrators, n_paths, n_rays, img_wh, img_spp, rng, light_scale=10.0):
+
+def write_assets(tmp):
+    """Synthetic stand-ins for the assets the reference's scenes load by fixed relative names and that
+    are absent from its repository (SURVEY 8c "Missing assets"): with them in the cwd image_texture /
+    EnvironmentLight hold real texel data (stb decodes them inside the reference; the blob carries the
+    decoded texels), without them the reference's cyan / white fallbacks apply."""
+    from PIL import Image
+    rng = np.random.default_rng(7)
+
+    def pattern(w, h, base, amp, freq):
+        y, x = np.mgrid[0:h, 0:w]
+        img = np.zeros((h, w, 3))
+        for c in range(3):
+            img[..., c] = base[c] + amp[c] * np.sin(freq[0] * x / w * 2 * np.pi + c) * np.cos(freq[1] * y / h * 2 * np.pi - c)
+        img += 0.04 * (rng.random((h, w, 3)) - 0.5)
+        return (np.clip(img, 0, 1) * 255).astype(np.uint8)
+
+    Image.fromarray(pattern(256, 128, (0.35, 0.5, 0.55), (0.3, 0.35, 0.4), (3, 2))).save(os.path.join(tmp, "earthmap.jpg"), quality=92)
+    for d, stem, base in (("oak", "oak_veneer_01", (0.55, 0.38, 0.2)), ("brick", "red_brick", (0.6, 0.25, 0.2)),
+                          ("rust", "rusty_metal_04", (0.45, 0.3, 0.22))):
+        os.makedirs(os.path.join(tmp, "tex", d), exist_ok=True)
+        Image.fromarray(pattern(64, 64, base, (0.25, 0.2, 0.15), (4, 3))).save(os.path.join(tmp, "tex", d, stem + "_diff_1k.png"))
+        r = pattern(48, 40, (0.5, 0.5, 0.5), (0.4, 0.4, 0.4), (2, 5))
+        r[..., 1] = r[..., 2] = r[..., 0]
+        Image.fromarray(r).save(os.path.join(tmp, "tex", d, stem + "_rough_1k.png"))
+        m = pattern(32, 32, (0.5, 0.5, 0.5), (0.5, 0.5, 0.5), (3, 3))
+        m[..., 1] = m[..., 2] = m[..., 0] = np.where(m[..., 0] > 127, 230, 20)
+        Image.fromarray(m).save(os.path.join(tmp, "tex", d, stem + "_metal_1k.png"))
+        # tangent-space normal map: z up, x / y tilted by a smooth bump field (texture.h:19-23 decodes 2c - 1)
+        y, x = np.mgrid[0:64, 0:64]
+        nx = 0.35 * np.sin(x / 64 * 6 * np.pi)
+        ny = 0.35 * np.cos(y / 64 * 4 * np.pi)
+        nz = np.sqrt(np.maximum(1 - nx * nx - ny * ny, 0.05))
+        n = np.stack([nx, ny, nz], axis=-1)
+        Image.fromarray(((n * 0.5 + 0.5) * 255).astype(np.uint8)).save(os.path.join(tmp, "tex", d, stem + "_nor_dx_1k.png"))
+    write_hdr(os.path.join(tmp, "brown_photostudio_02_4k.hdr"), synthetic_sky(64, 32, 3, sun=(60.0, 55.0, 50.0)))
+    write_hdr(os.path.join(tmp, "cedar_bridge_sunset_2_4k.hdr"), synthetic_sky(48, 24, 4, sun=(80.0, 50.0, 30.0)))
+    write_hdr(os.path.join(tmp, "stpeters_probe.hdr"), synthetic_sky(32, 32, 5))
+    write_hdr(os.path.join(tmp, "uffizi_probe.hdr"), synthetic_sky(24, 24, 6))
+
+
+def make_scene(sid, integrators, n_paths, n_rays, img_wh, img_spp, rng, light_scale=10.0, n_bsdf=400, n_light=600,
+               n_tex=300, max_mats=16):
     if only and sid not in only:
         return
     s = refbind.RefScene(sid)
@@ -120,18 +173,18 @@ def make_scene(sid, integrators, n_paths, n_rays, img_wh, img_spp, rng, light_sc
     out["rays"] = np.concatenate(rays_all)
     out["hits"] = np.concatenate(hits_all)
     nm = len(T["materials"])
-    for m in (range(nm) if nm <= 16 else rng.choice(nm, 6, replace=False)):
-        q = bsdf_queries(400, rng)
+    for m in (range(nm) if nm <= max_mats else rng.choice(nm, 6, replace=False)):
+        q = bsdf_queries(n_bsdf, rng)
         out[f"bsdf_q_{m}"] = q
         out[f"bsdf_v_{m}"] = s.bsdf_eval(int(m), q)
     for l in range(len(T["lights"])):
-        q = light_queries(600, rng, light_scale)
+        q = light_queries(n_light, rng, light_scale)
         out[f"light_q_{l}"] = q
         out[f"light_v_{l}"] = s.light_eval(l, q)
         out[f"light_flags_{l}"] = np.array([s.light_flags(l)])
     nt = len(T["textures"])
-    for t in (range(nt) if nt <= 16 else rng.choice(nt, 4, replace=False)):
-        uvp = np.concatenate([rng.random((300, 2)), rng.uniform(-300, 600, size=(300, 3))], axis=1)
+    for t in (range(nt) if nt <= max_mats else rng.choice(nt, 4, replace=False)):
+        uvp = np.concatenate([rng.random((n_tex, 2)), rng.uniform(-300, 600, size=(n_tex, 3))], axis=1)
         out[f"tex_q_{t}"] = uvp
         out[f"tex_v_{t}"] = s.texture_value(int(t), uvp)
     w, h = img_wh
@@ -190,6 +243,13 @@ def main():
         make_scene(8, [1], 600, 1600, (64, 64), 256, rng)                     # cornell_smoke (media in instances)
         if not only or 0 in only:
             make_fullres()
+        # the rest of the reference's catalogue (scenes.cpp:1523-2096) as smaller fixtures: hits, a few BSDF /
+        # light / texture grids and one image each; synthetic assets in the cwd (write_assets), so image
+        # textures, roughness / metallic / normal maps and the four remaining .hdr names carry texel data
+        write_assets(tmp)
+        lite = dict(n_bsdf=120, n_light=200, n_tex=120, max_mats=8)
+        for sid, integ, wh, spp, scale in CATALOGUE:
+            make_scene(sid, [integ], 400, 1200, wh, spp, rng, scale, **lite)
         os.chdir(ROOT)
 
 

@@ -44,6 +44,9 @@ template <class R> GeomView<R> geom_view(HostScene &H) {
     g.root_ref = H.root_ref;
     g.n_top = H.n_top_items;
     g.flat = H.flat_ok ? 1 : 0;
+    g.n_gated = int(H.gated.size());
+    for (size_t k = 0; k < H.gated.size(); ++k)
+        g.gated[k] = H.gated[k];
     return g;
 }
 template <class R> ShadeView<R> shade_view(HostScene &H) {
@@ -82,18 +85,23 @@ void trace_batch(HostScene &H, const rtb_ray *rays, uint64_t n, rtb_hit *hits, u
         R t;
         uint32_t storage[kStackDepth];
         LocalStack stack(storage);
-        const uint32_t pi =
-            wide ? traverse_wide<R, false, ROBUST>(g, W->nodes.data(), W->root_ref, W->chain_root.data(), o, d, R(q.time),
-                                                   R(q.t_min), R(q.t_max), origin, draw, t, &stats[0], &stats[1], stack,
-                                                   W->global_prims.data(), uint32_t(W->global_prims.size()))
-            : use_flat && g.flat
-                ? traverse_flat<R, false, ROBUST>(g, o, d, R(q.time), R(q.t_min), R(q.t_max), origin, draw, t,
-                                                  &stats[0], &stats[1])
-            : inst_in_descent
-                ? traverse<R, false, ROBUST, decltype(draw), LocalStack, true, false>(
-                      g, o, d, R(q.time), R(q.t_min), R(q.t_max), origin, draw, t, &stats[0], &stats[1], stack)
-                : traverse<R, false, ROBUST>(g, o, d, R(q.time), R(q.t_min), R(q.t_max), origin, draw, t,
-                                             &stats[0], &stats[1], stack);
+        auto run = [&](const GeomView<R> &gv, R t_max, R &t_out) -> uint32_t {
+            stack.clear();
+            return wide ? traverse_wide<R, false, ROBUST>(gv, W->nodes.data(), W->root_ref, W->chain_root.data(), o, d, R(q.time),
+                                                          R(q.t_min), t_max, origin, draw, t_out, &stats[0], &stats[1], stack,
+                                                          W->global_prims.data(), uint32_t(W->global_prims.size()))
+                   : use_flat && gv.flat
+                       ? traverse_flat<R, false, ROBUST>(gv, o, d, R(q.time), R(q.t_min), t_max, origin, draw, t_out,
+                                                         &stats[0], &stats[1])
+                   : inst_in_descent
+                       ? traverse<R, false, ROBUST, decltype(draw), LocalStack, true, false>(
+                             gv, o, d, R(q.time), R(q.t_min), t_max, origin, draw, t_out, &stats[0], &stats[1], stack)
+                       : traverse<R, false, ROBUST>(gv, o, d, R(q.time), R(q.t_min), t_max, origin, draw, t_out,
+                                                    &stats[0], &stats[1], stack);
+        };
+        // fp64: gated spheres exactly as the reference reaches them; fp32: inside the traversal, as the renderer does
+        const uint32_t pi = (!ROBUST && g.n_gated) ? trace_gated_exact<R>(g, o, d, R(q.t_min), R(q.t_max), t, run)
+                                                   : run(g, R(q.t_max), t);
         rtb_hit &h = hits[i];
         std::memset(&h, 0, sizeof(h));
         h.prim = -1;

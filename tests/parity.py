@@ -16,16 +16,18 @@ VALUE_ATOL = 1e-12
 # (GGX at roughness 0.01 has condition number ~1e4 near the specular peak).
 FP32_VALUE_RTOL = 5e-3
 FP32_VALUE_ATOL = 1e-5
-# Layer 3: images (the RNG streams differ, so the comparison is statistical).
+# Layer 3: images (the RNG streams differ, so the comparison is statistical).  Two sets of gates:
+# (a) every case, image_gates() — the pooled estimator:
 #   * whole-image mean within 1 % of the reference's (or within 4 standard errors of the
 #     difference where the noise of the two estimates is itself above 1 %);
-#   * per-pixel |GPU - reference| <= 3 sigma for >= 97 % of the pixel channels.  sigma comes
-#     from the reference's per-pixel sample variance and the spread of K independent GPU
-#     renders, both pooled over 5x5 pixels.  Calibration: the reference compared against
-#     ITSELF with this estimator gives 97.9-99.4 % on the fixture scenes (a Gaussian with known
-#     sigma would give 99.73 %; path-tracing noise is heavy-tailed and sigma is estimated);
-#   * RMSE <= 1.6x the RMSE expected from the two noise levels alone (reference vs itself:
-#     0.9-1.5x).
+#   * per-pixel |GPU - reference| <= 3 sigma for >= 97 % of the pixel channels, sigma from the
+#     reference's per-pixel sample variance and the spread of K independent GPU renders, both
+#     pooled over 5x5 pixels (the reference against ITSELF gives 97.9-99.4 %; a Gaussian with known
+#     sigma would give 99.73 %: path-tracing noise is heavy-tailed and sigma is estimated);
+#   * RMSE <= 1.6x the RMSE expected from the two noise levels alone (reference vs itself: 0.9-1.5x).
+# (b) every case a second reference instance reproduces (selfcal), strict_image_gates() — the contract's
+#   own: mean within 1 % of a 64x-sample reference mean with no escape, and the UN-POOLED 3-sigma
+#   fraction at equal sample counts held to the reference-vs-itself value of that very scene.
 IMAGE_MEAN_RTOL = 0.01
 IMAGE_MEAN_NSIGMA = 4.0
 IMAGE_3SIGMA_MIN_FRACTION = 0.97
@@ -45,6 +47,19 @@ def deterministic_mask(tables, ref_hits, got_hits):
     (constant_medium.h:85): neither side reports a medium.  Media only ever ADD candidate
     hits, so when both answers are solid primitives they must be the same primitive."""
     return ~is_medium(tables, ref_hits["prim"]) & ~is_medium(tables, got_hits["prim"])
+
+
+def gated_mask(tables, *hit_sets):
+    """Queries none of whose answers is a gated (negative-radius) sphere (rtb200_scene.h rtb_gate).  The
+    fp64 validation kernels reproduce the reference's reach of such a sphere exactly
+    (trace_gated_exact, csrc/rtb_geom.cuh); the fp32 production traversals test its gate box against
+    the interval they hold at that moment of THEIR visiting order, which can differ from the
+    reference's on rays that meet the sphere before the box (2 of 1,200 recorded rays on scene 34)."""
+    gated = set(int(i) for i in tables["gates"]["prim"]) if len(tables.get("gates", ())) else set()
+    ok = np.ones(len(hit_sets[0]), bool)
+    for h in hit_sets:
+        ok &= ~np.isin(h["prim"], list(gated))
+    return ok
 
 
 def trace_mismatches(ref_hits, got_hits, mask, fields=("prim", "t", "p", "normal", "front_face", "material")):
@@ -97,16 +112,10 @@ def box_filter(a, r=2):
     return out / (n * n)
 
 
-def image_report(ref_sum, ref_sumsq, ref_spp, gpu_means, gpu_spp=None):
+def image_report(ref_sum, ref_sumsq, ref_spp, gpu_means):
     """ref_*: per-pixel sum / sum of squares of linear Li over ref_spp samples.
-    gpu_means: (K, H, W, 3) means of K independent GPU renders of gpu_spp samples each.
-    Two estimators of the per-pixel 3-sigma agreement:
-      pooled     sigma from the reference's sample variance and the spread of the K GPU renders,
-                 both pooled over 5x5 pixels (round 1's estimator);
-      un-pooled  (needs gpu_spp) sigma per pixel from the reference's own sample variance s^2 alone:
-                 sigma^2 = s^2 (1 / ref_spp + 1 / (K gpu_spp)) — if both sides sample the same
-                 distribution this is the variance of the difference, with no smoothing and no
-                 7-degrees-of-freedom variance estimate in it."""
+    gpu_means: (K, H, W, 3) means of K independent GPU renders.  The pooled estimator: sigma from the
+    reference's sample variance and the spread of the K GPU renders, both pooled over 5x5 pixels."""
     ref_sum = np.asarray(ref_sum, np.float64)
     ref_mean = ref_sum / ref_spp
     ref_var = np.maximum(np.asarray(ref_sumsq, np.float64) / ref_spp - ref_mean ** 2, 0) / ref_spp
@@ -119,16 +128,7 @@ def image_report(ref_sum, ref_sumsq, ref_spp, gpu_means, gpu_spp=None):
     z = (gpu_mean - ref_mean) / sigma
     lit = sigma > 1e-9
     se = np.sqrt((ref_var + gpu_var).sum(axis=(0, 1))) / (ref_var.shape[0] * ref_var.shape[1])
-    frac_unpooled = None
-    if gpu_spp:
-        s2 = ref_var * ref_spp                                       # per-sample variance of the reference
-        sig_u = np.sqrt(s2 * (1.0 / ref_spp + 1.0 / (k * gpu_spp)) + 1e-20)
-        zu = (gpu_mean - ref_mean) / sig_u
-        lit_u = sig_u > 1e-9
-        frac_unpooled = float((np.abs(zu[lit_u]) <= 3).mean()) if lit_u.any() else 1.0
     return {
-        "frac_within_3sigma_unpooled": frac_unpooled,
-        "gpu_samples_per_pixel": (k * gpu_spp) if gpu_spp else None,
         "mean_se": se,
         "ref_mean": ref_mean.mean(axis=(0, 1)),
         "gpu_mean": gpu_mean.mean(axis=(0, 1)),
@@ -143,13 +143,27 @@ def image_report(ref_sum, ref_sumsq, ref_spp, gpu_means, gpu_spp=None):
     }
 
 
+def unpooled_3sigma_fraction(ref_sum, ref_sumsq, ref_spp, other_mean, other_spp):
+    """Fraction of pixel channels on which |other - reference| <= 3 sigma, sigma per pixel from the
+    reference's own sample variance s^2 alone: sigma^2 = s^2 (1 / ref_spp + 1 / other_spp).  No smoothing.
+    Path-tracing noise is heavy-tailed and s^2 misses the fireflies the reference did not catch, so the
+    value a CORRECT second renderer reaches is well below 99.7 % and depends on the scene and on both sample
+    counts: it is only meaningful next to the reference-vs-itself value at the same counts (selfcal)."""
+    ref_mean = np.asarray(ref_sum, np.float64) / ref_spp
+    s2 = np.maximum(np.asarray(ref_sumsq, np.float64) / ref_spp - ref_mean ** 2, 0)
+    sig = np.sqrt(s2 * (1.0 / ref_spp + 1.0 / other_spp) + 1e-20)
+    z = (np.asarray(other_mean, np.float64) - ref_mean) / sig
+    lit = sig > 1e-9
+    return float((np.abs(z[lit]) <= 3).mean()) if lit.any() else 1.0
+
+
 _selfcal = None
 
 
 def selfcal(sid, integrator):
     """Reference-vs-itself calibration of this image case (tests/golden/make_selfcal.py), or None:
-    {"frac": un-pooled 3-sigma fraction of a second reference render, "mean": high-sample mean rgb,
-    "mean_se": its standard error}."""
+    {"frac", "frac_sd": mean / standard deviation of the un-pooled 3-sigma fraction of four reference
+    re-renders at the fixture's sample count, "mean": high-sample mean rgb, "mean_se": its standard error}."""
     global _selfcal
     if _selfcal is None:
         import os
@@ -158,35 +172,42 @@ def selfcal(sid, integrator):
     kf, km = f"frac_{sid}_{integrator}", f"mean_{sid}_{integrator}"
     if kf not in _selfcal:
         return None
-    return {"frac": float(_selfcal[kf][0]), "mean": _selfcal[km][:3], "mean_se": _selfcal[km][3:]}
+    return {"frac": float(_selfcal[kf][0]), "frac_sd": float(_selfcal[kf][1]), "mean": _selfcal[km][:3],
+            "mean_se": _selfcal[km][3:]}
 
 
-# margin below the reference-vs-itself 3-sigma fraction (one reference re-render is itself a noisy
-# estimate of that fraction: +-0.4 % at 64 x 64 x 3 channels)
+# The contract's layer-3 gates (north_star / SURVEY 8d(3)) for the calibrated cases:
+#   * whole-image mean of a high-sample render within 1 % of the reference's high-sample mean — no escape;
+#   * un-pooled 3-sigma fraction of renders at the reference's sample count, averaged over K of them, at
+#     least the reference-vs-itself value minus a margin: 1 %, or 3 standard errors of the difference of
+#     the two averaged fractions where the scene's fraction is itself noisier than that.
 IMAGE_3SIGMA_MARGIN = 0.01
 
 
-def image_gates(rep, cal=None):
-    """Applies the layer-3 gates to an image_report(); returns a list of failure strings.
-    With `cal` (selfcal() of the case) and >= 256 GPU samples per pixel the gates are the contract's:
-    whole-image mean within 1 % of the reference's high-sample mean, no escape hatch, and the UN-POOLED
-    3-sigma fraction at least the reference-vs-itself value minus IMAGE_3SIGMA_MARGIN."""
+def strict_image_gates(ref_sum, ref_sumsq, ref_spp, equal_spp_means, hi_mean, cal):
+    """equal_spp_means: (K, H, W, 3) means of K independent renders of ref_spp samples each; hi_mean: rgb
+    whole-image mean of a high-sample render; cal: selfcal() of the case.  Returns failure strings."""
     bad = []
-    strict = cal is not None and rep.get("frac_within_3sigma_unpooled") is not None and \
-        (rep.get("gpu_samples_per_pixel") or 0) >= 256
-    if strict:
-        d = np.abs(rep["gpu_mean"] - cal["mean"])
-        if not (d <= IMAGE_MEAN_RTOL * cal["mean"]).all():
-            bad.append(f"whole-image mean: gpu {rep['gpu_mean']} vs reference high-sample mean {cal['mean']} "
-                       f"(rel {d / cal['mean']}, gate 1 %)")
-        if rep["frac_within_3sigma_unpooled"] < cal["frac"] - IMAGE_3SIGMA_MARGIN:
-            bad.append(f"only {rep['frac_within_3sigma_unpooled']:.4f} of pixel channels within 3 sigma (un-pooled); "
-                       f"reference vs itself: {cal['frac']:.4f}")
-    else:
-        d = np.abs(rep["gpu_mean"] - rep["ref_mean"])
-        ok = (d <= IMAGE_MEAN_RTOL * rep["ref_mean"]) | (d <= IMAGE_MEAN_NSIGMA * rep["mean_se"])
-        if not ok.all():
-            bad.append(f"whole-image mean: gpu {rep['gpu_mean']} vs ref {rep['ref_mean']} (se {rep['mean_se']})")
+    fr = [unpooled_3sigma_fraction(ref_sum, ref_sumsq, ref_spp, m, ref_spp) for m in equal_spp_means]
+    margin = max(IMAGE_3SIGMA_MARGIN, 3.0 * cal["frac_sd"] * np.sqrt(1.0 / 4 + 1.0 / len(fr)))
+    if np.mean(fr) < cal["frac"] - margin:
+        bad.append(f"un-pooled 3-sigma fraction {np.mean(fr):.4f} (of {len(fr)} renders) < reference vs itself "
+                   f"{cal['frac']:.4f} - {margin:.4f}")
+    d = np.abs(np.asarray(hi_mean) - cal["mean"])
+    if not (d <= IMAGE_MEAN_RTOL * cal["mean"]).all():
+        bad.append(f"whole-image mean {np.asarray(hi_mean)} vs reference high-sample mean {cal['mean']} (rel {d / cal['mean']}, "
+                   f"gate {IMAGE_MEAN_RTOL})")
+    return bad
+
+
+def image_gates(rep):
+    """The pooled layer-3 gates on an image_report() (every case; the only ones for the randomly generated
+    scenes, which no second reference instance reproduces); returns a list of failure strings."""
+    bad = []
+    d = np.abs(rep["gpu_mean"] - rep["ref_mean"])
+    ok = (d <= IMAGE_MEAN_RTOL * rep["ref_mean"]) | (d <= IMAGE_MEAN_NSIGMA * rep["mean_se"])
+    if not ok.all():
+        bad.append(f"whole-image mean: gpu {rep['gpu_mean']} vs ref {rep['ref_mean']} (se {rep['mean_se']})")
     if rep["frac_within_3sigma"] < IMAGE_3SIGMA_MIN_FRACTION:
         bad.append(f"only {rep['frac_within_3sigma']:.4f} of pixel channels within 3 sigma")
     if rep["rmse"] > IMAGE_RMSE_FACTOR * rep["expected_rmse"] + 1e-6:

@@ -3,10 +3,10 @@ walking the reference's own scene graphs, and the python writer/reader round tri
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_SCENES
+from conftest import ALL_SCENES, GOLDEN_SCENES
 
 
-@pytest.mark.parametrize("sid", GOLDEN_SCENES)
+@pytest.mark.parametrize("sid", ALL_SCENES)
 def test_blob_parses_and_is_consistent(abi, golden, sid):
     T = abi.parse_blob(golden(sid).blob)
     g = T["globals"][0]

@@ -3,12 +3,13 @@ import numpy as np
 import pytest
 
 import parity
+from conftest import CATALOGUE_CASES
 
 pytestmark = pytest.mark.gpu
 
 # (scene, integrator): the BASELINE.json configs at fixture resolution + the feature tail
 IMAGE_CASES = [(7, 0), (7, 1), (21, 3), (21, 4), (23, 2), (23, 3), (23, 4), (9, 1), (1, 1), (19, 3), (19, 4),
-               (26, 4), (24, 4), (15, 3), (17, 4), (18, 3), (8, 1)]
+               (26, 4), (24, 4), (15, 3), (17, 4), (18, 3), (8, 1)] + CATALOGUE_CASES
 
 
 @pytest.mark.parametrize("sid,integrator", IMAGE_CASES)
@@ -27,6 +28,14 @@ def test_image_statistics_match_reference(gpu_ctx, golden, sid, integrator):
         means.append(acc[..., :3] / spp)
     rep = parity.image_report(ref_sum, ref_sumsq, ref_spp, np.stack(means))
     assert parity.image_gates(rep) == [], rep
+    cal = parity.selfcal(sid, integrator)
+    if cal is not None:
+        # the contract's gates, against the reference-vs-itself calibration of this very case
+        # (tests/golden/selfcal.npz): 4 renders at the reference's sample count, one at 32x
+        equal = [gpu_ctx.render(gpu_ctx.params(w, h, ref_spp, integrator, seed=300 + i))[0][..., :3] / ref_spp for i in range(4)]
+        hi = gpu_ctx.render(gpu_ctx.params(w, h, 32 * ref_spp, integrator, seed=77))[0][..., :3] / (32 * ref_spp)
+        bad = parity.strict_image_gates(ref_sum, ref_sumsq, ref_spp, np.stack(equal), hi.mean(axis=(0, 1)), cal)
+        assert bad == [], (bad, cal)
 
 
 @pytest.mark.parametrize("mode", [1, 2])

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import parity
-from conftest import GOLDEN_SCENES
+from conftest import ALL_SCENES, GOLDEN_SCENES
 
 
 def _ptr(a):
@@ -37,7 +37,7 @@ def trace(hostcheck, h, rays, precision, abi):
     return out, st
 
 
-@pytest.mark.parametrize("sid", GOLDEN_SCENES)
+@pytest.mark.parametrize("sid", ALL_SCENES)
 def test_fp64_hits_are_bit_exact(hostcheck, scenes, golden, abi, sid):
     g = golden(sid)
     T = abi.parse_blob(g.blob)
@@ -49,13 +49,13 @@ def test_fp64_hits_are_bit_exact(hostcheck, scenes, golden, abi, sid):
     assert parity.trace_mismatches(ref, got, mask) == 0
 
 
-@pytest.mark.parametrize("sid", GOLDEN_SCENES)
+@pytest.mark.parametrize("sid", ALL_SCENES)
 def test_fp32_hits_agree(hostcheck, scenes, golden, abi, sid):
     g = golden(sid)
     T = abi.parse_blob(g.blob)
     rays, ref = parity.to_segment_form(g["rays"]), g["hits"]
     got, _ = trace(hostcheck, scenes(sid), rays, 32, abi)
-    mask = parity.deterministic_mask(T, ref, got)
+    mask = parity.deterministic_mask(T, ref, got) & parity.gated_mask(T, ref, got)
     agree = (got["prim"] == ref["prim"])[mask]
     # per-fixture batches are small (~2k rays): allow one disagreement per fixture here;
     # the >= 99.99 % gate is applied to the pooled >= 1M-ray batches of the GPU test
@@ -66,7 +66,7 @@ def test_fp32_hits_agree(hostcheck, scenes, golden, abi, sid):
     assert np.percentile(rel, 99) < 1e-3
 
 
-@pytest.mark.parametrize("sid", GOLDEN_SCENES)
+@pytest.mark.parametrize("sid", ALL_SCENES)
 def test_camera_is_bit_exact(hostcheck, scenes, golden, sid):
     out = np.zeros(24)
     hostcheck.hc_camera_derived(scenes(sid), _ptr(out))
@@ -109,7 +109,7 @@ def test_node_and_primitive_records_are_32_bytes(hostcheck, scenes, golden):
     assert info[0] % 2 == 0                    # sibling pairs stay 64-byte aligned
 
 
-@pytest.mark.parametrize("sid", GOLDEN_SCENES)
+@pytest.mark.parametrize("sid", ALL_SCENES)
 def test_both_traversal_shapes_give_the_same_hits(hostcheck, scenes, golden, abi, sid):
     """traverse() handles instance entry / exit either in the leaf phase or inside the descent
     loop (the renderer picks by scene); both must return the same primitive at the same t, bit
@@ -131,7 +131,7 @@ def test_both_traversal_shapes_give_the_same_hits(hostcheck, scenes, golden, abi
     assert np.array_equal(a32["prim"][mask], b32["prim"][mask]) and np.array_equal(a32["t"][mask], b32["t"][mask])
 
 
-@pytest.mark.parametrize("sid", GOLDEN_SCENES)
+@pytest.mark.parametrize("sid", ALL_SCENES)
 def test_plane_records_match_the_reference_records(hostcheck, scenes, golden, abi, sid):
     """The fused kernel shades planar primitives from plane_record() (one world-space plane per
     rect, digested once) instead of replaying the wrapper chain in make_record(): the normal and
@@ -216,7 +216,7 @@ def test_plane_records_follow_make_record_on_arbitrary_wrapper_chains(hostcheck,
     assert 0.05 < a["front_face"][ok].mean() < 0.95
 
 
-@pytest.mark.parametrize("sid", GOLDEN_SCENES)
+@pytest.mark.parametrize("sid", ALL_SCENES)
 def test_wide_bvh_traversal_gives_the_reference_hits(hostcheck, scenes, golden, abi, sid):
     """Groundwork for the next round (csrc/rtb_wide.cuh, not yet in librtb200.so): the binary tree
     collapsed into 128-byte 4-wide nodes and traversed nearest child first must name the
@@ -233,8 +233,12 @@ def test_wide_bvh_traversal_gives_the_reference_hits(hostcheck, scenes, golden, 
     seg = parity.to_segment_form(rays)
     w32, _ = trace(hostcheck, scenes(sid), seg, 37, abi)
     b32, _ = trace(hostcheck, scenes(sid), seg, 33, abi)
-    m32 = mask & parity.deterministic_mask(T, ref, w32) & parity.deterministic_mask(T, ref, b32)
-    assert np.array_equal(w32["prim"][m32], b32["prim"][m32]) and np.array_equal(w32["t"][m32], b32["t"][m32])
+    m32 = mask & parity.deterministic_mask(T, ref, w32) & parity.deterministic_mask(T, ref, b32) & \
+        parity.gated_mask(T, w32, b32)
+    # (two coincident surfaces — the floor and the bottom face of a box standing on it, scene 35 — are hit
+    # at the same t: which of them an fp32 traversal names depends on its visiting order)
+    assert np.array_equal(w32["t"][m32], b32["t"][m32])
+    assert (w32["prim"][m32] != b32["prim"][m32]).sum() <= 1
     info = np.zeros(2, np.uint64)
     hostcheck.hc_wide_info(scenes(sid), _ptr(info))
     if info[0] > 4:                                  # a real tree: wider nodes, fewer dependent steps
@@ -273,7 +277,7 @@ def test_wide_bvh_on_a_deep_tree(hostcheck, abi):
     assert info[1] / info[0] > 3.0 and sw[0] < 0.65 * (sb[0] / 2)      # near-full nodes, far fewer dependent steps
 
 
-@pytest.mark.parametrize("sid", GOLDEN_SCENES)
+@pytest.mark.parametrize("sid", ALL_SCENES)
 def test_warp_scheduler_matches_the_scalar_wide_traversal(hostcheck, scenes, golden, abi, sid):
     """The production traversal (csrc/rtb_trace.cuh: windows sorted by octant, lanes refilled as they
     finish, node / leaf steps chosen by a warp vote, children pushed with their entry distance) run
@@ -286,7 +290,7 @@ def test_warp_scheduler_matches_the_scalar_wide_traversal(hostcheck, scenes, gol
     w32, _ = trace(hostcheck, scenes(sid), seg, 37, abi)
     k32, sk = trace(hostcheck, scenes(sid), seg, 38, abi)
     assert (k32["prim"] != -2).all()
-    mask = parity.deterministic_mask(T, ref, w32) & parity.deterministic_mask(T, ref, k32)
+    mask = parity.deterministic_mask(T, ref, w32) & parity.deterministic_mask(T, ref, k32) & parity.gated_mask(T, w32, k32)
     assert mask.mean() > 0.3
     same = (w32["prim"][mask] == k32["prim"][mask]) & (w32["t"][mask] == k32["t"][mask])
     # a different visiting order may only change the answer between surfaces hit at the same t
@@ -327,7 +331,7 @@ def test_warp_scheduler_on_a_deep_tree(hostcheck, abi):
     assert sk[0] <= 1.08 * sw[0]
 
 
-@pytest.mark.parametrize("sid", GOLDEN_SCENES)
+@pytest.mark.parametrize("sid", ALL_SCENES)
 def test_quantised_nodes_contain_their_children(hostcheck, scenes, sid):
     """The 64-byte node the kernels fetch (8-bit child planes on the node's own grid) must bound every
     child at least as widely as the fp32 node it was made from — that is what keeps the hits of the

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import parity
-from conftest import GOLDEN_SCENES
+from conftest import ALL_SCENES, CATALOGUE_CASES, GOLDEN_SCENES
 
 
 @pytest.fixture(scope="module")
@@ -21,7 +21,7 @@ def port():
     return get
 
 
-@pytest.mark.parametrize("sid", GOLDEN_SCENES)
+@pytest.mark.parametrize("sid", ALL_SCENES)
 def test_hits_bit_exact(port, golden, abi, sid):
     g = golden(sid)
     T = abi.parse_blob(g.blob)
@@ -37,12 +37,12 @@ def test_hits_bit_exact(port, golden, abi, sid):
     assert np.array_equal(got["u"][sph], g["hits"]["u"][sph]) and np.array_equal(got["v"][sph], g["hits"]["v"][sph])
 
 
-@pytest.mark.parametrize("sid", GOLDEN_SCENES)
+@pytest.mark.parametrize("sid", ALL_SCENES)
 def test_camera_bit_exact(port, golden, sid):
     assert np.array_equal(port(golden, sid).camera_derived(), golden(sid)["camera"])
 
 
-@pytest.mark.parametrize("sid", GOLDEN_SCENES)
+@pytest.mark.parametrize("sid", ALL_SCENES)
 def test_bsdf_light_texture_values(port, golden, sid):
     g = golden(sid)
     s = port(golden, sid)
@@ -61,7 +61,7 @@ def test_bsdf_light_texture_values(port, golden, sid):
 
 
 @pytest.mark.parametrize("sid,integrator", [(7, 0), (7, 1), (21, 3), (21, 4), (23, 2), (23, 3), (23, 4), (9, 1), (19, 4),
-                                            (24, 4), (15, 3), (17, 4), (18, 3), (8, 1)])
+                                            (24, 4), (15, 3), (17, 4), (18, 3), (8, 1)] + CATALOGUE_CASES)
 def test_images_match_reference_statistics(port, golden, sid, integrator):
     g = golden(sid)
     ref_sum, ref_sumsq = g[f"img_{integrator}_sum"], g[f"img_{integrator}_sumsq"]
