@@ -200,15 +200,17 @@ def strict_image_gates(ref_sum, ref_sumsq, ref_spp, equal_spp_means, hi_mean, ca
     return bad
 
 
-def image_gates(rep):
+def image_gates(rep, calibrated=False):
     """The pooled layer-3 gates on an image_report() (every case; the only ones for the randomly generated
-    scenes, which no second reference instance reproduces); returns a list of failure strings."""
+    scenes, which no second reference instance reproduces); returns a list of failure strings.
+    calibrated: the case also goes through strict_image_gates(), whose per-scene 3-sigma gate replaces
+    the fixed 97 % one (scene 31's heavy-tailed caustics put the reference itself at 96.9-97.5 % there)."""
     bad = []
     d = np.abs(rep["gpu_mean"] - rep["ref_mean"])
     ok = (d <= IMAGE_MEAN_RTOL * rep["ref_mean"]) | (d <= IMAGE_MEAN_NSIGMA * rep["mean_se"])
     if not ok.all():
         bad.append(f"whole-image mean: gpu {rep['gpu_mean']} vs ref {rep['ref_mean']} (se {rep['mean_se']})")
-    if rep["frac_within_3sigma"] < IMAGE_3SIGMA_MIN_FRACTION:
+    if not calibrated and rep["frac_within_3sigma"] < IMAGE_3SIGMA_MIN_FRACTION:
         bad.append(f"only {rep['frac_within_3sigma']:.4f} of pixel channels within 3 sigma")
     if rep["rmse"] > IMAGE_RMSE_FACTOR * rep["expected_rmse"] + 1e-6:
         bad.append(f"rmse {rep['rmse']:.5f} > {IMAGE_RMSE_FACTOR} x expected {rep['expected_rmse']:.5f}")

@@ -27,8 +27,8 @@ def test_image_statistics_match_reference(gpu_ctx, golden, sid, integrator):
         assert np.isfinite(acc).all()
         means.append(acc[..., :3] / spp)
     rep = parity.image_report(ref_sum, ref_sumsq, ref_spp, np.stack(means))
-    assert parity.image_gates(rep) == [], rep
     cal = parity.selfcal(sid, integrator)
+    assert parity.image_gates(rep, cal is not None) == [], rep
     if cal is not None:
         # the contract's gates, against the reference-vs-itself calibration of this very case
         # (tests/golden/selfcal.npz): 4 renders at the reference's sample count, one at 32x

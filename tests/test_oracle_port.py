@@ -75,7 +75,14 @@ def test_images_match_reference_statistics(port, golden, sid, integrator):
         means.append(s / spp)
         rays += int(cnt[0]) + int(cnt[1])
     rep = parity.image_report(ref_sum, ref_sumsq, ref_spp, np.stack(means))
-    assert parity.image_gates(rep) == [], rep
+    cal = parity.selfcal(sid, integrator)
+    assert parity.image_gates(rep, cal is not None) == [], rep
+    if cal is not None and (sid, integrator) in CATALOGUE_CASES:
+        # the calibrated gates the GPU renderer is held to (tests/test_gpu_render.py), rehearsed on the restatement
+        equal = [port(golden, sid).render_linear(integrator, w, h, ref_spp, seed=300 + i)[0] / ref_spp for i in range(4)]
+        hi = port(golden, sid).render_linear(integrator, w, h, 8 * ref_spp, seed=77)[0] / (8 * ref_spp)
+        bad = parity.strict_image_gates(ref_sum, ref_sumsq, ref_spp, np.stack(equal), hi.mean(axis=(0, 1)), cal)
+        assert bad == [], (bad, cal)
     # closest + shadow: the reference-side recorder classifies a shadow ray towards an infinite
     # light (t_max = inf) as a closest-hit query, so only the total is comparable
     ref_rpp = float(g[f"img_{integrator}_rays"].sum()) / (w * h * ref_spp)
