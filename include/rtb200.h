@@ -249,6 +249,12 @@ RTB_API int rtb_accum_copy_device(rtb_context *ctx, void *dst_device, void *cuda
 /* hittable::hit of the world on caller rays (bvh.h:40-50 and everything below it).
  * precision 64: fp64 validation kernels (reference operation order, no FMA):
  *               t / primitive id bit-exact against the reference.
+ *               A constant_medium's free-flight draw comes from a per-ray stream of the library.
+ * precision 65 (rtb_trace_batch only): the fp64 primitive tests driven by the reference's own
+ *               left-to-right walk over the leaves (blob order, no tree) with the REFERENCE's random
+ *               stream: rtb_ray.reserved holds the xorshift32 state (rtweekend.h:24-34) the reference
+ *               had when it answered the same query, so constant_medium::hit (constant_medium.h:55-104)
+ *               is compared bit for bit as well.  O(primitives) per ray: a validation tool.
  * precision 32: the production fp32 traversal the wavefront uses.
  * precision 34 (rtb_trace_batch only): the renderer's warp-scheduled traversal of the 4-wide BVH
  *   (windows sorted by octant, lanes refilled as they finish) — the kernel k_extend runs, fed with

@@ -22,7 +22,7 @@ typedef struct rtb_ray {
     double t_min;
     double t_max;
     int32_t origin_prim;
-    int32_t reserved;
+    int32_t reserved; /* 0, or (rtb_trace_batch precision 65) the reference's xorshift32 state before the query */
 } rtb_ray;
 
 /* hit_record of the reference (src/geometry/hittable.h:10-23) + the flattened

@@ -1056,6 +1056,8 @@ void port_trace_batch(void *h, const rtb_ray *rays, uint64_t n, uint32_t seed, r
     for (uint64_t i = 0; i < n; ++i) {
         const Ray r{mk(rays[i].o), mk(rays[i].d), rays[i].time};
         Rec rec;
+        if (rays[i].reserved) // the state the reference's generator had when it answered this query (ref_harness recorder)
+            g = Rng(uint32_t(rays[i].reserved));
         const bool ok = scene_hit(sc, r, rays[i].t_min, rays[i].t_max, g, rec);
         fill_hit(ok, rec, hits[i]);
     }

@@ -140,6 +140,13 @@ struct recorder : public hittable {
     recorder(shared_ptr<hittable> in, const SceneHandle *hh) : inner(std::move(in)), h(hh) {}
     bool hit(const ray &r, double t_min, double t_max, hit_record &rec) const override {
         g_last_prim = -1;
+        // The state of the reference's xorshift32 (a function-local thread_local, rtweekend.h:24-34) is
+        // read off one extra draw: random_double() returns state * 2^-32 exactly.  The draws
+        // constant_medium::hit makes while answering THIS query are its successors, so a consumer that
+        // walks the leaves in the reference's order can reproduce the query bit for bit, media included.
+        uint32_t rng_state = 0;
+        if (g_log)
+            rng_state = uint32_t(random_double() * 4294967296.0);
         const bool ok = inner->hit(r, t_min, t_max, rec);
         RayLog *log = g_log;
         if (!log)
@@ -166,6 +173,7 @@ struct recorder : public hittable {
             q.t_min = t_min;
             q.t_max = t_max;
             q.origin_prim = origin_prim;
+            q.reserved = int32_t(rng_state);
             rtb_hit out;
             fill_hit(h, ok, rec, g_last_prim, out);
             log->rays.push_back(q);

@@ -372,11 +372,11 @@ int rtb_resolve_rgb8(rtb_context *ctx, int32_t spp, uint8_t *rgb8_host) {
 int rtb_trace_batch(rtb_context *ctx, const rtb_ray *rays, uint64_t n, int precision, rtb_hit *hits,
                     uint64_t *visits) {
     const bool p32 = precision == 33 || precision == 34 || precision == 35 || precision == 36;
-    const int rc = check_batch(ctx, rays, hits, n, p32 ? 32 : precision);
+    const int rc = check_batch(ctx, rays, hits, n, p32 ? 32 : (precision == 65 ? 64 : precision));
     if (rc != RTB_OK)
         return rc;
     return guarded(ctx, [&] {
-        if (precision == 64)
+        if (precision == 64 || precision == 65)
             ensure_f64(ctx);
         DeviceBuffer d_vis;
         unsigned long long *dv = nullptr;
@@ -387,8 +387,8 @@ int rtb_trace_batch(rtb_context *ctx, const rtb_ray *rays, uint64_t n, int preci
         }
         if (n)
             run_batch(ctx, rays, n, hits, [&](const rtb_ray *di, rtb_hit *dout) {
-                if (precision == 64)
-                    launch_trace_batch<double>(ctx, di, n, dout, dv);
+                if (precision == 64 || precision == 65)
+                    launch_trace_batch<double>(ctx, di, n, dout, dv, precision == 65);
                 else if (precision == 33 || precision == 35)
                     launch_trace_fast_batch(ctx, di, n, dout, dv, precision == 35);
                 else if (precision == 34 || precision == 36)

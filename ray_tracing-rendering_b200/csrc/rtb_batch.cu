@@ -48,7 +48,7 @@ template <bool INST>
 __global__ void __launch_bounds__(128)
 k_trace_batch(GeomView<Real> g, const int32_t *__restrict__ orig_to_sorted, int n_orig,
               const rtb_ray *__restrict__ rays, uint64_t n, rtb_hit *__restrict__ hits,
-              unsigned long long *visits) {
+              unsigned long long *visits, int reference_walk) {
     uint64_t nodes = 0, tests = 0;
     for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n;
          i += uint64_t(gridDim.x) * blockDim.x) {
@@ -71,8 +71,15 @@ k_trace_batch(GeomView<Real> g, const int32_t *__restrict__ orig_to_sorted, int 
                                          visits ? &nodes : nullptr, visits ? &tests : nullptr);
         };
         // fp64: gated (negative-radius) spheres exactly as the reference reaches them (rtb_geom.cuh)
-        const uint32_t pi = (!kRobust && g.n_gated) ? trace_gated_exact<Real>(g, o, d, Real(q.t_min), Real(q.t_max), t, run)
-                                                    : run(g, Real(q.t_max), t);
+        uint32_t pi;
+        if (!kRobust && reference_walk) {
+            // precision 65: the reference's left-to-right walk with ITS random stream (state in rtb_ray.reserved)
+            XorShift32Draw xs{uint32_t(q.reserved)};
+            pi = walk_reference_order<Real>(g, orig_to_sorted, n_orig, o, d, Real(q.time), Real(q.t_min), Real(q.t_max), xs, t);
+        } else {
+            pi = (!kRobust && g.n_gated) ? trace_gated_exact<Real>(g, o, d, Real(q.t_min), Real(q.t_max), t, run)
+                                         : run(g, Real(q.t_max), t);
+        }
         rtb_hit h;
         h.t = 0;
         h.p[0] = h.p[1] = h.p[2] = 0;
@@ -227,7 +234,7 @@ int grid_for(const rtb_context *ctx, uint64_t n, int block) {
 
 template <>
 void launch_trace_batch<Real>(rtb_context *ctx, const rtb_ray *d_rays, uint64_t n, rtb_hit *d_hits,
-                              unsigned long long *d_visits) {
+                              unsigned long long *d_visits, bool reference_walk) {
     if (!n)
         return;
     const DeviceScene &sc = *ctx->scene;
@@ -237,10 +244,11 @@ void launch_trace_batch<Real>(rtb_context *ctx, const rtb_ray *d_rays, uint64_t 
     // fp32: the renderer's choice of traversal shape; fp64 validation: always the leaf-phase shape
     if (kRobust && sc.host.n_instances == 0)
         k_trace_batch<false><<<grid_for(ctx, n, 128), 128, 0, ctx->stream>>>(
-            gv, sc.orig_to_sorted.as<int32_t>(), int(sc.host.orig_to_sorted.size()), d_rays, n, d_hits, d_visits);
+            gv, sc.orig_to_sorted.as<int32_t>(), int(sc.host.orig_to_sorted.size()), d_rays, n, d_hits, d_visits, 0);
     else
         k_trace_batch<true><<<grid_for(ctx, n, 128), 128, 0, ctx->stream>>>(
-            gv, sc.orig_to_sorted.as<int32_t>(), int(sc.host.orig_to_sorted.size()), d_rays, n, d_hits, d_visits);
+            gv, sc.orig_to_sorted.as<int32_t>(), int(sc.host.orig_to_sorted.size()), d_rays, n, d_hits, d_visits,
+            reference_walk ? 1 : 0);
     RTB_CUDA(cudaGetLastError());
 }
 template <>

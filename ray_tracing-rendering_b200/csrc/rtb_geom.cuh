@@ -127,6 +127,7 @@ template <class R> struct GeomView {
     // reference's order.  orig_limit: primitives whose blob index is >= it are skipped (fp64 paths only).
     int32_t gate_mode = 0;
     int32_t orig_limit = 0x7fffffff;
+    int32_t n_world = 0; // sorted primitives [n_world, n_prims) only exist as medium boundaries (RTB_PRIM_BOUNDARY_ONLY)
     int32_t n_gated = 0;
     uint32_t gated[4] = {0, 0, 0, 0}; // sorted indices of the gated spheres, ascending blob index
 };
@@ -359,10 +360,11 @@ RTB_HD bool hit_boundary(const GeomView<R> &g, uint32_t first, uint32_t count, V
     return any;
 }
 
-// constant_medium.h:55-104.  `xi` must be uniform in (0,1).
-template <class R, bool ROBUST>
-RTB_HD bool hit_medium(const GeomView<R> &g, const PrimT<R> &p, V3<R> o, V3<R> d, R time, R t_min,
-                       R t_max, R xi, R &t_out) {
+// constant_medium.h:55-104.  draw() — uniform in (0,1) — is called exactly where the reference calls
+// random_double() (constant_medium.h:85), i.e. only for a ray with a non-empty span inside the boundary.
+template <class R, bool ROBUST, class Draw>
+RTB_HD bool hit_medium_draw(const GeomView<R> &g, const PrimT<R> &p, V3<R> o, V3<R> d, R time, R t_min,
+                            R t_max, Draw &draw, R &t_out) {
     const R inf = Consts<R>::inf();
     R t1, t2;
     bool have = false;
@@ -409,11 +411,23 @@ RTB_HD bool hit_medium(const GeomView<R> &g, const PrimT<R> &p, V3<R> o, V3<R> d
         t1 = 0;
     const R ray_length = length(d);
     const R distance_inside_boundary = (t2 - t1) * ray_length;
-    const R hit_distance = p.d[0] * log_(xi);
+    const R hit_distance = p.d[0] * log_(draw());
     if (hit_distance > distance_inside_boundary)
         return false;
     t_out = t1 + hit_distance / ray_length;
     return true;
+}
+template <class R> struct FixedXi {
+    R xi;
+    RTB_HD R operator()() const { return xi; }
+};
+// with the draw made up front (the kernels: one draw per test keeps a ray's stream independent of the path
+// the traversal takes through the tree)
+template <class R, bool ROBUST>
+RTB_HD bool hit_medium(const GeomView<R> &g, const PrimT<R> &p, V3<R> o, V3<R> d, R time, R t_min,
+                       R t_max, R xi, R &t_out) {
+    FixedXi<R> f{xi};
+    return hit_medium_draw<R, ROBUST>(g, p, o, d, time, t_min, t_max, f, t_out);
 }
 
 // ---- BVH traversal -----------------------------------------------------------------------
@@ -737,6 +751,52 @@ RTB_HD uint32_t trace_gated_exact(const GeomView<R> &g, V3<R> o, V3<R> d, R t_mi
         t_gated = r;
     }
     t_hit = t_cur;
+    return best;
+}
+
+// The reference's own walk, for the fp64 validation entry point that pins constant_medium: every world
+// primitive in BLOB order — the order bvh_node::hit / hittable_list::hit reach the leaves in (bvh.h:40-50,
+// the flattener emits them so) — each through its wrapper chain, closest hit carried along, media drawing
+// from `draw` exactly when the reference draws.  With the reference's xorshift32 state (rtweekend.h:24-34)
+// behind `draw`, t and the primitive are the reference's bit for bit, media included.  No tree: O(n) per ray.
+struct XorShift32Draw { // random_double(), rtweekend.h:24-34
+    uint32_t s;
+    RTB_HD double operator()() {
+        s ^= s << 13;
+        s ^= s >> 17;
+        s ^= s << 5;
+        return s * 2.3283064365386963e-10;
+    }
+};
+template <class R, class Draw>
+RTB_HD uint32_t walk_reference_order(const GeomView<R> &g, const int32_t *orig_to_sorted, int n_orig, V3<R> o, V3<R> d,
+                                     R time, R t_min, R t_max, Draw &draw, R &t_hit) {
+    uint32_t best = kNoPrim;
+    for (int i = 0; i < n_orig; ++i) {
+        const uint32_t s = uint32_t(orig_to_sorted[i]);
+        if (int32_t(s) >= g.n_world)
+            continue;
+        const PrimT<R> p = g.prims[s];
+        R t;
+        bool h;
+        if ((p.type_mat & PT_TYPE_MASK) == PT_MEDIUM) {
+            h = hit_medium_draw<R, false>(g, p, o, d, time, t_min, t_max, draw, t);
+            if (p.type_mat & PT_DUP_LEAF) { // bvh.h:46-47 on a one-object node
+                R t2;
+                if (hit_medium_draw<R, false>(g, p, o, d, time, t_min, h ? t : t_max, draw, t2)) {
+                    h = true;
+                    t = t2;
+                }
+            }
+        } else {
+            h = hit_boundary<R, false>(g, s, 1u, o, d, time, t_min, t_max, t); // (one primitive through its chain)
+        }
+        if (h) {
+            best = s;
+            t_max = t;
+        }
+    }
+    t_hit = t_max;
     return best;
 }
 

@@ -102,6 +102,7 @@ struct DeviceScene {
         g.root_ref = host.root_ref;
         g.n_top = host.n_top_items;
         g.flat = host.flat_ok ? 1 : 0;
+        g.n_world = host.n_world_slots;
         g.n_gated = int32_t(host.gated.size());
         for (size_t k = 0; k < host.gated.size(); ++k)
             g.gated[k] = host.gated[k];
@@ -171,7 +172,7 @@ namespace rtb {
 // rtb_batch_f32.cu / rtb_batch_f64.cu (same source, RTB_REAL = float / double)
 template <class R>
 void launch_trace_batch(rtb_context *ctx, const rtb_ray *d_rays, uint64_t n, rtb_hit *d_hits,
-                        unsigned long long *d_visits);
+                        unsigned long long *d_visits, bool reference_walk = false);
 template <class R>
 void launch_bsdf_eval(rtb_context *ctx, int material, const rtb_bsdf_query *d_q, uint64_t n,
                       rtb_bsdf_value *d_out);

@@ -55,6 +55,7 @@ struct HostScene {
     int n_instances = 0;
     int n_top_items = 0; // primitives + instance records of the top level = prims[0 .. n_top_items)
     uint32_t root_ref = kEmptyRef; // ref of the top-level root
+    int n_world_slots = 0; // sorted primitives from here on are medium boundaries only (GeomView::n_world)
     std::vector<uint32_t> gated; // sorted indices of the PT_GATED spheres, ascending blob index (GeomView::gated)
     bool flat_ok = false; // small enough for the lockstep / shared-memory traversal
     bool has_f64 = true;  // f64.prims / maux / mats / texs were built (see build_host_scene)
@@ -458,6 +459,7 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double t
         if (slots[s].orig >= 0)
             H.orig_to_sorted[slots[s].orig] = int(s);
     // boundary-only prims keep their blob order (media reference them as ranges)
+    H.n_world_slots = int(slots.size());
     for (int i = 0; i < np; ++i)
         if (P[i].flags & RTB_PRIM_BOUNDARY_ONLY) {
             H.orig_to_sorted[i] = int(slots.size());

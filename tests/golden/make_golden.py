@@ -200,6 +200,17 @@ def make_scene(sid, integrators, n_paths, n_rays, img_wh, img_spp, rng, light_sc
           f" {nm} materials, {len(T['lights'])} lights")
 
 
+def make_media_seeded(rng):
+    """media08.npz / media09.npz: fresh instances of the two media scenes with the reference's generator
+    state recorded per query (rtb_ray.reserved), for the deterministic constant_medium parity tests."""
+    for sid, integ in ((8, 1), (9, 1)):
+        s = refbind.RefScene(sid)
+        r, h, _ = s.record_rays(integ, 1500, 4000)
+        path = os.path.join(HERE, f"media{sid:02d}.npz")
+        np.savez_compressed(path, blob=np.frombuffer(s.blob(), np.uint8), rays=r, hits=h)
+        print(f"media fixture {sid}: {os.path.getsize(path) / 1024:.0f} KiB, {len(r)} rays")
+
+
 def make_fullres():
     """Whole-image means of linear Li at the FULL resolution of the BASELINE.json configs
     (the image mean depends on the resolution through u=(i+xi)/(W-1), renderer.h:73-74).
@@ -220,7 +231,7 @@ def make_fullres():
 
 
 def main():
-    only.update(int(a) for a in sys.argv[1:])
+    only.update(int(a) for a in sys.argv[1:])      # scene ids; 0 = the full-resolution means; -1 = the seeded media fixtures
     if not refbind.available():
         raise SystemExit("oracle/_ref/libref_oracle.so missing: run `make -C oracle ref` first")
     rng = np.random.default_rng(20261018)
@@ -243,6 +254,8 @@ def main():
         make_scene(8, [1], 600, 1600, (64, 64), 256, rng)                     # cornell_smoke (media in instances)
         if not only or 0 in only:
             make_fullres()
+        if not only or -1 in only:
+            make_media_seeded(rng)
         # the rest of the reference's catalogue (scenes.cpp:1523-2096) as smaller fixtures: hits, a few BSDF /
         # light / texture grids and one image each; synthetic assets in the cwd (write_assets), so image
         # textures, roughness / metallic / normal maps and the four remaining .hdr names carry texel data

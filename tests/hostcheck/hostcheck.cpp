@@ -44,6 +44,7 @@ template <class R> GeomView<R> geom_view(HostScene &H) {
     g.root_ref = H.root_ref;
     g.n_top = H.n_top_items;
     g.flat = H.flat_ok ? 1 : 0;
+    g.n_world = H.n_world_slots;
     g.n_gated = int(H.gated.size());
     for (size_t k = 0; k < H.gated.size(); ++k)
         g.gated[k] = H.gated[k];
@@ -70,7 +71,7 @@ const WideTree &wide_of(HostScene &H) { return H.wide; }
 
 template <class R, bool ROBUST>
 void trace_batch(HostScene &H, const rtb_ray *rays, uint64_t n, rtb_hit *hits, uint64_t stats[2], bool use_flat,
-                 bool inst_in_descent = false, bool plane_records = false, bool wide = false) {
+                 bool inst_in_descent = false, bool plane_records = false, bool wide = false, bool reference_walk = false) {
     const GeomView<R> g = geom_view<R>(H);
     const WideTree *W = wide ? &wide_of(H) : nullptr;
     RngT<R> rng;
@@ -100,8 +101,14 @@ void trace_batch(HostScene &H, const rtb_ray *rays, uint64_t n, rtb_hit *hits, u
                                                     &stats[0], &stats[1], stack);
         };
         // fp64: gated spheres exactly as the reference reaches them; fp32: inside the traversal, as the renderer does
-        const uint32_t pi = (!ROBUST && g.n_gated) ? trace_gated_exact<R>(g, o, d, R(q.t_min), R(q.t_max), t, run)
-                                                   : run(g, R(q.t_max), t);
+        uint32_t pi;
+        if (reference_walk) { // the library's precision 65: the reference's walk with its random stream
+            XorShift32Draw xs{uint32_t(q.reserved)};
+            pi = walk_reference_order<R>(g, H.orig_to_sorted.data(), int(H.orig_to_sorted.size()), o, d, R(q.time), R(q.t_min),
+                                         R(q.t_max), xs, t);
+        } else {
+            pi = (!ROBUST && g.n_gated) ? trace_gated_exact<R>(g, o, d, R(q.t_min), R(q.t_max), t, run) : run(g, R(q.t_max), t);
+        }
         rtb_hit &h = hits[i];
         std::memset(&h, 0, sizeof(h));
         h.prim = -1;
@@ -404,6 +411,8 @@ void hc_trace_batch(void *h, const rtb_ray *rays, uint64_t n, int precision, rtb
         trace_batch<double, false>(*H, rays, n, hits, local, false, false, false, true);
     else if (precision == 37)
         trace_batch<float, true>(*H, rays, n, hits, local, false, false, false, true);
+    else if (precision == 69)
+        trace_batch<double, false>(*H, rays, n, hits, local, false, false, false, false, true);
     else if (precision >= 64)
         trace_batch<double, false>(*H, rays, n, hits, local, precision == 65, precision == 66);
     else

@@ -82,6 +82,13 @@ def test_million_ray_batches_vs_live_reference(up, golden, abi, sid, integrator)
     assert ties.sum() <= 1e-5 * len(rays), f"{ties.sum()} exact ties"
     if sid != 9:
         assert ties.sum() == 0
+    if (T["prims"]["type"] == parity.PRIM_MEDIUM).any():
+        # media join layer 1: the fp64 primitive tests walked in the reference's order with the reference's
+        # own generator state of every query (precision 65) — no mask, every query, t and primitive
+        k = 200_000
+        got65 = ctx.trace(rays[:k], 65)
+        assert parity.is_medium(T, hits["prim"][:k]).sum() > 1000
+        assert np.array_equal(got65["prim"], hits["prim"][:k]) and np.array_equal(got65["t"], hits["t"][:k])
     got32 = ctx.trace(parity.to_segment_form(rays), 32)
     mask = parity.deterministic_mask(T, hits, got32)
     agree = (got32["prim"] == hits["prim"])[mask].mean()
@@ -103,6 +110,22 @@ def test_million_ray_batches_vs_live_reference(up, golden, abi, sid, integrator)
     assert blocked[mask & ref_hit].mean() >= parity.FP32_MIN_AGREEMENT
     if not (T["prims"]["type"] == parity.PRIM_MEDIUM).any():   # media block shadow rays at random (constant_medium.h:85)
         assert (~blocked[mask & ~ref_hit]).mean() >= parity.FP32_MIN_AGREEMENT
+
+
+@pytest.mark.parametrize("name", ["media08", "media09", "scene22"])
+def test_media_hits_bit_exact_with_the_reference_random_stream(up, abi, name):
+    """constant_medium::hit (constant_medium.h:55-104) on the device, deterministically: the fixtures carry
+    the state of the reference's generator for every query (rtb_ray.reserved); rtb_trace_batch precision 65
+    walks the leaves in the reference's order and draws where it draws.  Every query, media included."""
+    from test_oracle_port import load_media
+    blob, rays, ref = load_media(name)
+    T = abi.parse_blob(blob)
+    got = up(None, blob).trace(rays, 65)
+    med = parity.is_medium(T, ref["prim"])
+    assert med.sum() > 50
+    assert np.array_equal(got["prim"], ref["prim"]) and np.array_equal(got["t"], ref["t"])
+    assert parity.trace_mismatches(ref, got, ~med) == 0
+    assert np.array_equal(got["p"][med], ref["p"][med])
 
 
 @pytest.mark.parametrize("sid", ALL_SCENES)

@@ -339,3 +339,25 @@ def test_quantised_nodes_contain_their_children(hostcheck, scenes, sid):
     out = np.zeros(3, np.uint64)
     hostcheck.hc_qnode_check(scenes(sid), _ptr(out))
     assert out[0] == 0, f"{out[0]} of {out[1]} children escape their quantised box"
+
+
+@pytest.mark.parametrize("name", ["media08", "media09", "scene22"])
+def test_device_medium_code_bit_exact_with_the_reference_random_stream(hostcheck, abi, name):
+    """The device's fp64 primitive tests (hit_medium_draw, hit_boundary, hit_simple: csrc/rtb_geom.cuh)
+    driven by walk_reference_order() with the reference's generator state of every query (the library's
+    rtb_trace_batch precision 65): the reference's t and primitive on every query, media included."""
+    from test_oracle_port import load_media
+    blob, rays, ref = load_media(name)
+    T = abi.parse_blob(blob)
+    h = hostcheck.hc_scene_create(blob, len(blob), 4)
+    assert h
+    try:
+        got, _ = trace(hostcheck, h, rays, 69, abi)
+    finally:
+        hostcheck.hc_scene_destroy(h)
+    med = parity.is_medium(T, ref["prim"])
+    assert med.sum() > 50
+    assert np.array_equal(got["prim"], ref["prim"]) and np.array_equal(got["t"], ref["t"])
+    solid = ~med            # (a medium's record is "arbitrary", constant_medium.h:99-100: p, normal only for solids)
+    assert parity.trace_mismatches(ref, got, solid) == 0
+    assert np.array_equal(got["p"][med], ref["p"][med])

@@ -87,3 +87,28 @@ def test_images_match_reference_statistics(port, golden, sid, integrator):
     # light (t_max = inf) as a closest-hit query, so only the total is comparable
     ref_rpp = float(g[f"img_{integrator}_rays"].sum()) / (w * h * ref_spp)
     assert abs(rays / (k * w * h * spp) - ref_rpp) <= 0.02 * ref_rpp
+
+
+MEDIA_FIXTURES = ["media08", "media09", "scene22"]
+
+
+def load_media(name):
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    return z["blob"].tobytes(), z["rays"], z["hits"]
+
+
+@pytest.mark.parametrize("name", MEDIA_FIXTURES)
+def test_media_hits_bit_exact_with_the_reference_random_stream(abi, name):
+    """constant_medium::hit draws its free-flight distance from the reference's generator
+    (constant_medium.h:85).  The fixtures carry that generator's state per query (rtb_ray.reserved, read
+    off by the harness), so the restatement — walking the leaves in the reference's order and drawing
+    where the reference draws — must give the reference's answer on EVERY query, media included."""
+    from oracle import portbind
+    blob, rays, ref = load_media(name)
+    assert (rays["reserved"] != 0).all()
+    T = abi.parse_blob(blob)
+    got = portbind.PortScene(blob).trace(rays)
+    every = np.ones(len(rays), bool)
+    assert parity.is_medium(T, ref["prim"]).sum() > 50          # the media are actually hit
+    assert parity.trace_mismatches(ref, got, every, fields=("prim", "t", "p", "normal", "front_face", "material")) == 0
