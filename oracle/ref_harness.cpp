@@ -833,6 +833,28 @@ double ref_render_timed(int scene_id, int integrator_id, int width, int spp, int
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// The reference's OUTPUT path on caller-supplied sums: Renderer::write_color_to_buffer (renderer.h:126-140)
+// for every pixel, then RenderBuffer::save_to_png (render_buffer.h:35-55) to `png_path`.  sums: height x
+// width x 3 linear sums, row 0 = the RenderBuffer's row 0 (bottom of the image).  buffer_out (optional):
+// the RenderBuffer's contents, same layout.
+int ref_output_path(int w, int h, const double *sums, int samples, const char *png_path, double *buffer_out) {
+    RenderBuffer buffer(w, h);
+    Renderer renderer;
+    for (int j = 0; j < h; ++j)
+        for (int i = 0; i < w; ++i) {
+            const double *s = sums + (size_t(j) * w + i) * 3;
+            renderer.write_color_to_buffer(buffer, i, j, color(s[0], s[1], s[2]), samples);
+        }
+    if (buffer_out) {
+        const auto &px = buffer.get_data();
+        for (int j = 0; j < h; ++j)
+            for (int i = 0; i < w; ++i)
+                for (int k = 0; k < 3; ++k)
+                    buffer_out[(size_t(j) * w + i) * 3 + k] = px[j][i][k];
+    }
+    return png_path ? (buffer.save_to_png(png_path) ? 1 : 0) : 1;
+}
+
 int ref_hardware_threads() { return int(std::thread::hardware_concurrency()); }
 
 } // extern "C"

@@ -46,6 +46,8 @@ def lib():
                                        C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p,
                                        C.c_uint64]
         L.ref_hardware_threads.restype = C.c_int
+        L.ref_output_path.restype = C.c_int
+        L.ref_output_path.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_char_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -159,6 +161,18 @@ def render_timed(scene_id, integrator, width=0, spp=0, max_depth=50, want_image=
     if img is not None:
         img = img[:w.value * h.value * 3].reshape(h.value, w.value, 3).copy()
     return s, w.value, h.value, img
+
+
+def output_path(sums, samples, png_path):
+    """The reference's own output path on caller-supplied linear sums (H x W x 3, row 0 = bottom of the
+    image): Renderer::write_color_to_buffer (renderer.h:126-140) per pixel, then RenderBuffer::save_to_png
+    (render_buffer.h:35-55) to png_path.  Returns the RenderBuffer's contents (H x W x 3, same layout)."""
+    sums = np.ascontiguousarray(sums, dtype=np.float64)
+    h, w, _ = sums.shape
+    buf = np.zeros((h, w, 3))
+    if not lib().ref_output_path(w, h, _ptr(sums), int(samples), os.fsencode(png_path), _ptr(buf)):
+        raise RuntimeError("save_to_png failed")
+    return buf
 
 
 def hardware_threads():

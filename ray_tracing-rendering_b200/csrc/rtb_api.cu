@@ -64,8 +64,12 @@ int check_params(rtb_context *ctx, const rtb_render_params *p) {
         return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "render: params is NULL");
     if (p->width < 2 || p->height < 2 || p->width > 65536 || p->height > 65536)
         return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "render: width/height must be in [2, 65536]");
+    if (uint64_t(p->width) * uint64_t(p->height) >= (uint64_t(1) << 31))
+        return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "render: width * height must be below 2^31 pixels");
     if (p->spp < 0 || p->max_depth < 0 || p->rr_start_depth < 0)
         return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "render: spp, max_depth, rr_start_depth must be >= 0");
+    if (p->max_depth > 65535) // the path state packs the depth into 16 bits
+        return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "render: max_depth must be <= 65535");
     if (p->integrator < 0 || p->integrator > RTB_INTEGRATOR_MIS)
         return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "render: integrator must be 0..4");
     if (p->sample_stride < 0 || p->sample_offset < 0 ||

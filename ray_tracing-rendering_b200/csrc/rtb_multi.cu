@@ -121,9 +121,11 @@ __global__ void k_finish_root(const float *__restrict__ mean3, int w, int h, flo
         if (rgb8) {
             const size_t row = i / w, col = i - row * w; // accumulator row 0 = bottom row of the image
             const size_t o = 3 * ((size_t(h) - 1 - row) * w + col);
-            rgb8[o] = uint8_t(clamp_(sqrtf(r), 0.0f, 1.0f) * 255.f);
-            rgb8[o + 1] = uint8_t(clamp_(sqrtf(g), 0.0f, 1.0f) * 255.f);
-            rgb8[o + 2] = uint8_t(clamp_(sqrtf(b), 0.0f, 1.0f) * 255.f);
+            // (double, as renderer.h:131-139 computes it)
+            const double vr = sqrt(double(r)), vg = sqrt(double(g)), vb = sqrt(double(b));
+            rgb8[o] = uint8_t((vr > 1.0 ? 1.0 : vr) * 255);
+            rgb8[o + 1] = uint8_t((vg > 1.0 ? 1.0 : vg) * 255);
+            rgb8[o + 2] = uint8_t((vb > 1.0 ? 1.0 : vb) * 255);
         }
     }
 }

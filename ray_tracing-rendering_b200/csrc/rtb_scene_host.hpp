@@ -694,6 +694,12 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double t
         throw std::runtime_error("scene: BVH of depth " + std::to_string(H.wide.max_depth) +
                                  " exceeds the traversal stack (kWideStack)");
 
+    // the binary traversals (rtb_geom.cuh traverse: validation kernels, round 1's extend) push at most one
+    // ref per binary level plus the instance sentinel; a wide level spans at most two binary ones.  A
+    // deeper tree would silently lose pushes (LocalStack / SmemStack drop them): refuse it here.
+    if (2 * H.wide.max_depth + 2 > kStackDepth)
+        throw std::runtime_error("scene: BVH of depth " + std::to_string(2 * H.wide.max_depth) +
+                                 " exceeds the binary traversal stack (kStackDepth)");
     timer.mark("4-wide collapse + quantise");
     // (gated spheres are only known to hit_simple(): no typed shared-memory copy for their scenes)
     H.flat_ok = S.n_gates() == 0 && int(H.prim_orig.size()) <= kFlatMaxPrims && int(S.n_xform_ops()) <= kFlatMaxOps &&

@@ -1868,19 +1868,22 @@ __global__ void __launch_bounds__(128) k_trace_fast_batch(GeomView<float> geom, 
     }
 }
 
-// renderer.h:126-140 + render_buffer.h:35-55: sqrt(sum/spp), clamp, (uchar)(x*255), y flip.
-__global__ void k_resolve_rgb8(const float4 *__restrict__ accum, int w, int h, float inv_spp,
+// renderer.h:126-140 + render_buffer.h:35-55: sqrt(sum/spp), clamp, (uchar)(x*255), y flip — in the
+// reference's own double arithmetic (scale = 1.0 / samples; sqrt(scale * sum)), so that the bytes are the
+// ones the reference's write_color_to_buffer + save_to_png produce from the same sums (3 DSQRT per pixel).
+__device__ __forceinline__ uint8_t resolve_channel(float sum, double scale) {
+    const double v = sqrt(scale * double(sum));
+    return uint8_t((v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v)) * 255);
+}
+__global__ void k_resolve_rgb8(const float4 *__restrict__ accum, int w, int h, double scale,
                                uint8_t *__restrict__ rgb8) {
-    const int n = w * h;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int row = i / w, col = i - row * w; // row in the PNG (top first)
-        const float4 a = accum[size_t(h - 1 - row) * w + col];
-        const float r = clamp_(sqrtf(inv_spp * a.x), 0.0f, 1.0f);
-        const float g = clamp_(sqrtf(inv_spp * a.y), 0.0f, 1.0f);
-        const float b = clamp_(sqrtf(inv_spp * a.z), 0.0f, 1.0f);
-        rgb8[3 * size_t(i)] = uint8_t(r * 255.f);
-        rgb8[3 * size_t(i) + 1] = uint8_t(g * 255.f);
-        rgb8[3 * size_t(i) + 2] = uint8_t(b * 255.f);
+    const size_t n = size_t(w) * h;
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        const size_t row = i / w, col = i - row * w; // row in the PNG (top first)
+        const float4 a = accum[(size_t(h) - 1 - row) * w + col];
+        rgb8[3 * i] = resolve_channel(a.x, scale);
+        rgb8[3 * i + 1] = resolve_channel(a.y, scale);
+        rgb8[3 * i + 2] = resolve_channel(a.z, scale);
     }
 }
 
@@ -2395,7 +2398,7 @@ void launch_trace_wide_batch(rtb_context *ctx, const rtb_ray *d_rays, uint64_t n
 void launch_resolve_rgb8(rtb_context *ctx, const float4 *d_accum, int w, int h, int spp, uint8_t *d_rgb8,
                          cudaStream_t st) {
     const int sms = ctx->sm_count > 0 ? ctx->sm_count : 148;
-    k_resolve_rgb8<<<sms * 4, 256, 0, st>>>(d_accum, w, h, 1.0f / float(spp), d_rgb8);
+    k_resolve_rgb8<<<sms * 4, 256, 0, st>>>(d_accum, w, h, 1.0 / spp, d_rgb8);
     RTB_CUDA(cudaGetLastError());
 }
 

@@ -461,4 +461,13 @@ void hc_camera_derived(void *h, double out[24]) {
     out[22] = c.time0;
     out[23] = c.time1;
 }
+// The renderer's per-sample random streams (rtb_shading.cuh): stream i = pcg_seed(first + i, seed); its first
+// `draws` float draws (next_f: the top 24 bits of the LCG state) go to out[i * draws ...].
+void hc_rng_draws(uint64_t first, uint64_t n_streams, uint64_t draws, uint64_t seed, float *out) {
+    for (uint64_t i = 0; i < n_streams; ++i) {
+        Pcg g = pcg_seed(first + i, seed);
+        for (uint64_t k = 0; k < draws; ++k)
+            out[i * draws + k] = g.next_f();
+    }
+}
 }

@@ -48,7 +48,7 @@ def test_bad_blobs_are_rejected(binding, golden):
 
 def test_invalid_params(gpu_ctx, golden, binding):
     gpu_ctx.upload_scene(golden(7).blob)
-    for kw in (dict(width=1), dict(integrator=7), dict(spp=-1), dict(sample_offset=2, sample_stride=2)):
+    for kw in (dict(width=1), dict(integrator=7), dict(spp=-1), dict(sample_offset=2, sample_stride=2), dict(max_depth=65536)):
         args = dict(width=32, height=32, spp=1, integrator=1)
         args.update(kw)
         with pytest.raises(binding.RtbError) as e:

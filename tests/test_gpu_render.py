@@ -165,16 +165,29 @@ def test_depth_limit_and_zero_work(gpu_ctx, golden):
     assert st["paths"] == 64 * 64 * 4 and not acc[..., :3].any()
 
 
-def test_resolve_rgb8_matches_reference_conversion(gpu_ctx, golden):
-    """renderer.h:126-140 + render_buffer.h:35-55: sqrt(sum/spp), clamp, (uchar)(x*255), y flip."""
+def test_resolve_rgb8_is_the_reference_output_path(gpu_ctx, golden, tmp_path):
+    """the device's resolve against the reference's OWN output path, not a formula — the
+    sums of a GPU render go through the reference's Renderer::write_color_to_buffer (renderer.h:126-140) and
+    RenderBuffer::save_to_png (render_buffer.h:35-55, stb's PNG encoder) inside oracle/_ref; the decoded
+    file must equal rtb_resolve_rgb8's bytes exactly (sqrt in double, clamp, truncation, y flip), on an
+    image with clamped highlights, black pixels and every byte value in between."""
+    from PIL import Image
+    from oracle import refbind
+    if not refbind.available():
+        pytest.fail("oracle/_ref/libref_oracle.so did not travel to this box")
     g = golden(23)
     gpu_ctx.upload_scene(g.blob)
-    w, h, spp = 160, 90, 32
-    acc, _ = gpu_ctx.render(gpu_ctx.params(w, h, spp, 4, seed=2))
-    got = gpu_ctx.resolve_rgb8(w, h, spp)
-    want = (np.clip(np.sqrt(acc[..., :3] * np.float32(1.0 / spp)), 0, 1) * np.float32(255)).astype(np.uint8)[::-1]
-    assert np.abs(got.astype(int) - want.astype(int)).max() <= 1
-    assert (got != want).mean() < 1e-3
+    for (w, h, spp, integ) in ((160, 90, 32, 4), (97, 31, 5, 3)):
+        acc, _ = gpu_ctx.render(gpu_ctx.params(w, h, spp, integ, seed=2))
+        got = gpu_ctx.resolve_rgb8(w, h, spp)
+        png = str(tmp_path / f"ref_{w}.png")
+        buf = refbind.output_path(acc[..., :3], spp, png)
+        want = np.asarray(Image.open(png).convert("RGB"))
+        assert want.shape == got.shape == (h, w, 3)
+        assert np.array_equal(got, want), f"{(got != want).sum()} bytes differ"
+        assert (want == 255).any() and len(np.unique(want)) > 200
+        # and the RenderBuffer itself (what the reference's window polls, main.cpp:119-126)
+        assert np.array_equal(buf, np.clip(np.sqrt((1.0 / spp) * acc[..., :3].astype(np.float64)), 0, 1))
 
 
 @pytest.mark.parametrize("sid,integrator", [(7, 1), (21, 4), (23, 4), (23, 3), (8, 1)])

@@ -112,3 +112,21 @@ def test_media_hits_bit_exact_with_the_reference_random_stream(abi, name):
     every = np.ones(len(rays), bool)
     assert parity.is_medium(T, ref["prim"]).sum() > 50          # the media are actually hit
     assert parity.trace_mismatches(ref, got, every, fields=("prim", "t", "p", "normal", "front_face", "material")) == 0
+
+
+def test_reference_output_path_is_the_documented_conversion(tmp_path):
+    """The formula the host-layer PNG test and the device resolve are held to IS the reference's output
+    path: random sums through the reference's write_color_to_buffer + save_to_png (oracle/_ref), decoded."""
+    from PIL import Image
+    from oracle import refbind
+    if not refbind.available():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(3)
+    sums = rng.random((37, 53, 3)) * 40.0                 # 16 samples: means up to 2.5 (clamped)
+    sums[0, 0] = 0
+    sums[1, 1] = 16.0                                     # exactly 1.0
+    buf = refbind.output_path(sums, 16, str(tmp_path / "o.png"))
+    img = np.asarray(Image.open(str(tmp_path / "o.png")).convert("RGB"))
+    want_buf = np.clip(np.sqrt((1.0 / 16) * sums), 0, 1)
+    assert np.array_equal(buf, want_buf)
+    assert np.array_equal(img, (want_buf[::-1] * 255).astype(np.uint8))
