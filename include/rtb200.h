@@ -177,6 +177,11 @@ RTB_API int rtb_scene_get_stats(rtb_context *ctx, rtb_scene_stats *out);
  * order: origin, lower_left_corner, horizontal, vertical, u, v, w, lens_radius,
  * time0, time1 (24 doubles). */
 RTB_API int rtb_camera_derived(rtb_context *ctx, double out[24]);
+/* Validation: the Distribution2D tables of the scene's environment lights (environmental_light.h:146-180,
+ * :15-27) as the device built them from the uploaded texels — per env light, in light order: cond_func
+ * [H*W], cond_cdf [H*(W+1)], cond_int [H], marg_cdf [H+1], marg_int [1].  Copies at most `capacity` doubles;
+ * *n_out (optional) = the number the scene holds. */
+RTB_API int rtb_scene_env_tables(rtb_context *ctx, double *out, uint64_t capacity, uint64_t *n_out);
 
 /* ---- render (replaces Renderer::render, renderer.h:30-102) ----------------------------- */
 

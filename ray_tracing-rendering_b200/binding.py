@@ -28,7 +28,7 @@ OPT_BVH_MAX_LEAF, OPT_BVH_TRAVERSAL_COST_PCT, OPT_BVH_LAYOUT_DFS, OPT_BINARY_TRA
 
 # Every symbol include/rtb200.h declares (tests check the library exports them all).
 EXPORTS = ["rtb_version", "rtb_context_create", "rtb_context_destroy", "rtb_last_error",
-           "rtb_set_option", "rtb_scene_upload", "rtb_scene_get_stats", "rtb_camera_derived", "rtb_render",
+           "rtb_set_option", "rtb_scene_upload", "rtb_scene_get_stats", "rtb_camera_derived", "rtb_scene_env_tables", "rtb_render",
            "rtb_render_device", "rtb_cancel", "rtb_resolve_rgb8", "rtb_trace_batch",
            "rtb_bsdf_eval_batch", "rtb_bsdf_sample_batch", "rtb_light_eval_batch",
            "rtb_texture_eval_batch",
@@ -95,6 +95,7 @@ def load():
     L.rtb_last_error.argtypes = [vp]
     L.rtb_last_error.restype = C.c_char_p
     L.rtb_set_option.argtypes = [vp, i32, C.c_int64]
+    L.rtb_scene_env_tables.argtypes = [vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.rtb_scene_upload.argtypes = [vp, vp, u64]
     L.rtb_scene_get_stats.argtypes = [vp, C.POINTER(SceneStats)]
     L.rtb_camera_derived.argtypes = [vp, vp]
@@ -178,6 +179,14 @@ class Context:
         s = SceneStats()
         self._check(self._lib.rtb_scene_get_stats(self._h, C.byref(s)))
         return s.as_dict()
+
+    def env_tables(self):
+        n = C.c_uint64()
+        self._check(self._lib.rtb_scene_env_tables(self._h, None, 0, C.byref(n)))
+        out = np.zeros(n.value)
+        if n.value:
+            self._check(self._lib.rtb_scene_env_tables(self._h, _ptr(out), n.value, None))
+        return out
 
     def camera_derived(self):
         out = np.zeros(24)

@@ -46,7 +46,9 @@ struct HostScene {
     std::vector<ImageRec> images;
     std::vector<uint8_t> image_bytes;
     std::vector<float> env_texels;
-    std::vector<double> env_tables;
+    std::vector<double> env_tables;          // Distribution2D tables of the env lights; EMPTY when env_on_device
+    uint64_t env_table_doubles = 0;          // their size (the device builds them: rtb_api.cu build_env_tables_device)
+    bool env_on_device = false;
     rtb_globals globals{};
     int n_infinite_lights = 0;
     uint32_t mat_type_mask = 0; // bit t set: some primitive uses a material of type t
@@ -288,8 +290,10 @@ struct PhaseTimer {
 
 // want_f64 = false: the large per-primitive / per-material fp64 tables (only the validation entry
 // points read them) are left empty; H.has_f64 says so and the API layer builds them on first use.
+// env_on_device = true: the env lights' Distribution2D tables are only sized here; the caller builds them
+// on the device from the uploaded texels (the library does; the CPU test harness keeps the host build).
 inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double trav_cost = 1.0,
-                                  bool layout_dfs = false, bool want_f64 = true) {
+                                  bool layout_dfs = false, bool want_f64 = true, bool env_on_device = false) {
     using namespace detail;
     PhaseTimer timer;
     S.validate();
@@ -634,6 +638,7 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double t
     }
 
     // ---- lights
+    H.env_on_device = env_on_device;
     if (S.n_env_texels())
         H.env_texels.assign(S.env_texels(), S.env_texels() + S.n_env_texels());
     for (uint64_t i = 0; i < S.n_lights(); ++i) {
@@ -661,8 +666,10 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double t
         if (l.type == RTB_LIGHT_ENV) {
             H.n_infinite_lights++;
             if (l.env_width > 0 && l.env_height > 0) {
-                d.env_table_offset = H.env_tables.size();
-                build_env_tables(H.env_texels.data() + l.env_offset, l.env_width, l.env_height, H.env_tables);
+                d.env_table_offset = H.env_table_doubles;
+                H.env_table_doubles += EnvTables::doubles(l.env_width, l.env_height);
+                if (!env_on_device)
+                    build_env_tables(H.env_texels.data() + l.env_offset, l.env_width, l.env_height, H.env_tables);
             }
         }
         LightT<float> f;

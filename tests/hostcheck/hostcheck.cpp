@@ -470,4 +470,12 @@ void hc_rng_draws(uint64_t first, uint64_t n_streams, uint64_t draws, uint64_t s
             out[i * draws + k] = g.next_f();
     }
 }
+// the env lights' Distribution2D tables as the HOST builds them (detail::build_env_tables); returns their size
+uint64_t hc_env_tables(void *h, double *out, uint64_t capacity) {
+    auto *H = static_cast<HostScene *>(h);
+    const uint64_t n = H->env_tables.size();
+    for (uint64_t i = 0; i < n && i < capacity; ++i)
+        out[i] = H->env_tables[i];
+    return n;
+}
 }

@@ -360,3 +360,23 @@ def test_fused_kernel_plane_records_match_reference_records(gpu_ctx, up, golden,
     other = hit & ~planar & (a["prim"] == b["prim"])
     for f in ("p", "normal", "front_face", "u", "v"):
         assert np.array_equal(a[f][other], b[f][other]), f
+
+
+@pytest.mark.parametrize("sid", [19, 26, 36])
+def test_env_distribution_built_on_the_device_equals_the_host_build(up, golden, hostcheck, sid):
+    """the Distribution2D of an environment map (environmental_light.h:146-180, :15-27) is built
+    by device kernels from the uploaded texels; every table entry must equal, bit for bit, the sequential
+    host construction the CPU suite pins to the reference's Light::sample / pdf values."""
+    import ctypes as C
+    g = golden(sid)
+    got = up(sid).env_tables()
+    hostcheck.hc_env_tables.restype = C.c_uint64
+    hostcheck.hc_env_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    h = hostcheck.hc_scene_create(g.blob, len(g.blob), 4)
+    try:
+        want = np.zeros(int(hostcheck.hc_env_tables(h, None, 0)))
+        hostcheck.hc_env_tables(h, want.ctypes.data, len(want))
+    finally:
+        hostcheck.hc_scene_destroy(h)
+    assert len(want) > 1000 and got.shape == want.shape
+    assert np.array_equal(got, want)
