@@ -54,63 +54,82 @@ inline uint32_t &rtb_host_rng_state() {
     return s;
 }
 inline void rtb_host_seed(uint32_t seed) { rtb_host_rng_state() = seed ? seed : 1u; }
+// Marsaglia's 13/17/5 xorshift, the generator rtweekend.h:24-34 uses, so that a scene built here from the
+// reference's seed has the reference's content; the draw is state / 2^32
+inline uint32_t rtb_host_xorshift32(uint32_t x) {
+    x ^= x << 13;
+    x ^= x >> 17;
+    return x ^ (x << 5);
+}
 inline double random_double() {
-    uint32_t &seed = rtb_host_rng_state();
-    seed ^= seed << 13;
-    seed ^= seed >> 17;
-    seed ^= seed << 5;
-    return seed * 2.3283064365386963e-10;
+    uint32_t &st = rtb_host_rng_state();
+    st = rtb_host_xorshift32(st);
+    return double(st) * (1.0 / 4294967296.0);
 }
 inline double random_double(double min, double max) noexcept { return min + (max - min) * random_double(); }
 inline double clamp(double x, double min, double max) noexcept { return x < min ? min : (x > max ? max : x); }
 inline int random_int(int min, int max) { return static_cast<int>(random_double(min, max + 1)); }
 
 // ---- src/core/vec3.h ------------------------------------------------------------------------
+// (same public interface as the reference's vec3 — scenes.cpp and user code compile against it — written
+// here over two element-wise helpers)
 class vec3 {
   public:
+    double e[3];
     vec3() : e{0, 0, 0} {}
     vec3(double e0, double e1, double e2) : e{e0, e1, e2} {}
+    template <class F> static vec3 map(const vec3 &a, F f) { return vec3(f(a.e[0]), f(a.e[1]), f(a.e[2])); }
+    template <class F> static vec3 zip(const vec3 &a, const vec3 &b, F f) {
+        return vec3(f(a.e[0], b.e[0]), f(a.e[1], b.e[1]), f(a.e[2], b.e[2]));
+    }
     double x() const noexcept { return e[0]; }
     double y() const noexcept { return e[1]; }
     double z() const noexcept { return e[2]; }
-    vec3 operator-() const { return vec3(-e[0], -e[1], -e[2]); }
     double operator[](int i) const { return e[i]; }
     double &operator[](int i) { return e[i]; }
-    vec3 &operator+=(const vec3 &v) { e[0] += v.e[0]; e[1] += v.e[1]; e[2] += v.e[2]; return *this; }
-    vec3 &operator*=(const double t) { e[0] *= t; e[1] *= t; e[2] *= t; return *this; }
-    vec3 &operator*=(const vec3 &v) { e[0] *= v.e[0]; e[1] *= v.e[1]; e[2] *= v.e[2]; return *this; }
+    vec3 operator-() const { return map(*this, [](double a) { return -a; }); }
+    vec3 &operator+=(const vec3 &v) { return *this = zip(*this, v, [](double a, double b) { return a + b; }); }
+    vec3 &operator*=(const vec3 &v) { return *this = zip(*this, v, [](double a, double b) { return a * b; }); }
+    vec3 &operator*=(const double t) { return *this = map(*this, [t](double a) { return a * t; }); }
     vec3 &operator/=(const double t) { return *this *= 1 / t; }
-    double length() const { return sqrt(length_squared()); }
     double length_squared() const noexcept { return e[0] * e[0] + e[1] * e[1] + e[2] * e[2]; }
-    inline static vec3 random() { return vec3(random_double(), random_double(), random_double()); }
-    inline static vec3 random(double min, double max) {
-        return vec3(random_double(min, max), random_double(min, max), random_double(min, max));
+    double length() const { return sqrt(length_squared()); }
+    bool near_zero() const noexcept {
+        const double tiny = 1e-8;
+        return fabs(e[0]) < tiny && fabs(e[1]) < tiny && fabs(e[2]) < tiny;
     }
-    bool near_zero() const noexcept { return fabs(e[0]) < 1e-8 && fabs(e[1]) < 1e-8 && fabs(e[2]) < 1e-8; }
-    double e[3];
+    static vec3 random() {
+        const double a = random_double(), b = random_double(), c = random_double(); // (a fixed order: the reference leaves it to the compiler)
+        return vec3(a, b, c);
+    }
+    static vec3 random(double min, double max) {
+        const double a = random_double(min, max), b = random_double(min, max), c = random_double(min, max);
+        return vec3(a, b, c);
+    }
 };
 class vec2 {
   public:
+    double e[2];
     vec2() : e{0, 0} {}
     vec2(double e0, double e1) : e{e0, e1} {}
     double x() const { return e[0]; }
     double y() const { return e[1]; }
     double operator[](int i) const { return e[i]; }
     double &operator[](int i) { return e[i]; }
-    double e[2];
 };
 using point3 = vec3;
 using color = vec3;
 inline std::ostream &operator<<(std::ostream &out, const vec3 &v) { return out << v.e[0] << ' ' << v.e[1] << ' ' << v.e[2]; }
-inline vec3 operator+(const vec3 &u, const vec3 &v) { return vec3(u.e[0] + v.e[0], u.e[1] + v.e[1], u.e[2] + v.e[2]); }
-inline vec3 operator-(const vec3 &u, const vec3 &v) { return vec3(u.e[0] - v.e[0], u.e[1] - v.e[1], u.e[2] - v.e[2]); }
-inline vec3 operator*(const vec3 &u, const vec3 &v) { return vec3(u.e[0] * v.e[0], u.e[1] * v.e[1], u.e[2] * v.e[2]); }
-inline vec3 operator*(double t, const vec3 &v) { return vec3(t * v.e[0], t * v.e[1], t * v.e[2]); }
+inline vec3 operator+(const vec3 &u, const vec3 &v) { return vec3::zip(u, v, [](double a, double b) { return a + b; }); }
+inline vec3 operator-(const vec3 &u, const vec3 &v) { return vec3::zip(u, v, [](double a, double b) { return a - b; }); }
+inline vec3 operator*(const vec3 &u, const vec3 &v) { return vec3::zip(u, v, [](double a, double b) { return a * b; }); }
+inline vec3 operator*(double t, const vec3 &v) { return vec3::map(v, [t](double a) { return t * a; }); }
 inline vec3 operator*(const vec3 &v, double t) { return t * v; }
 inline vec3 operator/(vec3 v, double t) { return (1 / t) * v; }
 inline double dot(const vec3 &u, const vec3 &v) { return u.e[0] * v.e[0] + u.e[1] * v.e[1] + u.e[2] * v.e[2]; }
 inline vec3 cross(const vec3 &u, const vec3 &v) {
-    return vec3(u.e[1] * v.e[2] - u.e[2] * v.e[1], u.e[2] * v.e[0] - u.e[0] * v.e[2], u.e[0] * v.e[1] - u.e[1] * v.e[0]);
+    const double *a = u.e, *b = v.e;
+    return vec3(a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]);
 }
 inline vec3 unit_vector(const vec3 &v) { return v / v.length(); }
 
@@ -645,20 +664,18 @@ class rotate_y : public hittable {
         sin_theta = sin(radians);
         cos_theta = cos(radians);
         hasbox = ptr->bounding_box(0, 1, bbox);
-        point3 mn(infinity, infinity, infinity), mx(-infinity, -infinity, -infinity);
-        for (int i = 0; i < 2; i++)
-            for (int j = 0; j < 2; j++)
-                for (int k = 0; k < 2; k++) {
-                    auto x = i * bbox.max().x() + (1 - i) * bbox.min().x();
-                    auto y = j * bbox.max().y() + (1 - j) * bbox.min().y();
-                    auto z = k * bbox.max().z() + (1 - k) * bbox.min().z();
-                    vec3 tester(cos_theta * x + sin_theta * z, y, -sin_theta * x + cos_theta * z);
-                    for (int c = 0; c < 3; c++) {
-                        mn[c] = fmin(mn[c], tester[c]);
-                        mx[c] = fmax(mx[c], tester[c]);
-                    }
-                }
-        bbox = aabb(mn, mx);
+        // bounds of the rotated box = bounds of its eight rotated corners (y is untouched by the rotation)
+        const point3 lo = bbox.min(), hi = bbox.max();
+        double x0 = infinity, x1 = -infinity, z0 = infinity, z1 = -infinity;
+        for (int corner = 0; corner < 4; ++corner) {
+            const double x = (corner & 1) ? hi.x() : lo.x(), z = (corner & 2) ? hi.z() : lo.z();
+            const double rx = cos_theta * x + sin_theta * z, rz = -sin_theta * x + cos_theta * z;
+            x0 = fmin(x0, rx);
+            x1 = fmax(x1, rx);
+            z0 = fmin(z0, rz);
+            z1 = fmax(z1, rz);
+        }
+        bbox = aabb(point3(x0, lo.y(), z0), point3(x1, hi.y(), z1));
     }
     void flatten(rtb::Flattener &F, int flags) const override {
         F.push(this, RTB_XF_ROTATE_Y, sin_theta, cos_theta, 0);
