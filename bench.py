@@ -347,6 +347,12 @@ class Bench:
         common = {"rays_per_launch": rays_dom / launches, "us_per_launch": 1e6 * secs / launches,
                   "share_of_step": st_t["extend_ms"] / st_t["device_ms"], "grays_per_s_in_kernel": grays,
                   "stage_ms": st_t.get("stage_ms"), "traffic": cap.get("dram_bytes_per_launch"), "ncu": cap.get("ncu")}
+        ncu = cap.get("ncu") or {}
+        if ncu.get("issue_slots_busy_pct") is not None:
+            # the roof that actually binds these kernels (instruction issue, then the ALU pipe), from the committed
+            # ncu capture of the same kernel on the same configuration (not re-measured by this run)
+            common["issue_roof"] = {"frac": ncu["issue_slots_busy_pct"] / 100.0, "alu_pipe_frac": ncu.get("alu_pipe_pct", 0) / 100.0,
+                                    "active_lanes_of_32": ncu.get("active_lanes_of_32"), "source": ncu.get("source")}
         if fused:
             # The scene (<= 64 records) lives in shared memory, path state in registers: nothing streams
             # from HBM (ncu: 5 MB of DRAM traffic per launch).  The kernel is bound by instruction issue;
@@ -361,22 +367,25 @@ class Bench:
                   "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                   "peak_source": "tools/microbench FP32 FMA rate (profiles/microbench.json); nominal 74.5",
                   "flops_per_ray": f_ray, "records_per_ray": n_rec,
-                  "note": "issue bound (ncu, profiles/: 82 % of the issue slots, 24.4 of 32 lanes): the algorithmic "
-                          "flops are ~1/4 of the instructions a ray needs (compares, selects, RNG, control)"}
+                  "note": "issue bound (ncu, profiles/r02_c1_fused_metrics.txt: 83 % of the issue slots, ALU pipe 66 %, 24.4 of "
+                          "32 lanes): the algorithmic flops are ~1/4 of the instructions a ray needs (compares, selects, RNG, control)"}
             b_ray = 32.0 * n_node + 32.0 * n_rec + 48.0
         else:
             # BVH scenes: the tree and the primitive records are served by L1 / L2 (they fit the 126 MB L2);
             # DRAM carries the streaming queues.  Algorithmic bytes per ray as SURVEY 8(d) defines them, with
             # this round's 64-byte nodes: 64 n_node + 32 n_prim + 48, against the measured L2 stream rate.
-            node_bytes = 32.0 if st_t.get("binary_traversal") else 64.0
+            node_bytes = 32.0 if st_t.get("traversal") == 1 else 64.0   # binary: n_node counts 32-byte child boxes; 4-wide: 64-byte nodes
             b_ray = node_bytes * n_node + 32.0 * n_prim + 48.0
             peak = float(self.micro.get("l2_stream_read_gbs", 21000.0))
             ach = grays * b_ray
-            rl = {"kernel": "k_extend_w (warp-scheduled 4-wide traversal: closest hit, refill, material sort)", "bound": "l2",
-                  "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            binary = st_t.get("traversal") == 1
+            rl = {"kernel": ("k_extend (binary while-while traversal: the per-scene rule keeps it where media / instances sit in the tree)"
+                             if binary else "k_extend_w (warp-scheduled 4-wide traversal: closest hit, refill, material sort)"),
+                  "bound": "l2", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                   "peak_source": "tools/microbench L2 stream read (profiles/microbench.json)",
-                  "note": "latency / issue bound (ncu, profiles/r02_*): ~23 of 32 lanes, ~50 % of the issue slots, "
-                          "L1 data pipe 60-80 %; DRAM traffic per launch (`traffic`) is the queue streaming, not the tree"}
+                  "note": ("ALU-pipe / issue bound, not bandwidth bound (ncu, profiles/r02_c5_extend_w_metrics.txt: ALU pipe 69 %, issue "
+                           "slots 68 %, 21.7 of 32 lanes; r02_c2_extend_metrics.txt: issue 59 %, 12.3 lanes); DRAM traffic per launch "
+                           "(`traffic`) is the queue streaming, not the tree")}
         rl.update(common)
         rl.update({"bytes_per_ray": b_ray, "nodes_per_ray": n_node, "prims_per_ray": n_prim,
                    "hbm_8d": {"achieved": grays * b_ray, "peak": self.hbm_peak, "unit": "GB/s", "frac": grays * b_ray / self.hbm_peak,

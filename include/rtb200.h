@@ -105,7 +105,8 @@ typedef struct rtb_render_stats {
     double extend_ms;        /* CUDA-event time spent in the extend kernel (0 unless timed) */
     uint64_t extend_launches;
     int32_t schedule;        /* 0 = wavefront (queues in HBM), 1 = fused (small scene, state in registers) */
-    int32_t reserved;
+    int32_t traversal;       /* wavefront schedule: 1 = binary while-while kernels, 2 = warp-scheduled 4-wide kernels,
+                              * 0 = lockstep walk of the shared-memory scene copy; fused schedule: 0 */
     /* with RTB_RENDER_TIME_EXTEND on the wavefront schedule: CUDA-event time per stage, summed
      * over the iterations: [0] extend, [1] shade (all material kernels), [2] miss, [3] connect */
     double stage_ms[4];

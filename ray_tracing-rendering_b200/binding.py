@@ -50,7 +50,7 @@ class RenderStats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("rays_closest", C.c_uint64), ("rays_shadow", C.c_uint64),
                 ("nodes_visited", C.c_uint64), ("prim_tests", C.c_uint64), ("iterations", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("device_ms", C.c_double), ("extend_ms", C.c_double),
-                ("extend_launches", C.c_uint64), ("schedule", C.c_int32), ("reserved", C.c_int32), ("stage_ms", C.c_double * 4),
+                ("extend_launches", C.c_uint64), ("schedule", C.c_int32), ("traversal", C.c_int32), ("stage_ms", C.c_double * 4),
                 ("max_nodes_per_ray", C.c_uint64), ("extend_nodes", C.c_uint64),
                 ("extend_chunk_max_nodes", C.c_uint64)]
 

@@ -210,6 +210,7 @@ std::shared_ptr<const HostScene> build_scene_for(rtb_context *ctx, const void *b
 }
 
 void upload_scene(rtb_context *ctx, std::shared_ptr<const HostScene> host) {
+    PhaseTimer timer; // RTB200_TIMING=1
     std::unique_ptr<DeviceScene> sc(new DeviceScene(std::move(host)));
     const HostScene &H = sc->host;
     cudaStream_t s = ctx->stream;
@@ -243,6 +244,7 @@ void upload_scene(rtb_context *ctx, std::shared_ptr<const HostScene> host) {
              sc->env_texels.bytes() + sc->env_tables.bytes();
     sc->device_bytes = bytes;
     RTB_CUDA(cudaStreamSynchronize(s));
+    timer.mark("device: alloc + H2D + env tables");
     ctx->scene = std::move(sc);
     ++ctx->scene_serial;
 }

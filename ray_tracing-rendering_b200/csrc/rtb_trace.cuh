@@ -55,6 +55,12 @@ namespace rtb {
 #ifndef RTB_TRACE_SORT
 #define RTB_TRACE_SORT 0 // counting-sort each window by direction octant (measured on B200: no gain)
 #endif
+#ifndef RTB_TRACE_FULL_SORT
+#define RTB_TRACE_FULL_SORT 1 // 1: children pushed far to near (five-comparator network); 0: nearest child next, the others pushed unsorted
+#endif
+#ifndef RTB_TRACE_TOP_CACHE
+#define RTB_TRACE_TOP_CACHE 0 // 1: the top entry of a lane's stack lives in registers: a pop uses it at once and starts the load of the next one early
+#endif
 #ifndef RTB_TRACE_GUARD
 #define RTB_TRACE_GUARD 1 // bound the scheduler loop (an internal error becomes a flag, not a hung GPU)
 #endif
@@ -244,7 +250,30 @@ struct TravLane {
     float time, t_min, t_max;
     uint32_t best, best_key, origin, cur, sp;
     Pcg rng;
+#if RTB_TRACE_TOP_CACHE
+    Vec2u top; // entry sp - 1 of the stack (the array holds the entries below it)
+#endif
 };
+RTB_WD void stk_push(TravLane &L, Vec2u *stack, Vec2u e) {
+#if RTB_TRACE_TOP_CACHE
+    if (L.sp)
+        stack[L.sp - 1] = L.top;
+    L.top = e;
+    ++L.sp;
+#else
+    stack[L.sp++] = e;
+#endif
+}
+RTB_WD Vec2u stk_pop(TravLane &L, Vec2u *stack) { // L.sp > 0
+#if RTB_TRACE_TOP_CACHE
+    const Vec2u e = L.top;
+    if (--L.sp)
+        L.top = stack[L.sp - 1];
+    return e;
+#else
+    return stack[--L.sp];
+#endif
+}
 
 // Next subtree off the lane's stack (skipping those behind the closest hit so far), or kDoneRef.
 template <bool INST, class Job> RTB_WD void trav_pop(TravLane &L, Vec2u *stack, Job &job, uint32_t tag) {
@@ -253,7 +282,7 @@ template <bool INST, class Job> RTB_WD void trav_pop(TravLane &L, Vec2u *stack, 
             L.cur = kDoneRef;
             return;
         }
-        const Vec2u e = stack[--L.sp];
+        const Vec2u e = stk_pop(L, stack);
         if (INST && e.x == kSentinelRef) { // leaving the instance: back to the world ray
             V3<float> wo, wd;
             job.world_ray(tag, wo, wd);
@@ -277,6 +306,7 @@ RTB_WD void trav_node_step(const WideView &w, const Vec4f *s_top, uint32_t n_top
     float k[4];
     qnode_slabs(q0, q1, q2, L.r, L.t_min, L.t_max, k);
     uint32_t r0 = f2u(rr.x), r1 = f2u(rr.y), r2 = f2u(rr.z), r3 = f2u(rr.w);
+#if RTB_TRACE_FULL_SORT
     // sorting network, ascending entry distance: (0,1) (2,3) (0,2) (1,3) (1,2)
     cmp_swap(k[0], r0, k[1], r1);
     cmp_swap(k[2], r2, k[3], r3);
@@ -289,12 +319,33 @@ RTB_WD void trav_node_step(const WideView &w, const Vec4f *s_top, uint32_t n_top
             overflow = 1u;
         } else {
             if (k[3] < inf)
-                stack[L.sp++] = Vec2u{r3, f2u(k[3])};
+                stk_push(L, stack, Vec2u{r3, f2u(k[3])});
             if (k[2] < inf)
-                stack[L.sp++] = Vec2u{r2, f2u(k[2])};
-            stack[L.sp++] = Vec2u{r1, f2u(k[1])};
+                stk_push(L, stack, Vec2u{r2, f2u(k[2])});
+            stk_push(L, stack, Vec2u{r1, f2u(k[1])});
         }
     }
+#else
+    // The nearest child goes to slot 0 (three comparators), the others are pushed as they lie: a popped
+    // entry carries its entry distance and is dropped when it lies behind the closest hit found meanwhile,
+    // so their order only decides how soon that happens.  15 ALU-pipe instructions fewer per node step.
+    cmp_swap(k[0], r0, k[1], r1);
+    cmp_swap(k[0], r0, k[2], r2);
+    cmp_swap(k[0], r0, k[3], r3);
+    const bool h1 = k[1] < inf, h2 = k[2] < inf, h3 = k[3] < inf;
+    if (h1 | h2 | h3) {
+        if (L.sp + 3u > uint32_t(kWideStack)) {
+            overflow = 1u;
+        } else {
+            if (h3)
+                stk_push(L, stack, Vec2u{r3, f2u(k[3])});
+            if (h2)
+                stk_push(L, stack, Vec2u{r2, f2u(k[2])});
+            if (h1)
+                stk_push(L, stack, Vec2u{r1, f2u(k[1])});
+        }
+    }
+#endif
     if (k[0] < inf && r0 != kEmptyRef)
         L.cur = r0;
     else
@@ -344,7 +395,7 @@ RTB_WD void trav_leaf_step(const GeomView<float> &g, const WideView &w, TravLane
             trav_pop<INST>(L, stack, job, tag);
             return;
         }
-        stack[L.sp++] = Vec2u{kSentinelRef, f2u(-Consts<float>::inf())};
+        stk_push(L, stack, Vec2u{kSentinelRef, f2u(-Consts<float>::inf())});
         V3<float> co = L.r.o, cd = L.r.d;
         enter_instance<float, true>(g, int(p.aux2), co, cd);
         L.r.set(co, cd);

@@ -2102,6 +2102,7 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
         }
     };
 
+    int traversal_used = 0; // rtb_render_stats.traversal
     auto run_wavefront = [&](unsigned long long begin, unsigned long long end, bool first_segment) {
         const unsigned long long seg = end - begin;
         uint32_t P = rp.pool_paths > 0 ? uint32_t(rp.pool_paths) : kDefaultPool;
@@ -2151,12 +2152,13 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
                                     (1u << RTB_MAT_ISOTROPIC);
         // the warp-scheduled 4-wide traversal, unless round 1's kernels are asked for (or the scene is
         // small enough for the lockstep walk of the shared-memory copy, which those kernels hold)
-        // Measured on B200 (profiles/r02_traversal.txt): on the 1 M-sphere field (one primitive type, no
+        // Measured on B200 (profiles/r02_trace_knobs_and_upload_phases.txt, gpurun d_sweep of this round): on the 1 M-sphere field (one primitive type, no
         // wrappers) the 4-wide kernels are 16 % faster in extend; on scene09 (rects, spheres, an instance
         // and two media in one tree) the heterogeneous leaf steps run at 5-10 lanes and round 1's plain
         // kernels are 12 % faster.  opt_binary_traversal: 0 = by that rule, 1 = always binary, 2 = always wide.
         const bool mixed = media || inst;
         const bool wide = !geom.flat && (ctx->opt_binary_traversal == 2 || (ctx->opt_binary_traversal == 0 && !mixed));
+        traversal_used = geom.flat ? 0 : (wide ? 2 : 1);
         int trace_grid = 0, connect_grid = 0;
         constexpr int kBatch = 4; // iterations between two host-side liveness probes
         int probe = 0, zero_probes = 0;
@@ -2333,6 +2335,7 @@ void wavefront_render(rtb_context *ctx, const rtb_render_params &rp, float4 *d_a
             stats->extend_launches = n_ext_events / 5;
         }
         stats->schedule = fused ? 1 : 0;
+        stats->traversal = fused ? 0 : traversal_used;
     }
     if (pool.h_glob->overflow)
         throw std::runtime_error("wavefront: queue overflow (internal error " + std::to_string(pool.h_glob->overflow) + ")");

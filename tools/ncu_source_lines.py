@@ -18,8 +18,11 @@ def main():
     ap.add_argument("--top", type=int, default=40)
     ap.add_argument("--by", default="inst", choices=["inst", "samples"])
     a = ap.parse_args()
-    out = subprocess.run(["ncu", "-i", a.report, "--page", "source", "--csv", "--print-source", "cuda,sass"],
-                         capture_output=True, text=True).stdout
+    if a.report.endswith(".csv"):        # the source page exported on the GPU box (tools/gpu_g.sh)
+        out = open(a.report).read()
+    else:
+        out = subprocess.run(["ncu", "-i", a.report, "--page", "source", "--csv", "--print-source", "cuda,sass"],
+                             capture_output=True, text=True).stdout
     rows, fname, hdr = [], "?", None
     for r in csv.reader(io.StringIO(out)):
         if not r:

@@ -28,7 +28,10 @@ STALLS = ["long_scoreboard", "wait", "branch_resolving", "short_scoreboard", "no
 
 
 def main():
-    out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if sys.argv[1].endswith(".csv"):     # the raw page exported on the GPU box (tools/gpu_g.sh)
+        out = open(sys.argv[1]).read()
+    else:
+        out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     for r in rows[2:]:
