@@ -18,9 +18,10 @@
 //     window is counting-sorted by direction octant in shared memory before its rays are handed
 //     out, so the rays a warp walks at any moment share their traversal order.
 // A node step is one 64-byte fetch (four LDG.128: the node's grid, its children's boxes as 8-bit
-// planes, four refs — rtb_wide.cuh QNode64), a byte-permute per plane that drops the byte into the
-// mantissa of 2^15 (so it IS the float 32768 + q, no conversion), twelve packed FFMA2 (two children
-// per instruction, sm_100a) with the near / far words picked by the ray's signs, FMNMX3
+// planes, four refs — rtb_wide.cuh QNode64), one IDP4A per plane that adds the byte to the bits of 2^23
+// (so the result IS the float 2^23 + q; a packed FADD2 takes the 2^23 off again, exactly — both on the FMA
+// pipe: the first version used a byte-permute per plane, 15 % of all executed instructions on the half-rate
+// ALU pipe that binds this kernel), twelve packed FFMA2 (two children per instruction, sm_100a) with the near / far words picked by the ray's signs, FMNMX3
 // reductions, and a five-comparator sorting network over (entry distance, ref); children are
 // pushed far to near with their entry distance, so a popped subtree that lies behind the closest
 // hit found meanwhile is dropped without touching memory.
@@ -60,6 +61,9 @@ namespace rtb {
 #endif
 #ifndef RTB_TRACE_TOP_CACHE
 #define RTB_TRACE_TOP_CACHE 0 // 1: the top entry of a lane's stack lives in registers: a pop uses it at once and starts the load of the next one early
+#endif
+#ifndef RTB_TRACE_DP4A
+#define RTB_TRACE_DP4A 1 // 1: plane bytes expanded by IDP4A + FADD2 (FMA pipe) instead of PRMT (ALU pipe, half rate): C5 -4 % (B200)
 #endif
 #ifndef RTB_TRACE_GUARD
 #define RTB_TRACE_GUARD 1 // bound the scheduler loop (an internal error becomes a flag, not a hung GPU)
@@ -173,17 +177,40 @@ RTB_WD float magic_byte(uint32_t word, int i) {
 }
 // t of the four children's planes `word` (8-bit grid coordinates q): (32768 + q) * a + b, where the
 // caller folded the grid into a = s * idir and b = (o * idir + ood) - 32768 * a.  Two packed FFMA2.
+#if RTB_TRACE_DP4A && defined(__CUDACC__)
+// one-hot byte selectors for IDP4A, in constant memory so that ptxas cannot fold the dot product back into PRMT
+static __constant__ uint32_t g_onehot[4] = {0x00000001u, 0x00000100u, 0x00010000u, 0x01000000u};
+#endif
 RTB_WD void fma4q(uint32_t word, float a, float b, float out[4]) {
 #ifdef __CUDA_ARCH__
+#if RTB_TRACE_DP4A
+    // 2^23 + q from one IDP4A (byte i of `word` times a one-hot byte, added to the bits of 2^23); minus 2^23
+    // (exact) by a packed add; then the FFMA2.  `b` here is the plain o * idir + ood (see qnode_slabs).
+    const float2 two23 = make_float2(-8388608.0f, -8388608.0f);
+    uint32_t e0, e1, e2, e3;
+    asm("dp4a.u32.u32 %0, %1, %2, 0x4B000000;" : "=r"(e0) : "r"(word), "r"(g_onehot[0]));
+    asm("dp4a.u32.u32 %0, %1, %2, 0x4B000000;" : "=r"(e1) : "r"(word), "r"(g_onehot[1]));
+    asm("dp4a.u32.u32 %0, %1, %2, 0x4B000000;" : "=r"(e2) : "r"(word), "r"(g_onehot[2]));
+    asm("dp4a.u32.u32 %0, %1, %2, 0x4B000000;" : "=r"(e3) : "r"(word), "r"(g_onehot[3]));
+    const float2 q01 = __fadd2_rn(make_float2(__uint_as_float(e0), __uint_as_float(e1)), two23);
+    const float2 q23 = __fadd2_rn(make_float2(__uint_as_float(e2), __uint_as_float(e3)), two23);
+    const float2 lo = __ffma2_rn(q01, make_float2(a, a), make_float2(b, b));
+    const float2 hi = __ffma2_rn(q23, make_float2(a, a), make_float2(b, b));
+#else
     const float2 lo = __ffma2_rn(make_float2(magic_byte(word, 0), magic_byte(word, 1)), make_float2(a, a), make_float2(b, b));
     const float2 hi = __ffma2_rn(make_float2(magic_byte(word, 2), magic_byte(word, 3)), make_float2(a, a), make_float2(b, b));
+#endif
     out[0] = lo.x;
     out[1] = lo.y;
     out[2] = hi.x;
     out[3] = hi.y;
 #else
     for (int i = 0; i < 4; ++i)
+#if RTB_TRACE_DP4A
+        out[i] = fmaf(float((word >> (8 * i)) & 0xffu), a, b);
+#else
         out[i] = fmaf(magic_byte(word, i), a, b);
+#endif
 #endif
 }
 
@@ -193,9 +220,13 @@ RTB_WD void fma4q(uint32_t word, float a, float b, float out[4]) {
 RTB_WD void qnode_slabs(const Vec4f &r0, const Vec4f &r1, const Vec4f &r2, const TravRay &r, float t_min, float t_max,
                         float k[4]) {
     const float ax = r0.w * r.idir.x, ay = r2.z * r.idir.y, az = r2.w * r.idir.z;
+#if RTB_TRACE_DP4A
+    const float bx = fmaf(r0.x, r.idir.x, r.ood.x), by = fmaf(r0.y, r.idir.y, r.ood.y), bz = fmaf(r0.z, r.idir.z, r.ood.z);
+#else
     const float bx = fmaf(-32768.0f, ax, fmaf(r0.x, r.idir.x, r.ood.x));
     const float by = fmaf(-32768.0f, ay, fmaf(r0.y, r.idir.y, r.ood.y));
     const float bz = fmaf(-32768.0f, az, fmaf(r0.z, r.idir.z, r.ood.z));
+#endif
     const uint32_t lox = f2u(r1.x), loy = f2u(r1.y), loz = f2u(r1.z), hix = f2u(r1.w), hiy = f2u(r2.x), hiz = f2u(r2.y);
     const bool nx = (r.neg & 1u) != 0, ny = (r.neg & 2u) != 0, nz = (r.neg & 4u) != 0;
     float tnx[4], tny[4], tnz[4], tfx[4], tfy[4], tfz[4];
