@@ -25,9 +25,9 @@ native arm      value   Mpaths/s with the scene resident in HBM: K steps bracket
                         kept as a secondary key), cpu_baseline = the unmodified reference's
                         Renderer::render on this box's host cores.
                 configs every other BASELINE configuration (C2, C3, C4, C4env, C5), measured in the
-                        same run on rank 0's GPU (N = 1 only; spp of a step stated per entry).
+                        same run on rank 0's GPU at its FULL sample count (N = 1 only; C5 = 4.2 s per step).
                 strong  strong scaling inside the same run: C1 (400 spp in total) and C5 (4K,
-                        1 M spheres, 256 spp in total per step) with the work split over all N GPUs.
+                        1 M spheres, its full 1024 spp in total per step) with the work split over all N GPUs.
 reference arm   --impl reference: the unmodified reference (oracle/_ref, compiled from
                 /root/reference in the build container) on all host threads; rank 0 only.
 Prints ONE JSON line.
@@ -411,15 +411,16 @@ def run_native(args, rank, local_rank, world):
     if not args.no_extras:
         if world == 1:
             # the other BASELINE configurations, same run, same GPU (spp of a step stated per entry)
-            for name, spp in (("C2", 0), ("C3", 0), ("C4", 0), ("C4env", 0), ("C5", 64)):
+            # (every configuration at its FULL sample count; C5 = 1024 spp of a 4K image = 4.2 s per step: two steps)
+            for name, steps in (("C2", 3), ("C3", 3), ("C4", 3), ("C4env", 3), ("C5", 2)):
                 if name == CONFIG:
                     continue
                 cfg = B.configs.get(name)
-                m = B.measure(name, spp or cfg.spp, 3, 1, False, with_e2e=True)
+                m = B.measure(name, cfg.spp, steps, 1, False, with_e2e=True)
                 m["roofline"] = B.roofline(name)
                 extras[name] = m
         # strong scaling: the total work of a step is fixed, the library splits it over the N GPUs
-        for name, spp in (("C1", 400), ("C5", 256)):
+        for name, spp in (("C1", 400), ("C5", 1024)):
             strong_runs[name] = B.measure(name, spp, 2 if name == "C5" else 5, 1, True, with_e2e=False)
     if rank == 0:
         out = {"metric": "Mpaths/s", "value": head["mpaths_per_s"], "unit": "Mpaths/s", "n_gpus": world,
