@@ -379,7 +379,10 @@ class Bench:
             peak = float(self.micro.get("l2_stream_read_gbs", 21000.0))
             ach = grays * b_ray
             binary = st_t.get("traversal") == 1
-            rl = {"kernel": ("k_extend (binary while-while traversal: the per-scene rule keeps it where media / instances sit in the tree)"
+            flat = st_t.get("traversal") == 0
+            rl = {"kernel": ("k_extend (lockstep walk of the shared-memory scene copy: a scene of <= 64 records on the wavefront schedule)"
+                             if flat else
+                             "k_extend (binary while-while traversal: the per-scene rule keeps it where media / instances sit in the tree)"
                              if binary else "k_extend_w (warp-scheduled 4-wide traversal: closest hit, refill, material sort)"),
                   "bound": "l2", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                   "peak_source": "tools/microbench L2 stream read (profiles/microbench.json)",
