@@ -20,5 +20,24 @@ for blob, w, h, spp, integ, flags, pool in jobs:
     print("ok", w, h, spp, integ, flags, st["schedule"], st["rays_closest"], st["rays_shadow"], flush=True)
 g = conftest.load_golden(9)
 ctx.upload_scene(g.blob)
-ctx.trace(g["rays"][:512], 64); ctx.trace(g["rays"][:512], 32)
+ctx.trace(g["rays"][:512], 64); ctx.trace(g["rays"][:512], 32); ctx.trace(g["rays"][:512], 34); ctx.trace(g["rays"][:512], 36)
+ctx.set_option(b.OPT_BINARY_TRAVERSAL, 2)          # the 4-wide kernels on the scene with media and an instance
+ctx.upload_scene(g.blob)
+acc, st = ctx.render(ctx.params(40, 40, 4, 1, seed=5))
+assert st["traversal"] == 2 and np.isfinite(acc).all()
+ctx.set_option(b.OPT_BINARY_TRAVERSAL, 0)
+# round 2's additions: the reference-order walk with seeded draws, gated spheres (exact and in-tree), image textures,
+# the device-built environment tables, the lazy fp64 tables
+z = np.load(os.path.join(ROOT, "tests", "golden", "media09.npz"))
+ctx.upload_scene(z["blob"].tobytes()); ctx.trace(z["rays"][:256], 65)
+for sid, integ in ((34, 4), (35, 4), (36, 4), (22, 4)):
+    gg = conftest.load_golden(sid)
+    ctx.set_option(b.OPT_LAZY_F64_PRIMS, 0 if sid == 22 else 100000)
+    ctx.upload_scene(gg.blob)
+    acc, st = ctx.render(ctx.params(48, 27, 4, integ, seed=3))
+    assert np.isfinite(acc).all()
+    ctx.trace(gg["rays"][:256], 64); ctx.trace(gg["rays"][:256], 34)
+    if sid == 36:
+        assert len(ctx.env_tables()) > 0
+    print("ok scene", sid, st["schedule"], st["traversal"], flush=True)
 print("done")
