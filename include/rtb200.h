@@ -170,7 +170,9 @@ RTB_API int rtb_set_option(rtb_context *ctx, int option, int64_t value);
 
 /* Copies the flattened scene (rtb200_scene.h) to the device: builds the two-level
  * SAH BVH that replaces bvh_node (src/geometry/bvh.h:52-94), the fp32 production
- * tables and the fp64 validation tables (large scenes: on their first use, RTB_OPT_LAZY_F64_PRIMS).  The blob may be freed on return.
+ * tables and the fp64 validation tables (large scenes: on their first use, RTB_OPT_LAZY_F64_PRIMS).
+ * A re-upload reuses the device allocations of the scene it replaces.  A blob that fails validation
+ * leaves the current scene in place; a CUDA failure during the copy leaves the context without one.  The blob may be freed on return.
  * Replaces: the shared_ptr graph handed to Renderer::render (renderer.h:30). */
 RTB_API int rtb_scene_upload(rtb_context *ctx, const void *blob, uint64_t nbytes);
 RTB_API int rtb_scene_get_stats(rtb_context *ctx, rtb_scene_stats *out);

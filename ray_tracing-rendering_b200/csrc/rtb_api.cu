@@ -215,6 +215,10 @@ void upload_scene(rtb_context *ctx, std::shared_ptr<const HostScene> host) {
     const HostScene &H = sc->host;
     cudaStream_t s = ctx->stream;
     size_t bytes = 0;
+    if (ctx->scene) { // re-upload: reuse the tables' allocations; from here on a failure leaves the context without a scene
+        std::unique_ptr<DeviceScene> old = std::move(ctx->scene);
+        sc->adopt_allocations(*old);
+    }
     upload_typed(sc->f32, H.f32, s, bytes);
     upload_typed(sc->f64, H.f64, s, bytes); // (large tables empty when H.has_f64 is false)
     sc->f64_ready = H.has_f64;
@@ -229,7 +233,20 @@ void upload_scene(rtb_context *ctx, std::shared_ptr<const HostScene> host) {
     sc->orig_to_sorted.upload(H.orig_to_sorted, s);
     sc->images.upload(H.images, s);
     sc->image_bytes.upload(H.image_bytes, s);
-    sc->env_texels.upload(H.env_texels, s);
+    if (timer.on)
+        RTB_CUDA(cudaStreamSynchronize(s));
+    timer.mark("device: tables alloc + H2D");
+    if (H.env_on_device) { // straight from the caller's blob (alive until rtb_scene_upload / rtb_group_scene_upload returns)
+        sc->env_texels.alloc(H.n_env_texels * sizeof(float));
+        if (H.n_env_texels)
+            RTB_CUDA(cudaMemcpyAsync(sc->env_texels.as<float>(), H.env_texels_src, H.n_env_texels * sizeof(float),
+                                     cudaMemcpyHostToDevice, s));
+    } else {
+        sc->env_texels.upload(H.env_texels, s);
+    }
+    if (timer.on)
+        RTB_CUDA(cudaStreamSynchronize(s));
+    timer.mark("device: env texels alloc + H2D");
     if (H.env_on_device) {
         if (H.env_table_doubles)
             build_env_tables_device(ctx, *sc);
@@ -244,8 +261,9 @@ void upload_scene(rtb_context *ctx, std::shared_ptr<const HostScene> host) {
              sc->env_texels.bytes() + sc->env_tables.bytes();
     sc->device_bytes = bytes;
     RTB_CUDA(cudaStreamSynchronize(s));
-    timer.mark("device: alloc + H2D + env tables");
-    ctx->scene = std::move(sc);
+    timer.mark("device: env tables + wide nodes");
+    ctx->scene = std::move(sc); // (frees the previous scene's tables)
+    timer.mark("device: previous scene freed");
     ++ctx->scene_serial;
 }
 

@@ -45,7 +45,9 @@ struct HostScene {
     std::vector<int32_t> orig_to_sorted; // blob prim id -> sorted index
     std::vector<ImageRec> images;
     std::vector<uint8_t> image_bytes;
-    std::vector<float> env_texels;
+    std::vector<float> env_texels;           // EMPTY when env_on_device: the texels go from the caller's blob to the device
+    const float *env_texels_src = nullptr;   // (env_on_device) the blob's texel pool: valid DURING the upload call only
+    uint64_t n_env_texels = 0;
     std::vector<double> env_tables;          // Distribution2D tables of the env lights; EMPTY when env_on_device
     uint64_t env_table_doubles = 0;          // their size (the device builds them: rtb_api.cu build_env_tables_device)
     bool env_on_device = false;
@@ -639,7 +641,9 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double t
 
     // ---- lights
     H.env_on_device = env_on_device;
-    if (S.n_env_texels())
+    H.n_env_texels = S.n_env_texels();
+    H.env_texels_src = S.env_texels();
+    if (S.n_env_texels() && !env_on_device) // (a 2048 x 1024 map is 25 MB: no second host copy on the upload path)
         H.env_texels.assign(S.env_texels(), S.env_texels() + S.n_env_texels());
     for (uint64_t i = 0; i < S.n_lights(); ++i) {
         const rtb_light &l = S.lights()[i];
