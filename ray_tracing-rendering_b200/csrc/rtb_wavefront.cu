@@ -729,12 +729,47 @@ __device__ __forceinline__ float power_heuristic(float a, float b) {
     const float a2 = a * a, b2 = b * b, denom = a2 + b2;
     return denom > 0.f ? a2 / denom : 0.f;
 }
+// The light table in shared memory (north_star: "stage the top BVH levels and light tables in shared
+// memory"): with RTB_SMEM_LIGHTS=1 every kernel that shades (k_shade, k_shade_minor, k_miss, k_fused) copies
+// the first kSmemLights records (100 bytes each; no reference scene has more than four lights) at its start
+// and light_at() serves them from there.  MEASURED on B200 (round 2, same box, same run order): C3 17.61 ->
+// 17.73 ms, C4-env 42.57 -> 44.49 ms, C5 shade stage 486 -> 493 ms — slower everywhere: a light record is read
+// with warp-uniform addresses, which the read-only path already serves as one L1 broadcast per field, while the
+// shared-memory copy adds a block barrier per launch, a bounds select per access and generic-space loads.  Off
+// by default; the top BVH levels, where lanes read DIFFERENT nodes, are staged (rtb_trace.cuh).
+#ifndef RTB_SMEM_LIGHTS
+#define RTB_SMEM_LIGHTS 0
+#endif
+constexpr int kSmemLights = 8;
+#if RTB_SMEM_LIGHTS
+__shared__ LightT<float> s_light_table[kSmemLights];
+#endif
+__device__ __forceinline__ void stage_lights(const WfParams &p) {
+#if RTB_SMEM_LIGHTS
+    const int n = p.shade.n_lights < kSmemLights ? p.shade.n_lights : kSmemLights;
+    constexpr int kWords = int(sizeof(LightT<float>) / 4);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(p.shade.lights);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(s_light_table);
+    for (int i = threadIdx.x; i < n * kWords; i += blockDim.x)
+        dst[i] = __ldg(src + i);
+    __syncthreads();
+#else
+    (void)p;
+#endif
+}
+__device__ __forceinline__ const LightT<float> &light_at(const WfParams &p, int i) {
+#if RTB_SMEM_LIGHTS
+    return i < kSmemLights ? s_light_table[i] : p.shade.lights[i];
+#else
+    return p.shade.lights[i];
+#endif
+}
 // mis_path_integrator.h:173-188 (also :53-60): sum over ALL lights of pdf(o,d)/N
 __device__ float all_lights_pdf(const WfParams &p, V3<float> o, V3<float> d) {
     float total = 0.f;
     const float sel = 1.0f / float(p.shade.n_lights);
     for (int i = 0; i < p.shade.n_lights; ++i)
-        total += light_pdf(p.shade, p.shade.lights[i], o, d) * sel;
+        total += light_pdf(p.shade, light_at(p, i), o, d) * sel;
     return total;
 }
 
@@ -822,7 +857,7 @@ __device__ __forceinline__ void shade_surface(const WfParams &p, const GeomView<
             li = li < nl ? li : nl - 1;
             const float sel = 1.0f / float(nl);
             const float u0 = rng.next(), u1 = rng.next();
-            const LightT<float> &L = p.shade.lights[li];
+            const LightT<float> &L = light_at(p, li);
             const LightSampleT<float> ls = light_sample(p.shade, L, rec.p, u0, u1, rng);
             if (ls.pdf > 0.f && length_squared(ls.Li) > 0.f) {
                 const V3<float> f = mat_eval(p.shade, m, rec, wo, ls.wi);
@@ -922,8 +957,8 @@ __device__ __forceinline__ void miss_surface(const WfParams &p, const PathState 
     if (!OLD && p.integrator >= RTB_INTEGRATOR_DIRECT && p.shade.n_infinite_lights > 0) {
         V3<float> env(0, 0, 0);
         for (int i = 0; i < p.shade.n_lights; ++i)
-            if (p.shade.lights[i].type == RTB_LIGHT_ENV)
-                env = env + light_Le(p.shade, p.shade.lights[i], s.d);
+            if (light_at(p, i).type == RTB_LIGHT_ENV)
+                env = env + light_Le(p.shade, light_at(p, i), s.d);
         if (p.integrator == RTB_INTEGRATOR_DIRECT || s.depth == 0 || s.spec)
             L = s.T * env;
         else
@@ -1237,12 +1272,16 @@ __device__ __forceinline__ void shade_queue(const WfParams &p, int it, int q) {
 }
 template <int M, bool OLD>
 __global__ void __launch_bounds__(kWfBlock, RTB_SHADE_MIN_BLOCKS) k_shade(WfParams p, int it, int q) {
+    if (!OLD)
+        stage_lights(p);
     shade_queue<M, OLD>(p, it, q);
 }
 // The cheap, usually sparsely hit material types (metal, dielectric, emitter, isotropic) in ONE
 // launch, queue after queue: each still runs its own shade_surface<M> over its own queue, so
 // nothing diverges, but three launches (and their tails) per iteration are saved.
 template <bool OLD> __global__ void __launch_bounds__(kWfBlock, RTB_SHADE_MIN_BLOCKS) k_shade_minor(WfParams p, int it) {
+    if (!OLD)
+        stage_lights(p);
     if ((p.mat_mask >> RTB_MAT_METAL) & 1u)
         shade_queue<RTB_MAT_METAL, OLD>(p, it, RTB_MAT_METAL);
     if ((p.mat_mask >> RTB_MAT_DIELECTRIC) & 1u)
@@ -1257,6 +1296,8 @@ template <bool OLD> __global__ void __launch_bounds__(kWfBlock, RTB_SHADE_MIN_BL
 // the next extend queue become empty.  SHADE = false when that radiance is identically zero
 // (black background, no environment light): then nothing is read at all.
 template <bool SHADE> __global__ void __launch_bounds__(128) k_miss(WfParams p, int it) {
+    if (SHADE)
+        stage_lights(p);
     Counters &C = p.ctr[it % 3];
     const uint32_t n = C.key.v[kMissKey];
     const uint32_t base_out = out_base(C, kMissKey);
@@ -1697,6 +1738,8 @@ __global__ void __launch_bounds__(128, OLD ? RTB_FUSED_MIN_BLOCKS_OLD : (SIMPLE 
     k_fused(WfParams p) {
     __shared__ FlatSmem sm;
     __shared__ FlatFast ff;
+    if (!OLD)
+        stage_lights(p);
     const GeomView<float> g = stage_scene_flat(p.geom, sm);
     if (threadIdx.x == 0)
         build_flat_fast(g, ff);
