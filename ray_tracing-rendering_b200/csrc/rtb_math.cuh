@@ -19,9 +19,11 @@
 #include <cuda_runtime.h>
 #define RTB_HD __host__ __device__ __forceinline__
 #define RTB_D __device__ __forceinline__
+#define RTB_HD_OUTLINE __host__ __device__ __noinline__ // one copy per kernel: for large bodies reached from many call sites
 #else
 #define RTB_HD inline
 #define RTB_D inline
+#define RTB_HD_OUTLINE inline
 #endif
 
 namespace rtb {

@@ -177,6 +177,7 @@ template <class R> RTB_HD R perlin_noise(const PerlinT<R> &P, V3<R> p) {
 template <class R> RTB_HD R perlin_turb(const PerlinT<R> &P, V3<R> p) {
     R accum = 0, weight = 1;
     V3<R> tp = p;
+#pragma unroll 1
     for (int i = 0; i < 7; i++) {
         accum += weight * perlin_noise(P, tp);
         weight *= R(0.5);
@@ -185,9 +186,15 @@ template <class R> RTB_HD R perlin_turb(const PerlinT<R> &P, V3<R> p) {
     return fabs_(accum);
 }
 
-template <class R> RTB_HD V3<R> tex_value(const ShadeView<R> &S, int tex, R u, R v, V3<R> p) {
+// Out of line, with the tables passed by pointer: mat_tex() reaches it from every BSDF entry point (albedo,
+// roughness, metallic, normal map, emission), and the inlined copies — seven unrolled octaves of Perlin noise
+// each — were 27 % of the general fused kernel's 20,000 instructions, a kernel ncu showed waiting for
+// instructions (`no_instruction`, issue slots 30 % on C4-env).
+template <class R>
+RTB_HD_OUTLINE V3<R> tex_value_tables(const TexT<R> *texs, const ImageRec *images, const uint8_t *image_bytes,
+                                      const PerlinT<R> *perlins, int tex, R u, R v, V3<R> p) {
     for (int hop = 0; hop < 8; ++hop) {
-        const TexT<R> &t = S.texs[tex];
+        const TexT<R> &t = texs[tex];
         switch (t.type) {
         case 0: // solid_color, texture.h:47-49
             return V3<R>(t.color[0], t.color[1], t.color[2]);
@@ -197,7 +204,7 @@ template <class R> RTB_HD V3<R> tex_value(const ShadeView<R> &S, int tex, R u, R
             break;
         }
         case 2: { // image_texture, texture.h:115-139
-            const ImageRec im = S.images[t.image];
+            const ImageRec im = images[t.image];
             if (im.width == 0)
                 return V3<R>(0, 1, 1);
             const R uc = clamp_(u, R(0), R(1));
@@ -207,17 +214,20 @@ template <class R> RTB_HD V3<R> tex_value(const ShadeView<R> &S, int tex, R u, R
                 i = im.width - 1;
             if (j >= im.height)
                 j = im.height - 1;
-            const uint8_t *px = S.image_bytes + im.offset + (size_t(j) * im.width + i) * 3;
+            const uint8_t *px = image_bytes + im.offset + (size_t(j) * im.width + i) * 3;
             const R s = R(1.0 / 255.0);
             return V3<R>(s * px[0], s * px[1], s * px[2]);
         }
         default: { // noise_texture, texture.h:155-158
-            const R n = R(0.5) * (R(1) + sin_(t.scale * p.z + R(10) * perlin_turb(S.perlins[t.perlin], p)));
+            const R n = R(0.5) * (R(1) + sin_(t.scale * p.z + R(10) * perlin_turb(perlins[t.perlin], p)));
             return V3<R>(n, n, n);
         }
         }
     }
     return V3<R>(0, 0, 0);
+}
+template <class R> RTB_HD V3<R> tex_value(const ShadeView<R> &S, int tex, R u, R v, V3<R> p) {
+    return tex_value_tables<R>(S.texs, S.images, S.image_bytes, S.perlins, tex, u, v, p);
 }
 
 // ---- materials ---------------------------------------------------------------------------

@@ -765,7 +765,8 @@ __device__ __forceinline__ const LightT<float> &light_at(const WfParams &p, int 
 #endif
 }
 // mis_path_integrator.h:173-188 (also :53-60): sum over ALL lights of pdf(o,d)/N
-__device__ float all_lights_pdf(const WfParams &p, V3<float> o, V3<float> d) {
+// (out of line: two call sites, emitted-radiance MIS and miss MIS, each would inline light_pdf of every light type)
+__device__ __noinline__ float all_lights_pdf(const WfParams &p, V3<float> o, V3<float> d) {
     float total = 0.f;
     const float sel = 1.0f / float(p.shade.n_lights);
     for (int i = 0; i < p.shade.n_lights; ++i)
@@ -796,10 +797,18 @@ __device__ __forceinline__ void shade_surface(const WfParams &p, const GeomView<
     } else {
         m = p.shade.mats[g.prims[pi].type_mat >> PT_MAT_SHIFT];
     }
-    m.type = M; // compile-time constant: prunes the per-type switches
+    // M >= 0: the type is a compile-time constant, which prunes the per-type switches (the material-sorted
+    // k_shade<M> kernels, the SIMPLE fused kernels).  M < 0: the record's own type, ONE copy of the code for all
+    // types (the general fused kernel: six inlined copies were 25,600 instructions = 410 KB, and ncu showed that
+    // kernel waiting for instructions — `no_instruction` 10 warps per issue, issue slots 30 % on C4-env).
+    if (M >= 0)
+        m.type = M;
+    const int MT = M >= 0 ? M : m.type;
     RecT<float> rec;
     if (ALL_PLANAR || (plane != nullptr && !(m.flags & 1) && plane[pi].valid))
         rec = plane_record<float>(plane[pi], s.o, s.d, t);
+    else if (M < 0) // (one copy of make_record in the one-copy kernel)
+        rec = make_record<float, true, true>(g, pi, s.o, s.d, s.time, t);
     else
         rec = (m.flags & 1) ? make_record<float, true, true>(g, pi, s.o, s.d, s.time, t)
                             : make_record<float, true, false>(g, pi, s.o, s.d, s.time, t);
@@ -808,7 +817,7 @@ __device__ __forceinline__ void shade_surface(const WfParams &p, const GeomView<
     alive = true;
     if (OLD) {
         // path_integrator.h:32-44, rr_path_integrator.h:35-57
-        if (M == RTB_MAT_DIFFUSE_LIGHT)
+        if (MT == RTB_MAT_DIFFUSE_LIGHT)
             accum_add(p.accum, s.pix, s.T * mat_emitted_old(p.shade, m, rec));
         V3<float> atten, dout;
         if (!mat_scatter(p.shade, m, rec, s.d, rng, atten, dout)) {
@@ -828,7 +837,7 @@ __device__ __forceinline__ void shade_surface(const WfParams &p, const GeomView<
         }
     } else {
         const V3<float> wo = -unit_vector(s.d);
-        if (M == RTB_MAT_DIFFUSE_LIGHT) {
+        if (MT == RTB_MAT_DIFFUSE_LIGHT) {
             const V3<float> e = mat_emitted_new(p.shade, m, rec);
             if (p.integrator == RTB_INTEGRATOR_PBR) {
                 accum_add(p.accum, s.pix, s.T * e); // pbr_path_integrator.h:38-39
@@ -850,7 +859,7 @@ __device__ __forceinline__ void shade_surface(const WfParams &p, const GeomView<
         // next-event estimation: direct_light_integrator.h:98-142, mis_path_integrator.h:192-234.
         // eval() is identically 0 for metal / dielectric / diffuse_light / isotropic, so only
         // lambertian and PBR can contribute; the others skip the (wasted) shadow ray.
-        if ((M == RTB_MAT_LAMBERTIAN || M == RTB_MAT_PBR) && p.integrator >= RTB_INTEGRATOR_DIRECT &&
+        if ((MT == RTB_MAT_LAMBERTIAN || MT == RTB_MAT_PBR) && p.integrator >= RTB_INTEGRATOR_DIRECT &&
             p.shade.n_lights > 0) {
             const int nl = p.shade.n_lights;
             int li = int(float(nl) * rng.next()); // random_int(0, n-1), rtweekend.h:48-50
@@ -1726,6 +1735,9 @@ __global__ void k_batch_hits_out(GeomView<float> g, const rtb_ray *__restrict__ 
 // ---- (B) fused kernel for shared-memory-resident scenes ----------------------------------------
 
 constexpr uint32_t kSampleChunk = 256; // samples a warp reserves per atomic
+#ifndef RTB_FUSED_DYNAMIC_SHADE
+#define RTB_FUSED_DYNAMIC_SHADE 1 // the general fused kernel shades through ONE copy of shade_surface (see there)
+#endif
 
 // SIMPLE >= 1: the scene only uses lambertian and diffuse_light materials (the Cornell boxes): the
 // other four shade_surface instantiations are left out, which halves the kernel's code size
@@ -1811,6 +1823,9 @@ __global__ void __launch_bounds__(128, OLD ? RTB_FUSED_MIN_BLOCKS_OLD : (SIMPLE 
                     else
                         shade_surface<3, OLD, SIMPLE == 2>(p, g, s, t, pi, alive, sh, ff.plane);
                 } else {
+#if RTB_FUSED_DYNAMIC_SHADE
+                    shade_surface<-1, OLD>(p, g, s, t, pi, alive, sh, ff.plane); // one copy, the record's own type
+#else
                     switch (mtype) {
                     case 0: shade_surface<0, OLD>(p, g, s, t, pi, alive, sh, ff.plane); break;
                     case 1: shade_surface<1, OLD>(p, g, s, t, pi, alive, sh, ff.plane); break;
@@ -1819,6 +1834,7 @@ __global__ void __launch_bounds__(128, OLD ? RTB_FUSED_MIN_BLOCKS_OLD : (SIMPLE 
                     case 4: shade_surface<4, OLD>(p, g, s, t, pi, alive, sh, ff.plane); break;
                     default: shade_surface<5, OLD>(p, g, s, t, pi, alive, sh, ff.plane); break;
                     }
+#endif
                 }
                 if (!OLD && sh.want) {
                     ++n_shadow;
