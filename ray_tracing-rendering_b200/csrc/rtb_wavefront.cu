@@ -1735,6 +1735,13 @@ __global__ void k_batch_hits_out(GeomView<float> g, const rtb_ray *__restrict__ 
 // ---- (B) fused kernel for shared-memory-resident scenes ----------------------------------------
 
 constexpr uint32_t kSampleChunk = 256; // samples a warp reserves per atomic
+#ifndef RTB_FUSED_DECK
+#define RTB_FUSED_DECK 1 // camera samples are generated 32 at a time by the whole warp into a shared-memory deck
+#endif
+struct FusedDeck { // one per warp: origin + time, direction + pixel, generator state after the camera's draws
+    float4 a[32], b[32];
+    uint2 r[32];
+};
 #ifndef RTB_FUSED_DYNAMIC_SHADE
 #define RTB_FUSED_DYNAMIC_SHADE 1 // the general fused kernel shades through ONE copy of shade_surface (see there)
 #endif
@@ -1772,11 +1779,79 @@ __global__ void __launch_bounds__(128, OLD ? RTB_FUSED_MIN_BLOCKS_OLD : (SIMPLE 
     unsigned long long chunk_next = 0, chunk_end = 0; // warp-uniform: this warp's private sample range
     uint32_t n_closest = 0, n_shadow = 0, n_paths = 0; // per thread and launch (a launch is <= 2^28 samples)
     uint64_t nodes = 0, tests = 0;
+    // The deck pays where the kernel is small (C1 9.03 -> 8.31 ms, C3 17.81 -> 17.18 ms); the general kernel, which
+    // already waits for instructions and spills, loses with it (C4-env 40.5 -> 46.2 ms) and keeps the lane-by-lane form.
+    constexpr bool DECK = RTB_FUSED_DECK && SIMPLE != 0;
+    __shared__ FusedDeck decks[DECK ? 4 : 1];
+    FusedDeck &dk = decks[DECK ? (threadIdx.x >> 5) : 0];
+    uint32_t deck_n = 0;   // warp-uniform: camera samples waiting in the deck
+    bool gen_done = false; // warp-uniform: the launch has no samples left for this warp
     while (true) {
         // regeneration: every idle lane takes the next sample of the warp's chunk
         const bool need = !alive && !exhausted;
         const uint32_t m = __ballot_sync(kFullMask, need);
-        if (m) {
+        if (DECK && m) {
+            uint32_t want = __popc(m), r = __popc(m & ((1u << lane_id()) - 1u));
+            bool pending = need;
+            for (;;) {
+                const uint32_t take = want < deck_n ? want : deck_n;
+                if (pending) {
+                    if (r < take) { // entry deck_n - 1 - r
+                        const uint32_t e = deck_n - 1u - r;
+                        const float4 a = dk.a[e], b = dk.b[e];
+                        const uint2 g2 = dk.r[e];
+                        s.o = V3<float>(a.x, a.y, a.z);
+                        s.time = a.w;
+                        s.d = V3<float>(b.x, b.y, b.z);
+                        s.pix = __float_as_uint(b.w);
+                        s.rng.s = uint64_t(g2.x) | (uint64_t(g2.y) << 32);
+                        s.T = V3<float>(1, 1, 1);
+                        s.depth = 0;
+                        s.spec = false;
+                        s.prev_pdf = 0.f;
+                        s.origin_prim = kNoPrim;
+                        alive = true;
+                        pending = false;
+                        ++n_paths;
+                    } else {
+                        r -= take;
+                    }
+                }
+                deck_n -= take;
+                want -= take;
+                if (want == 0 || gen_done)
+                    break;
+                // the deck is empty: the WHOLE warp generates the next 32 camera samples (at 32 lanes; lane by
+                // lane regeneration ran at 10 of 32 and was 17 % of the kernel's issued instructions)
+                if (chunk_next == chunk_end) {
+                    unsigned long long base = 0;
+                    if (lane_id() == 0)
+                        base = atomicAdd(&p.glob->next_sample, (unsigned long long)kSampleChunk);
+                    chunk_next = __shfl_sync(kFullMask, base, 0);
+                    chunk_end = chunk_next + kSampleChunk;
+                }
+                const unsigned long long id0 = chunk_next;
+                chunk_next += 32u;
+                if (id0 >= p.window_end) {
+                    gen_done = true;
+                    break;
+                }
+                const unsigned long long left = p.window_end - id0;
+                deck_n = left < 32ull ? uint32_t(left) : 32u;
+                __syncwarp();
+                {
+                    PathState q;
+                    new_path(p, id0 + lane_id(), q); // (lanes past the end compute a sample nobody pops)
+                    dk.a[lane_id()] = make_float4(q.o.x, q.o.y, q.o.z, q.time);
+                    dk.b[lane_id()] = make_float4(q.d.x, q.d.y, q.d.z, __uint_as_float(q.pix));
+                    dk.r[lane_id()] = make_uint2(uint32_t(q.rng.s), uint32_t(q.rng.s >> 32));
+                }
+                __syncwarp();
+            }
+            if (pending)
+                exhausted = true;
+        }
+        if (!DECK && m) {
             const uint32_t n = __popc(m), rank = __popc(m & ((1u << lane_id()) - 1u));
             const unsigned long long avail = chunk_end - chunk_next;
             unsigned long long id;
