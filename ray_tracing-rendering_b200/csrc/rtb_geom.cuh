@@ -162,10 +162,21 @@ template <class R> RTB_HD void apply_op(const XfOp<R> &op, V3<R> &o, V3<R> &d) {
     }
 }
 
+// (measured knobs, both off: the general fused kernel shrinks from 13,700 to 10,500 instructions with them and gets
+// SLOWER — C4-env 40.8 -> 44.5 ms: the calls pin registers around the traversal loop)
+#ifndef RTB_SLIM_CHAIN
+#define RTB_SLIM_CHAIN 0
+#endif
+#ifndef RTB_SLIM_BOUNDARY
+#define RTB_SLIM_BOUNDARY 0
+#endif
 template <class R> RTB_HD void apply_chain(const GeomView<R> &g, int chain, V3<R> &o, V3<R> &d) {
     if (chain < 0)
         return;
     const ChainRec c = g.chains[chain];
+#if RTB_SLIM_CHAIN
+#pragma unroll 1
+#endif
     for (int i = 0; i < c.count; ++i)
         apply_op(g.ops[c.first + i], o, d);
 }
@@ -334,7 +345,12 @@ template <class R> RTB_HD V3<R> safe_inv(V3<R> d) { return V3<R>(R(1) / d.x, R(1
 // — constant_medium's `boundary->hit()` (constant_medium.h:64-68).  Each boundary
 // primitive carries its full wrapper chain.
 template <class R, bool ROBUST>
-RTB_HD bool hit_boundary(const GeomView<R> &g, uint32_t first, uint32_t count, V3<R> o, V3<R> d,
+#if RTB_SLIM_BOUNDARY
+RTB_HD_OUTLINE
+#else
+RTB_HD
+#endif
+bool hit_boundary(const GeomView<R> &g, uint32_t first, uint32_t count, V3<R> o, V3<R> d,
                          R time, R t_min, R t_max, R &t_out) {
     bool any = false;
     int cur_chain = -2;
