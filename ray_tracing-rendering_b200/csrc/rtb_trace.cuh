@@ -65,6 +65,14 @@ namespace rtb {
 #ifndef RTB_TRACE_DP4A
 #define RTB_TRACE_DP4A 1 // 1: plane bytes expanded by IDP4A + FADD2 (FMA pipe) instead of PRMT (ALU pipe, half rate): C5 -4 % (B200)
 #endif
+#ifndef RTB_TRACE_POSTPONE
+#define RTB_TRACE_POSTPONE 0 // 1: a lane that reaches a leaf parks it and keeps descending (scenes without instances).  MEASURED on
+                             // B200: the emulated warps gain lanes (0.65 -> 0.71 of them busy), the GPU loses 12 % (C5 68.3 -> 76.9 ms per
+                             // 16 spp): the kernel is bound by the latency of a warp's dependent steps, not by idle lanes; off
+#endif
+#ifndef RTB_TRACE_LEAF_MIN
+#define RTB_TRACE_LEAF_MIN 20 // with parked leaves: a primitive step runs when at least this many lanes have one (or no node quorum)
+#endif
 #ifndef RTB_TRACE_GUARD
 #define RTB_TRACE_GUARD 1 // bound the scheduler loop (an internal error becomes a flag, not a hung GPU)
 #endif
@@ -280,6 +288,7 @@ struct TravLane {
     TravRay r;
     float time, t_min, t_max;
     uint32_t best, best_key, origin, cur, sp;
+    uint32_t pend; // a parked leaf (the rest of it), or kIdleRef
     Pcg rng;
 #if RTB_TRACE_TOP_CACHE
     Vec2u top; // entry sp - 1 of the stack (the array holds the entries below it)
@@ -417,6 +426,25 @@ RTB_WD bool trav_test_prim(const GeomView<float> &g, TravLane &L, const PrimT<fl
 template <bool ANY, bool MEDIA, bool INST, class Job>
 RTB_WD void trav_leaf_step(const GeomView<float> &g, const WideView &w, TravLane &L, Vec2u *stack, uint32_t &overflow,
                            uint32_t &tests, Job &job, uint32_t tag) {
+    if (!INST && L.pend != kIdleRef) { // a parked leaf goes first: one primitive of it (no instances, no stack)
+        const uint32_t first = L.pend & kLeafFirstMask, more = (L.pend >> 27) & 15u;
+        const PrimT<float> p = g.prims[first];
+        if (trav_test_prim<ANY, MEDIA>(g, L, p, p.type_mat & PT_TYPE_MASK, first, tests)) {
+            L.cur = kDoneRef;
+            L.pend = kIdleRef;
+            return;
+        }
+        L.pend = more ? (kLeafFlag | ((more - 1u) << 27) | (first + 1u)) : kIdleRef;
+        if (L.pend == kIdleRef) {
+            // the closest hit may have moved: a node the lane is about to visit can now lie behind it, which the
+            // node step's own slab test against t_max sorts out; a leaf waiting in cur is parked and replaced
+            if (ref_is_leaf(L.cur)) {
+                L.pend = L.cur;
+                trav_pop<INST>(L, stack, job, tag);
+            }
+        }
+        return;
+    }
     const uint32_t first = L.cur & kLeafFirstMask, more = (L.cur >> 27) & 15u;
     const PrimT<float> p = g.prims[first];
     const uint32_t type = p.type_mat & PT_TYPE_MASK;
@@ -512,7 +540,8 @@ RTB_WD uint32_t window_place(TraceWarpSmem &s, uint32_t cnt, uint32_t n_keys, ui
 #if !defined(__CUDACC__)
 // host emulation only: the scheduler's thresholds as run-time values (tools/sched_sim.py sweeps them)
 struct TraceTuning {
-    uint32_t node_min = RTB_TRACE_NODE_MIN, switch_min = RTB_TRACE_SWITCH_MIN;
+    uint32_t node_min = RTB_TRACE_NODE_MIN, switch_min = RTB_TRACE_SWITCH_MIN, leaf_min = RTB_TRACE_LEAF_MIN;
+    bool postpone = RTB_TRACE_POSTPONE != 0;
 };
 inline TraceTuning &trace_tuning() {
     static TraceTuning t;
@@ -520,6 +549,7 @@ inline TraceTuning &trace_tuning() {
 }
 #define RTB_NODE_MIN_ (trace_tuning().node_min)
 #define RTB_SWITCH_MIN_ (trace_tuning().switch_min)
+#define RTB_LEAF_MIN_ (trace_tuning().leaf_min)
 // what the votes decided (steps) and how many lanes took part (lanes)
 struct TraceSchedStats {
     uint64_t node_steps = 0, node_lanes = 0, leaf_steps = 0, leaf_lanes = 0, switches = 0, switch_lanes = 0;
@@ -531,6 +561,7 @@ inline TraceSchedStats &trace_sched_stats() {
 #else
 #define RTB_NODE_MIN_ uint32_t(RTB_TRACE_NODE_MIN)
 #define RTB_SWITCH_MIN_ uint32_t(RTB_TRACE_SWITCH_MIN)
+#define RTB_LEAF_MIN_ uint32_t(RTB_TRACE_LEAF_MIN)
 #endif
 
 // ---- the scheduler ----------------------------------------------------------------------------
@@ -548,10 +579,16 @@ inline TraceSchedStats &trace_sched_stats() {
 template <class Job, bool ANY, bool MEDIA, bool INST, bool TOP>
 RTB_WD void warp_trace(const GeomView<float> &g, const WideView &w, const Vec4f *s_top, uint32_t n_top, TraceWarpSmem &s,
                        Job &job, uint64_t counters[3], uint32_t &overflow) {
+#if defined(__CUDACC__)
+    constexpr bool POSTPONE = RTB_TRACE_POSTPONE && !INST; // (a parked leaf belongs to the space the ray was in)
+#else
+    const bool POSTPONE = trace_tuning().postpone && !INST;
+#endif
     const uint32_t lane = WarpOps::lane();
     Vec2u stack[kWideStack];
     TravLane L;
     L.cur = kIdleRef;
+    L.pend = kIdleRef;
     L.sp = 0;
     L.best = kNoPrim;
     L.best_key = 0;
@@ -564,7 +601,7 @@ RTB_WD void warp_trace(const GeomView<float> &g, const WideView &w, const Vec4f 
 #endif
     for (;;) {
         // ---- switch point: commit finished rays, hand out the window's next ones
-        if (L.cur == kDoneRef) {
+        if (L.cur == kDoneRef && (!POSTPONE || L.pend == kIdleRef)) {
             job.commit(s, tag, L);
             L.cur = kIdleRef;
             ray_max = nodes - ray_start > ray_max ? nodes - ray_start : ray_max;
@@ -586,6 +623,7 @@ RTB_WD void warp_trace(const GeomView<float> &g, const WideView &w, const Vec4f 
                 job.fetch(s, k, L, o, d, tag);
                 ray_start = nodes;
                 L.best = kNoPrim;
+                L.pend = kIdleRef;
                 L.sp = 0;
                 L.r.set(o, d);
                 L.cur = w.root_ref == kEmptyRef ? kDoneRef : w.root_ref;
@@ -623,7 +661,35 @@ RTB_WD void warp_trace(const GeomView<float> &g, const WideView &w, const Vec4f 
         for (;;) {
             const uint32_t m_node = WarpOps::ballot(ref_is_node(L.cur));
             bool node_step = WarpOps::popc(m_node) >= RTB_NODE_MIN_;
-            if (!node_step) {
+            if (POSTPONE) {
+                // Parked leaves: a lane with a leaf in `pend` still takes node steps, so the lanes at a node and the
+                // lanes with primitive work overlap.  Primitive step when enough lanes have one, or the node
+                // quorum fails; refill when enough lanes have neither.
+                const uint32_t m_leaf = WarpOps::ballot(L.pend != kIdleRef || ref_is_leaf(L.cur));
+                if ((m_node | m_leaf) == 0)
+                    break;
+                if (can_refill && 32u - WarpOps::popc(m_node | m_leaf) >= RTB_SWITCH_MIN_)
+                    break;
+#if RTB_TRACE_GUARD
+                if (++guard > (1u << 28)) {
+                    overflow = 2u;
+                    L.cur = kIdleRef;
+                    L.pend = kIdleRef;
+                    win_next = win_count;
+                    break;
+                }
+#endif
+                if (WarpOps::popc(m_leaf) >= RTB_LEAF_MIN_)
+                    node_step = false;
+                else if (!node_step)
+                    node_step = m_leaf == 0 || (m_node != 0 && WarpOps::popc(m_node) >= WarpOps::popc(m_leaf));
+#if !defined(__CUDACC__)
+                if (lane == 0 && !node_step) {
+                    trace_sched_stats().leaf_steps += 1;
+                    trace_sched_stats().leaf_lanes += WarpOps::popc(m_leaf);
+                }
+#endif
+            } else if (!node_step) {
                 const uint32_t m_leaf = WarpOps::ballot(ref_is_leaf(L.cur));
                 if ((m_node | m_leaf) == 0)
                     break;
@@ -655,9 +721,13 @@ RTB_WD void warp_trace(const GeomView<float> &g, const WideView &w, const Vec4f 
                 if (ref_is_node(L.cur)) {
                     ++nodes;
                     trav_node_step<ANY, TOP, INST>(w, s_top, n_top, L, stack, overflow, job, tag);
+                    if (POSTPONE && L.pend == kIdleRef && ref_is_leaf(L.cur)) { // park the leaf, keep walking
+                        L.pend = L.cur;
+                        trav_pop<INST>(L, stack, job, tag);
+                    }
                 }
             } else {
-                if (ref_is_leaf(L.cur))
+                if ((POSTPONE && L.pend != kIdleRef) || ref_is_leaf(L.cur))
                     trav_leaf_step<ANY, MEDIA, INST>(g, w, L, stack, overflow, tests, job, tag);
             }
         }

@@ -138,6 +138,7 @@ void trace_batch(HostScene &H, const rtb_ray *rays, uint64_t n, rtb_hit *hits, u
 // The production scheduler of rtb_trace.cuh (votes, window sort, refill) on emulated warps
 // (rtb_warp.cuh): `warps` warps of 32 fibers pull windows off one cursor, as the persistent
 // kernel's warps do.  Fills t / primitive only (records are tested through the scalar paths).
+static uint32_t g_sim_warps = 24u;
 void trace_batch_warp(HostScene &H, const rtb_ray *rays, uint64_t n, rtb_hit *hits, uint64_t stats[2], bool any_hit,
                       int warps) {
     const GeomView<float> g = geom_view<float>(H);
@@ -183,7 +184,7 @@ void trace_batch_warp(HostScene &H, const rtb_ray *rays, uint64_t n, rtb_hit *hi
             job.head = &head;
             job.base = 0;
             job.win = 0;
-            job.warps = 24u;
+            job.warps = g_sim_warps; // (24: windows shrink quickly, the tail logic is exercised; 1: full-size windows, as in a long launch)
             job.seed = 0x51ed270b;
             uint64_t c[3] = {0, 0, 0};
             uint32_t ov = 0;
@@ -362,6 +363,9 @@ void hc_sched_tuning(int node_min, int switch_min) {
     trace_tuning().node_min = uint32_t(node_min);
     trace_tuning().switch_min = uint32_t(switch_min);
 }
+void hc_sched_leaf_min(int leaf_min) { trace_tuning().leaf_min = uint32_t(leaf_min); }
+void hc_sched_sim_warps(int w) { g_sim_warps = uint32_t(w); }
+void hc_sched_postpone(int on) { trace_tuning().postpone = on != 0; }
 
 // sizes = {nodes, sorted prims, instances}
 void hc_scene_info(void *h, int64_t sizes[3]) {

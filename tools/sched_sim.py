@@ -32,6 +32,10 @@ def load_hostcheck():
     L.hc_trace_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
     L.hc_sched_stats.argtypes = [C.c_void_p]
     L.hc_sched_tuning.argtypes = [C.c_int, C.c_int]
+    L.hc_sched_leaf_min.argtypes = [C.c_int]
+    L.hc_sched_sim_warps.argtypes = [C.c_int]
+    L.hc_sched_postpone.argtypes = [C.c_int]
+    L.hc_sched_sim_warps(1)  # full-size windows, as in a long launch
     return L
 
 
@@ -86,8 +90,10 @@ def main():
         return out, st
 
     def report(name, r):
-        for node_min, switch_min in [(32, 32), (14, 6), (20, 6), (24, 8), (8, 6), (16, 12), (16, 3)]:
+        for node_min, switch_min, leaf_min in [(16, 8, 0), (20, 8, 0), (16, 8, 33), (16, 8, 16), (16, 8, 12), (16, 8, 10), (16, 8, 8), (20, 8, 12), (12, 8, 12), (16, 4, 12)]:
             L.hc_sched_tuning(node_min, switch_min)
+            L.hc_sched_leaf_min(leaf_min)
+            L.hc_sched_postpone(1 if leaf_min else 0)  # leaf_min 0: leaves are not parked (round 2's first scheduler)
             s = np.zeros(6, np.uint64)
             L.hc_sched_stats(ptr(s))
             _, st = run(r, 38)
@@ -96,7 +102,7 @@ def main():
             cn, cl = 100.0, 70.0
             useful = s[1] * cn + s[3] * cl
             issued = 32 * (s[0] * cn + s[2] * cl)
-            print(f"{name:>10} node_min {node_min:2d} switch_min {switch_min:2d}: node steps {int(s[0]):8d} x {s[1] / max(s[0], 1):5.1f} lanes,"
+            print(f"{name:>10} node_min {node_min:2d} switch_min {switch_min:2d} leaf_min {leaf_min:2d}: node steps {int(s[0]):8d} x {s[1] / max(s[0], 1):5.1f} lanes,"
                   f" prim steps {int(s[2]):8d} x {s[3] / max(s[2], 1):5.1f} lanes, refills {int(s[4]):6d} x {s[5] / max(s[4], 1):4.1f};"
                   f" utilisation {useful / issued:.3f}; nodes/ray {st[0] / len(r):.1f} prims/ray {st[1] / len(r):.2f}", flush=True)
 
