@@ -162,7 +162,12 @@ enum rtb_option {
     /* scenes with more primitives than this (default 100000) get their fp64 validation tables on the
      * first precision-64 call instead of at rtb_scene_upload (a third of the upload of the 1 M-sphere
      * scene); 0 = always on first use.  Applied by the NEXT rtb_scene_upload */
-    RTB_OPT_LAZY_F64_PRIMS = 7
+    RTB_OPT_LAZY_F64_PRIMS = 7,
+    /* 1 (default): the `box` objects (box.h: six rects, one material, no wrapper) of a scene too large for the
+     * shared-memory kernels enter the BVH as one item each, tested by one slab test in the production kernels
+     * (hits, records and shading still name the face's own rect); 0: every rect is its own tree item (A/B
+     * measurements, tests).  Applied by the NEXT rtb_scene_upload */
+    RTB_OPT_GROUP_BOXES = 8
 };
 RTB_API int rtb_set_option(rtb_context *ctx, int option, int64_t value);
 

@@ -25,6 +25,7 @@ RENDER_FORCE_WAVEFRONT = 4
 RENDER_FORCE_FUSED = 8
 OPT_FLAT_TRAVERSAL, OPT_FUSED_SCHEDULE = 1, 2
 OPT_BVH_MAX_LEAF, OPT_BVH_TRAVERSAL_COST_PCT, OPT_BVH_LAYOUT_DFS, OPT_BINARY_TRAVERSAL, OPT_LAZY_F64_PRIMS = 3, 4, 5, 6, 7
+OPT_GROUP_BOXES = 8
 
 # Every symbol include/rtb200.h declares (tests check the library exports them all).
 EXPORTS = ["rtb_version", "rtb_context_create", "rtb_context_destroy", "rtb_last_error",

@@ -198,7 +198,8 @@ std::shared_ptr<const HostScene> build_scene_for(rtb_context *ctx, const void *b
         // quarter of the host time and a third of the bytes of every upload of the 1 M-sphere scene.
         const bool want_f64 = int64_t(view.n_prims()) <= ctx->opt_lazy_f64_prims;
         auto host = std::make_shared<HostScene>(
-            build_host_scene(view, ctx->opt_max_leaf, 0.01 * ctx->opt_trav_cost_pct, ctx->opt_layout_dfs != 0, want_f64, true));
+            build_host_scene(view, ctx->opt_max_leaf, 0.01 * ctx->opt_trav_cost_pct, ctx->opt_layout_dfs != 0, want_f64, true,
+                             ctx->opt_group_boxes != 0));
         if (!want_f64)
             host->blob_copy.assign(static_cast<const char *>(blob), static_cast<const char *>(blob) + nbytes);
         return host;
@@ -225,6 +226,7 @@ void upload_scene(rtb_context *ctx, std::shared_ptr<const HostScene> host) {
     sc->build_max_leaf = ctx->opt_max_leaf;
     sc->build_trav_cost = 0.01 * ctx->opt_trav_cost_pct;
     sc->build_layout_dfs = ctx->opt_layout_dfs != 0;
+    sc->build_group_boxes = ctx->opt_group_boxes != 0;
     sc->nodes.upload(H.nodes, s);
     sc->chains.upload(H.chains, s);
     sc->affine.upload(H.affine, s);
@@ -274,7 +276,7 @@ void ensure_f64(rtb_context *ctx) {
     if (sc.f64_ready)
         return;
     SceneView view(sc.host.blob_copy.data(), sc.host.blob_copy.size());
-    const HostScene H = build_host_scene(view, sc.build_max_leaf, sc.build_trav_cost, sc.build_layout_dfs, true);
+    const HostScene H = build_host_scene(view, sc.build_max_leaf, sc.build_trav_cost, sc.build_layout_dfs, true, false, sc.build_group_boxes);
     if (H.prim_orig != sc.host.prim_orig)
         throw std::runtime_error("internal error: the fp64 rebuild ordered the primitives differently");
     size_t bytes = 0;
@@ -363,6 +365,8 @@ int rtb_set_option(rtb_context *ctx, int option, int64_t value) {
         ctx->opt_binary_traversal = int(value);
     else if (option == RTB_OPT_LAZY_F64_PRIMS)
         ctx->opt_lazy_f64_prims = value < 0 ? 0 : value;
+    else if (option == RTB_OPT_GROUP_BOXES)
+        ctx->opt_group_boxes = value != 0;
     else
         return fail(ctx, RTB_ERR_INVALID_ARGUMENT, "rtb_set_option: unknown option");
     return RTB_OK;

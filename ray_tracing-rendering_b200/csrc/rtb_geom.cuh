@@ -31,6 +31,7 @@ enum : uint32_t {
     PT_YZ = 4,
     PT_MEDIUM = 5,
     PT_INSTANCE = 6,
+    PT_BOX = 7, // a `box` object (box.h) of a large scene as ONE tree item: rtb_scene_host.hpp, box_slot() below
     PT_TYPE_MASK = 7,
     PT_DUP_LEAF = 8, // reference tests this object twice per ray (bvh.h:68-69)
     // bits 4-6: the hit queue a path that hits this primitive goes to (its material's type, or 6 for
@@ -54,6 +55,8 @@ constexpr int kStackDepth = 48;
 //   RECT     d = a0 a1 b0 b1 k   (XY: a=x b=y | XZ: a=x b=z | YZ: a=y b=z)
 //   MEDIUM   d[0] = neg_inv_density ; aux = first boundary prim, aux2 = count
 //   INSTANCE aux = BLAS root node, aux2 = chain id
+//   BOX      d = lox loy loz hix hiy, aux = hiz (float bits), aux2 = first of its six face records
+//            (z hi, z lo, y hi, y lo, x hi, x lo: the order of box.h); the fp64 record only carries aux2
 template <class R> struct PrimT {
     R d[5];
     uint32_t type_mat;
@@ -340,6 +343,60 @@ RTB_HD bool hit_simple(const GeomView<R> &g, const PrimT<R> &p, uint32_t type, V
 }
 
 template <class R> RTB_HD V3<R> safe_inv(V3<R> d) { return V3<R>(R(1) / d.x, R(1) / d.y, R(1) / d.z); }
+
+// ---- a grouped box (PT_BOX) as one leaf slot ------------------------------------------------------
+// Production (fp32, ROBUST): one slab test; the face the ray enters (or, for a ray that starts on this box or
+// inside it, leaves) through is the hit, named by the index of that face's own rect record — the same plane
+// arithmetic as hit_rect ((k - o) * idir), the rect's in-plane bounds replaced by the slab interval.
+// Validation (fp64 / !ROBUST): the six face records one by one, exactly what the tree did before the faces
+// were grouped (tie rule and orig_limit of the callers included) — grouping changes which tree node holds a
+// rect, never which rect wins.  Returns true when an any-hit query is decided.
+template <class R, bool ANY, bool ROBUST>
+RTB_HD bool box_slot(const GeomView<R> &g, const PrimT<R> &p, V3<R> o, V3<R> d, V3<R> idir, R time, R t_min, R &t_max,
+                     uint32_t origin_prim, uint32_t &best, uint64_t *n_tests) {
+    const uint32_t first = p.aux2;
+    if (ROBUST && sizeof(R) == 4) {
+        if (n_tests)
+            ++*n_tests;
+        float hzf;
+        memcpy(&hzf, &p.aux, 4);
+        const R hz = R(hzf);
+        const R tx0 = (p.d[0] - o.x) * idir.x, tx1 = (p.d[3] - o.x) * idir.x;
+        const R ty0 = (p.d[1] - o.y) * idir.y, ty1 = (p.d[4] - o.y) * idir.y;
+        const R tz0 = (p.d[2] - o.z) * idir.z, tz1 = (hz - o.z) * idir.z;
+        const R tn = fmax_(fmax_(fmin_(tx0, tx1), fmin_(ty0, ty1)), fmin_(tz0, tz1));
+        const R tf = fmin_(fmin_(fmax_(tx0, tx1), fmax_(ty0, ty1)), fmax_(tz0, tz1));
+        const bool mine = (origin_prim - first) < 6u; // the ray starts on this box: it can only leave it
+        const bool enter = !mine & (tn >= t_min);
+        const R cand = enter ? tn : tf;
+        const uint32_t face = cand == tz1 ? 0u : (cand == tz0 ? 1u : (cand == ty1 ? 2u : (cand == ty0 ? 3u : (cand == tx1 ? 4u : 5u))));
+        const bool ok = (tn <= tf) & (cand >= t_min) & (cand <= t_max) & (first + face != origin_prim);
+        if (ok) {
+            best = first + face;
+            t_max = cand;
+        }
+        return ANY && ok;
+    }
+    for (uint32_t f = 0; f < 6u; ++f) {
+        const uint32_t i = first + f;
+        if (!ROBUST && g.prim_orig[i] >= g.orig_limit)
+            continue;
+        if (n_tests)
+            ++*n_tests;
+        const PrimT<R> q = g.prims[i];
+        R t;
+        bool h = hit_simple<R, ROBUST>(g, q, q.type_mat & PT_TYPE_MASK, o, d, idir, time, t_min, t_max, ROBUST && i == origin_prim, t);
+        if (!ROBUST && h && best != kNoPrim && t == t_max && g.prim_orig[i] < g.prim_orig[best])
+            h = false;
+        if (h) {
+            best = i;
+            t_max = t;
+            if (ANY)
+                return true;
+        }
+    }
+    return false;
+}
 
 // Closest hit of the WORLD-space ray against boundary primitives [first, first+count)
 // — constant_medium's `boundary->hit()` (constant_medium.h:64-68).  Each boundary
@@ -667,6 +724,13 @@ RTB_HD uint32_t traverse(const GeomView<R> &g, V3<R> o, V3<R> d, R time, R t_min
                     cur = p.aux; // the bottom-level tree's root ref
                     entered = true;
                     break;
+                }
+                if (type == PT_BOX) {
+                    if (box_slot<R, ANY, ROBUST>(g, p, co, cd, cid, time, t_min, t_max, origin_prim, best, n_tests)) {
+                        t_hit = t_max;
+                        return best;
+                    }
+                    continue;
                 }
                 if (!ROBUST && g.prim_orig[i] >= g.orig_limit)
                     continue;

@@ -116,6 +116,7 @@ struct DeviceScene {
     int build_max_leaf = 4;    // builder options this scene was flattened with
     double build_trav_cost = 1.0;
     bool build_layout_dfs = false;
+    bool build_group_boxes = true;
 
     template <class R> const DeviceTyped<R> &typed() const;
     template <class R> GeomView<R> geom() const {
@@ -194,6 +195,7 @@ struct rtb_context {
     int opt_layout_dfs = 0;      // RTB_OPT_BVH_LAYOUT_DFS
     int opt_binary_traversal = 0; // RTB_OPT_BINARY_TRAVERSAL: 0 by scene, 1 binary, 2 wide
     int64_t opt_lazy_f64_prims = 100000; // RTB_OPT_LAZY_F64_PRIMS
+    int opt_group_boxes = 1;             // RTB_OPT_GROUP_BOXES
     // multi-GPU (rtb_multi.cu): this context's rank in an NCCL communicator and its staging buffers
     void *comm = nullptr; // ncclComm_t
     int comm_rank = 0, comm_size = 1;

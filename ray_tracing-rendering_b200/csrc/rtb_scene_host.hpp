@@ -59,6 +59,7 @@ struct HostScene {
     int n_instances = 0;
     int n_top_items = 0; // primitives + instance records of the top level = prims[0 .. n_top_items)
     uint32_t root_ref = kEmptyRef; // ref of the top-level root
+    int n_boxes = 0;       // grouped `box` objects (PT_BOX records; their faces sit at the end of the world slots)
     int n_world_slots = 0; // sorted primitives from here on are medium boundaries only (GeomView::n_world)
     std::vector<uint32_t> gated; // sorted indices of the PT_GATED spheres, ascending blob index (GeomView::gated)
     bool flat_ok = false; // small enough for the lockstep / shared-memory traversal
@@ -295,7 +296,8 @@ struct PhaseTimer {
 // env_on_device = true: the env lights' Distribution2D tables are only sized here; the caller builds them
 // on the device from the uploaded texels (the library does; the CPU test harness keeps the host build).
 inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double trav_cost = 1.0,
-                                  bool layout_dfs = false, bool want_f64 = true, bool env_on_device = false) {
+                                  bool layout_dfs = false, bool want_f64 = true, bool env_on_device = false,
+                                  bool group_boxes = true) {
     using namespace detail;
     PhaseTimer timer;
     S.validate();
@@ -361,6 +363,49 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double t
         return prim_box(p, cam);
     };
 
+    // ---- `box` objects (box.h: six rects in a fixed order — z hi, z lo, y hi, y lo, x hi, x lo — one material,
+    // no wrapper) of scenes too large for the shared-memory kernels become ONE tree item each, a PT_BOX record
+    // whose fp32 test is a slab test (the fp64 paths walk its six face records one by one); the faces keep their
+    // own records behind the tree-ordered ones, so hits, records and shading name the rect as before.
+    // scene09's ground is 400 such boxes = 2,400 rects whose side faces coincide pairwise.
+    struct BoxGroup {
+        int first; // blob index of its first face
+        Box box;
+    };
+    std::vector<BoxGroup> boxes;
+    std::vector<int> box_of(size_t(np), -1);
+    if (group_boxes && np > kFlatMaxPrims) {
+        for (int i = 0; i + 5 < np;) {
+            const rtb_prim *q = P + i;
+            bool ok = q[0].type == RTB_PRIM_XY_RECT && q[1].type == RTB_PRIM_XY_RECT && q[2].type == RTB_PRIM_XZ_RECT &&
+                      q[3].type == RTB_PRIM_XZ_RECT && q[4].type == RTB_PRIM_YZ_RECT && q[5].type == RTB_PRIM_YZ_RECT;
+            for (int k = 0; ok && k < 6; ++k)
+                ok = (q[k].flags & ~uint32_t(RTB_PRIM_DUP_LEAF)) == 0 && q[k].chain < 0 && q[k].material == q[0].material; // (a rect tested twice answers twice the same)
+            if (ok) {
+                const double x0 = q[0].d[0], x1 = q[0].d[1], y0 = q[0].d[2], y1 = q[0].d[3], z1 = q[0].d[4], z0 = q[1].d[4];
+                ok = x0 < x1 && y0 < y1 && z0 < z1 &&
+                     q[1].d[0] == x0 && q[1].d[1] == x1 && q[1].d[2] == y0 && q[1].d[3] == y1 &&
+                     q[2].d[0] == x0 && q[2].d[1] == x1 && q[2].d[2] == z0 && q[2].d[3] == z1 && q[2].d[4] == y1 &&
+                     q[3].d[0] == x0 && q[3].d[1] == x1 && q[3].d[2] == z0 && q[3].d[3] == z1 && q[3].d[4] == y0 &&
+                     q[4].d[0] == y0 && q[4].d[1] == y1 && q[4].d[2] == z0 && q[4].d[3] == z1 && q[4].d[4] == x1 &&
+                     q[5].d[0] == y0 && q[5].d[1] == y1 && q[5].d[2] == z0 && q[5].d[3] == z1 && q[5].d[4] == x0;
+            }
+            if (!ok) {
+                ++i;
+                continue;
+            }
+            BoxGroup b;
+            b.first = i;
+            for (int k = 0; k < 6; ++k) {
+                b.box.grow(prim_box(q[k], cam));
+                box_of[size_t(i + k)] = int(boxes.size());
+            }
+            boxes.push_back(b);
+            i += 6;
+        }
+    }
+    constexpr uint32_t kBoxItem = 0x80000000u; // BuildItem ids: blob primitive < np <= instance < kBoxItem <= box
+
     // ---- group world primitives: top-level items and one BLAS per moving chain
     std::vector<BuildItem> top;
     std::map<int, std::vector<BuildItem>> groups; // chain id -> object-space items
@@ -378,9 +423,17 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double t
         if (P[i].type == RTB_PRIM_MEDIUM && chain_moves(P[i].chain))
             throw std::runtime_error("scene: a constant_medium under translate/rotate_y is not supported");
         BuildItem it;
+        it.solitary = false;
+        if (box_of[size_t(i)] >= 0) { // a face: its box joins the top level once
+            if (boxes[size_t(box_of[size_t(i)])].first == i) {
+                it.box = boxes[size_t(box_of[size_t(i)])].box;
+                it.id = kBoxItem | uint32_t(box_of[size_t(i)]);
+                top.push_back(it);
+            }
+            continue;
+        }
         it.box = world_box_of(i);
         it.id = uint32_t(i);
-        it.solitary = false;
         if (chain_moves(P[i].chain))
             groups[P[i].chain].push_back(it);
         else
@@ -397,7 +450,7 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double t
             all.grow(it.box);
         std::vector<size_t> cand;
         for (size_t i = 0; i < top.size(); ++i)
-            if (top[i].box.area() >= 0.25 * all.area())
+            if (top[i].box.area() >= 0.25 * all.area() && top[i].id < kBoxItem)
                 cand.push_back(i);
         if (!cand.empty() && cand.size() <= size_t(kMaxGlobalPrims)) {
             Box rest;
@@ -436,13 +489,18 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double t
     struct Slot { // what sits at each sorted position
         int orig; // blob prim id, or -1 for an instance
         int inst; // instance index, or -1
+        int box;  // box index (the record of a grouped box; orig = its first face), or -1
     };
     std::vector<Slot> slots;
     timer.mark("items + bounds");
     BuildResult tlas = build_bvh(top, max_leaf, 0, 0, trav_cost, layout_dfs);
     timer.mark("binary SAH build (top level)");
-    for (uint32_t id : tlas.order)
-        slots.push_back(id < uint32_t(np) ? Slot{int(id), -1} : Slot{-1, int(id) - np});
+    for (uint32_t id : tlas.order) {
+        if (id >= kBoxItem)
+            slots.push_back(Slot{boxes[id - kBoxItem].first, -1, int(id - kBoxItem)});
+        else
+            slots.push_back(id < uint32_t(np) ? Slot{int(id), -1, -1} : Slot{-1, int(id) - np, -1});
+    }
     H.nodes = tlas.nodes;
     H.root_ref = tlas.nodes[0].ref;
     H.n_top_items = int(slots.size());
@@ -456,20 +514,30 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double t
             blas_count[gi] = uint32_t(b.order.size());
             blas_root[gi++] = b.nodes[0].ref; // the instance record carries the root REF
             for (uint32_t id : b.order)
-                slots.push_back(Slot{int(id), -1});
+                slots.push_back(Slot{int(id), -1, -1});
             H.nodes.insert(H.nodes.end(), b.nodes.begin(), b.nodes.end());
         }
     }
     H.orig_to_sorted.assign(np, -1);
     for (size_t s = 0; s < slots.size(); ++s)
-        if (slots[s].orig >= 0)
+        if (slots[s].orig >= 0 && slots[s].box < 0)
             H.orig_to_sorted[slots[s].orig] = int(s);
+    // the faces of grouped boxes: six consecutive records per box, behind everything the trees point at
+    std::vector<uint32_t> box_faces(boxes.size());
+    for (size_t b = 0; b < boxes.size(); ++b) {
+        box_faces[b] = uint32_t(slots.size());
+        for (int k = 0; k < 6; ++k) {
+            H.orig_to_sorted[boxes[b].first + k] = int(slots.size());
+            slots.push_back(Slot{boxes[b].first + k, -1, -1});
+        }
+    }
+    H.n_boxes = int(boxes.size());
     // boundary-only prims keep their blob order (media reference them as ranges)
     H.n_world_slots = int(slots.size());
     for (int i = 0; i < np; ++i)
         if (P[i].flags & RTB_PRIM_BOUNDARY_ONLY) {
             H.orig_to_sorted[i] = int(slots.size());
-            slots.push_back(Slot{i, -1});
+            slots.push_back(Slot{i, -1, -1});
         }
 
     // ---- emit typed primitive records
@@ -489,6 +557,22 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double t
                 q.d[0] = R(blas_first[s.inst]);
                 q.d[1] = R(blas_count[s.inst]);
                 T.prims.push_back(q);
+                continue;
+            }
+            if (s.box >= 0) { // lo, hi (the sixth number in aux, as float bits; the fp64 paths never read them), first face
+                const rtb_prim *q = P + s.orig;
+                PrimT<R> b;
+                std::memset(&b, 0, sizeof(b));
+                b.d[0] = R(q[5].d[4]);
+                b.d[1] = R(q[3].d[4]);
+                b.d[2] = R(q[1].d[4]);
+                b.d[3] = R(q[4].d[4]);
+                b.d[4] = R(q[2].d[4]);
+                const float hz = float(q[0].d[4]);
+                std::memcpy(&b.aux, &hz, 4);
+                b.aux2 = box_faces[size_t(s.box)];
+                b.type_mat = uint32_t(PT_BOX) | (uint32_t(q[0].material) << PT_MAT_SHIFT);
+                T.prims.push_back(b);
                 continue;
             }
             const rtb_prim &p = P[s.orig];
@@ -534,7 +618,7 @@ inline HostScene build_host_scene(const SceneView &S, int max_leaf = 4, double t
     timer.mark("emit fp64 primitives");
     for (const Slot &s : slots) {
         H.prim_orig.push_back(s.orig);
-        H.prim_chain.push_back(s.inst >= 0 ? insts[s.inst].chain : P[s.orig].chain);
+        H.prim_chain.push_back(s.inst >= 0 ? insts[s.inst].chain : (s.box >= 0 ? -1 : P[s.orig].chain));
     }
 
     for (uint64_t i = 0; i < S.n_prims(); ++i) // (ascending blob index = the reference's traversal order)

@@ -73,6 +73,9 @@ namespace rtb {
 #ifndef RTB_TRACE_LEAF_MIN
 #define RTB_TRACE_LEAF_MIN 20 // with parked leaves: a primitive step runs when at least this many lanes have one (or no node quorum)
 #endif
+#ifndef RTB_TRACE_PREFETCH
+#define RTB_TRACE_PREFETCH 0 // 1: the second-nearest child's node is prefetched into L1 when it is pushed; 2: the nearest one's too
+#endif
 #ifndef RTB_TRACE_GUARD
 #define RTB_TRACE_GUARD 1 // bound the scheduler loop (an internal error becomes a flag, not a hung GPU)
 #endif
@@ -353,6 +356,14 @@ RTB_WD void trav_node_step(const WideView &w, const Vec4f *s_top, uint32_t n_top
     cmp_swap(k[0], r0, k[2], r2);
     cmp_swap(k[1], r1, k[3], r3);
     cmp_swap(k[1], r1, k[2], r2);
+#if RTB_TRACE_PREFETCH && defined(__CUDA_ARCH__)
+    if (k[1] < inf && ref_is_node(r1) && !(TOP && r1 < n_top))
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(w.nodes + size_t(r1) * kNodeRows));
+#if RTB_TRACE_PREFETCH >= 2
+    if (k[0] < inf && ref_is_node(r0) && !(TOP && r0 < n_top))
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(w.nodes + size_t(r0) * kNodeRows));
+#endif
+#endif
     // far to near onto the stack; the nearest is next
     if (k[1] < inf) {
         if (L.sp + 3u > uint32_t(kWideStack)) {
@@ -397,6 +408,15 @@ RTB_WD void trav_node_step(const WideView &w, const Vec4f *s_top, uint32_t n_top
 template <bool ANY, bool MEDIA>
 RTB_WD bool trav_test_prim(const GeomView<float> &g, TravLane &L, const PrimT<float> &p, uint32_t type, uint32_t index,
                            uint32_t &tests) {
+    if (type == PT_BOX) { // a grouped box: one slab test, the hit names the face's own rect record
+        uint64_t one = 0;
+        const uint32_t before = L.best;
+        const bool done = box_slot<float, ANY, true>(g, p, L.r.o, L.r.d, L.r.idir, L.time, L.t_min, L.t_max, L.origin, L.best, &one);
+        tests += uint32_t(one);
+        if (L.best != before)
+            L.best_key = (p.type_mat >> PT_KEY_SHIFT) & PT_KEY_MASK;
+        return done;
+    }
     ++tests;
     float t;
     bool h;

@@ -364,6 +364,13 @@ RTB_HD uint32_t traverse_wide(const GeomView<R> &g, const Node128 *nodes4, uint3
                     entered = true;
                     break;
                 }
+                if (type == PT_BOX) {
+                    if (box_slot<R, ANY, ROBUST>(g, p, co, cd, cid, time, t_min, t_max, origin_prim, best, n_tests)) {
+                        t_hit = t_max;
+                        return best;
+                    }
+                    continue;
+                }
                 if (!ROBUST && g.prim_orig[i] >= g.orig_limit)
                     continue;
                 if (n_tests)

@@ -297,10 +297,13 @@ void light_eval(HostScene &H, int light, const rtb_light_query *q, uint64_t n, u
 
 extern "C" {
 
+static bool g_group_boxes = true;
+void hc_group_boxes(int on) { g_group_boxes = on != 0; } // RTB_OPT_GROUP_BOXES of the scenes created from now on
+int hc_scene_boxes(void *h) { return static_cast<HostScene *>(h)->n_boxes; }
 void *hc_scene_create(const void *blob, uint64_t nbytes, int max_leaf) {
     try {
         SceneView S(blob, nbytes);
-        return new HostScene(build_host_scene(S, max_leaf));
+        return new HostScene(build_host_scene(S, max_leaf, 1.0, false, true, false, g_group_boxes));
     } catch (const std::exception &e) {
         std::fprintf(stderr, "hc_scene_create: %s\n", e.what());
         return nullptr;

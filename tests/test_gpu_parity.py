@@ -47,6 +47,31 @@ def test_fp32_hits_agree_vs_golden(up, golden, abi, sid):
     assert ((got["prim"] != g["hits"]["prim"]) & mask).sum() <= 1
 
 
+def test_group_boxes_option_changes_the_tree_not_the_hits(up, golden, abi):
+    """RTB_OPT_GROUP_BOXES through the C-ABI on scene09 (400 `box` objects): fp64 answers identical with and
+    without grouping, fp32 production traversals (binary 32, warp-scheduled 4-wide 34) name the same rects."""
+    import importlib
+    binding = importlib.import_module("ray_tracing-rendering_b200.binding")
+    g = golden(9)
+    T = abi.parse_blob(g.blob)
+    seg = parity.to_segment_form(g["rays"])
+    res = {}
+    ctx = up(None, g.blob)
+    try:
+        for on in (0, 1):
+            ctx.set_option(binding.OPT_GROUP_BOXES, on)
+            ctx = up(None, g.blob)
+            res[on] = (ctx.trace(g["rays"], 64), ctx.trace(seg, 32), ctx.trace(seg, 34))
+    finally:
+        ctx.set_option(binding.OPT_GROUP_BOXES, 1)
+        up(None, g.blob)
+    m = parity.deterministic_mask(T, res[0][0], res[1][0])
+    assert m.mean() > 0.3 and parity.trace_mismatches(res[0][0], res[1][0], m) == 0
+    for k in (1, 2):
+        mm = parity.deterministic_mask(T, res[0][k], res[1][k])
+        assert ((res[0][k]["prim"] != res[1][k]["prim"]) & mm).sum() <= 1
+
+
 @pytest.mark.parametrize("sid,integrator", [(7, 1), (21, 3), (21, 4), (23, 4), (9, 1), (1, 1)])
 def test_million_ray_batches_vs_live_reference(up, golden, abi, sid, integrator):
     """SURVEY §8d gate (1): >= 1M rays per config (camera + recorded bounce + shadow rays):

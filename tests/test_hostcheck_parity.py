@@ -363,6 +363,57 @@ def test_parked_leaf_scheduler_gives_the_same_hits(hostcheck, abi):
     assert sk[0] <= 1.15 * sw[0]
 
 
+def test_grouped_boxes_change_the_tree_not_the_hits(hostcheck, golden, abi):
+    """RTB_OPT_GROUP_BOXES (csrc/rtb_scene_host.hpp, box_slot in csrc/rtb_geom.cuh): scene09's ground — 400
+    `box` objects (box.h), 2,400 rects — enters the trees as 400 items.  The fp64 walk must answer every
+    recorded ray exactly as with one item per rect (and as the reference: test_fp64_hits_are_bit_exact[9] runs
+    on the grouped tree); the fp32 slab test must name the same face rect as the six rect tests, for rays
+    from outside AND for bounce rays that start on a face (origin primitive set), with far fewer nodes."""
+    import ctypes as C
+    hostcheck.hc_group_boxes.argtypes = [C.c_int]
+    hostcheck.hc_scene_boxes.argtypes = [C.c_void_p]
+    g = golden(9)
+    T = abi.parse_blob(g.blob)
+    handles = []
+    try:
+        for on in (0, 1):
+            hostcheck.hc_group_boxes(on)
+            h = hostcheck.hc_scene_create(g.blob, len(g.blob), 4)
+            assert h
+            handles.append(h)
+    finally:
+        hostcheck.hc_group_boxes(1)
+    try:
+        assert hostcheck.hc_scene_boxes(handles[0]) == 0 and hostcheck.hc_scene_boxes(handles[1]) == 400
+        rays = g["rays"]
+        a64, s0 = trace(hostcheck, handles[0], rays, 64, abi)
+        b64, s1 = trace(hostcheck, handles[1], rays, 64, abi)
+        m = parity.deterministic_mask(T, a64, b64)
+        assert m.mean() > 0.3 and parity.trace_mismatches(a64, b64, m) == 0
+        assert s1[0] < 0.8 * s0[0]                                  # a quarter fewer child boxes per ray
+        # bounce rays off the recorded hit points, each starting ON the primitive it left
+        hit = (a64["prim"] >= 0) & ~parity.is_medium(T, a64["prim"])
+        rng = np.random.default_rng(11)
+        n = int(hit.sum())
+        d = rng.normal(size=(n, 3))
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        d *= np.where((d * a64["normal"][hit]).sum(1) < 0, -1.0, 1.0)[:, None]   # off the surface
+        b = np.zeros(n, abi.RAY)
+        b["o"], b["d"], b["time"] = a64["p"][hit], d, rays["time"][hit]
+        b["t_min"], b["t_max"], b["origin_prim"] = 0.001, np.inf, a64["prim"][hit]
+        for batch in (parity.to_segment_form(rays), b):
+            a32, _ = trace(hostcheck, handles[0], batch, 32, abi)
+            b32, _ = trace(hostcheck, handles[1], batch, 32, abi)
+            mm = parity.deterministic_mask(T, a32, b32)
+            same = (a32["prim"] == b32["prim"])[mm]
+            assert (~same).sum() <= max(1, mm.sum() // 5000), f"{(~same).sum()} of {mm.sum()} rays name another primitive"
+            both = mm & (a32["prim"] == b32["prim"]) & (a32["prim"] >= 0)
+            assert np.allclose(a32["t"][both], b32["t"][both], rtol=1e-5, atol=0)
+    finally:
+        for h in handles:
+            hostcheck.hc_scene_destroy(h)
+
+
 @pytest.mark.parametrize("sid", ALL_SCENES)
 def test_quantised_nodes_contain_their_children(hostcheck, scenes, sid):
     """The 64-byte node the kernels fetch (8-bit child planes on the node's own grid) must bound every

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--warm", type=int, default=1)
     ap.add_argument("--binary", action="store_true", help="round 1's traversal kernels (RTB_OPT_BINARY_TRAVERSAL = 1)")
     ap.add_argument("--wide", action="store_true", help="the warp-scheduled 4-wide kernels whatever the scene (RTB_OPT_BINARY_TRAVERSAL = 2)")
+    ap.add_argument("--nogroup", action="store_true", help="every rect of a box object its own tree item (RTB_OPT_GROUP_BOXES = 0)")
     a = ap.parse_args()
     pkg = importlib.import_module(PKG)
     configs = importlib.import_module(PKG + ".configs")
@@ -36,6 +37,8 @@ def main():
     ctx = pkg.Context(0)
     if a.binary or a.wide:
         ctx.set_option(binding.OPT_BINARY_TRAVERSAL, 1 if a.binary else 2)
+    if a.nogroup:
+        ctx.set_option(binding.OPT_GROUP_BOXES, 0)
     ctx.upload_scene(cfg.blob())
     flags = (binding.RENDER_FORCE_WAVEFRONT if a.wavefront else 0) | (binding.RENDER_FORCE_FUSED if a.fused else 0) | (binding.RENDER_TIME_EXTEND if a.time else 0) \
         | (binding.RENDER_COUNT_VISITS if a.count else 0)
