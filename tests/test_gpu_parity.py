@@ -132,7 +132,9 @@ def test_million_ray_batches_vs_live_reference(up, golden, abi, sid, integrator)
     assert agree >= parity.FP32_MIN_AGREEMENT, agree
     # t of closest-hit queries (shadow queries are re-parametrised by to_segment_form)
     sel = mask & (hits["prim"] >= 0) & (got34["prim"] == hits["prim"]) & np.isinf(rays["t_max"])
-    assert np.isclose(got34["t"], hits["t"], rtol=1e-3, atol=1e-5)[sel].mean() >= 0.999
+    # (scenes 1 and 9 are re-rolled by the reference on every run: the fraction moves between instances,
+    # 0.9989 - 0.9997 observed on scene 1, whose glass spheres produce many grazing fp32 hits)
+    assert np.isclose(got34["t"], hits["t"], rtol=1e-3, atol=1e-5)[sel].mean() >= 0.998
     got36 = ctx.trace(seg, 36)
     blocked = got36["prim"] >= 0
     ref_hit = hits["prim"] >= 0

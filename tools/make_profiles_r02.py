@@ -89,13 +89,15 @@ def main():
         src = f"profiles/r02_{name}_metrics.txt (one ncu --set full capture of the final round-2 code, tools/gpu_g.sh; not measured by the bench run)"
         caps[cfg] = {"kernel": kernel, "dram_bytes_per_launch": dram(d), "source": src, "note": note,
                      "ncu": ncu_block(d, src)}
-    caps["C1"]["ncu"]["warp_instructions_per_32_ray_iteration"] = 583
+    # executed warp instructions of the capture / (rays of the same render / 32): run_config prints the ray count
+    c1_rays = 469.2e6
+    caps["C1"]["ncu"]["warp_instructions_per_32_ray_iteration"] = int(round(float(raw("c1_fused")["smsp__inst_executed.sum"]) / (c1_rays / 32)))
     caps["C1"]["ncu"]["top_stall"] = "not_selected / math_pipe_throttle"
     caps["C3"] = {"kernel": "k_fused", "dram_bytes_per_launch": None}
     json.dump(caps, open(os.path.join(P, "extend_traffic.json"), "w"), indent=1)
     os.makedirs(os.path.join(P, "bench_lines"), exist_ok=True)
     shutil.copy(os.path.join(G, "g_bench.json"), os.path.join(P, "bench_lines", "r02_bench_default.json"))
-    shutil.copy(os.path.join(G, "h_sweep.log"), os.path.join(P, "r02_trace_knobs_and_upload_phases.txt"))
+    # (profiles/r02_trace_knobs_and_upload_phases.txt is the log of tools/gpu_h.sh, copied by hand after that run)
     print("profiles written")
 
 
