@@ -367,8 +367,9 @@ class Bench:
                   "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                   "peak_source": "tools/microbench FP32 FMA rate (profiles/microbench.json); nominal 74.5",
                   "flops_per_ray": f_ray, "records_per_ray": n_rec,
-                  "note": "issue bound (ncu, profiles/r02_c1_fused_metrics.txt: 83 % of the issue slots, ALU pipe 66 %, 24.4 of "
-                          "32 lanes): the algorithmic flops are ~1/4 of the instructions a ray needs (compares, selects, RNG, control)"}
+                  "note": (f"issue bound (ncu, profiles/r02_c1_fused_metrics.txt: {ncu.get('issue_slots_busy_pct', '?')} % of the issue slots, "
+                           f"ALU pipe {ncu.get('alu_pipe_pct', '?')} %, {ncu.get('active_lanes_of_32', '?')} of 32 lanes on C1; see `issue_roof`): "
+                           "the algorithmic flops are a fraction of the instructions a ray needs (compares, selects, RNG, control)")}
             b_ray = 32.0 * n_node + 32.0 * n_rec + 48.0
         else:
             # BVH scenes: the tree and the primitive records are served by L1 / L2 (they fit the 126 MB L2);
@@ -386,9 +387,10 @@ class Bench:
                              if binary else "k_extend_w (warp-scheduled 4-wide traversal: closest hit, refill, material sort)"),
                   "bound": "l2", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                   "peak_source": "tools/microbench L2 stream read (profiles/microbench.json)",
-                  "note": ("ALU-pipe / issue bound, not bandwidth bound (ncu, profiles/r02_c5_extend_w_metrics.txt: ALU pipe 69 %, issue "
-                           "slots 68 %, 21.7 of 32 lanes; r02_c2_extend_metrics.txt: issue 59 %, 12.3 lanes); DRAM traffic per launch "
-                           "(`traffic`) is the queue streaming, not the tree")}
+                  "note": ("issue / latency bound, not bandwidth bound (ncu of this kernel on this configuration, `ncu` / `issue_roof`: "
+                           f"issue slots {ncu.get('issue_slots_busy_pct', '?')} %, ALU pipe {ncu.get('alu_pipe_pct', '?')} %, "
+                           f"{ncu.get('active_lanes_of_32', '?')} of 32 lanes; profiles/r02_c5_extend_w_metrics.txt, r02_c2_extend_metrics.txt); "
+                           "DRAM traffic per launch (`traffic`) is the queue streaming, not the tree")}
         rl.update(common)
         rl.update({"bytes_per_ray": b_ray, "nodes_per_ray": n_node, "prims_per_ray": n_prim,
                    "hbm_8d": {"achieved": grays * b_ray, "peak": self.hbm_peak, "unit": "GB/s", "frac": grays * b_ray / self.hbm_peak,
