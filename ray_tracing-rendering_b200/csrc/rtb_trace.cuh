@@ -73,6 +73,9 @@ namespace rtb {
 #ifndef RTB_TRACE_LEAF_MIN
 #define RTB_TRACE_LEAF_MIN 20 // with parked leaves: a primitive step runs when at least this many lanes have one (or no node quorum)
 #endif
+#ifndef RTB_TRACE_ANY_UNSORTED
+#define RTB_TRACE_ANY_UNSORTED 0 // 1: any-hit queries walk a node's children in slot order (no sorting network)
+#endif
 #ifndef RTB_TRACE_PREFETCH
 #define RTB_TRACE_PREFETCH 0 // 1: the second-nearest child's node is prefetched into L1 when it is pushed; 2: the nearest one's too
 #endif
@@ -349,6 +352,30 @@ RTB_WD void trav_node_step(const WideView &w, const Vec4f *s_top, uint32_t n_top
     float k[4];
     qnode_slabs(q0, q1, q2, L.r, L.t_min, L.t_max, k);
     uint32_t r0 = f2u(rr.x), r1 = f2u(rr.y), r2 = f2u(rr.z), r3 = f2u(rr.w);
+#if RTB_TRACE_ANY_UNSORTED
+    if (ANY) {
+        // any-hit queries (shadow rays) do not need the nearest child first: the children are walked in slot order,
+        // no sorting network (25 ALU-pipe instructions of a node step)
+        const bool h1 = k[1] < inf, h2 = k[2] < inf, h3 = k[3] < inf;
+        if (h1 | h2 | h3) {
+            if (L.sp + 3u > uint32_t(kWideStack)) {
+                overflow = 1u;
+            } else {
+                if (h3)
+                    stk_push(L, stack, Vec2u{r3, f2u(k[3])});
+                if (h2)
+                    stk_push(L, stack, Vec2u{r2, f2u(k[2])});
+                if (h1)
+                    stk_push(L, stack, Vec2u{r1, f2u(k[1])});
+            }
+        }
+        if (k[0] < inf && r0 != kEmptyRef)
+            L.cur = r0;
+        else
+            trav_pop<INST>(L, stack, job, tag);
+        return;
+    }
+#endif
 #if RTB_TRACE_FULL_SORT
     // sorting network, ascending entry distance: (0,1) (2,3) (0,2) (1,3) (1,2)
     cmp_swap(k[0], r0, k[1], r1);
