@@ -75,13 +75,17 @@ constexpr int kFlatUnroll = RTB_FLAT_UNROLL; // unroll factor of the typed rect 
 #define RTB_FUSED_MIN_BLOCKS_OLD 7
 #endif
 #ifndef RTB_FUSED_MIN_BLOCKS_NEW
-#define RTB_FUSED_MIN_BLOCKS_NEW 6
-#endif
+#define RTB_FUSED_MIN_BLOCKS_NEW 4 // BSDF-API, lambertian + emitter scenes with spheres (SIMPLE == 1); was 6: catalogue scenes 2 / 10 / 18 / 20
+#endif                             // under integrator 4: 0.96 -> 0.85, 1.91 -> 1.74, 1.56 -> 1.16, 1.01 -> 0.73 ms (400x400, 64 spp), scene 5 0.47 -> 0.50
 // The general BSDF-API kernel (any material / texture / light mix; 13,700 instructions, instruction-fetch bound): FEWER
 // resident warps run it faster — 6 CTAs (80 registers, 926 B spilled): C4-env 40.5 ms, scene23 fused 8.72 ms; 5 (96):
 // 39.7 / 7.9; 4 (128, 110 B spilled): 38.5 / 6.78; 3 (166, none): 41.9 / 8.1; 2: 41.2 / 8.0 (B200, profiles/r02_late_knobs.txt).
 #ifndef RTB_FUSED_MIN_BLOCKS_NEW_GENERAL
 #define RTB_FUSED_MIN_BLOCKS_NEW_GENERAL 4
+#endif
+#ifndef RTB_FUSED_MIN_BLOCKS_OLD_GENERAL
+#define RTB_FUSED_MIN_BLOCKS_OLD_GENERAL RTB_FUSED_MIN_BLOCKS_OLD // the legacy-API kernels that are not all-planar (SIMPLE 0 / 1): 5 and 4
+                                                                 // measured 3-5 % slower over the catalogue (tools/fused_catalogue_probe.py)
 #endif
 #ifndef RTB_BOX_UNROLL
 #define RTB_BOX_UNROLL 1 // box instances per trip of the box loop of k_fused (2: 66 registers, 7 CTAs/SM, C1 9.18 ms; 1: 55, 9 CTAs, 9.03 ms)
@@ -1764,7 +1768,7 @@ struct FusedDeck { // one per warp: origin + time, direction + pixel, generator 
 // the per-primitive plane digest only (ALL_PLANAR), the traversal holds the rect and box loops
 // only (RECTS_ONLY) and no texture code is compiled in.
 template <bool OLD, bool COUNT, int SIMPLE>
-__global__ void __launch_bounds__(128, OLD ? RTB_FUSED_MIN_BLOCKS_OLD
+__global__ void __launch_bounds__(128, OLD ? (SIMPLE == 2 ? RTB_FUSED_MIN_BLOCKS_OLD : RTB_FUSED_MIN_BLOCKS_OLD_GENERAL)
                            : (SIMPLE == 2 ? RTB_FUSED_MIN_BLOCKS_NEW_PLANAR : (SIMPLE == 1 ? RTB_FUSED_MIN_BLOCKS_NEW : RTB_FUSED_MIN_BLOCKS_NEW_GENERAL)))
     k_fused(WfParams p) {
     __shared__ FlatSmem sm;
