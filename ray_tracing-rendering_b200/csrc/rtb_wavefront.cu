@@ -92,7 +92,8 @@ constexpr int kFlatUnroll = RTB_FLAT_UNROLL; // unroll factor of the typed rect 
 #endif
 constexpr int kBoxUnroll = RTB_BOX_UNROLL;
 #ifndef RTB_FUSED_MIN_BLOCKS_NEW_PLANAR
-#define RTB_FUSED_MIN_BLOCKS_NEW_PLANAR 8 // the all-planar BSDF-API kernel (C3 6 -> 23.98 ms, 7 -> 22.95, 8 -> 22.68)
+#define RTB_FUSED_MIN_BLOCKS_NEW_PLANAR 7 // the all-planar BSDF-API kernel (C3 at an earlier step: 6 -> 23.98 ms, 7 -> 22.95, 8 -> 22.68; with
+                                          // the sample deck: 6 -> 16.76, 7 -> 16.35, 8 -> 16.62, 9 -> 17.87)
 #endif
 #ifndef RTB_SHADE_MIN_BLOCKS
 #define RTB_SHADE_MIN_BLOCKS 1
