@@ -982,7 +982,8 @@ template <class R> RTB_HD void sphere_uv(V3<R> p, R &u, R &v) {
 // post-processes it (hittable.h:58-59, 142-153, 168).  WANT_UV = false skips the
 // acos/atan2 of sphere uv (only textures that read u,v need it).
 template <class R, bool ROBUST, bool WANT_UV>
-RTB_HD RecT<R> make_record(const GeomView<R> &g, uint32_t pi, V3<R> o, V3<R> d, R time, R t) {
+RTB_HD RecT<R> make_record(const GeomView<R> &g, uint32_t pi, V3<R> o, V3<R> d, R time, R t, bool uv = true) {
+    // uv: run-time form of WANT_UV for callers that keep ONE instantiation (the general fused kernel)
     RecT<R> rec;
     rec.t = t;
     rec.u = 0;
@@ -1010,7 +1011,7 @@ RTB_HD RecT<R> make_record(const GeomView<R> &g, uint32_t pi, V3<R> o, V3<R> d, 
             rec.p = c + p.d[3] * outward;
         }
         set_face_normal(rec, ld, outward);
-        if (WANT_UV && type == PT_SPHERE)
+        if (WANT_UV && uv && type == PT_SPHERE)
             sphere_uv(outward, rec.u, rec.v);
     } else if (type == PT_MEDIUM) {
         rec.normal = V3<R>(1, 0, 0); // constant_medium.h:99-100, "arbitrary"

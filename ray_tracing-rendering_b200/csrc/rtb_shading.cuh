@@ -593,12 +593,8 @@ template <class R> RTB_HD void env_dir_to_uv(const LightT<R> &l, V3<R> unit_dir,
         v = theta / pi;
     }
 }
-template <class R> RTB_HD V3<R> env_Le(const ShadeView<R> &S, const LightT<R> &l, V3<R> dir) {
-    if (l.env_w == 0)
-        return V3<R>(1, 1, 1);
-    const V3<R> ud = unit_vector(dir);
-    R u, v, theta;
-    env_dir_to_uv(l, ud, u, v, theta);
+// (u, v) of the map -> bilinear radiance: the second half of EnvironmentLight::Le (environmental_light.h:250-311)
+template <class R> RTB_HD V3<R> env_Le_uv(const ShadeView<R> &S, const LightT<R> &l, R u, R v) {
     const R u_img = u * l.env_w - R(0.5);
     const R v_img = v * l.env_h - R(0.5);
     const int i0 = int(floor_(u_img));
@@ -613,6 +609,31 @@ template <class R> RTB_HD V3<R> env_Le(const ShadeView<R> &S, const LightT<R> &l
     const V3<R> c0 = c00 * (R(1) - du) + c10 * du;
     const V3<R> c1 = c01 * (R(1) - du) + c11 * du;
     return c0 * (R(1) - dv) + c1 * dv;
+}
+template <class R> RTB_HD V3<R> env_Le(const ShadeView<R> &S, const LightT<R> &l, V3<R> dir) {
+    if (l.env_w == 0)
+        return V3<R>(1, 1, 1);
+    const V3<R> ud = unit_vector(dir);
+    R u, v, theta;
+    env_dir_to_uv(l, ud, u, v, theta);
+    return env_Le_uv(S, l, u, v);
+}
+// (u, v, theta) of the map -> solid-angle density: the second half of EnvironmentLight::pdf (environmental_light.h:314-356)
+template <class R> RTB_HD R env_pdf_uv(const ShadeView<R> &S, const LightT<R> &l, R u, R v, R theta) {
+    const R pi = Consts<R>::pi();
+    const R sin_theta = sin_(theta);
+    if (sin_theta < R(1e-6))
+        return 0;
+    const int W = l.env_w, H = l.env_h;
+    const int u_idx = int(clamp_(R(int(u * W)), R(0), R(W - 1)));
+    const int v_idx = int(clamp_(R(int(v * H)), R(0), R(H - 1)));
+    const EnvTables T(S.env_tables + l.env_table_offset, W, H);
+    // Distribution1D::pdf(i) = func[i] / (func_int * n), environmental_light.h:46-48
+    const double ci = T.cond_int[v_idx];
+    const double pc = ci > 0 ? T.cond_func[size_t(v_idx) * W + u_idx] / (ci * W) : 0;
+    const double pm = T.marg_int > 0 ? ci / (T.marg_int * H) : 0;
+    const double map_pdf = pc * pm;
+    return R(map_pdf * W * H / (2.0 * double(pi) * double(pi) * double(sin_theta)));
 }
 
 // Light::Le(ray)  (light.h:38-40; only EnvironmentLight overrides it)
@@ -650,19 +671,7 @@ template <class R> RTB_HD R light_pdf(const ShadeView<R> &S, const LightT<R> &l,
         const V3<R> ud = unit_vector(direction);
         R u, v, theta;
         env_dir_to_uv(l, ud, u, v, theta);
-        const R sin_theta = sin_(theta);
-        if (sin_theta < R(1e-6))
-            return 0;
-        const int W = l.env_w, H = l.env_h;
-        const int u_idx = int(clamp_(R(int(u * W)), R(0), R(W - 1)));
-        const int v_idx = int(clamp_(R(int(v * H)), R(0), R(H - 1)));
-        const EnvTables T(S.env_tables + l.env_table_offset, W, H);
-        // Distribution1D::pdf(i) = func[i] / (func_int * n), environmental_light.h:46-48
-        const double ci = T.cond_int[v_idx];
-        const double pc = ci > 0 ? T.cond_func[size_t(v_idx) * W + u_idx] / (ci * W) : 0;
-        const double pm = T.marg_int > 0 ? ci / (T.marg_int * H) : 0;
-        const double map_pdf = pc * pm;
-        return R(map_pdf * W * H / (2.0 * double(pi) * double(pi) * double(sin_theta)));
+        return env_pdf_uv(S, l, u, v, theta);
     }
     return 0;
 }

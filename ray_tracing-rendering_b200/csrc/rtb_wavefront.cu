@@ -818,8 +818,8 @@ __device__ __forceinline__ void shade_surface(const WfParams &p, const GeomView<
     RecT<float> rec;
     if (ALL_PLANAR || (plane != nullptr && !(m.flags & 1) && plane[pi].valid))
         rec = plane_record<float>(plane[pi], s.o, s.d, t);
-    else if (M < 0) // (one copy of make_record in the one-copy kernel)
-        rec = make_record<float, true, true>(g, pi, s.o, s.d, s.time, t);
+    else if (M < 0) // (one copy of make_record in the one-copy kernel; the sphere's acos / atan2 only for textures that read u,v)
+        rec = make_record<float, true, true>(g, pi, s.o, s.d, s.time, t, (m.flags & 1) != 0);
     else
         rec = (m.flags & 1) ? make_record<float, true, true>(g, pi, s.o, s.d, s.time, t)
                             : make_record<float, true, false>(g, pi, s.o, s.d, s.time, t);
@@ -975,14 +975,31 @@ __device__ __forceinline__ void miss_surface(const WfParams &p, const PathState 
     const V3<float> bg(p.bg[0], p.bg[1], p.bg[2]);
     V3<float> L = s.T * bg;
     if (!OLD && p.integrator >= RTB_INTEGRATOR_DIRECT && p.shade.n_infinite_lights > 0) {
+        // Le of every environment light and — where the MIS weight wants it — the sum over ALL lights of pdf / N
+        // (all_lights_pdf), with ONE direction -> (u, v, theta) conversion per map shared by the two (acos + atan2 were
+        // 9 % of the general fused kernel's instructions on C4-env, a third of them this duplicate and unread sphere uv)
+        const bool want_pdf = !(p.integrator == RTB_INTEGRATOR_DIRECT || s.depth == 0 || s.spec);
         V3<float> env(0, 0, 0);
-        for (int i = 0; i < p.shade.n_lights; ++i)
-            if (light_at(p, i).type == RTB_LIGHT_ENV)
-                env = env + light_Le(p.shade, light_at(p, i), s.d);
-        if (p.integrator == RTB_INTEGRATOR_DIRECT || s.depth == 0 || s.spec)
-            L = s.T * env;
-        else
-            L = (s.T * env) * power_heuristic(s.prev_pdf, all_lights_pdf(p, s.o, s.d));
+        float pdf_sum = 0.f;
+        const V3<float> ud = unit_vector(s.d);
+        for (int i = 0; i < p.shade.n_lights; ++i) {
+            const LightT<float> &l = light_at(p, i);
+            if (l.type == RTB_LIGHT_ENV) {
+                if (l.env_w == 0) {
+                    env = env + V3<float>(1, 1, 1);
+                    pdf_sum += 1.0f / (4.0f * Consts<float>::pi());
+                } else {
+                    float u, v, theta;
+                    env_dir_to_uv(l, ud, u, v, theta);
+                    env = env + env_Le_uv(p.shade, l, u, v);
+                    if (want_pdf)
+                        pdf_sum += env_pdf_uv(p.shade, l, u, v, theta);
+                }
+            } else if (want_pdf) {
+                pdf_sum += light_pdf(p.shade, l, s.o, s.d);
+            }
+        }
+        L = want_pdf ? (s.T * env) * power_heuristic(s.prev_pdf, pdf_sum / float(p.shade.n_lights)) : s.T * env;
     }
     accum_add(p.accum, s.pix, L);
 }
