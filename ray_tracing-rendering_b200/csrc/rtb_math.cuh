@@ -89,9 +89,53 @@ RTB_HD float sin_(float x) { return sinf(x); }
 RTB_HD double sin_(double x) { return sin(x); }
 RTB_HD float cos_(float x) { return cosf(x); }
 RTB_HD double cos_(double x) { return cos(x); }
-RTB_HD float acos_(float x) { return acosf(x); }
+// fp32 acos / atan2 (sphere u,v and every direction -> environment-map look-up): polynomial forms, a third of the
+// instructions of acosf / atan2f, which were 9 % of the general fused kernel on C4-env.  acos(x) = sqrt(1 - |x|) P6(|x|)
+// (Chebyshev fit on [0, 1]); atan(a) = a Q6(a^2) on [0, 1] with the octant folded in.  Absolute error against the exact
+// functions of the same fp32 argument: acos <= 5e-7 rad, atan2 <= 8e-7 rad (tests/test_fast_invtrig.py, 2 x 10^5 arguments
+// each): 3e-4 of an environment-map texel at 2048 x 1024.  The fp64 validation
+// instantiations call the C library.
+#ifndef RTB_FAST_INVTRIG
+#define RTB_FAST_INVTRIG 1
+#endif
+RTB_HD float acos_(float x) {
+#if RTB_FAST_INVTRIG
+    const float ax = fminf(fabsf(x), 1.0f);
+    float p = 0.00225136825f;
+    p = fmaf(p, ax, -0.0110123861f);
+    p = fmaf(p, ax, 0.0267493312f);
+    p = fmaf(p, ax, -0.0487244023f);
+    p = fmaf(p, ax, 0.0887373288f);
+    p = fmaf(p, ax, -0.214583696f);
+    p = fmaf(p, ax, 1.57079615f);
+    const float r = sqrtf(1.0f - ax) * p;
+    return x < 0.0f ? 3.14159265358979f - r : r;
+#else
+    return acosf(x);
+#endif
+}
 RTB_HD double acos_(double x) { return acos(x); }
-RTB_HD float atan2_(float y, float x) { return atan2f(y, x); }
+RTB_HD float atan2_(float y, float x) {
+#if RTB_FAST_INVTRIG
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float a = mx > 0.0f ? mn / mx : 0.0f;
+    const float s = a * a;
+    float q = 0.00782548295f;
+    q = fmaf(q, s, -0.0368986292f);
+    q = fmaf(q, s, 0.0837415565f);
+    q = fmaf(q, s, -0.134804056f);
+    q = fmaf(q, s, 0.198798722f);
+    q = fmaf(q, s, -0.333263745f);
+    q = fmaf(q, s, 0.999999328f);
+    float r = a * q;
+    r = ay > ax ? 1.57079632679490f - r : r;
+    r = x < 0.0f ? 3.14159265358979f - r : r;
+    return y < 0.0f ? -r : r;
+#else
+    return atan2f(y, x);
+#endif
+}
 RTB_HD double atan2_(double y, double x) { return atan2(y, x); }
 RTB_HD float log_(float x) { return logf(x); }
 RTB_HD double log_(double x) { return log(x); }

@@ -470,6 +470,14 @@ void hc_camera_derived(void *h, double out[24]) {
 }
 // The renderer's per-sample random streams (rtb_shading.cuh): stream i = pcg_seed(first + i, seed); its first
 // `draws` float draws (next_f: the top 24 bits of the LCG state) go to out[i * draws ...].
+// the fp32 acos_ / atan2_ of csrc/rtb_math.cuh (polynomial forms) on n arguments
+void hc_invtrig(const float *x, const float *y, uint64_t n, float *acos_out, float *atan2_out) {
+    for (uint64_t i = 0; i < n; ++i) {
+        acos_out[i] = acos_(x[i]);
+        atan2_out[i] = atan2_(y[i], x[i]);
+    }
+}
+
 void hc_rng_draws(uint64_t first, uint64_t n_streams, uint64_t draws, uint64_t seed, float *out) {
     for (uint64_t i = 0; i < n_streams; ++i) {
         Pcg g = pcg_seed(first + i, seed);

@@ -1,10 +1,12 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-{
-timeout 600 python tools/run_config.py C4env --reps 2 --time | tail -n 2
-timeout 600 python tools/run_config.py C4env --wavefront --reps 2 --time | tail -n 2
-timeout 600 python tools/run_config.py C4 --reps 2 --time | tail -n 2
-timeout 600 python tools/run_config.py C4 --fused --reps 2 --time | tail -n 2
-} > gpurun_out/q_sweep.log 2>&1
-cat gpurun_out/q_sweep.log
+timeout 900 python bench.py > gpurun_out/f_bench.json 2> gpurun_out/f_bench.err
+echo "bench exit $?"
+python - <<'PY'
+import json
+d = json.loads(open("gpurun_out/f_bench.json").read().strip().splitlines()[-1])
+print("C1", d["value"], d["ms_per_step"], "e2e", d["e2e"]["value"])
+for k, v in d["configs"].items():
+    print(k, round(v["mpaths_per_s"], 1), "Mpaths/s", round(v["ms_per_step"], 2), "ms e2e", round(v["e2e"]["value"], 1), v["schedule"])
+PY
