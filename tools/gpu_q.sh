@@ -1,12 +1,13 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 900 python bench.py > gpurun_out/f_bench.json 2> gpurun_out/f_bench.err
-echo "bench exit $?"
-python - <<'PY'
-import json
-d = json.loads(open("gpurun_out/f_bench.json").read().strip().splitlines()[-1])
-print("C1", d["value"], d["ms_per_step"], "e2e", d["e2e"]["value"])
-for k, v in d["configs"].items():
-    print(k, round(v["mpaths_per_s"], 1), "Mpaths/s", round(v["ms_per_step"], 2), "ms e2e", round(v["e2e"]["value"], 1), v["schedule"])
-PY
+{
+for v in "" $(ls ray_tracing-rendering_b200/variants/ | grep "^librtb200_.*\.so$" | sed 's/librtb200_//; s/\.so//'); do
+  if [ -n "$v" ]; then export RTB200_LIBRARY=$PWD/ray_tracing-rendering_b200/variants/librtb200_$v.so; else unset RTB200_LIBRARY; fi
+  echo "== variant '$v'"
+  timeout 600 python tools/run_config.py C5 --spp 16 --reps 3 --time | tail -n 2
+  timeout 600 python tools/run_config.py C2 --spp 100 --reps 3 --time | tail -n 2
+  timeout 600 python tools/run_config.py C4 --reps 3 | tail -n 2
+done
+} > gpurun_out/q_sweep.log 2>&1
+cat gpurun_out/q_sweep.log
